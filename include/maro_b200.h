@@ -1,0 +1,184 @@
+/*
+ * maro_b200.h — C ABI of the B200-native batched discrete-event simulation core.
+ *
+ * This is the drop-in boundary (seam 3): everything `maro.simulator.Env` /
+ * `maro.vector_env.VectorEnv` need from the step path, for B independent replicas at once, as plain
+ * pointers and sizes.  No torch / Python types.  The reference has no C ABI for this path (its seams are a
+ * Cython vtable and Python classes); each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on failure; maro_last_error() returns the message of
+ *     the last failure on the calling thread.
+ *   - The caller owns every in/out buffer; the library owns device memory, streams and snapshot rings.
+ *     No pointer handed out by the library outlives maro_cim_destroy().
+ *   - A handle is NOT thread-safe (the reference Env is single-threaded: maro/simulator/core.py:20).
+ *   - "host" entry points take host buffers and perform H2D / D2H inside the call; "_device" entry points
+ *     take device pointers and only enqueue work on the handle's stream.
+ */
+#ifndef MARO_B200_H
+#define MARO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARO_B200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------
+ * Static tables of one CIM topology instance (config + max_tick + seed).
+ * Produced on the host by maro_b200.scenarios.cim.topology.build_topology(), which restates
+ * maro/data_lib/cim/cim_data_generator.py:18-205 and maro/data_lib/cim/parsers.py:14-211.
+ * All arrays are caller-owned and copied during maro_cim_create().
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MaroCimTopology {
+    int32_t n_ports, n_vessels, n_routes;
+    int32_t past_stop_number, future_stop_number; /* config "stop_number"                            */
+    int32_t max_tick;                             /* start_tick + durations                          */
+    int32_t order_mode;                           /* 0 = fixed, 1 = unfixed (entities.py:74-84)      */
+    int32_t total_containers;
+    double container_volume;                      /* config container_volumes[0]                     */
+    /* ports [n_ports] */
+    const int32_t* port_capacity;
+    const int32_t* port_init_empty;
+    const double* full_return_base;
+    const double* full_return_noise;
+    const double* empty_return_base;
+    const double* empty_return_noise;
+    const double* source_base;
+    const double* source_noise;
+    const int32_t* target_offset; /* [n_ports + 1] into target_* */
+    const int32_t* target_port;
+    const double* target_base;
+    const double* target_noise;
+    /* vessels [n_vessels] */
+    const int32_t* vessel_capacity;
+    const int32_t* vessel_init_empty;
+    const int32_t* vessel_route;
+    const int32_t* vessel_period;      /* vessel_period_without_noise (cim_data_container.py:218-229)    */
+    const int32_t* vessel_route_start; /* index of the start port inside the vessel's route             */
+    const int32_t* vessel_leg_offset;  /* [n_vessels + 1] into vessel_leg                                */
+    const int32_t* vessel_leg;         /* parking duration + ceil(distance / speed) per route position  */
+    const int32_t* stop_offset;        /* [n_vessels + 1] into stop_*                                    */
+    const int32_t* stop_arrival;
+    const int32_t* stop_leave;
+    const int32_t* stop_port;
+    /* routes */
+    const int32_t* route_offset; /* [n_routes + 1] into route_port */
+    const int32_t* route_port;
+    /* per-tick order budget, [max_tick] (parsers.py:63-107) */
+    const int32_t* order_proportion;
+    /* MT19937 seeds of the two in-step random streams (sim_random.py:48-63). */
+    uint32_t order_number_seed;
+    uint32_t buffer_time_seed;
+} MaroCimTopology;
+
+typedef struct MaroCimConfig {
+    int32_t n_replicas;
+    int32_t start_tick;          /* Env(start_tick=)            core.py:46                            */
+    int32_t snapshot_resolution; /* Env(snapshot_resolution=)   core.py:48                            */
+    int32_t max_snapshots;       /* Env(max_snapshots=), <=0: keep every frame  core.py:49            */
+    int32_t device;              /* CUDA device ordinal                                               */
+    int32_t queue_capacity;      /* per-replica dynamic-event slots; <=0: library default             */
+    int32_t max_actions;         /* actions per replica per step (A_MAX); <=0: 1                      */
+    const int32_t* replica_topology; /* [n_replicas] index into topos[], NULL: all 0                  */
+} MaroCimConfig;
+
+/* Row layout of the decision output, one row of MARO_CIM_DECISION_WORDS int32 per replica.
+ * Mirrors DecisionEvent (maro/simulator/scenarios/cim/common.py:72-150) + step status. */
+enum {
+    MARO_DEC_TICK = 0,
+    MARO_DEC_PORT = 1,
+    MARO_DEC_VESSEL = 2,
+    MARO_DEC_SCOPE_LOAD = 3,      /* ActionScope.load      = min(port.empty, vessel.remaining_space) */
+    MARO_DEC_SCOPE_DISCHARGE = 4, /* ActionScope.discharge = vessel.empty                            */
+    MARO_DEC_EARLY_DISCHARGE = 5,
+    MARO_DEC_STATUS = 6,          /* MARO_STATUS_*                                                   */
+    MARO_DEC_EVENTS = 7,          /* events executed by this step (for events/s accounting)          */
+    MARO_CIM_DECISION_WORDS = 8
+};
+
+enum {
+    MARO_STATUS_DECISION = 0, /* (metrics, decision, False)                     core.py:350            */
+    MARO_STATUS_DONE = 1,     /* (metrics, None, True) — episode just ended     core.py:381            */
+    MARO_STATUS_FINISHED = 2, /* (None, None, True) — stepping a finished env   core.py:128-131        */
+    MARO_STATUS_INACTIVE = 3, /* replica not selected by the active mask (VectorEnv dict stepping)     */
+    MARO_STATUS_BAD_ACTION = -1,   /* the reference would raise AssertionError (business_engine.py:731,736) */
+    MARO_STATUS_QUEUE_OVERFLOW = -2
+};
+
+/* Action row: 4 int32 {vessel_idx, port_idx, quantity, action_type}; Action in cim/common.py:25-53. */
+enum { MARO_ACTION_LOAD = 0, MARO_ACTION_DISCHARGE = 1, MARO_CIM_ACTION_WORDS = 4 };
+
+/* Metrics row: 3 int64 {order_requirements, container_shortage, operation_number};
+ * CimBusinessEngine.get_metrics, business_engine.py:270-282. */
+enum { MARO_CIM_METRIC_WORDS = 3 };
+
+/* Node types for snapshot queries (frame_builder.py:11-33). */
+enum { MARO_CIM_NODE_PORTS = 0, MARO_CIM_NODE_VESSELS = 1, MARO_CIM_NODE_MATRICES = 2 };
+
+typedef struct MaroCimEnv MaroCimEnv;
+
+const char* maro_last_error(void);
+int maro_abi_version(void);
+
+/* Env.__init__ / VectorEnv.__init__ (core.py:42-90, vector_env.py:55-93): allocate B replicas on one GPU. */
+int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCimConfig* cfg, MaroCimEnv** out);
+/* VectorEnv.stop / __del__ (vector_env.py:146-160). */
+int maro_cim_destroy(MaroCimEnv* env);
+/* Use an externally created CUDA stream (cudaStream_t) for all subsequent work; NULL = library stream. */
+int maro_cim_set_stream(MaroCimEnv* env, void* cuda_stream);
+
+/* Env.step / VectorEnv.step (core.py:92-133, vector_env.py:116-144), host buffers.
+ *   active      [B] uint8 or NULL (all)            — dict/subset stepping of VectorEnv
+ *   actions     [B][max_actions][4] int32 or NULL  — NULL = step(None) for every replica
+ *   n_actions   [B] int32 or NULL (NULL with actions != NULL means 1 each)
+ *   decisions   [B][8] int32 out, metrics [B][3] int64 out                                           */
+int maro_cim_step(MaroCimEnv* env, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
+                  int32_t* decisions, int64_t* metrics);
+/* Same, device pointers, asynchronous on the handle's stream (no host<->device copies). */
+int maro_cim_step_device(MaroCimEnv* env, const uint8_t* d_active, const int32_t* d_actions,
+                         const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
+
+/* Env.reset (core.py:143-170) for the replicas selected by mask (NULL = all).  Tables of the replicas'
+ * topologies must already be resident (see maro_cim_set_topology for keep_seed=False / set_seed). */
+int maro_cim_reset(MaroCimEnv* env, const uint8_t* mask);
+/* Replace topology slot `index` (same shape) — used for reset(keep_seed=False) and Env.set_seed. */
+int maro_cim_set_topology(MaroCimEnv* env, int32_t index, const MaroCimTopology* topo);
+
+/* env.snapshot_list[node][ticks:nodes:attrs] (frame.pyx:754-801, np_backend.pyx:520-549), static-backend
+ * semantics: out[replica][tick][node][attr][slot] as float64, frames not in the ring -> zeros.
+ * `frame_indices` are snapshot frame indices (tick // resolution), attrs are attribute ids from
+ * maro_cim_attr_id().  Returns the number of doubles written per replica through *out_per_replica. */
+int maro_cim_query(MaroCimEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
+                   const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
+                   const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
+/* Same gather, output left in device memory (float64). */
+int maro_cim_query_device(MaroCimEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
+                          const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes,
+                          int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* d_out,
+                          int64_t* out_per_replica);
+/* Attribute id / slot count by name for a node type; -1 if unknown. */
+int32_t maro_cim_attr_id(MaroCimEnv* env, int32_t node_type, const char* name);
+int32_t maro_cim_attr_slots(MaroCimEnv* env, int32_t node_type, int32_t attr_id);
+
+/* env.current_frame (core.py:190-193): copy the live frame words of one replica to the host. */
+int maro_cim_read_frame(MaroCimEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);
+int32_t maro_cim_frame_words(MaroCimEnv* env);
+/* env.tick (core.py:196-198) for all replicas. */
+int maro_cim_ticks(MaroCimEnv* env, int32_t* out_ticks);
+/* Cumulative per-replica work counters {env_steps, ticks, events, snapshots} as int64[B][4]. */
+int maro_cim_counters(MaroCimEnv* env, int64_t* out);
+/* Frame indices currently held by the snapshot ring of one replica (SnapshotList.get_frame_index_list). */
+int maro_cim_snapshot_frames(MaroCimEnv* env, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out);
+
+/* Agent helper used by bench.py: the hello-world random policy (examples/hello_world/cim/hello.py:24-32)
+ * as a counter-based hash of (replica, step), evaluated on the device so the env state never leaves HBM. */
+int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t* d_actions,
+                                  uint32_t seed, uint32_t step_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARO_B200_H */

@@ -1,0 +1,108 @@
+"""ctypes mirror of ``include/maro_b200.h`` (struct layouts + enums).  Pure declarations, no library loading."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+
+DEC_TICK, DEC_PORT, DEC_VESSEL, DEC_SCOPE_LOAD, DEC_SCOPE_DISCHARGE, DEC_EARLY_DISCHARGE, DEC_STATUS, DEC_EVENTS = range(8)
+DECISION_WORDS = 8
+ACTION_WORDS = 4
+METRIC_WORDS = 3
+STATUS_DECISION, STATUS_DONE, STATUS_FINISHED, STATUS_INACTIVE = 0, 1, 2, 3
+STATUS_BAD_ACTION, STATUS_QUEUE_OVERFLOW = -1, -2
+ACTION_LOAD, ACTION_DISCHARGE = 0, 1
+NODE_PORTS, NODE_VESSELS, NODE_MATRICES = 0, 1, 2
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class MaroCimTopology(C.Structure):
+    _fields_ = [
+        ("n_ports", C.c_int32), ("n_vessels", C.c_int32), ("n_routes", C.c_int32),
+        ("past_stop_number", C.c_int32), ("future_stop_number", C.c_int32),
+        ("max_tick", C.c_int32), ("order_mode", C.c_int32), ("total_containers", C.c_int32),
+        ("container_volume", C.c_double),
+        ("port_capacity", _i32p), ("port_init_empty", _i32p),
+        ("full_return_base", _f64p), ("full_return_noise", _f64p),
+        ("empty_return_base", _f64p), ("empty_return_noise", _f64p),
+        ("source_base", _f64p), ("source_noise", _f64p),
+        ("target_offset", _i32p), ("target_port", _i32p), ("target_base", _f64p), ("target_noise", _f64p),
+        ("vessel_capacity", _i32p), ("vessel_init_empty", _i32p), ("vessel_route", _i32p),
+        ("vessel_period", _i32p), ("vessel_route_start", _i32p), ("vessel_leg_offset", _i32p),
+        ("vessel_leg", _i32p), ("stop_offset", _i32p), ("stop_arrival", _i32p), ("stop_leave", _i32p),
+        ("stop_port", _i32p), ("route_offset", _i32p), ("route_port", _i32p), ("order_proportion", _i32p),
+        ("order_number_seed", C.c_uint32), ("buffer_time_seed", C.c_uint32),
+    ]
+
+
+class MaroCimConfig(C.Structure):
+    _fields_ = [
+        ("n_replicas", C.c_int32), ("start_tick", C.c_int32), ("snapshot_resolution", C.c_int32),
+        ("max_snapshots", C.c_int32), ("device", C.c_int32), ("queue_capacity", C.c_int32),
+        ("max_actions", C.c_int32), ("replica_topology", _i32p),
+    ]
+
+
+_I32_FIELDS = ("port_capacity", "port_init_empty", "target_offset", "target_port", "vessel_capacity",
+               "vessel_init_empty", "vessel_route", "vessel_period", "vessel_route_start", "vessel_leg_offset",
+               "vessel_leg", "stop_offset", "stop_arrival", "stop_leave", "stop_port", "route_offset", "route_port",
+               "order_proportion")
+_F64_FIELDS = ("full_return_base", "full_return_noise", "empty_return_base", "empty_return_noise", "source_base",
+               "source_noise", "target_base", "target_noise")
+
+
+def topology_struct(topo):
+    """Build a ``MaroCimTopology`` from a ``CimTopology``; returns (struct, keepalive list of arrays)."""
+    s = MaroCimTopology()
+    keep = []
+    for name in ("n_ports", "n_vessels", "n_routes", "past_stop_number", "future_stop_number", "max_tick",
+                 "order_mode", "total_containers"):
+        setattr(s, name, int(getattr(topo, name)))
+    s.container_volume = float(topo.container_volume)
+    for name in _I32_FIELDS:
+        a = np.ascontiguousarray(getattr(topo, name), dtype=np.int32)
+        if a.size == 0:
+            a = np.zeros(1, np.int32)
+        keep.append(a)
+        setattr(s, name, a.ctypes.data_as(_i32p))
+    for name in _F64_FIELDS:
+        a = np.ascontiguousarray(getattr(topo, name), dtype=np.float64)
+        if a.size == 0:
+            a = np.zeros(1, np.float64)
+        keep.append(a)
+        setattr(s, name, a.ctypes.data_as(_f64p))
+    s.order_number_seed = int(topo.stream_seeds["order_number"]) & 0xFFFFFFFF
+    s.buffer_time_seed = int(topo.stream_seeds["buffer_time"]) & 0xFFFFFFFF
+    return s, keep
+
+
+# canonical frame layout helpers (DESIGN.md "Frame layout") -------------------------------------------------
+PORT_ATTRS = ("acc_booking", "acc_fulfillment", "acc_shortage", "booking", "capacity", "empty", "fulfillment",
+              "full", "on_consignee", "on_shipper", "shortage", "transfer_cost")
+VESSEL_SCALAR_ATTRS = ("capacity", "early_discharge", "empty", "full", "is_parking", "last_loc_idx",
+                       "loc_port_idx", "next_loc_idx", "remaining_space", "route_idx")
+VESSEL_LIST_ATTRS = ("past_stop_list", "past_stop_tick_list", "future_stop_list", "future_stop_tick_list")
+MATRIX_ATTRS = ("full_on_ports", "full_on_vessels", "vessel_plans")
+
+
+def frame_layout(P: int, V: int, past_n: int, future_n: int):
+    """name -> (word offset, n_nodes, slots) for every attribute of every node type."""
+    lay = {"ports": {}, "vessels": {}, "matrices": {}}
+    off = 0
+    for a in PORT_ATTRS:
+        lay["ports"][a] = (off, P, 1)
+        off += P
+    for a in VESSEL_SCALAR_ATTRS:
+        lay["vessels"][a] = (off, V, 1)
+        off += V
+    for a, n in zip(VESSEL_LIST_ATTRS, (past_n, past_n, future_n, future_n)):
+        lay["vessels"][a] = (off, V, n)
+        off += V * n
+    for a, n in zip(MATRIX_ATTRS, (P * P, V * P, V * P)):
+        lay["matrices"][a] = (off, 1, n)
+        off += n
+    return lay, off
