@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched CIM Env.step hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W           # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...           # the reference's own CPU path on the host cores
+
+A bench "step" = one batched Env.step over all replicas of a rank (hashed random agent + step kernel).
+Workload (config.workload): BASELINE.json configs[1] — CIM toy.4p_ssdd_l0.0, 1024 parallel envs per GPU,
+1000 ticks, random actions; episodes are restarted (Env.reset, inside the timed region) when they end.
+
+Printed JSON (rank 0, one line): see the keys at the bottom.  `value` = whole-job env-steps/s with state resident
+in HBM, L2 flushed between timed steps, device-timed per step with CUDA events, max over ranks.  `e2e` = the same
+metric through the host-buffer C-ABI call (maro_cim_step: pinned H2D of the actions, kernel, D2H of decisions +
+metrics every step) with the agent evaluated on the host.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_DECLARED = {"toy.4p_ssdd_l0.0": 886}  # frame bytes per replica in the reference's declared dtypes
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=1024, help="parallel envs per GPU")
+    ap.add_argument("--ticks", type=int, default=1000)
+    ap.add_argument("--topology", default="toy.4p_ssdd_l0.0")
+    ap.add_argument("--max-snapshots", type=int, default=0, help="0 = keep every frame (reference default)")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self._nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation on the host cores: maro.vector_env.VectorEnv(batch_num=cpu_count)
+    from oracle/_ref (the unmodified reference built by oracle/build_ref.sh) when present, else the C port."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    cores = os.cpu_count() or 1
+    line = {"metric": "env-steps/sec", "unit": "env-steps/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"CIM {args.topology}, {args.ticks} ticks, random actions", "replicas": cores}}
+    if os.path.isdir(os.path.join(ref_root, "maro")):
+        os.environ["SKIP_DEPLOYMENT"] = "TRUE"
+        os.environ.setdefault("DEFAULT_BACKEND_NAME", "dynamic")  # the Cython/C++ RawBackend the north-star names
+        sys.path.insert(0, ref_root)
+        sys.path.insert(1, os.path.join(ref_root, "_stubs"))
+        from maro.simulator.scenarios.cim.common import Action, ActionType
+        from maro.vector_env import VectorEnv
+
+        from tests.golden.gen_cim_golden import policy_random
+
+        with VectorEnv(batch_num=cores, scenario="cim", topology=args.topology, durations=args.ticks) as env:
+            def agent(decisions, step):
+                acts = {}
+                for i, d in enumerate(decisions):
+                    if d is None:
+                        continue
+                    row = [d.tick, d.port_idx, d.vessel_idx, d.action_scope.load, d.action_scope.discharge,
+                           d.early_discharge]
+                    v, p, q, t = policy_random(row, 0, i, step)
+                    acts[i] = Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD)
+                return acts
+
+            def loop(n):
+                nonlocal metrics, decisions, done, step, env_steps
+                for _ in range(n):
+                    if done:
+                        env.reset()
+                        metrics, decisions, done = env.step(None)
+                        step = 0
+                        env_steps += cores
+                        continue
+                    metrics, decisions, done = env.step(agent(decisions, step))
+                    step += 1
+                    env_steps += cores
+
+            env_steps, step = 0, 0
+            metrics, decisions, done = env.step(None)
+            loop(args.warmup)
+            env_steps = 0
+            t0 = time.perf_counter()
+            loop(args.steps)
+            dt = time.perf_counter() - t0
+        kind, sample = "reference", f"VectorEnv(batch_num={cores}) x {args.steps} steps, backend={os.environ['DEFAULT_BACKEND_NAME']}"
+        value = env_steps / dt
+    else:
+        from maro_b200.scenarios.cim.topology import build_topology
+        from oracle.cim_oracle import CimOracle
+
+        topo = build_topology(args.topology, args.ticks)
+        o = CimOracle(topo)
+        env_steps, t0, ep = 0, time.perf_counter(), 0
+        while env_steps < args.steps * 1024 and time.perf_counter() - t0 < 60:
+            o.reset()
+            n, _ = o.run_episode(1, 0, ep)
+            env_steps += n
+            ep += 1
+        dt = time.perf_counter() - t0
+        kind, sample, cores = "port", f"{ep} episodes of the C restatement, 1 thread", 1
+        value = env_steps / dt
+    line.update({"value": value, "ms_per_step": 1000.0 * dt / max(1, args.steps),
+                 "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def cpu_baseline_port(args, topo):
+    from oracle.cim_oracle import CimOracle
+
+    o = CimOracle(topo)
+    env_steps, ep, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < args.cpu_seconds:
+        o.reset()
+        n, _ = o.run_episode(1, 0, ep)
+        env_steps += n
+        ep += 1
+    dt = time.perf_counter() - t0
+    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/cim_oracle.c, same topology/ticks/policy, 1 thread"}
+
+
+def host_policy(dec, seed, step, base, np):
+    """numpy-vectorised twin of cim_policy_kernel (uint32 arithmetic)."""
+    def h(x):
+        x = x.astype(np.uint32)
+        x ^= x >> np.uint32(16); x *= np.uint32(0x7FEB352D); x ^= x >> np.uint32(15)
+        x *= np.uint32(0x846CA68B); x ^= x >> np.uint32(16)
+        return x
+    B = dec.shape[0]
+    rid = (np.arange(B, dtype=np.uint32) + np.uint32(base))
+    with np.errstate(over="ignore"):
+        h1 = h(np.uint32(seed) ^ h(rid * np.uint32(0x9E3779B9) + np.uint32((step * 0x85EBCA6B) & 0xFFFFFFFF) + np.uint32(0x1234567)))
+        h2 = h(h1 + np.uint32(0x68BC21EB))
+    load, dis = dec[:, 3], dec[:, 4]
+    to_dis = (dis > 0) & ((h1 & 1) == 1)
+    scope = np.where(to_dis, dis, load)
+    qty = np.where(scope > 0, h2 % (scope.astype(np.uint32) + np.uint32(1)), 0).astype(np.int32)
+    act = np.empty((B, 1, 4), np.int32)
+    act[:, 0, 0] = dec[:, 2]; act[:, 0, 1] = dec[:, 1]; act[:, 0, 2] = qty; act[:, 0, 3] = to_dis
+    return act
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from maro_b200.batch import CimBatch
+    from maro_b200.scenarios.cim.topology import build_topology
+    from oracle.cim_oracle import CimOracle  # checker / cpu_baseline leg only
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.replicas
+    topo = build_topology(args.topology, args.ticks)
+    steps_per_episode = CimOracle(topo).run_episode(0)[0]  # decisions + final step (static for a given stop table)
+    env = CimBatch(topo, B, device=local_rank, max_snapshots=args.max_snapshots or None)
+    stream = torch.cuda.current_stream()
+    env.set_stream(stream.cuda_stream)
+    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    base = rank * B
+    pos = {"i": 0}
+
+    def one_step(ev=None):
+        """policy + step (or the episode's first step / reset at an episode boundary)."""
+        i = pos["i"] % steps_per_episode
+        if flush is not None:
+            flush.fill_(1)
+        if ev:
+            ev[0].record(stream)
+        if i == 0:
+            if pos["i"] > 0:
+                env.reset()  # Env.reset (synchronous); part of the job
+            if ev:
+                ev[1].record(stream)
+            env.step_device(dec.data_ptr(), met.data_ptr())
+        else:
+            env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, i - 1, base)
+            if ev:
+                ev[1].record(stream)
+            env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+        if ev:
+            ev[2].record(stream)
+        pos["i"] += 1
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    c0 = env.counters().sum(0)
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        one_step(events[k])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(e[0].elapsed_time(e[2]) for e in events)
+    kernel_ms = sum(e[1].elapsed_time(e[2]) for e in events)
+    c1 = env.counters().sum(0)
+    d_steps, d_ticks, d_events, d_snaps = (int(x) for x in (c1 - c0))
+
+    # ---- e2e: host-buffer C-ABI path, agent on the host, one episode-aligned run of min(steps, 2000) steps
+    e2e = None
+    if not args.skip_e2e:
+        env.reset()
+        n_e2e = min(args.steps, 2000)
+        d, m = env.step(None)
+        for k in range(3):
+            d, m = env.step(host_policy(d, 0, k, base, np))
+        env.reset()
+        torch.cuda.synchronize()
+        cc0 = env.counters().sum(0)
+        t0 = time.perf_counter()
+        i = 0
+        for k in range(n_e2e):
+            if i == 0:
+                if k > 0:
+                    env.reset()
+                d, m = env.step(None)
+            else:
+                d, m = env.step(host_policy(d, 0, i - 1, base, np))
+            i = (i + 1) % steps_per_episode
+        dt = time.perf_counter() - t0
+        cc1 = env.counters().sum(0)
+        e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt}
+
+    t = torch.tensor([total_ms, kernel_ms, wall * 1000.0, (e2e or {}).get("seconds", 0.0) * 1000.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([d_steps, d_ticks, d_events, d_snaps, (e2e or {}).get("steps", 0)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        # the path's single collective: collate per-replica episode metrics on every rank
+        gathered = torch.empty((world * B, 3), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(gathered, met)
+    total_ms, kernel_ms, wall_ms, e2e_ms = (float(x) for x in t.cpu())
+    g_steps, g_ticks, g_events, g_snaps, g_e2e_steps = (int(x) for x in cnt.cpu())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
+                peaks = json.load(fp)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        F = F_DECLARED.get(args.topology, env.frame_words * 4)
+        n_snap = g_snaps / max(1, g_steps)
+        n_ev = g_events / max(1, g_steps)
+        bytes_per_step = 2 * F + n_snap * F + 32 * n_ev + 64
+        achieved = bytes_per_step * g_steps / world / (kernel_ms / 1000.0) / 1e9  # per GPU
+        value = g_steps / (total_ms / 1000.0)
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"CIM {args.topology}, {B} parallel envs per GPU, {args.ticks} ticks, random actions "
+                                   f"(hashed hello-world agent), snapshot_resolution 1, max_snapshots "
+                                   f"{args.max_snapshots or 'all'}",
+                       "replicas_per_gpu": B, "l2": "state resident (no flush)" if args.no_flush else "flushed between timed steps (256 MiB write)",
+                       "steps_per_episode": steps_per_episode},
+            "ticks_per_s": g_ticks / (total_ms / 1000.0), "events_per_s": g_events / (total_ms / 1000.0),
+            "wall_ms": wall_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "cim_step_kernel", "bytes_per_env_step": bytes_per_step,
+                         "n_snap": n_snap, "n_ev": n_ev, "kernel_us": 1000.0 * kernel_ms / args.steps,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
+            "clocks": clocks,
+            "gpu_launches": 2 * args.steps,
+        }
+        if e2e:
+            line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
+                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * 56,
+                           "api": "maro_cim_step (host buffers) + numpy agent"}
+        line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

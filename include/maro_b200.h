@@ -174,9 +174,10 @@ int maro_cim_counters(MaroCimEnv* env, int64_t* out);
 int maro_cim_snapshot_frames(MaroCimEnv* env, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out);
 
 /* Agent helper used by bench.py: the hello-world random policy (examples/hello_world/cim/hello.py:24-32)
- * as a counter-based hash of (replica, step), evaluated on the device so the env state never leaves HBM. */
+ * as a counter-based hash of (replica_base + replica, step), evaluated on the device so the env state never
+ * leaves HBM. */
 int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t* d_actions,
-                                  uint32_t seed, uint32_t step_index);
+                                  uint32_t seed, uint32_t step_index, uint32_t replica_base);
 
 #ifdef __cplusplus
 }

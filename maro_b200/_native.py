@@ -1,0 +1,71 @@
+"""Loader for the CUDA library (``libmaro_b200.so``, built in-tree by ``__graft_entry__.build()``).
+
+There is deliberately no CPU fallback: if the extension is missing or no GPU is present, the product fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaro_b200.so")
+_lib = None
+
+#: every symbol ``include/maro_b200.h`` declares
+EXPORTS = (
+    "maro_last_error", "maro_abi_version", "maro_cim_create", "maro_cim_destroy", "maro_cim_set_stream",
+    "maro_cim_step", "maro_cim_step_device", "maro_cim_reset", "maro_cim_set_topology", "maro_cim_query",
+    "maro_cim_query_device", "maro_cim_attr_id", "maro_cim_attr_slots", "maro_cim_read_frame",
+    "maro_cim_frame_words", "maro_cim_ticks", "maro_cim_counters", "maro_cim_snapshot_frames",
+    "maro_cim_random_policy_device",
+)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Return the loaded library (ctypes.CDLL) with argtypes declared; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  maro_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
+    L.maro_last_error.restype = C.c_char_p
+    L.maro_abi_version.restype = C.c_int
+    L.maro_cim_create.argtypes = [vp, i32, vp, C.POINTER(vp)]
+    L.maro_cim_destroy.argtypes = [vp]
+    L.maro_cim_set_stream.argtypes = [vp, vp]
+    L.maro_cim_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.maro_cim_step_device.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.maro_cim_reset.argtypes = [vp, vp]
+    L.maro_cim_set_topology.argtypes = [vp, i32, vp]
+    L.maro_cim_query.argtypes = [vp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+    L.maro_cim_query_device.argtypes = [vp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+    L.maro_cim_attr_id.argtypes = [vp, i32, C.c_char_p]
+    L.maro_cim_attr_id.restype = i32
+    L.maro_cim_attr_slots.argtypes = [vp, i32, i32]
+    L.maro_cim_attr_slots.restype = i32
+    L.maro_cim_read_frame.argtypes = [vp, i32, vp, i32]
+    L.maro_cim_frame_words.argtypes = [vp]
+    L.maro_cim_frame_words.restype = i32
+    L.maro_cim_ticks.argtypes = [vp, vp]
+    L.maro_cim_counters.argtypes = [vp, vp]
+    L.maro_cim_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
+    L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32, u32]
+    if L.maro_abi_version() != _abi.ABI_VERSION:
+        raise NativeLibraryError("libmaro_b200.so ABI version mismatch; rebuild")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(lib().maro_last_error().decode())

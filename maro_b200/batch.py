@@ -1,0 +1,181 @@
+"""``CimBatch`` — thin columnar wrapper over the C ABI: B CIM replicas resident on one GPU.
+
+This is the layer both drop-in surfaces (``maro_b200.simulator.Env`` and ``maro_b200.vector_env.VectorEnv``)
+sit on.  All arrays are numpy (host) unless a method says ``_device``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi, _native
+from .scenarios.cim.topology import CimTopology
+
+_NODE_TYPE = {"ports": _abi.NODE_PORTS, "vessels": _abi.NODE_VESSELS, "matrices": _abi.NODE_MATRICES}
+
+
+class CimBatch:
+    def __init__(self, topologies, n_replicas: int, start_tick: int = 0, snapshot_resolution: int = 1,
+                 max_snapshots: Optional[int] = None, device: int = 0, max_actions: int = 1,
+                 replica_topology: Optional[Sequence[int]] = None, queue_capacity: int = 0):
+        if isinstance(topologies, CimTopology):
+            topologies = [topologies]
+        self.topologies = list(topologies)
+        self.n_replicas = int(n_replicas)
+        self.max_actions = int(max_actions)
+        self.start_tick = int(start_tick)
+        self.snapshot_resolution = int(snapshot_resolution)
+        self.device = int(device)
+        L = _native.lib()
+        self._keep = []
+        arr = (_abi.MaroCimTopology * len(self.topologies))()
+        for i, t in enumerate(self.topologies):
+            s, keep = _abi.topology_struct(t)
+            arr[i] = s
+            self._keep.append(keep)
+        cfg = _abi.MaroCimConfig()
+        cfg.n_replicas = self.n_replicas
+        cfg.start_tick = self.start_tick
+        cfg.snapshot_resolution = self.snapshot_resolution
+        cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
+        cfg.device = self.device
+        cfg.queue_capacity = int(queue_capacity)
+        cfg.max_actions = self.max_actions
+        if replica_topology is not None:
+            rt = np.ascontiguousarray(replica_topology, np.int32)
+            assert rt.shape == (self.n_replicas,)
+            self._keep.append(rt)
+            cfg.replica_topology = rt.ctypes.data_as(C.POINTER(C.c_int32))
+        h = C.c_void_p()
+        _native.check(L.maro_cim_create(arr, len(self.topologies), C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.frame_words = L.maro_cim_frame_words(self._h)
+        # reusable host output buffers
+        self.decisions = np.zeros((self.n_replicas, _abi.DECISION_WORDS), np.int32)
+        self.metrics = np.zeros((self.n_replicas, _abi.METRIC_WORDS), np.int64)
+
+    # -- lifecycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            _native.lib().maro_cim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _native.check(_native.lib().maro_cim_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        _native.check(_native.lib().maro_cim_reset(self._h, None if m is None else m.ctypes.data))
+
+    def set_topology(self, index: int, topo: CimTopology):
+        s, keep = _abi.topology_struct(topo)
+        _native.check(_native.lib().maro_cim_set_topology(self._h, index, C.byref(s)))
+        self.topologies[index] = topo
+
+    # -- stepping ----------------------------------------------------------------------------------
+    def step(self, actions=None, n_actions=None, active=None):
+        """One Env.step for every (active) replica.  actions: int32 [B][max_actions][4] or None."""
+        a = n = m = None
+        if actions is not None:
+            a = np.ascontiguousarray(actions, np.int32)
+            assert a.size == self.n_replicas * self.max_actions * 4, a.shape
+        if n_actions is not None:
+            n = np.ascontiguousarray(n_actions, np.int32)
+        if active is not None:
+            m = np.ascontiguousarray(active, np.uint8)
+        _native.check(_native.lib().maro_cim_step(
+            self._h, None if m is None else m.ctypes.data, None if a is None else a.ctypes.data,
+            None if n is None else n.ctypes.data, self.decisions.ctypes.data, self.metrics.ctypes.data))
+        return self.decisions, self.metrics
+
+    def step_device(self, d_decisions: int, d_metrics: int, d_actions: int = 0, d_n_actions: int = 0, d_active: int = 0):
+        """Asynchronous step on device pointers (ints, e.g. ``tensor.data_ptr()``)."""
+        _native.check(_native.lib().maro_cim_step_device(self._h, d_active or None, d_actions or None,
+                                                         d_n_actions or None, d_decisions, d_metrics))
+
+    def random_policy_device(self, d_decisions: int, d_actions: int, seed: int, step_index: int, replica_base: int = 0):
+        _native.check(_native.lib().maro_cim_random_policy_device(self._h, d_decisions, d_actions, seed, step_index,
+                                                                  replica_base))
+
+    # -- inspection --------------------------------------------------------------------------------
+    def attr_id(self, node: str, name: str) -> int:
+        i = _native.lib().maro_cim_attr_id(self._h, _NODE_TYPE[node], name.encode())
+        if i < 0:
+            raise KeyError(f"{node}.{name}")
+        return i
+
+    def attr_slots(self, node: str, attr_id: int) -> int:
+        return _native.lib().maro_cim_attr_slots(self._h, _NODE_TYPE[node], attr_id)
+
+    def query(self, node: str, frame_indices, nodes, attrs, replicas=None) -> np.ndarray:
+        """float64 [n_replicas_queried, per_replica] in tick -> node -> attr -> slot order (np_backend.pyx:520-549)."""
+        reps = np.arange(self.n_replicas, dtype=np.int32) if replicas is None else np.ascontiguousarray(replicas, np.int32)
+        fr = np.ascontiguousarray(frame_indices, np.int32)
+        nd = np.ascontiguousarray(nodes, np.int32)
+        at = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id(node, a) for a in attrs], np.int32)
+        per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
+        out = np.zeros((len(reps), per), np.float64)
+        pr = C.c_int64()
+        _native.check(_native.lib().maro_cim_query(self._h, reps.ctypes.data, len(reps), _NODE_TYPE[node], fr.ctypes.data,
+                                                   len(fr), nd.ctypes.data, len(nd), at.ctypes.data, len(at),
+                                                   out.ctypes.data, C.byref(pr)))
+        assert pr.value == per
+        return out
+
+    def read_frame(self, replica: int = 0) -> np.ndarray:
+        out = np.zeros(self.frame_words, np.int32)
+        _native.check(_native.lib().maro_cim_read_frame(self._h, replica, out.ctypes.data, out.size))
+        return out
+
+    def ticks(self) -> np.ndarray:
+        out = np.zeros(self.n_replicas, np.int32)
+        _native.check(_native.lib().maro_cim_ticks(self._h, out.ctypes.data))
+        return out
+
+    def counters(self) -> np.ndarray:
+        """int64 [B][4] cumulative {env_steps, ticks, events, snapshots}."""
+        out = np.zeros((self.n_replicas, 4), np.int64)
+        _native.check(_native.lib().maro_cim_counters(self._h, out.ctypes.data))
+        return out
+
+    def snapshot_frames(self, replica: int = 0) -> np.ndarray:
+        cap = 1 << 16
+        out = np.zeros(cap, np.int32)
+        n = C.c_int32()
+        _native.check(_native.lib().maro_cim_snapshot_frames(self._h, replica, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def snapshot_row(self, frame_index: int, replica: int = 0):
+        """Raw frame words of one snapshot (None if the ring does not hold it) — assembled from queries."""
+        if frame_index not in set(self.snapshot_frames(replica).tolist()):
+            return None
+        lay, fw = _abi.frame_layout(self.topologies[0].n_ports, self.topologies[0].n_vessels,
+                                    self.topologies[0].past_stop_number, self.topologies[0].future_stop_number)
+        row = np.zeros(fw, np.int32)
+        for node, attrs in lay.items():
+            n_nodes = next(iter(attrs.values()))[1]
+            names = list(attrs)
+            vals = self.query(node, [frame_index], np.arange(n_nodes), names, [replica])[0]
+            pos = 0
+            per_node = sum(attrs[a][2] for a in names)
+            for nd in range(n_nodes):
+                base = nd * per_node
+                p = 0
+                for a in names:
+                    off, _, slots = attrs[a]
+                    chunk = vals[base + p: base + p + slots]
+                    if node == "ports" and a == "transfer_cost":
+                        row[off + nd * slots: off + (nd + 1) * slots] = chunk.astype(np.float32).view(np.int32)
+                    else:
+                        row[off + nd * slots: off + (nd + 1) * slots] = chunk.astype(np.int64).astype(np.int32)
+                    p += slots
+            pos += 1
+        return row

@@ -1,0 +1,189 @@
+// cim_host.hpp — host-side (plain C++) shape + static-table serialisation shared by des_core.cu and the
+// test-only host-emulation harness (tests/_emul).  No CUDA here.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/maro_b200.h"
+#include "cim_core.cuh"
+
+namespace maro {
+
+inline void mt_init_by_array(uint32_t seed, uint32_t* mt) {
+    mt[0] = 19650218u;
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for (int k = 624; k; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + seed + (uint32_t)j;
+        i++; j++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        if (j >= 1) j = 0;
+    }
+    for (int k = 623; k; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct BlobBuilder {
+    std::vector<int32_t>& w;
+    explicit BlobBuilder(std::vector<int32_t>& v) : w(v) {}
+    int put_i(const int32_t* p, int n, int reserve) {
+        int off = (int)w.size();
+        w.insert(w.end(), p, p + n);
+        w.resize(off + std::max(reserve, n), 0);
+        return off;
+    }
+    int put_d(const double* p, int n, int reserve) {
+        if (w.size() & 1) w.push_back(0);
+        int off = (int)w.size();
+        w.resize(off + 2 * std::max(reserve, n), 0);
+        memcpy(w.data() + off, p, sizeof(double) * n);
+        return off;
+    }
+};
+
+// Serialise one topology into a blob; every array is padded to the per-handle maxima so that all topologies of
+// a handle share the same offsets (CimShape::t_*).
+inline int build_blob(const MaroCimTopology& t, CimShape& s, std::vector<int32_t>& out, int max_stops, int max_targets,
+                      bool first) {
+    std::vector<int32_t> w;
+    BlobBuilder b(w);
+    const int P = t.n_ports, V = t.n_vessels;
+    CimShape o = s;
+    o.t_port_capacity = b.put_i(t.port_capacity, P, P);
+    o.t_port_init_empty = b.put_i(t.port_init_empty, P, P);
+    o.t_frb_d = b.put_d(t.full_return_base, P, P);
+    o.t_frn_d = b.put_d(t.full_return_noise, P, P);
+    o.t_erb_d = b.put_d(t.empty_return_base, P, P);
+    o.t_ern_d = b.put_d(t.empty_return_noise, P, P);
+    o.t_sb_d = b.put_d(t.source_base, P, P);
+    o.t_sn_d = b.put_d(t.source_noise, P, P);
+    o.t_target_offset = b.put_i(t.target_offset, P + 1, P + 1);
+    const int nt = t.target_offset[P];
+    o.t_target_port = b.put_i(t.target_port, nt, max_targets);
+    o.t_tb_d = b.put_d(t.target_base, nt, max_targets);
+    o.t_tn_d = b.put_d(t.target_noise, nt, max_targets);
+    o.t_vessel_capacity = b.put_i(t.vessel_capacity, V, V);
+    o.t_vessel_init_empty = b.put_i(t.vessel_init_empty, V, V);
+    o.t_vessel_route = b.put_i(t.vessel_route, V, V);
+    o.t_vessel_period = b.put_i(t.vessel_period, V, V);
+    o.t_vessel_route_start = b.put_i(t.vessel_route_start, V, V);
+    o.t_vessel_leg_offset = b.put_i(t.vessel_leg_offset, V + 1, V + 1);
+    o.t_vessel_leg = b.put_i(t.vessel_leg, t.vessel_leg_offset[V], t.vessel_leg_offset[V]);
+    o.t_stop_offset = b.put_i(t.stop_offset, V + 1, V + 1);
+    const int ns = t.stop_offset[V];
+    o.t_stop_arrival = b.put_i(t.stop_arrival, ns, max_stops);
+    o.t_stop_leave = b.put_i(t.stop_leave, ns, max_stops);
+    o.t_stop_port = b.put_i(t.stop_port, ns, max_stops);
+    o.t_route_offset = b.put_i(t.route_offset, t.n_routes + 1, t.n_routes + 1);
+    o.t_route_port = b.put_i(t.route_port, t.route_offset[t.n_routes], t.route_offset[t.n_routes]);
+    o.t_order_proportion = b.put_i(t.order_proportion, t.max_tick, t.max_tick);
+    uint32_t mt[624];
+    mt_init_by_array(t.order_number_seed, mt);
+    o.t_mt_order = b.put_i(reinterpret_cast<int32_t*>(mt), 624, 624);
+    mt_init_by_array(t.buffer_time_seed, mt);
+    o.t_mt_buffer = b.put_i(reinterpret_cast<int32_t*>(mt), 624, 624);
+    w.resize(round_up((int)w.size(), 4), 0);
+    o.table_words = (int)w.size();
+    if (first) s = o;
+    else if (o.table_words != s.table_words || o.t_mt_buffer != s.t_mt_buffer) return 1;
+    out.insert(out.end(), w.begin(), w.end());
+    return 0;
+}
+
+inline int check_same_shape(const MaroCimTopology& a, const MaroCimTopology& b) {
+    if (a.n_ports != b.n_ports || a.n_vessels != b.n_vessels || a.n_routes != b.n_routes ||
+        a.past_stop_number != b.past_stop_number || a.future_stop_number != b.future_stop_number ||
+        a.max_tick != b.max_tick || a.order_mode != b.order_mode || a.container_volume != b.container_volume ||
+        a.total_containers != b.total_containers)
+        return 1;
+    for (int i = 0; i <= a.n_routes; i++)
+        if (a.route_offset[i] != b.route_offset[i]) return 1;
+    for (int i = 0; i <= a.n_ports; i++)
+        if (a.target_offset[i] != b.target_offset[i]) return 1;
+    return 0;
+}
+
+
+// Fill `s` (layout, queue sizing) and serialise every topology into `tables`.  Returns non-zero on mismatch.
+inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg, CimShape& s,
+                                    std::vector<int32_t>& tables, int& max_stops_out, int& max_targets_out) {
+    const MaroCimTopology& t0 = topos[0];
+    memset(&s, 0, sizeof(s));
+    const int P = t0.n_ports, V = t0.n_vessels;
+    s.P = P; s.V = V; s.R = t0.n_routes; s.past = t0.past_stop_number; s.fut = t0.future_stop_number;
+    s.max_tick = t0.max_tick; s.start_tick = cfg->start_tick;
+    s.resolution = cfg->snapshot_resolution > 0 ? cfg->snapshot_resolution : 1;
+    const int durations = s.max_tick - s.start_tick;
+    if (durations < 1) return 1;
+    const int total_frames = (durations + s.resolution - 1) / s.resolution;
+    s.ring_rows = cfg->max_snapshots > 0 ? std::min(cfg->max_snapshots, total_frames) : total_frames;
+    s.order_mode = t0.order_mode; s.total_containers = t0.total_containers; s.vol = t0.container_volume;
+    s.max_actions = cfg->max_actions > 0 ? cfg->max_actions : 1;
+    s.n_replicas = cfg->n_replicas;
+    int max_stops = 0, max_targets = t0.target_offset[P], max_delay = 2, max_rl = 1, buf_full = 1, buf_empty = 1;
+    for (int r = 0; r < t0.n_routes; r++) max_rl = std::max(max_rl, t0.route_offset[r + 1] - t0.route_offset[r]);
+    s.max_route_len = max_rl;
+    for (int k = 0; k < n_topos; k++) {
+        const MaroCimTopology& t = topos[k];
+        max_stops = std::max(max_stops, t.stop_offset[V]);
+        for (int p = 0; p < P; p++) {
+            if (t.source_noise[p] != 0) s.order_noise = 1;
+            if (t.full_return_noise[p] != 0 || t.empty_return_noise[p] != 0) s.buffer_noise = 1;
+            buf_full = std::max(buf_full, (int)ceil(t.full_return_base[p] + fabs(t.full_return_noise[p])));
+            buf_empty = std::max(buf_empty, (int)ceil(t.empty_return_base[p] + fabs(t.empty_return_noise[p])));
+        }
+        for (int i = 0; i < t.target_offset[P]; i++)
+            if (t.target_noise[i] != 0) s.order_noise = 1;
+        for (int v = 0; v < V; v++) {
+            int rl = t.route_offset[t.vessel_route[v] + 1] - t.route_offset[t.vessel_route[v]];
+            for (int i = t.stop_offset[v]; i < t.stop_offset[v + 1]; i++) {
+                int j = std::min(i + rl, t.stop_offset[v + 1] - 1);
+                max_delay = std::max(max_delay, t.stop_arrival[j] - t.stop_arrival[i] + 1);
+            }
+        }
+    }
+    max_delay = std::max(max_delay, std::max(buf_full, buf_empty) + 1);
+    // frame layout (DESIGN.md "Frame layout")
+    s.o_vs = 12 * P;
+    s.o_past = s.o_vs + 10 * V;
+    s.o_past_tick = s.o_past + V * s.past;
+    s.o_fut = s.o_past_tick + V * s.past;
+    s.o_fut_tick = s.o_fut + V * s.fut;
+    s.o_fop = s.o_fut_tick + V * s.fut;
+    s.o_fov = s.o_fop + P * P;
+    s.o_vp = s.o_fov + V * P;
+    s.FW = s.o_vp + V * P;
+    s.FWp = round_up(s.FW, 4);
+    s.CWp = round_up(C_FIXED + V, 4);
+    int qh = 16;
+    while (qh < max_delay + 1) qh <<= 1;
+    s.QH = qh;
+    // outstanding dynamic events: RETURN_FULL <= orders/tick x buffer, DISCHARGE_FULL <= V x route, RETURN_EMPTY
+    int qn = cfg->queue_capacity > 0 ? cfg->queue_capacity
+                                     : std::max(32, max_targets * buf_full + V * max_rl * (1 + buf_empty) + 16);
+    if (qn > 65000) qn = 65000;
+    s.QN = round_up(qn, 4);
+    s.SW = round_up(s.FWp + s.CWp + s.QN * 4 + s.QH, 4);
+    // tables (stop arrays get 12.5% head-room so that re-seeded topologies of the same config still fit)
+    max_stops += max_stops / 8 + 8;
+    max_stops_out = max_stops;
+    max_targets_out = max_targets;
+    tables.clear();
+    for (int k = 0; k < n_topos; k++) {
+        if (k > 0 && check_same_shape(t0, topos[k])) return 1;
+        if (build_blob(topos[k], s, tables, max_stops, max_targets, k == 0)) return 1;
+    }
+    return 0;
+}
+
+}  // namespace maro

@@ -1,0 +1,574 @@
+// des_core.cu — kernels + C ABI (include/maro_b200.h) of the batched CIM discrete-event core for sm_100a.
+//
+// Kernels
+//   cim_step_kernel    one warp = one replica.  The replica's state block (frame | control | event queue) is
+//                      staged HBM -> shared memory with one TMA bulk copy (cp.async.bulk + mbarrier), the step
+//                      runs out of shared memory (cim_core.cuh), snapshot rows stream to the ring with 128-bit
+//                      coalesced stores, and the block is written back with 128-bit stores.
+//   cim_reset_kernel   Env.reset for masked replicas.
+//   cim_query_kernel   snapshot_list[node][ticks:nodes:attrs] gather -> float64.
+//   cim_policy_kernel  hashed random agent (bench helper).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+//   (-fmad=false: CPython never contracts a*b+c; order generation must round like the reference.)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/maro_b200.h"
+#include "cim_core.cuh"
+#include "cim_host.hpp"
+
+using namespace maro;
+
+// =====================================================================================================
+// PTX helpers: mbarrier + TMA bulk copy (1-D cp.async.bulk)
+// =====================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// =====================================================================================================
+// Kernels
+// =====================================================================================================
+struct StepArgs {
+    int32_t* state;        // [B][SW]
+    int32_t* snap;         // [B][ring][FWp]
+    int32_t* snap_frame;   // [B][ring]
+    uint32_t* mt;          // [B][MTW] or nullptr
+    const int32_t* tables; // [K][table_words]
+    const int32_t* replica_topology;  // [B]
+    const uint8_t* active;            // [B] or nullptr
+    const int32_t* actions;           // [B][A][4] or nullptr
+    const int32_t* n_actions;         // [B] or nullptr
+    int32_t* decisions;               // [B][8]
+    int64_t* metrics;                 // [B][3]
+    int mt_words;
+};
+
+__device__ __forceinline__ Replica make_replica(const CimShape& s, const StepArgs& a, int rep, int32_t* st) {
+    Replica r;
+    r.f = st;
+    r.c = st + s.FWp;
+    r.q = st + s.FWp + s.CWp;
+    r.t = a.tables + (int64_t)a.replica_topology[rep] * s.table_words;
+    r.mt = a.mt ? a.mt + (int64_t)rep * a.mt_words : nullptr;
+    r.snap = a.snap + (int64_t)rep * s.ring_rows * s.FWp;
+    r.snap_frame = a.snap_frame + (int64_t)rep * s.ring_rows;
+    return r;
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) cim_step_kernel(const __grid_constant__ CimShape s,
+                                                               const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per warp (first 128 B)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 128) + (size_t)warp * s.SW;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    const uint32_t bytes = (uint32_t)s.SW * 4u;
+    for (int rep = blockIdx.x * kWarps + warp; rep < s.n_replicas; rep += gridDim.x * kWarps) {
+        if (a.active && !a.active[rep]) {
+            if (lane == 0) a.decisions[rep * 8 + 6] = MARO_STATUS_INACTIVE;
+            continue;
+        }
+        int32_t* gstate = a.state + (int64_t)rep * s.SW;
+        // ---- stage in: one TMA bulk copy of the whole state block, completion on the warp's mbarrier
+        if (lane == 0) {
+            fence_proxy_async();  // order earlier generic-proxy accesses to this smem before the async write
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(st, gstate, bytes, bar);
+        }
+        while (!mbar_try_wait(bar, phase)) {}
+        phase ^= 1u;
+        Replica r = make_replica(s, a, rep, st);
+        const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), s.max_actions) : 1) : 0;
+        const int32_t* act = a.actions ? a.actions + (int64_t)rep * s.max_actions * 4 : nullptr;
+        replica_step(s, r, lane, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
+        // ---- write back (128-bit coalesced)
+        const int4* src4 = reinterpret_cast<const int4*>(st);
+        int4* dst4 = reinterpret_cast<int4*>(gstate);
+        for (int i = lane; i < s.SW / 4; i += 32) dst4[i] = src4[i];
+        __syncwarp();
+    }
+}
+
+__global__ void cim_reset_kernel(const __grid_constant__ CimShape s, const __grid_constant__ StepArgs a) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int rep = warp_global; rep < s.n_replicas; rep += n_warps) {
+        if (a.active && !a.active[rep]) continue;
+        Replica r = make_replica(s, a, rep, a.state + (int64_t)rep * s.SW);  // operate directly on global memory
+        replica_reset(s, r, lane);
+    }
+}
+
+struct QueryArgs {
+    const int32_t* snap;
+    const int32_t* snap_frame;
+    const int32_t* replicas;  // [nr]
+    const int32_t* frames;    // [nf]
+    const int32_t* nodes;     // [nn]
+    const int32_t* attr_off;  // [na] frame word offset of attr (node 0, slot 0)
+    const int32_t* attr_slots;
+    const int32_t* attr_isf;
+    const int32_t* attr_prefix;  // [na] prefix sum of slots
+    int nr, nf, nn, na, slots_per_node, ring_rows, FWp;
+    double* out;
+};
+
+// out[rep][frame][node][attr][slot]; frames not held by the ring -> 0  (np_backend.pyx:536-549)
+__global__ void cim_query_kernel(const __grid_constant__ QueryArgs q) {
+    const int64_t per_rep = (int64_t)q.nf * q.nn * q.slots_per_node;
+    const int64_t total = per_rep * q.nr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t x = i;
+        int sl = (int)(x % q.slots_per_node); x /= q.slots_per_node;
+        int nd = (int)(x % q.nn); x /= q.nn;
+        int fi = (int)(x % q.nf); x /= q.nf;
+        int rp = q.replicas[(int)x];
+        int ai = 0;
+        while (ai + 1 < q.na && q.attr_prefix[ai + 1] <= sl) ai++;
+        int slot = sl - q.attr_prefix[ai];
+        int frame = q.frames[fi];
+        double v = 0.0;
+        if (frame >= 0) {
+            int row = frame % q.ring_rows;
+            if (q.snap_frame[(int64_t)rp * q.ring_rows + row] == frame) {
+                int w = q.snap[((int64_t)rp * q.ring_rows + row) * q.FWp + q.attr_off[ai] + q.nodes[nd] * q.attr_slots[ai] + slot];
+                v = q.attr_isf[ai] ? (double)__int_as_float(w) : (double)w;
+            }
+        }
+        q.out[i] = v;
+    }
+}
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// hello-world random agent (examples/hello_world/cim/hello.py:24-32) as a counter hash of (replica, step)
+__global__ void cim_policy_kernel(const int32_t* __restrict__ dec, int32_t* __restrict__ act, int n, int max_actions,
+                                  uint32_t seed, uint32_t step, uint32_t replica_base) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* d = dec + i * 8;
+    uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + step * 0x85ebca6bu + 0x1234567u));
+    uint32_t h2 = hash_u32(h1 + 0x68bc21ebu);
+    int load = d[3], dis = d[4];
+    bool to_discharge = dis > 0 && (h1 & 1u);
+    int scope = to_discharge ? dis : load;
+    int qty = scope > 0 ? (int)(h2 % (uint32_t)(scope + 1)) : 0;
+    int4 o = make_int4(d[2], d[1], qty, to_discharge ? 1 : 0);
+    *reinterpret_cast<int4*>(act + (int64_t)i * max_actions * 4) = o;
+}
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+struct AttrInfo { const char* name; int off, slots, isf, n_nodes; };
+
+struct MaroCimEnv {
+    CimShape s;
+    int device = 0, B = 0, K = 0, mt_words = 0, warps_per_cta = 4, grid = 0, max_stops = 0, max_targets = 0;
+    size_t smem_bytes = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int32_t *d_state = nullptr, *d_snap = nullptr, *d_snap_frame = nullptr, *d_tables = nullptr, *d_topo = nullptr;
+    uint32_t* d_mt = nullptr;
+    // host-call staging
+    uint8_t* d_in = nullptr;   // [actions B*A*4 i32][n_actions B i32][active B u8]
+    uint8_t* d_out = nullptr;  // [decisions B*8 i32][metrics B*3 i64]
+    uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned mirrors
+    size_t in_bytes = 0, out_bytes = 0;
+    int32_t* d_qidx = nullptr;  // query index scratch
+    size_t qidx_cap = 0;
+    double* d_qout = nullptr;
+    size_t qout_cap = 0;
+    std::vector<AttrInfo> attrs[3];
+    std::vector<int32_t> h_tables;
+};
+
+static void register_attrs(MaroCimEnv* e) {
+    const CimShape& s = e->s;
+    static const char* pn[] = {"acc_booking", "acc_fulfillment", "acc_shortage", "booking", "capacity", "empty",
+                               "fulfillment", "full", "on_consignee", "on_shipper", "shortage", "transfer_cost"};
+    for (int a = 0; a < 12; a++) e->attrs[0].push_back({pn[a], a * s.P, 1, a == 11, s.P});
+    static const char* vn[] = {"capacity", "early_discharge", "empty", "full", "is_parking", "last_loc_idx",
+                               "loc_port_idx", "next_loc_idx", "remaining_space", "route_idx"};
+    for (int a = 0; a < 10; a++) e->attrs[1].push_back({vn[a], s.o_vs + a * s.V, 1, 0, s.V});
+    e->attrs[1].push_back({"past_stop_list", s.o_past, s.past, 0, s.V});
+    e->attrs[1].push_back({"past_stop_tick_list", s.o_past_tick, s.past, 0, s.V});
+    e->attrs[1].push_back({"future_stop_list", s.o_fut, s.fut, 0, s.V});
+    e->attrs[1].push_back({"future_stop_tick_list", s.o_fut_tick, s.fut, 0, s.V});
+    e->attrs[2].push_back({"full_on_ports", s.o_fop, s.P * s.P, 0, 1});
+    e->attrs[2].push_back({"full_on_vessels", s.o_fov, s.V * s.P, 0, 1});
+    e->attrs[2].push_back({"vessel_plans", s.o_vp, s.V * s.P, 0, 1});
+}
+
+static StepArgs base_args(MaroCimEnv* e) {
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.state = e->d_state;
+    a.snap = e->d_snap;
+    a.snap_frame = e->d_snap_frame;
+    a.mt = e->d_mt;
+    a.tables = e->d_tables;
+    a.replica_topology = e->d_topo;
+    a.mt_words = e->mt_words;
+    return a;
+}
+
+template <int W>
+static cudaError_t launch_step_w(MaroCimEnv* e, const StepArgs& a) {
+    cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    if (err != cudaSuccess) return err;
+    cim_step_kernel<W><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_step(MaroCimEnv* e, const StepArgs& a) {
+    switch (e->warps_per_cta) {
+        case 1: return launch_step_w<1>(e, a);
+        case 2: return launch_step_w<2>(e, a);
+        case 4: return launch_step_w<4>(e, a);
+        default: return launch_step_w<8>(e, a);
+    }
+}
+
+extern "C" {
+
+const char* maro_last_error(void) { return g_err.c_str(); }
+int maro_abi_version(void) { return MARO_B200_ABI_VERSION; }
+
+int maro_cim_destroy(MaroCimEnv* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_state); cudaFree(e->d_snap); cudaFree(e->d_snap_frame); cudaFree(e->d_tables); cudaFree(e->d_topo);
+    cudaFree(e->d_mt); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_qidx); cudaFree(e->d_qout);
+    if (e->h_in) cudaFreeHost(e->h_in);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return 0;
+}
+
+int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCimConfig* cfg, MaroCimEnv** out) {
+    if (!topos || n_topos < 1 || !cfg || !out || cfg->n_replicas < 1) return fail("maro_cim_create: bad arguments");
+    const MaroCimTopology& t0 = topos[0];
+    if (t0.n_ports < 1 || t0.n_ports > 255 || t0.n_vessels < 1 || t0.n_vessels > 64)
+        return fail("maro_cim_create: supported sizes are 1..255 ports and 1..64 vessels");
+    for (int k = 1; k < n_topos; k++)
+        if (check_same_shape(t0, topos[k])) return fail("maro_cim_create: all topologies of one handle must share a shape");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("maro_cim_create: no CUDA device — this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("maro_cim_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+
+    MaroCimEnv* e = new MaroCimEnv();
+    e->device = cfg->device;
+    e->B = cfg->n_replicas;
+    e->K = n_topos;
+    CimShape& s = e->s;
+    if (compute_shape_and_tables(topos, n_topos, cfg, s, e->h_tables, e->max_stops, e->max_targets)) {
+        delete e;
+        return fail("maro_cim_create: inconsistent topology tables / durations must be positive");
+    }
+    const int P = s.P;
+    const int max_targets = e->max_targets;
+    register_attrs(e);
+
+    // launch geometry: as many warps per CTA as shared memory allows (<= 8), persistent grid over replicas
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, e->device));
+    const size_t per_warp = (size_t)s.SW * 4;
+    const size_t max_smem = prop.sharedMemPerBlockOptin;
+    int w = 8;
+    while (w > 1 && 128 + per_warp * w > std::min<size_t>(max_smem, 96 * 1024)) w >>= 1;
+    if (128 + per_warp * w > max_smem) { delete e; return fail("maro_cim_create: replica state does not fit in shared memory"); }
+    // small batches: spread replicas over all SMs
+    while (w > 1 && (e->B + w - 1) / w < prop.multiProcessorCount) w >>= 1;
+    e->warps_per_cta = w;
+    e->smem_bytes = 128 + per_warp * w;
+    int ctas_needed = (e->B + w - 1) / w;
+    int resident = std::max<int>(1, (int)std::min<size_t>(64 / w, max_smem / e->smem_bytes));
+    e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
+
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    const int B = e->B;
+    CK(cudaMalloc(&e->d_state, (size_t)B * s.SW * 4));
+    CK(cudaMalloc(&e->d_snap, (size_t)B * s.ring_rows * s.FWp * 4));
+    CK(cudaMalloc(&e->d_snap_frame, (size_t)B * s.ring_rows * 4));
+    CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
+    CK(cudaMalloc(&e->d_topo, (size_t)B * 4));
+    CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int32_t> topo(B, 0);
+    if (cfg->replica_topology)
+        for (int i = 0; i < B; i++) {
+            if (cfg->replica_topology[i] < 0 || cfg->replica_topology[i] >= n_topos) { maro_cim_destroy(e); return fail("maro_cim_create: replica_topology out of range"); }
+            topo[i] = cfg->replica_topology[i];
+        }
+    CK(cudaMemcpy(e->d_topo, topo.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+    if (s.order_noise || s.buffer_noise) {
+        e->mt_words = round_up(2 * 640 + 4 * (P + max_targets) + 8, 4);
+        CK(cudaMalloc(&e->d_mt, (size_t)B * e->mt_words * 4));
+    }
+    e->in_bytes = (size_t)B * s.max_actions * 16 + (size_t)B * 4 + round_up(B, 16);
+    e->out_bytes = (size_t)B * 32 + (size_t)B * 24;
+    CK(cudaMalloc(&e->d_in, e->in_bytes));
+    CK(cudaMalloc(&e->d_out, e->out_bytes));
+    CK(cudaMallocHost(&e->h_in, e->in_bytes));
+    CK(cudaMallocHost(&e->h_out, e->out_bytes));
+    CK(cudaMemset(e->d_out, 0, e->out_bytes));
+    *out = e;
+    int rc = maro_cim_reset(e, nullptr);
+    if (rc) { maro_cim_destroy(e); *out = nullptr; return rc; }
+    return 0;
+}
+
+int maro_cim_set_stream(MaroCimEnv* e, void* cuda_stream) {
+    if (!e) return fail("null handle");
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+
+int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask) {
+    if (!e) return fail("null handle");
+    CK(cudaSetDevice(e->device));
+    StepArgs a = base_args(e);
+    if (mask) {
+        uint8_t* d_active = e->d_in + (size_t)e->B * e->s.max_actions * 16 + (size_t)e->B * 4;
+        memcpy(e->h_in, mask, e->B);
+        CK(cudaMemcpyAsync(d_active, e->h_in, e->B, cudaMemcpyHostToDevice, e->stream));
+        a.active = d_active;
+    }
+    int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
+    cim_reset_kernel<<<blocks, threads, 0, e->stream>>>(e->s, a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int maro_cim_set_topology(MaroCimEnv* e, int32_t index, const MaroCimTopology* topo) {
+    if (!e || !topo || index < 0 || index >= e->K) return fail("maro_cim_set_topology: bad arguments");
+    CK(cudaSetDevice(e->device));
+    std::vector<int32_t> blob;
+    if (topo->n_ports != e->s.P || topo->n_vessels != e->s.V || topo->max_tick != e->s.max_tick)
+        return fail("maro_cim_set_topology: shape differs from the handle's");
+    if (topo->stop_offset[topo->n_vessels] > e->max_stops || topo->target_offset[topo->n_ports] > e->max_targets)
+        return fail("maro_cim_set_topology: more stops/targets than the handle was sized for");
+    CimShape probe = e->s;  // rebuild with identical padding; offsets must come out the same
+    if (build_blob(*topo, probe, blob, e->max_stops, e->max_targets, true) || probe.table_words != e->s.table_words ||
+        probe.t_mt_buffer != e->s.t_mt_buffer || probe.t_order_proportion != e->s.t_order_proportion)
+        return fail("maro_cim_set_topology: shape differs from the handle's");
+    memcpy(e->h_tables.data() + (size_t)index * e->s.table_words, blob.data(), blob.size() * 4);
+    CK(cudaMemcpy(e->d_tables + (size_t)index * e->s.table_words, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int maro_cim_step_device(MaroCimEnv* e, const uint8_t* d_active, const int32_t* d_actions, const int32_t* d_n_actions,
+                         int32_t* d_decisions, int64_t* d_metrics) {
+    if (!e || !d_decisions || !d_metrics) return fail("maro_cim_step_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    StepArgs a = base_args(e);
+    a.active = d_active; a.actions = d_actions; a.n_actions = d_n_actions;
+    a.decisions = d_decisions; a.metrics = d_metrics;
+    CK(launch_step(e, a));
+    return 0;
+}
+
+int maro_cim_step(MaroCimEnv* e, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
+                  int32_t* decisions, int64_t* metrics) {
+    if (!e || !decisions || !metrics) return fail("maro_cim_step: bad arguments");
+    CK(cudaSetDevice(e->device));
+    const int B = e->B, A = e->s.max_actions;
+    const size_t act_bytes = (size_t)B * A * 16, nact_off = act_bytes, active_off = act_bytes + (size_t)B * 4;
+    size_t lo = e->in_bytes, hi = 0;  // byte range of the staging buffer that must travel
+    if (actions) { memcpy(e->h_in, actions, act_bytes); lo = 0; hi = act_bytes; }
+    if (actions && n_actions) { memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4); hi = nact_off + (size_t)B * 4; }
+    if (active) { memcpy(e->h_in + active_off, active, B); lo = std::min(lo, active_off); hi = active_off + B; }
+    if (hi > lo) CK(cudaMemcpyAsync(e->d_in + lo, e->h_in + lo, hi - lo, cudaMemcpyHostToDevice, e->stream));
+    int rc = maro_cim_step_device(e, active ? e->d_in + active_off : nullptr,
+                                  actions ? reinterpret_cast<const int32_t*>(e->d_in) : nullptr,
+                                  actions && n_actions ? reinterpret_cast<const int32_t*>(e->d_in + nact_off) : nullptr,
+                                  reinterpret_cast<int32_t*>(e->d_out), reinterpret_cast<int64_t*>(e->d_out + (size_t)B * 32));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(decisions, e->h_out, (size_t)B * 32);
+    memcpy(metrics, e->h_out + (size_t)B * 32, (size_t)B * 24);
+    return 0;
+}
+
+int32_t maro_cim_attr_id(MaroCimEnv* e, int32_t node_type, const char* name) {
+    if (!e || node_type < 0 || node_type > 2 || !name) return -1;
+    for (size_t i = 0; i < e->attrs[node_type].size(); i++)
+        if (!strcmp(e->attrs[node_type][i].name, name)) return (int32_t)i;
+    return -1;
+}
+int32_t maro_cim_attr_slots(MaroCimEnv* e, int32_t node_type, int32_t attr_id) {
+    if (!e || node_type < 0 || node_type > 2 || attr_id < 0 || attr_id >= (int)e->attrs[node_type].size()) return -1;
+    return e->attrs[node_type][attr_id].slots;
+}
+int32_t maro_cim_frame_words(MaroCimEnv* e) { return e ? e->s.FW : -1; }
+
+static int query_impl(MaroCimEnv* e, const int32_t* replicas, int32_t nr, int32_t node_type, const int32_t* frames,
+                      int32_t nf, const int32_t* nodes, int32_t nn, const int32_t* attrs, int32_t na, double* d_out,
+                      double* h_out, int64_t* out_per_replica) {
+    if (!e || node_type < 0 || node_type > 2 || nr < 1 || nf < 1 || nn < 1 || na < 1 || !replicas || !frames || !nodes || !attrs)
+        return fail("maro_cim_query: bad arguments");
+    CK(cudaSetDevice(e->device));
+    const auto& reg = e->attrs[node_type];
+    std::vector<int32_t> idx;
+    idx.reserve(nr + nf + nn + 4 * na);
+    for (int i = 0; i < nr; i++) { if (replicas[i] < 0 || replicas[i] >= e->B) return fail("maro_cim_query: replica out of range"); idx.push_back(replicas[i]); }
+    for (int i = 0; i < nf; i++) idx.push_back(frames[i]);
+    for (int i = 0; i < nn; i++) { if (nodes[i] < 0 || nodes[i] >= reg[0].n_nodes) return fail("maro_cim_query: node index out of range"); idx.push_back(nodes[i]); }
+    int prefix = 0;
+    std::vector<int32_t> off(na), slots(na), isf(na), pre(na);
+    for (int i = 0; i < na; i++) {
+        if (attrs[i] < 0 || attrs[i] >= (int)reg.size()) return fail("maro_cim_query: attribute id out of range");
+        off[i] = reg[attrs[i]].off; slots[i] = reg[attrs[i]].slots; isf[i] = reg[attrs[i]].isf; pre[i] = prefix;
+        prefix += slots[i];
+    }
+    idx.insert(idx.end(), off.begin(), off.end());
+    idx.insert(idx.end(), slots.begin(), slots.end());
+    idx.insert(idx.end(), isf.begin(), isf.end());
+    idx.insert(idx.end(), pre.begin(), pre.end());
+    if (idx.size() > e->qidx_cap) {
+        cudaFree(e->d_qidx);
+        e->qidx_cap = idx.size() * 2;
+        CK(cudaMalloc(&e->d_qidx, e->qidx_cap * 4));
+    }
+    CK(cudaMemcpyAsync(e->d_qidx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    const int64_t per_rep = (int64_t)nf * nn * prefix, total = per_rep * nr;
+    if (out_per_replica) *out_per_replica = per_rep;
+    double* dst = d_out;
+    if (!dst) {
+        if ((size_t)total > e->qout_cap) {
+            cudaFree(e->d_qout);
+            e->qout_cap = (size_t)total * 2;
+            CK(cudaMalloc(&e->d_qout, e->qout_cap * 8));
+        }
+        dst = e->d_qout;
+    }
+    QueryArgs q;
+    q.snap = e->d_snap; q.snap_frame = e->d_snap_frame;
+    q.replicas = e->d_qidx; q.frames = q.replicas + nr; q.nodes = q.frames + nf;
+    q.attr_off = q.nodes + nn; q.attr_slots = q.attr_off + na; q.attr_isf = q.attr_slots + na; q.attr_prefix = q.attr_isf + na;
+    q.nr = nr; q.nf = nf; q.nn = nn; q.na = na; q.slots_per_node = prefix; q.ring_rows = e->s.ring_rows; q.FWp = e->s.FWp;
+    q.out = dst;
+    int threads = 256;
+    int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
+    cim_query_kernel<<<blocks, threads, 0, e->stream>>>(q);
+    CK(cudaGetLastError());
+    if (h_out) CK(cudaMemcpyAsync(h_out, dst, (size_t)total * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // idx vector must outlive the async H2D
+    return 0;
+}
+
+int maro_cim_query(MaroCimEnv* e, const int32_t* replicas, int32_t n_replicas, int32_t node_type, const int32_t* frame_indices,
+                   int32_t n_frames, const int32_t* nodes, int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* out,
+                   int64_t* out_per_replica) {
+    if (!out) return fail("maro_cim_query: null output");
+    return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, nullptr, out, out_per_replica);
+}
+
+int maro_cim_query_device(MaroCimEnv* e, const int32_t* replicas, int32_t n_replicas, int32_t node_type, const int32_t* frame_indices,
+                          int32_t n_frames, const int32_t* nodes, int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* d_out,
+                          int64_t* out_per_replica) {
+    if (!d_out) return fail("maro_cim_query_device: null output");
+    return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, d_out, nullptr, out_per_replica);
+}
+
+int maro_cim_read_frame(MaroCimEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) {
+    if (!e || replica < 0 || replica >= e->B || !out_words || n_words < e->s.FW) return fail("maro_cim_read_frame: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out_words, e->d_state + (size_t)replica * e->s.SW, (size_t)e->s.FW * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int maro_cim_ticks(MaroCimEnv* e, int32_t* out_ticks) {
+    if (!e || !out_ticks) return fail("maro_cim_ticks: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy2D(out_ticks, 4, e->d_state + e->s.FWp + C_TICK, (size_t)e->s.SW * 4, 4, e->B, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int maro_cim_counters(MaroCimEnv* e, int64_t* out) {
+    if (!e || !out) return fail("maro_cim_counters: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy2D(out, 32, e->d_state + e->s.FWp + C_NSTEPS_LO, (size_t)e->s.SW * 4, 32, e->B, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int maro_cim_snapshot_frames(MaroCimEnv* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
+    if (!e || replica < 0 || replica >= e->B || !out || !n_out) return fail("maro_cim_snapshot_frames: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    std::vector<int32_t> rows(e->s.ring_rows);
+    CK(cudaMemcpy(rows.data(), e->d_snap_frame + (size_t)replica * e->s.ring_rows, rows.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> have;
+    for (int32_t f : rows) if (f >= 0) have.push_back(f);
+    std::sort(have.begin(), have.end());
+    *n_out = (int32_t)have.size();
+    for (int i = 0; i < (int)have.size() && i < cap; i++) out[i] = have[i];
+    return 0;
+}
+
+int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t* d_actions, uint32_t seed, uint32_t step_index,
+                                  uint32_t replica_base) {
+    if (!e || !d_decisions || !d_actions) return fail("maro_cim_random_policy_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    int threads = 256, blocks = (e->B + threads - 1) / threads;
+    cim_policy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.max_actions, seed, step_index, replica_base);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

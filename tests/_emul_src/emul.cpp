@@ -1,0 +1,64 @@
+// TEST INFRASTRUCTURE ONLY — compiles maro_b200/csrc/cim_core.cuh for the host with one "lane" so that the
+// kernel's per-replica logic can be debugged against the oracle without a GPU.  Never loaded by the package.
+// Build: g++ -O1 -g -ffp-contract=off -DMARO_HOST_EMULATION -shared -fPIC emul.cpp -o ../_emul/libmaro_emul.so
+#define MARO_HOST_EMULATION 1
+#include "../../maro_b200/csrc/cim_host.hpp"
+
+using namespace maro;
+
+struct Emul {
+    CimShape s;
+    std::vector<int32_t> tables, state, snap, snap_frame, topo;
+    std::vector<uint32_t> mt;
+    int mt_words = 0, B = 0;
+};
+
+static Replica rep_of(Emul* e, int i) {
+    Replica r;
+    int32_t* st = e->state.data() + (size_t)i * e->s.SW;
+    r.f = st; r.c = st + e->s.FWp; r.q = st + e->s.FWp + e->s.CWp;
+    r.t = e->tables.data() + (size_t)e->topo[i] * e->s.table_words;
+    r.mt = e->mt_words ? e->mt.data() + (size_t)i * e->mt_words : nullptr;
+    r.snap = e->snap.data() + (size_t)i * e->s.ring_rows * e->s.FWp;
+    r.snap_frame = e->snap_frame.data() + (size_t)i * e->s.ring_rows;
+    return r;
+}
+
+extern "C" {
+Emul* emul_create(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg) {
+    Emul* e = new Emul();
+    int ms, mt;
+    if (compute_shape_and_tables(topos, n_topos, cfg, e->s, e->tables, ms, mt)) { delete e; return nullptr; }
+    e->B = cfg->n_replicas;
+    e->state.assign((size_t)e->B * e->s.SW, 0);
+    e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
+    e->snap_frame.assign((size_t)e->B * e->s.ring_rows, -1);
+    e->topo.assign(e->B, 0);
+    if (cfg->replica_topology) for (int i = 0; i < e->B; i++) e->topo[i] = cfg->replica_topology[i];
+    if (e->s.order_noise || e->s.buffer_noise) {
+        e->mt_words = round_up(2 * 640 + 4 * (e->s.P + mt) + 8, 4);
+        e->mt.assign((size_t)e->B * e->mt_words, 0);
+    }
+    for (int i = 0; i < e->B; i++) replica_reset(e->s, rep_of(e, i), 0);
+    return e;
+}
+void emul_destroy(Emul* e) { delete e; }
+void emul_reset(Emul* e) { for (int i = 0; i < e->B; i++) replica_reset(e->s, rep_of(e, i), 0); }
+void emul_step(Emul* e, const int32_t* actions, const int32_t* n_actions, int32_t* decisions, int64_t* metrics) {
+    for (int i = 0; i < e->B; i++) {
+        int n = actions ? (n_actions ? n_actions[i] : 1) : 0;
+        replica_step(e->s, rep_of(e, i), 0, actions ? actions + (size_t)i * e->s.max_actions * 4 : nullptr, n,
+                     decisions + i * 8, metrics + i * 3);
+    }
+}
+int emul_frame_words(Emul* e) { return e->s.FW; }
+void emul_read_frame(Emul* e, int rep, int32_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW, 4 * e->s.FW); }
+int emul_read_snapshot(Emul* e, int rep, int frame, int32_t* out) {
+    int row = frame % e->s.ring_rows;
+    if (frame < 0 || e->snap_frame[(size_t)rep * e->s.ring_rows + row] != frame) return 0;
+    memcpy(out, e->snap.data() + ((size_t)rep * e->s.ring_rows + row) * e->s.FWp, 4 * e->s.FW);
+    return 1;
+}
+int emul_tick(Emul* e, int rep) { return e->state[(size_t)rep * e->s.SW + e->s.FWp + C_TICK]; }
+void emul_counters(Emul* e, int rep, int64_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW + e->s.FWp + C_NSTEPS_LO, 32); }
+}

@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE — host emulation of the kernel's per-replica logic (tests/_emul_src/emul.cpp).
+
+Same device source (maro_b200/csrc/cim_core.cuh) compiled for the CPU with one lane.  Used only by the CPU test
+suite to check the kernel logic against the golden traces without a GPU; the package never loads it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from maro_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_emul", "libmaro_emul.so")
+SRC = os.path.join(HERE, "_emul_src", "emul.cpp")
+CORE = os.path.join(HERE, "..", "maro_b200", "csrc")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [SRC, os.path.join(CORE, "cim_core.cuh"), os.path.join(CORE, "cim_host.hpp")]
+        if not os.path.isfile(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+            os.makedirs(os.path.dirname(LIB), exist_ok=True)
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-DMARO_HOST_EMULATION",
+                                   "-shared", "-fPIC", SRC, "-o", LIB])
+        _lib = C.CDLL(LIB)
+        _lib.emul_create.restype = C.c_void_p
+        _lib.emul_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        for name, args in [("emul_destroy", 1), ("emul_reset", 1)]:
+            getattr(_lib, name).argtypes = [C.c_void_p]
+        _lib.emul_step.argtypes = [C.c_void_p] * 5
+        _lib.emul_frame_words.argtypes = [C.c_void_p]
+        _lib.emul_read_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.emul_read_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib.emul_tick.argtypes = [C.c_void_p, C.c_int]
+        _lib.emul_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    return _lib
+
+
+class EmulEnv:
+    def __init__(self, topos, n_replicas=1, start_tick=0, snapshot_resolution=1, max_snapshots=None, max_actions=2,
+                 replica_topology=None):
+        if not isinstance(topos, (list, tuple)):
+            topos = [topos]
+        self._keep = []
+        arr = (_abi.MaroCimTopology * len(topos))()
+        for i, t in enumerate(topos):
+            s, keep = _abi.topology_struct(t)
+            arr[i] = s
+            self._keep.append(keep)
+        cfg = _abi.MaroCimConfig()
+        cfg.n_replicas = n_replicas
+        cfg.start_tick = start_tick
+        cfg.snapshot_resolution = snapshot_resolution
+        cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
+        cfg.max_actions = max_actions
+        if replica_topology is not None:
+            rt = np.ascontiguousarray(replica_topology, np.int32)
+            self._keep.append(rt)
+            cfg.replica_topology = rt.ctypes.data_as(C.POINTER(C.c_int32))
+        self.B, self.A = n_replicas, max_actions
+        self._h = lib().emul_create(arr, len(topos), C.byref(cfg))
+        assert self._h
+        self.frame_words = lib().emul_frame_words(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().emul_destroy(self._h)
+            self._h = None
+
+    def step(self, actions=None, n_actions=None):
+        dec = np.zeros((self.B, 8), np.int32)
+        met = np.zeros((self.B, 3), np.int64)
+        if actions is None:
+            lib().emul_step(self._h, None, None, dec.ctypes.data, met.ctypes.data)
+        else:
+            a = np.zeros((self.B, self.A, 4), np.int32)
+            src = np.asarray(actions, np.int32).reshape(self.B, -1, 4)
+            a[:, :src.shape[1]] = src
+            n = np.full(self.B, src.shape[1], np.int32) if n_actions is None else np.ascontiguousarray(n_actions, np.int32)
+            lib().emul_step(self._h, a.ctypes.data, n.ctypes.data, dec.ctypes.data, met.ctypes.data)
+        return dec, met
+
+    def step1(self, actions=None):
+        """single-replica convenience: (status, dec[8], met[3])"""
+        dec, met = self.step(None if actions is None else np.asarray(actions, np.int32).reshape(1, -1, 4))
+        return int(dec[0, 6]), dec[0], met[0]
+
+    def frame(self, rep=0):
+        out = np.zeros(self.frame_words, np.int32)
+        lib().emul_read_frame(self._h, rep, out.ctypes.data)
+        return out
+
+    def snapshot(self, frame_index, rep=0):
+        out = np.zeros(self.frame_words, np.int32)
+        return out if lib().emul_read_snapshot(self._h, rep, frame_index, out.ctypes.data) else None
+
+    def tick(self, rep=0):
+        return lib().emul_tick(self._h, rep)
+
+    def counters(self, rep=0):
+        out = np.zeros(4, np.int64)
+        lib().emul_counters(self._h, rep, out.ctypes.data)
+        return out
