@@ -230,7 +230,8 @@ def run_ours(args, rank, local_rank, world):
     topo = build_topology(args.topology, args.ticks)
     steps_per_episode = CimOracle(topo).run_episode(0)[0]  # decisions + final step (static for a given stop table)
     env = CimBatch(topo, B, device=local_rank, max_snapshots=args.max_snapshots or None)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     env.set_stream(stream.cuda_stream)
     dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
     met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
@@ -297,17 +298,21 @@ def run_ours(args, rank, local_rank, world):
         cc0 = env.counters().sum(0)
         t0 = time.perf_counter()
         i = 0
+        t_agent = 0.0
         for k in range(n_e2e):
             if i == 0:
                 if k > 0:
                     env.reset()
                 d, m = env.step(None)
             else:
-                d, m = env.step(host_policy(d, 0, i - 1, base, np))
+                ta = time.perf_counter()
+                a = host_policy(d, 0, i - 1, base, np)
+                t_agent += time.perf_counter() - ta
+                d, m = env.step(a)
             i = (i + 1) % steps_per_episode
         dt = time.perf_counter() - t0
         cc1 = env.counters().sum(0)
-        e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt}
+        e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt, "agent_seconds": t_agent}
 
     t = torch.tensor([total_ms, kernel_ms, wall * 1000.0, (e2e or {}).get("seconds", 0.0) * 1000.0], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([d_steps, d_ticks, d_events, d_snaps, (e2e or {}).get("steps", 0)], dtype=torch.int64, device="cuda")
@@ -355,7 +360,9 @@ def run_ours(args, rank, local_rank, world):
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
                            "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * 56,
-                           "api": "maro_cim_step (host buffers) + numpy agent"}
+                           "api": "maro_cim_step (host buffers) + numpy agent",
+                           "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
+                           "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
         line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
         print(json.dumps(line), flush=True)
     env.close()

@@ -127,8 +127,9 @@ int maro_abi_version(void);
 int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCimConfig* cfg, MaroCimEnv** out);
 /* VectorEnv.stop / __del__ (vector_env.py:146-160). */
 int maro_cim_destroy(MaroCimEnv* env);
-/* Use an externally created CUDA stream (cudaStream_t) for all subsequent work; NULL = library stream. */
-int maro_cim_set_stream(MaroCimEnv* env, void* cuda_stream);
+/* Stream for all subsequent work.  external != 0: use `cuda_stream` (a cudaStream_t; 0 is the legacy default
+ * stream, e.g. torch's default current stream).  external == 0: back to the library's own stream. */
+int maro_cim_set_stream(MaroCimEnv* env, void* cuda_stream, int32_t external);
 
 /* Env.step / VectorEnv.step (core.py:92-133, vector_env.py:116-144), host buffers.
  *   active      [B] uint8 or NULL (all)            — dict/subset stepping of VectorEnv

@@ -42,7 +42,7 @@ def lib():
     L.maro_abi_version.restype = C.c_int
     L.maro_cim_create.argtypes = [vp, i32, vp, C.POINTER(vp)]
     L.maro_cim_destroy.argtypes = [vp]
-    L.maro_cim_set_stream.argtypes = [vp, vp]
+    L.maro_cim_set_stream.argtypes = [vp, vp, i32]
     L.maro_cim_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.maro_cim_step_device.argtypes = [vp, vp, vp, vp, vp, vp]
     L.maro_cim_reset.argtypes = [vp, vp]

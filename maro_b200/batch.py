@@ -68,8 +68,13 @@ class CimBatch:
         except Exception:
             pass
 
-    def set_stream(self, cuda_stream_ptr: int):
-        _native.check(_native.lib().maro_cim_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        """Run on an external CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``; 0 = legacy default
+        stream); ``None`` returns to the library's own stream."""
+        if cuda_stream_ptr is None:
+            _native.check(_native.lib().maro_cim_set_stream(self._h, None, 0))
+        else:
+            _native.check(_native.lib().maro_cim_set_stream(self._h, C.c_void_p(cuda_stream_ptr), 1))
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)

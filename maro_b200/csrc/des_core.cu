@@ -368,9 +368,9 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     return 0;
 }
 
-int maro_cim_set_stream(MaroCimEnv* e, void* cuda_stream) {
+int maro_cim_set_stream(MaroCimEnv* e, void* cuda_stream, int32_t external) {
     if (!e) return fail("null handle");
-    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    e->stream = external ? (cudaStream_t)cuda_stream : e->own_stream;
     return 0;
 }
 

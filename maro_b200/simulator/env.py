@@ -1,0 +1,266 @@
+"""``Env`` — drop-in for ``maro.simulator.Env`` (maro/simulator/core.py:20-259, abs_core.py:25-176) for the CIM
+scenario, backed by one replica (or a view on one replica of a shared batch) of the CUDA core."""
+from __future__ import annotations
+
+from enum import IntEnum
+from math import ceil, floor
+from typing import List, Optional
+
+import numpy as np
+
+from .. import _abi
+from ..batch import CimBatch
+from ..scenarios.cim.common import Action, ActionScope, ActionType, DecisionEvent, encode_action
+from ..scenarios.cim.topology import CimTopology, build_topology, load_config, next_topology_seed
+
+
+class DecisionMode(IntEnum):
+    Sequential = 0
+    Joint = 1
+
+
+class DocableDict(dict):
+    """dict with a docstring, like maro/simulator/scenarios/helpers.py:DocableDict."""
+
+    def __init__(self, doc: str, origin: dict):
+        super().__init__(origin)
+        self.__doc__ = doc
+
+
+_METRICS_DOC = """CIM metrics: order_requirements (int), container_shortage (int), operation_number (int)."""
+
+
+def make_metrics(row) -> DocableDict:
+    return DocableDict(_METRICS_DOC, {"order_requirements": int(row[0]), "container_shortage": int(row[1]),
+                                     "operation_number": int(row[2])})
+
+
+class SnapshotNode:
+    """``env.snapshot_list["ports"][ticks:nodes:attrs]`` (frame.pyx:734-801) -> 1-D float64 (np_backend.pyx:520-549)."""
+
+    def __init__(self, owner: "SnapshotList", node: str, n_nodes: int):
+        self._owner, self._node, self._n = owner, node, n_nodes
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, key: slice):
+        ticks = [] if key.start is None else (list(key.start) if isinstance(key.start, (tuple, list)) else [key.start])
+        nodes = [] if key.stop is None else (list(key.stop) if isinstance(key.stop, (tuple, list)) else [key.stop])
+        if key.step is None:
+            return None
+        attrs = list(key.step) if isinstance(key.step, (tuple, list)) else [key.step]
+        return self._owner._query(self._node, ticks, nodes, attrs)
+
+
+class SnapshotList:
+    """Read-only façade over the device snapshot ring of one replica (frame.pyx:804-846)."""
+
+    def __init__(self, batch: CimBatch, replica: int):
+        self._batch, self._replica = batch, replica
+        t = batch.topologies[0]
+        self._nodes = {"ports": SnapshotNode(self, "ports", t.n_ports),
+                       "vessels": SnapshotNode(self, "vessels", t.n_vessels),
+                       "matrices": SnapshotNode(self, "matrices", 1)}
+
+    def __getitem__(self, name: str):
+        return self._nodes.get(name)
+
+    def __len__(self):
+        return len(self.get_frame_index_list())
+
+    def get_frame_index_list(self) -> List[int]:
+        return self._batch.snapshot_frames(self._replica).tolist()
+
+    def _query(self, node, ticks, nodes, attrs):
+        if len(ticks) == 0:
+            ticks = self.get_frame_index_list()
+        if len(nodes) == 0:
+            nodes = list(range(len(self._nodes[node])))
+        try:
+            ids = [self._batch.attr_id(node, a) for a in attrs]
+        except KeyError:
+            raise KeyError(f"invalid attribute for {node}: {attrs}")
+        if len(ticks) == 0:
+            return np.zeros(0, np.float64)
+        return self._batch.query(node, ticks, nodes, ids, [self._replica])[0]
+
+
+class _NodeView:
+    def __init__(self, values: dict, index: int):
+        self.__dict__["_v"], self.__dict__["index"] = values, index
+
+    def __getattr__(self, name):
+        v = self._v[name]
+        return v.item() if v.shape == () else v
+
+
+class FrameView:
+    """Read-only copy of the live frame (``env.current_frame``): ``.ports[i].empty``, ``.vessels[i].full`` …"""
+
+    def __init__(self, words: np.ndarray, topo: CimTopology):
+        lay, _ = _abi.frame_layout(topo.n_ports, topo.n_vessels, topo.past_stop_number, topo.future_stop_number)
+        self.ports, self.vessels = [], []
+        for node, target, n in (("ports", self.ports, topo.n_ports), ("vessels", self.vessels, topo.n_vessels)):
+            for i in range(n):
+                vals = {}
+                for a, (off, _, slots) in lay[node].items():
+                    w = words[off + i * slots: off + (i + 1) * slots]
+                    if a == "transfer_cost":
+                        w = w.view(np.float32)
+                    vals[a] = w[0] if slots == 1 else w.copy()
+                target.append(_NodeView(vals, i))
+        self.matrix = [{a: words[off: off + slots].copy() for a, (off, _, slots) in lay["matrices"].items()}]
+
+
+class Env:
+    """Same constructor and members as ``maro.simulator.Env``; only ``scenario="cim"`` is implemented on the GPU."""
+
+    def __init__(self, scenario: str = None, topology: str = None, start_tick: int = 0, durations: int = 100,
+                 snapshot_resolution: int = 1, max_snapshots: int = None, decision_mode=DecisionMode.Sequential,
+                 business_engine_cls: type = None, disable_finished_events: bool = False,
+                 record_finished_events: bool = False, record_file_path: str = None, options: Optional[dict] = None,
+                 device: int = 0):
+        if scenario != "cim":
+            raise NotImplementedError(f"scenario {scenario!r}: only 'cim' runs on the CUDA core in this build")
+        if business_engine_cls is not None:
+            raise NotImplementedError("custom business engines run on the reference Env, not on the CUDA core")
+        if int(decision_mode) != int(DecisionMode.Sequential):
+            raise NotImplementedError("DecisionMode.Joint is not implemented on the CUDA core")
+        self._scenario, self._topology = scenario, topology
+        self._start_tick, self._durations = start_tick, durations
+        self._snapshot_resolution, self._max_snapshots = snapshot_resolution, max_snapshots
+        self._device = device
+        self._name = f"{scenario}:{topology}"
+        self._config = load_config(topology)
+        self._topo = build_topology(self._config, start_tick + durations)
+        self._pending_seed: Optional[int] = None
+        self._batch = CimBatch(self._topo, 1, start_tick, snapshot_resolution, max_snapshots, device=device,
+                               max_actions=8)
+        self._snapshots = SnapshotList(self._batch, 0)
+        self._tick = start_tick
+        self._last_metrics = make_metrics((0, 0, 0))
+        self._act = np.zeros((1, 8, 4), np.int32)
+        self._nact = np.zeros(1, np.int32)
+
+    # ---- stepping (core.py:92-133)
+    def step(self, action=None):
+        if action is None:
+            actions = []
+        elif not isinstance(action, list):
+            actions = [action]
+        else:
+            actions = action
+        if len(actions) > self._act.shape[1]:
+            raise ValueError("too many actions for one decision event")
+        for i, a in enumerate(actions):
+            encode_action(a, self._act[0, i])
+        self._nact[0] = len(actions)
+        dec, met = self._batch.step(self._act, self._nact)
+        d = dec[0]
+        status = int(d[_abi.DEC_STATUS])
+        if status == _abi.STATUS_BAD_ACTION:
+            raise AssertionError("invalid action: quantity exceeds the action scope (business_engine.py:731,736)")
+        if status == _abi.STATUS_QUEUE_OVERFLOW:
+            raise RuntimeError("event queue overflow: recreate the Env with a larger queue_capacity")
+        if status == _abi.STATUS_FINISHED:
+            return None, None, True
+        self._tick = int(d[_abi.DEC_TICK])
+        self._last_metrics = make_metrics(met[0])
+        if status == _abi.STATUS_DONE:
+            return self._last_metrics, None, True
+        event = DecisionEvent(int(d[0]), int(d[1]), int(d[2]), self._snapshots, ActionScope(int(d[3]), int(d[4])), int(d[5]))
+        return self._last_metrics, event, False
+
+    def dump(self) -> None:
+        return
+
+    def reset(self, keep_seed: bool = False) -> None:
+        """core.py:143-170 + cim_data_container_helpers.py:56-66: ``keep_seed=False`` draws a new topology seed from
+        the route_init stream; a seed set with ``set_seed`` takes effect here."""
+        seed = self._pending_seed
+        if not keep_seed:
+            seed = next_topology_seed(self._topo)
+        if seed is not None:
+            self._topo = build_topology(self._config, self._start_tick + self._durations, seed=seed)
+            self._batch.set_topology(0, self._topo)
+            self._pending_seed = None
+        self._batch.reset()
+        self._tick = self._start_tick
+        self._last_metrics = make_metrics((0, 0, 0))
+
+    def set_seed(self, seed: int) -> None:
+        assert seed is not None and isinstance(seed, int)
+        self._pending_seed = seed
+
+    # ---- properties (core.py:172-259)
+    @property
+    def configs(self) -> dict:
+        return self._config
+
+    @property
+    def summary(self) -> dict:
+        t = self._topo
+        lay, _ = _abi.frame_layout(t.n_ports, t.n_vessels, t.past_stop_number, t.future_stop_number)
+        detail = {}
+        for node, n in (("ports", t.n_ports), ("vessels", t.n_vessels), ("matrices", 1)):
+            detail[node] = {"number": n, "attributes": {a: {"slots": slots} for a, (_, _, slots) in lay[node].items()}}
+        return {
+            "node_mapping": {"ports": {n: i for i, n in enumerate(t.port_names)},
+                             "vessels": {n: i for i, n in enumerate(t.vessel_names)}},
+            "node_detail": detail,
+            "event_payload": {
+                "ORDER": ["tick", "src_port_idx", "dest_port_idx", "quantity"],
+                "RETURN_FULL": ["src_port_idx", "dest_port_idx", "quantity"],
+                "VESSEL_ARRIVAL": ["port_idx", "vessel_idx"], "LOAD_FULL": ["port_idx", "vessel_idx"],
+                "DISCHARGE_FULL": ["vessel_idx", "port_idx", "from_port_idx", "quantity"],
+                "PENDING_DECISION": DecisionEvent.summary_key, "LOAD_EMPTY": Action.summary_key,
+                "DISCHARGE_EMPTY": Action.summary_key, "VESSEL_DEPARTURE": ["port_idx", "vessel_idx"],
+                "RETURN_EMPTY": ["port_idx", "quantity"]},
+        }
+
+    @property
+    def name(self) -> str:
+        return self._name
+
+    @property
+    def current_frame(self) -> FrameView:
+        return FrameView(self._batch.read_frame(0), self._topo)
+
+    @property
+    def tick(self) -> int:
+        return self._tick
+
+    @property
+    def frame_index(self) -> int:
+        return floor((self._tick - self._start_tick) / self._snapshot_resolution)
+
+    @property
+    def snapshot_list(self) -> SnapshotList:
+        return self._snapshots
+
+    @property
+    def agent_idx_list(self) -> List[int]:
+        return list(range(self._topo.n_ports))
+
+    @property
+    def metrics(self) -> dict:
+        return self._last_metrics
+
+    def get_finished_events(self) -> list:
+        return []  # events live on the device; the finished-event list is not materialised
+
+    def get_pending_events(self, tick) -> list:
+        return []
+
+    def get_ticks_frame_index_mapping(self) -> dict:
+        mapping = {}
+        res = self._snapshot_resolution
+        for f in self._snapshots.get_frame_index_list():
+            lo = self._start_tick + f * res
+            for t in range(lo, min(lo + res, self._start_tick + self._durations)):
+                mapping[t] = f
+        return mapping
+
+    def close(self):
+        self._batch.close()

@@ -1,0 +1,165 @@
+"""``VectorEnv`` — drop-in for ``maro.vector_env.VectorEnv`` (maro/vector_env/vector_env.py:20-232).
+
+The reference forks one OS process per environment and caps ``batch_num`` at ``os.cpu_count()``; here the batch is
+``batch_num`` replicas of one CUDA handle (no cap), and one ``step`` is one kernel launch.  ``step`` keeps the
+reference's list / dict / broadcast conventions and return shapes; ``step_columnar`` is the allocation-free variant
+that returns the raw decision / metric arrays."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from .. import _abi
+from ..batch import CimBatch
+from ..scenarios.cim.common import ActionScope, DecisionEvent, encode_action
+from ..scenarios.cim.topology import build_topology, load_config
+from ..simulator.env import DecisionMode, SnapshotList, make_metrics
+
+
+class VectorEnv:
+    class SnapshotListNodeWrapper:
+        def __init__(self, env, node_name: str):
+            self.node_name, self._env = node_name, env
+
+        def __getitem__(self, args) -> List[np.ndarray]:
+            return self._env._query(self.node_name, args)
+
+    class SnapshotListWrapper:
+        def __init__(self, env):
+            self._env = env
+
+        def __getitem__(self, node_name: str):
+            return VectorEnv.SnapshotListNodeWrapper(self._env, node_name)
+
+    def __init__(self, batch_num: int, scenario: str = None, topology: str = None, start_tick: int = 0,
+                 durations: int = 100, snapshot_resolution: int = 1, max_snapshots: int = None,
+                 decision_mode=DecisionMode.Sequential, business_engine_cls: type = None,
+                 disable_finished_events: bool = False, options: dict = {}, device: int = 0, seeds=None):
+        assert batch_num > 0
+        if scenario != "cim" or business_engine_cls is not None or int(decision_mode) != 0:
+            raise NotImplementedError("the CUDA core implements scenario='cim', Sequential mode")
+        self._batch_num = batch_num
+        self._start_tick, self._resolution = start_tick, snapshot_resolution
+        conf = load_config(topology)
+        if seeds is None:
+            topos, rt = [build_topology(conf, start_tick + durations)], None
+        else:  # one topology instance per distinct seed (per-process seeds of the reference's VectorEnv)
+            seeds = [int(s) for s in seeds]
+            assert len(seeds) == batch_num
+            uniq = sorted(set(seeds))
+            topos = [build_topology(conf, start_tick + durations, seed=s) for s in uniq]
+            rt = np.asarray([uniq.index(s) for s in seeds], np.int32)
+        self._batch = CimBatch(topos, batch_num, start_tick, snapshot_resolution, max_snapshots, device=device,
+                               max_actions=4, replica_topology=rt)
+        self._snapshot_wrapper = VectorEnv.SnapshotListWrapper(self)
+        self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(batch_num)]
+        self._done = np.zeros(batch_num, bool)
+        self._ticks = np.full(batch_num, start_tick, np.int64)
+        self._act = np.zeros((batch_num, 4, 4), np.int32)
+        self._nact = np.zeros(batch_num, np.int32)
+        self._active = np.ones(batch_num, np.uint8)
+
+    # ---- reference surface
+    @property
+    def batch_number(self) -> int:
+        return self._batch_num
+
+    @property
+    def snapshot_list(self):
+        return self._snapshot_wrapper
+
+    @property
+    def tick(self) -> List[int]:
+        return [int(t) for t in self._ticks]
+
+    @property
+    def frame_index(self) -> List[int]:
+        return [int((t - self._start_tick) // self._resolution) for t in self._ticks]
+
+    def _encode(self, i, action):
+        if action is None:
+            self._nact[i] = 0
+            return
+        acts = action if isinstance(action, list) else [action]
+        for k, a in enumerate(acts):
+            encode_action(a, self._act[i, k])
+        self._nact[i] = len(acts)
+
+    def step(self, action):
+        """list -> one action per env; dict -> only those envs advance; anything else -> broadcast."""
+        B = self._batch_num
+        if type(action) is list:
+            assert len(action) == B
+            for i in range(B):
+                self._encode(i, action[i])
+            self._active[:] = 1
+        elif type(action) is dict:
+            self._active[:] = 0
+            for i, a in action.items():
+                self._encode(i, a)
+                self._active[i] = 1
+        else:
+            for i in range(B):
+                self._encode(i, action)
+            self._active[:] = 1
+        dec, met = self._batch.step(self._act, self._nact, self._active)
+        metrics, events = [], []
+        for i in range(B):
+            if not self._active[i]:
+                continue
+            st = int(dec[i, _abi.DEC_STATUS])
+            if st == _abi.STATUS_BAD_ACTION:
+                raise AssertionError(f"env {i}: invalid action (quantity exceeds the action scope)")
+            if st == _abi.STATUS_QUEUE_OVERFLOW:
+                raise RuntimeError(f"env {i}: event queue overflow")
+            if st == _abi.STATUS_FINISHED:  # env_process.py:37-40
+                metrics.append(None)
+                events.append(None)
+                continue
+            self._ticks[i] = dec[i, 0]
+            metrics.append(make_metrics(met[i]))
+            if st == _abi.STATUS_DONE:
+                self._done[i] = True
+                events.append(None)
+            else:
+                d = dec[i]
+                events.append(DecisionEvent(int(d[0]), int(d[1]), int(d[2]), self._snapshot_lists[i],
+                                            ActionScope(int(d[3]), int(d[4])), int(d[5])))
+        return metrics, events, bool(self._done.all())
+
+    def step_columnar(self, actions: Optional[np.ndarray] = None, n_actions=None, active=None):
+        """Array-in / array-out step: actions int32 [B][4][4] (or None), returns (decisions [B][8], metrics [B][3], done)."""
+        dec, met = self._batch.step(actions, n_actions, active)
+        st = dec[:, _abi.DEC_STATUS]
+        live = (st == _abi.STATUS_DECISION) | (st == _abi.STATUS_DONE)
+        self._ticks[live] = dec[live, 0]
+        self._done |= (st == _abi.STATUS_DONE) | (st == _abi.STATUS_FINISHED)
+        return dec, met, bool(self._done.all())
+
+    def reset(self):
+        self._batch.reset()
+        self._done[:] = False
+        self._ticks[:] = self._start_tick
+
+    def stop(self):
+        self._batch.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        self.stop()
+
+    def __del__(self):
+        try:
+            self.stop()
+        except Exception:
+            pass
+
+    def _query(self, node_name: str, args: slice):
+        return [sl[node_name][args] for sl in self._snapshot_lists]
+
+    @property
+    def batch(self) -> CimBatch:
+        return self._batch

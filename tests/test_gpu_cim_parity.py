@@ -165,7 +165,7 @@ def test_cuda_full_size_properties():
     topo = build_topology("toy.4p_ssdd_l0.0", 1000)
     B = 1024
     env = _batch(topo, B, max_snapshots=64)
-    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    env.set_stream(torch.cuda.current_stream().cuda_stream)  # legacy default stream (handle 0), external
     dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
     met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
     act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")

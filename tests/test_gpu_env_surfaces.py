@@ -1,0 +1,127 @@
+"""GPU (-m gpu): the drop-in Python surfaces (Env / VectorEnv) — written like the reference's own tests
+(tests/cim/test_cim_scenario.py, tests/test_vector_env.py, examples/hello_world/cim/hello.py)."""
+import pickle
+
+import numpy as np
+import pytest
+
+from helpers import CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_env_hello_world_null_policy():
+    """SURVEY.md A.3 / BASELINE config #0: 100 ticks, null actions -> 70 decisions, metrics (200000, 150000, 0)."""
+    from maro_b200.simulator import Env
+
+    env = Env(scenario="cim", topology="toy.4p_ssdd_l0.0", start_tick=0, durations=100)
+    gold = load_golden("toy4p_l00_100_null")["steps"]
+    metrics, decision_event, is_done = env.step(None)
+    n = 0
+    while not is_done:
+        row = [decision_event.tick, decision_event.port_idx, decision_event.vessel_idx,
+               decision_event.action_scope.load, decision_event.action_scope.discharge, decision_event.early_discharge,
+               metrics["order_requirements"], metrics["container_shortage"], metrics["operation_number"]]
+        assert row == gold[n].tolist()
+        n += 1
+        metrics, decision_event, is_done = env.step(None)
+    assert n == 70 and env.tick == 99 and env.frame_index == 99
+    assert dict(metrics) == {"order_requirements": 200000, "container_shortage": 150000, "operation_number": 0}
+    assert env.step(None) == (None, None, True)
+    # snapshot_list slicing, static-backend shape conventions
+    sl = env.snapshot_list
+    x = sl["ports"][99::["empty", "full", "shortage", "acc_shortage"]].reshape(4, 4)
+    assert x.tolist() == [[0, 0, 660, 41000], [0, 0, 1340, 109000], [55092, 0, 0, 0], [44908, 0, 0, 0]]
+    vp = sl["matrices"][99::"vessel_plans"]
+    assert vp.astype(int).tolist() == [105, -1, 112, -1, 112, -1, 105, -1, -1, 119, 105, 112, -1, 112, 119, 105, -1, 105, 112, 119]
+    assert sl["ports"][[98, 1000]:0:"empty"].tolist() == [0.0, 0.0]  # unknown frame -> zero padding
+    assert len(sl) == 100 and len(sl["vessels"]) == 5
+    assert env.agent_idx_list == [0, 1, 2, 3]
+    assert env.current_frame.ports[2].empty == 55092
+    assert env.summary["node_mapping"]["ports"]["supply_port_001"] == 2
+    env.close()
+
+
+def test_env_actions_pickle_reset_and_seed():
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.simulator import Env
+
+    env = Env("cim", "toy.4p_ssdd_l0.8", durations=200)
+    spec = CASES["toy4p_l08_200_rand"]
+    gold = load_golden("toy4p_l08_200_rand")["steps"]
+    from helpers import policy_random_py
+
+    def run():
+        rows = []
+        metrics, ev, done = env.step(None)
+        step = 0
+        while not done:
+            ev = pickle.loads(pickle.dumps(ev))  # DecisionEvent pickling (test_cim_scenario.py:409)
+            d = [ev.tick, ev.port_idx, ev.vessel_idx, ev.action_scope.load, ev.action_scope.discharge, ev.early_discharge]
+            rows.append(d + [metrics["order_requirements"], metrics["container_shortage"], metrics["operation_number"]])
+            v, p, q, t = policy_random_py(d, spec["pseed"], spec["replica"], step)
+            metrics, ev, done = env.step(Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD))
+            step += 1
+        return np.asarray(rows)
+
+    a = run()
+    assert np.array_equal(a, gold)
+    env.reset(keep_seed=True)  # same seed -> same episode (test_keep_seed)
+    assert np.array_equal(run(), gold)
+    env.set_seed(7)
+    env.reset(keep_seed=True)  # set_seed takes effect at reset (cim_data_container_helpers.py:56-70)
+    spec7 = CASES["toy4p_l08_200_seed7"]
+    rows = []
+    metrics, ev, done = env.step(None)
+    step = 0
+    while not done:
+        d = [ev.tick, ev.port_idx, ev.vessel_idx, ev.action_scope.load, ev.action_scope.discharge, ev.early_discharge]
+        rows.append(d + [metrics["order_requirements"], metrics["container_shortage"], metrics["operation_number"]])
+        v, p, q, t = policy_random_py(d, spec7["pseed"], spec7["replica"], step)
+        metrics, ev, done = env.step(Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD))
+        step += 1
+    assert np.array_equal(np.asarray(rows), load_golden("toy4p_l08_200_seed7")["steps"])
+    with pytest.raises(AssertionError):
+        env.reset(keep_seed=True)
+        m, ev, done = env.step(None)
+        env.step(Action(ev.vessel_idx, ev.port_idx, 10 ** 8, ActionType.LOAD))
+    env.close()
+
+
+def test_vector_env_like_reference_test():
+    """tests/test_vector_env.py:25-53: push one env with a dict, then all; final ticks [99, 99]."""
+    from maro_b200.vector_env import VectorEnv
+
+    with VectorEnv(batch_num=2, scenario="cim", topology="toy.4p_ssdd_l0.0", durations=100) as env:
+        metrics, decision_event, is_done = env.step(None)
+        assert env.tick == [7, 7]
+        metrics, decision_event, is_done = env.step({0: None})
+        assert len(metrics) == 1 and len(decision_event) == 1
+        for _ in range(10):
+            env.step({0: None})
+        assert env.tick[0] > env.tick[1]
+        states = env.snapshot_list["ports"][0::"empty"]
+        assert len(states) == 2 and states[0].shape == (4,)
+        while not is_done:
+            metrics, decision_event, is_done = env.step(None)
+        assert env.tick == [99, 99]
+        assert metrics[0] is None or metrics[0]["order_requirements"] == 200000
+        env.reset()
+        assert env.tick == [0, 0]
+        metrics, decision_event, is_done = env.step(None)
+        assert env.tick == [7, 7] and not is_done
+
+
+def test_vector_env_large_batch_and_seeds():
+    """No cpu_count cap: 512 replicas with 4 distinct seeds of a noisy topology; per-seed groups agree, seeds differ."""
+    from maro_b200.vector_env import VectorEnv
+
+    seeds = [4096 + (i % 4) for i in range(512)]
+    with VectorEnv(batch_num=512, scenario="cim", topology="toy.4p_ssdd_l0.8", durations=150, seeds=seeds) as env:
+        dec, met, done = env.step_columnar(None)
+        while not done:
+            dec, met, done = env.step_columnar(None)
+        for g in range(4):
+            rows = met[g::4]
+            assert (rows == rows[0]).all()
+        assert len({tuple(met[g]) for g in range(4)}) > 1
