@@ -51,10 +51,50 @@ struct BlobBuilder {
     }
 };
 
+// Order list of one tick for a noise-free, fixed-mode topology: the arithmetic of
+// CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398) with every noise term == 0.
+inline void gen_orders_noise_free(const MaroCimTopology& t, int orders_to_gen, std::vector<int32_t>& out) {
+    const int P = t.n_ports;
+    int remaining = orders_to_gen;
+    double tot = 0.0;
+    for (int p = 0; p < P; p++) tot = tot + (t.source_base[p] + 0.0);
+    for (int p = 0; p < P; p++) {
+        if (remaining == 0) break;
+        int lo = t.target_offset[p], hi = t.target_offset[p + 1];
+        double ttot = 0.0;
+        for (int i = lo; i < hi; i++) ttot = ttot + (t.target_base[i] + 0.0);
+        double sp = t.source_base[p] + 0.0;
+        if (tot != 0.0) sp = sp / tot;
+        int cur = (int)ceil((double)orders_to_gen * sp);
+        if (cur > remaining) cur = remaining;
+        remaining -= cur;
+        if (cur > 0) {
+            int trem = cur;
+            for (int i = lo; i < hi; i++) {
+                double tp = t.target_base[i] + 0.0;
+                if (ttot != 0.0) tp = tp / ttot;
+                int num = (int)ceil((double)cur * tp);
+                if (num > trem) num = trem;
+                trem -= num;
+                if (num > 0) {
+                    out.push_back(p | (t.target_port[i] << 8));
+                    out.push_back(num);
+                }
+            }
+        }
+    }
+}
+
+inline int count_distinct_orders(const MaroCimTopology& t) {
+    std::vector<int32_t> v(t.order_proportion, t.order_proportion + t.max_tick);
+    std::sort(v.begin(), v.end());
+    return (int)(std::unique(v.begin(), v.end()) - v.begin());
+}
+
 // Serialise one topology into a blob; every array is padded to the per-handle maxima so that all topologies of
 // a handle share the same offsets (CimShape::t_*).
 inline int build_blob(const MaroCimTopology& t, CimShape& s, std::vector<int32_t>& out, int max_stops, int max_targets,
-                      bool first) {
+                      bool first, int max_distinct = 0) {
     std::vector<int32_t> w;
     BlobBuilder b(w);
     const int P = t.n_ports, V = t.n_vessels;
@@ -92,6 +132,30 @@ inline int build_blob(const MaroCimTopology& t, CimShape& s, std::vector<int32_t
     o.t_mt_order = b.put_i(reinterpret_cast<int32_t*>(mt), 624, 624);
     mt_init_by_array(t.buffer_time_seed, mt);
     o.t_mt_buffer = b.put_i(reinterpret_cast<int32_t*>(mt), 624, 624);
+    {   // integer buffer ticks (valid when the buffer stream is noise-free)
+        std::vector<int32_t> fi(P), ei(P);
+        for (int p = 0; p < P; p++) {
+            fi[p] = (int)ceil(t.full_return_base[p] + 0.0);
+            ei[p] = (int)ceil(t.empty_return_base[p] + 0.0);
+        }
+        o.t_frb_i = b.put_i(fi.data(), P, P);
+        o.t_erb_i = b.put_i(ei.data(), P, P);
+    }
+    if (s.order_table) {
+        std::vector<int32_t> vals(t.order_proportion, t.order_proportion + t.max_tick);
+        std::sort(vals.begin(), vals.end());
+        vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+        std::vector<int32_t> slot(t.max_tick), off(1, 0), list;
+        for (int k = 0; k < t.max_tick; k++)
+            slot[k] = (int)(std::lower_bound(vals.begin(), vals.end(), t.order_proportion[k]) - vals.begin());
+        for (int32_t v : vals) {
+            gen_orders_noise_free(t, v, list);
+            off.push_back((int)list.size() / 2);
+        }
+        o.t_ord_slot = b.put_i(slot.data(), t.max_tick, t.max_tick);
+        o.t_ord_off = b.put_i(off.data(), (int)off.size(), max_distinct + 1);
+        o.t_ord_list = b.put_i(list.data(), (int)list.size(), 2 * max_distinct * std::max(1, max_targets));
+    }
     w.resize(round_up((int)w.size(), 4), 0);
     o.table_words = (int)w.size();
     if (first) s = o;
@@ -116,7 +180,8 @@ inline int check_same_shape(const MaroCimTopology& a, const MaroCimTopology& b) 
 
 // Fill `s` (layout, queue sizing) and serialise every topology into `tables`.  Returns non-zero on mismatch.
 inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg, CimShape& s,
-                                    std::vector<int32_t>& tables, int& max_stops_out, int& max_targets_out) {
+                                    std::vector<int32_t>& tables, int& max_stops_out, int& max_targets_out,
+                                    int& max_distinct_out) {
     const MaroCimTopology& t0 = topos[0];
     memset(&s, 0, sizeof(s));
     const int P = t0.n_ports, V = t0.n_vessels;
@@ -178,10 +243,15 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
     max_stops += max_stops / 8 + 8;
     max_stops_out = max_stops;
     max_targets_out = max_targets;
+    s.order_table = (!s.order_noise && s.order_mode == 0) ? 1 : 0;
+    int max_distinct = 0;
+    if (s.order_table)
+        for (int k = 0; k < n_topos; k++) max_distinct = std::max(max_distinct, count_distinct_orders(topos[k]));
+    max_distinct_out = max_distinct;
     tables.clear();
     for (int k = 0; k < n_topos; k++) {
         if (k > 0 && check_same_shape(t0, topos[k])) return 1;
-        if (build_blob(topos[k], s, tables, max_stops, max_targets, k == 0)) return 1;
+        if (build_blob(topos[k], s, tables, max_stops, max_targets, k == 0, max_distinct)) return 1;
     }
     return 0;
 }

@@ -211,7 +211,7 @@ struct AttrInfo { const char* name; int off, slots, isf, n_nodes; };
 
 struct MaroCimEnv {
     CimShape s;
-    int device = 0, B = 0, K = 0, mt_words = 0, warps_per_cta = 4, grid = 0, max_stops = 0, max_targets = 0;
+    int device = 0, B = 0, K = 0, mt_words = 0, warps_per_cta = 4, grid = 0, max_stops = 0, max_targets = 0, max_distinct = 0;
     size_t smem_bytes = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int32_t *d_state = nullptr, *d_snap = nullptr, *d_snap_frame = nullptr, *d_tables = nullptr, *d_topo = nullptr;
@@ -311,7 +311,7 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     e->B = cfg->n_replicas;
     e->K = n_topos;
     CimShape& s = e->s;
-    if (compute_shape_and_tables(topos, n_topos, cfg, s, e->h_tables, e->max_stops, e->max_targets)) {
+    if (compute_shape_and_tables(topos, n_topos, cfg, s, e->h_tables, e->max_stops, e->max_targets, e->max_distinct)) {
         delete e;
         return fail("maro_cim_create: inconsistent topology tables / durations must be positive");
     }
@@ -400,7 +400,8 @@ int maro_cim_set_topology(MaroCimEnv* e, int32_t index, const MaroCimTopology* t
     if (topo->stop_offset[topo->n_vessels] > e->max_stops || topo->target_offset[topo->n_ports] > e->max_targets)
         return fail("maro_cim_set_topology: more stops/targets than the handle was sized for");
     CimShape probe = e->s;  // rebuild with identical padding; offsets must come out the same
-    if (build_blob(*topo, probe, blob, e->max_stops, e->max_targets, true) || probe.table_words != e->s.table_words ||
+    if ((e->s.order_table && count_distinct_orders(*topo) > e->max_distinct) ||
+        build_blob(*topo, probe, blob, e->max_stops, e->max_targets, true, e->max_distinct) || probe.table_words != e->s.table_words ||
         probe.t_mt_buffer != e->s.t_mt_buffer || probe.t_order_proportion != e->s.t_order_proportion)
         return fail("maro_cim_set_topology: shape differs from the handle's");
     memcpy(e->h_tables.data() + (size_t)index * e->s.table_words, blob.data(), blob.size() * 4);

@@ -27,8 +27,8 @@ static Replica rep_of(Emul* e, int i) {
 extern "C" {
 Emul* emul_create(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg) {
     Emul* e = new Emul();
-    int ms, mt;
-    if (compute_shape_and_tables(topos, n_topos, cfg, e->s, e->tables, ms, mt)) { delete e; return nullptr; }
+    int ms, mt, md;
+    if (compute_shape_and_tables(topos, n_topos, cfg, e->s, e->tables, ms, mt, md)) { delete e; return nullptr; }
     e->B = cfg->n_replicas;
     e->state.assign((size_t)e->B * e->s.SW, 0);
     e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
