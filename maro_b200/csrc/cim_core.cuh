@@ -1,60 +1,180 @@
-// cim_core.cuh — per-replica CIM simulation core (device code, one warp = one replica).
+// cim_core.cuh — per-replica CIM simulation core (device code; one lane group of G lanes = one replica, G = 32 is
+// "one warp = one replica", smaller G packs 32/G replicas of a small topology into a warp).
 //
-// This is a from-scratch formulation of the reference's Env.step hot path
+// A from-scratch formulation of the reference's Env.step hot path
 // (maro/simulator/core.py:317-381, maro/event_buffer/event_buffer.py:190-247,
 //  maro/simulator/scenarios/cim/business_engine.py:122-224, 448-748) for a SIMT machine:
 //
 //   * The reference keeps one linked list of event objects per tick.  Here the per-tick execution order is
-//     reconstructed from its three sources (DESIGN.md "Event order"):
-//       (a) VESSEL_DEPARTURE events pre-inserted at init  -> read off the static stop table (vessel order),
-//       (b) events inserted by earlier ticks (RETURN_FULL / DISCHARGE_FULL / RETURN_EMPTY) -> a calendar queue
-//           (FIFO bucket per target tick) in shared memory,
-//       (c) ORDER events generated by BusinessEngine.step -> generated and consumed in place,
+//     reconstructed from its sources:
+//       (a) VESSEL_DEPARTURE events pre-inserted at init  -> read off the static stop table, one lane per vessel,
+//       (b) events inserted by earlier ticks (RETURN_FULL / DISCHARGE_FULL / RETURN_EMPTY) -> calendar queue bucket,
+//       (c) ORDER events of BusinessEngine.step -> precomputed schedule (noise-free) or generated in place,
 //       (d) VESSEL_ARRIVAL + LOAD_FULL per arriving vessel, then (e) the decision events, vessel order.
-//     Immediate (cascade) events are executed inline right after their parent.
-//   * Lanes cooperate on the wide parts (stage-in/out, snapshots, per-port / per-vessel sweeps, reductions);
-//     the data-dependent event chain is executed by the leader lane on shared memory.
+//   * Every phase is a cooperative group operation: lane i takes the i-th event of the phase.  Order dependence
+//     inside a phase is resolved with shuffles / ballots instead of serial execution:
+//       - phase (b) handlers are pure adds/subtracts -> shared-memory atomics, any order;
+//       - ORDERs of one source port consume `empty` in sequence -> segmented prefix sum over the lanes;
+//       - LOAD_FULL hands `acceptable` space to the reachable stops in sequence -> prefix sum over the lanes;
+//       - events pushed by several lanes keep FIFO order per target bucket via match_any + lane ranks;
+//       - MT19937 draws are indexed by event rank (random access into the stream, parallel twist).
 //
-// The same source compiles for the host with MARO_HOST_EMULATION (NL = 1 lane, no staging); that build exists
-// only for tests (tests/_emul) to debug the kernel logic without a GPU and is never part of the shipped library.
+// The same source compiles for the host with MARO_HOST_EMULATION (tests/_emul_src: one host thread per lane); that
+// build exists only to debug the kernel logic without a GPU and is never part of the shipped library.
 #pragma once
 #include <stdint.h>
 
 #ifdef MARO_HOST_EMULATION
 #include <math.h>
 #include <string.h>
-#define MARO_DEV
-#define MARO_NL 1
-#define WARP_SYNC() ((void)0)
-static inline uint32_t warp_or32(uint32_t x) { return x; }
-static inline int64_t warp_sum64(int64_t x) { return x; }
+
+#include "warp_emul.hpp"
+#define MARO_DEV inline
+#else
+#define MARO_DEV __device__ __forceinline__
+#endif
+
+namespace maro {
+
+// =====================================================================================================
+// Lane-group primitives
+// =====================================================================================================
+#ifdef MARO_HOST_EMULATION
+template <int G>
+struct Grp {
+    int lane;
+    explicit Grp(int l) : lane(l) {}
+    void sync() const { wemu::barrier(); }
+    int shfl(int x, int src) const {
+        uint64_t o[32];
+        wemu::exchange((uint64_t)(uint32_t)x, o);
+        return (int)(uint32_t)o[src & (G - 1)];
+    }
+    int shfl_up(int x, int d) const {
+        uint64_t o[32];
+        wemu::exchange((uint64_t)(uint32_t)x, o);
+        return lane >= d ? (int)(uint32_t)o[lane - d] : x;
+    }
+    int shfl_down(int x, int d) const {
+        uint64_t o[32];
+        wemu::exchange((uint64_t)(uint32_t)x, o);
+        return lane + d < G ? (int)(uint32_t)o[lane + d] : x;
+    }
+    uint32_t ballot(bool p) const {
+        uint64_t o[32];
+        wemu::exchange(p ? 1 : 0, o);
+        uint32_t m = 0;
+        for (int i = 0; i < G; i++) m |= (uint32_t)o[i] << i;
+        return m;
+    }
+    uint32_t match(int v) const {
+        uint64_t o[32];
+        wemu::exchange((uint64_t)(uint32_t)v, o);
+        uint32_t m = 0;
+        for (int i = 0; i < G; i++) if ((uint32_t)o[i] == (uint32_t)v) m |= 1u << i;
+        return m;
+    }
+    int64_t sum64(int64_t x) const {
+        uint64_t o[32];
+        wemu::exchange((uint64_t)x, o);
+        int64_t s = 0;
+        for (int i = 0; i < G; i++) s += (int64_t)o[i];
+        return s;
+    }
+    int sum(int x) const { return (int)sum64(x); }
+    uint32_t or32(uint32_t x) const {
+        uint64_t o[32];
+        wemu::exchange(x, o);
+        uint32_t m = 0;
+        for (int i = 0; i < G; i++) m |= (uint32_t)o[i];
+        return m;
+    }
+};
+static inline void atomic_add(int32_t* p, int32_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline double maro_ceil(double x) { return ceil(x); }
 static inline double maro_floor(double x) { return floor(x); }
 static inline float maro_d2f(double x) { return (float)x; }
 static inline int32_t maro_f2i(float x) { int32_t i; memcpy(&i, &x, 4); return i; }
 static inline float maro_i2f(int32_t i) { float x; memcpy(&x, &i, 4); return x; }
 static inline int maro_ffs64(uint64_t x) { return __builtin_ffsll((long long)x); }
+static inline int maro_ffs32(uint32_t x) { return __builtin_ffs((int)x); }
+static inline int maro_popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int maro_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 #else
-#define MARO_DEV __device__ __forceinline__
-#define MARO_NL 32
-#define WARP_SYNC() __syncwarp()
-__device__ __forceinline__ uint32_t warp_or32(uint32_t x) { return __reduce_or_sync(0xffffffffu, x); }
-__device__ __forceinline__ int64_t warp_sum64(int64_t x) {
+template <int G>
+struct Grp {
+    int lane;       // 0..G-1 inside the group
+    unsigned mask;  // lanes of this group inside the warp
+    int base;
+    __device__ __forceinline__ explicit Grp(int lane_in_warp) {
+        lane = lane_in_warp & (G - 1);
+        base = lane_in_warp & ~(G - 1);
+        mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << base);
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ int shfl(int x, int src) const { return __shfl_sync(mask, x, src, G); }
+    __device__ __forceinline__ int shfl_up(int x, int d) const { return __shfl_up_sync(mask, x, d, G); }
+    __device__ __forceinline__ int shfl_down(int x, int d) const { return __shfl_down_sync(mask, x, d, G); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const {
+        uint32_t b = __ballot_sync(mask, p);
+        return G == 32 ? b : ((b >> base) & ((1u << G) - 1u));
+    }
+    __device__ __forceinline__ uint32_t match(int v) const {
+        uint32_t b = __match_any_sync(mask, v);
+        return G == 32 ? b : ((b >> base) & ((1u << G) - 1u));
+    }
+    __device__ __forceinline__ int64_t sum64(int64_t x) const {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-}
+        for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, G);
+        return x;
+    }
+    __device__ __forceinline__ int sum(int x) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, G);
+        return x;
+    }
+    __device__ __forceinline__ uint32_t or32(uint32_t x) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) x |= __shfl_xor_sync(mask, x, o, G);
+        return x;
+    }
+};
+__device__ __forceinline__ void atomic_add(int32_t* p, int32_t v) { atomicAdd(p, v); }
 __device__ __forceinline__ double maro_ceil(double x) { return ceil(x); }
 __device__ __forceinline__ double maro_floor(double x) { return floor(x); }
 __device__ __forceinline__ float maro_d2f(double x) { return __double2float_rn(x); }
 __device__ __forceinline__ int32_t maro_f2i(float x) { return __float_as_int(x); }
 __device__ __forceinline__ float maro_i2f(int32_t i) { return __int_as_float(i); }
 __device__ __forceinline__ int maro_ffs64(uint64_t x) { return __ffsll((long long)x); }
+__device__ __forceinline__ int maro_ffs32(uint32_t x) { return __ffs((int)x); }
+__device__ __forceinline__ int maro_popc(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int maro_clz(uint32_t x) { return __clz((int)x); }
 #endif
 
-#define LANE_LOOP(i, n) for (int i = lane; i < (n); i += MARO_NL)
+#define LANE_LOOP(i, n) for (int i = g.lane; i < (n); i += G)
 
-namespace maro {
+// inclusive prefix sum over the lanes of a group
+template <int G>
+MARO_DEV int scan_incl(const Grp<G>& g, int x) {
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        int t = g.shfl_up(x, d);
+        if (g.lane >= d) x += t;
+    }
+    return x;
+}
+
+// inclusive prefix sum restricted to runs of equal `key` (keys sorted / contiguous)
+template <int G>
+MARO_DEV int scan_incl_seg(const Grp<G>& g, int x, int key) {
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        int t = g.shfl_up(x, d);
+        int k = g.shfl_up(key, d);
+        if (g.lane >= d && k == key) x += t;
+    }
+    return x;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Shape / layout shared by every replica of a handle (kernel parameter; offsets are in 4-byte words).
@@ -66,10 +186,10 @@ enum VesselAttr { VA_CAPACITY, VA_EARLY_DISCHARGE, VA_EMPTY, VA_FULL, VA_IS_PARK
 
 // control words (per replica, after the frame)
 enum Ctrl {
-    C_STATE, C_TICK, C_ARR_LO, C_ARR_HI, C_DEC_POS, C_FREE_HEAD, C_Q_COUNT, C_ERR,
+    C_STATE, C_TICK, C_ARR_LO, C_ARR_HI, C_DEC_POS, C_FREE_TOP, C_Q_COUNT, C_ERR,
     C_OPNUM_LO, C_OPNUM_HI, C_MT_ORDER_IDX, C_MT_BUFFER_IDX,
     C_NSTEPS_LO, C_NSTEPS_HI, C_NTICKS_LO, C_NTICKS_HI, C_NEVENTS_LO, C_NEVENTS_HI, C_NSNAPS_LO, C_NSNAPS_HI,
-    C_LAST_FRAME, C_RESERVED0, C_RESERVED1, C_RESERVED2,
+    C_LAST_FRAME, C_N_ORDERS, C_RESERVED1, C_RESERVED2,
     C_FIXED  // followed by dep_cursor[V]
 };
 enum State { ST_START = 0, ST_TICK_BEGIN = 1, ST_DECISIONS = 2, ST_AWAIT = 3, ST_DONE = 4, ST_FINISHED = 5, ST_ERROR = 6 };
@@ -79,8 +199,9 @@ struct CimShape {
     int P, V, R, past, fut, max_route_len;
     int max_tick, start_tick, resolution, ring_rows, order_mode, total_containers;
     int order_noise, buffer_noise, max_actions, n_replicas;
+    int vol_is_one, max_targets;
     double vol;
-    // per-replica state block: [frame FWp][ctrl CWp][queue: pool QN*4 | buckets QH]
+    // per-replica state block: [frame FWp][ctrl CWp][queue: pool QN*4 | buckets QH | free stack QN]
     int FW, FWp, CWp, QN, QH, SW;
     int o_vs, o_past, o_past_tick, o_fut, o_fut_tick, o_fop, o_fov, o_vp;  // frame offsets (ports start at 0)
     // static table blob offsets (words from the blob start); *_d are offsets of double arrays (even)
@@ -93,15 +214,16 @@ struct CimShape {
     int order_table;                        // 1: per-tick order lists are static (fixed mode, no order noise)
     int t_ord_slot, t_ord_off, t_ord_list;  // slot[max_tick] -> off[slot..slot+1] -> list {src | dst << 8, qty}
     int t_frb_i, t_erb_i;                   // ceil(buffer_ticks) per port, valid when buffer_noise == 0
-    int table_words;  // stride between topology blobs
+    int table_words;                        // stride between topology blobs
+    int mt_scratch;                         // word offset of the scratch area inside a replica's MT block
 };
 
 struct Replica {
     int32_t* f;          // frame words (shared memory on the device)
     int32_t* c;          // control words
-    int32_t* q;          // queue: pool then buckets
+    int32_t* q;          // queue: pool | buckets | free stack
     const int32_t* t;    // static table blob of this replica's topology
-    uint32_t* mt;        // [2][640] MT19937 states in global memory (NULL when the topology has no noise)
+    uint32_t* mt;        // [2][640] MT19937 states + scratch, global memory (NULL when the topology has no noise)
     int32_t* snap;       // [ring_rows][FWp] snapshot ring (global)
     int32_t* snap_frame; // [ring_rows] frame index held by each row
 };
@@ -122,116 +244,156 @@ MARO_DEV void ctrl_set64(const Replica& r, int lo, int64_t v) {
 MARO_DEV void ctrl_add64(const Replica& r, int lo, int64_t d) { ctrl_set64(r, lo, ctrl_get64(r, lo) + d); }
 
 // ------------------------------------------------------------------------------------------------
-// MT19937, bit-compatible with CPython's random.Random (Modules/_randommodule.c); leader lane only.
-// State words live in global memory (2.5 KB per stream): r.mt[stream * 640 + i].
+// MT19937, bit-compatible with CPython's random.Random (Modules/_randommodule.c).
+// State words live in global memory: r.mt[stream * 640 + i]; scratch (for the stream tail) at r.mt + mt_scratch.
 // ------------------------------------------------------------------------------------------------
-MARO_DEV uint32_t mt_next(const Replica& r, int stream) {
-    uint32_t* mt = r.mt + stream * 640;
-    int idx = r.c[C_MT_ORDER_IDX + stream];
-    if (idx >= 624) {
-        int kk;
-        for (kk = 0; kk < 624 - 397; kk++) {
-            uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        }
-        for (; kk < 623; kk++) {
-            uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        }
-        uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
-        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        idx = 0;
-    }
-    uint32_t y = mt[idx++];
-    r.c[C_MT_ORDER_IDX + stream] = idx;
+MARO_DEV uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     return y;
 }
+MARO_DEV uint32_t mt_mix(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// serial generator step (leader lane only) — used by the noisy order generator
+MARO_DEV uint32_t mt_next(const Replica& r, int stream) {
+    uint32_t* mt = r.mt + stream * 640;
+    int idx = r.c[C_MT_ORDER_IDX + stream];
+    if (idx >= 624) {
+        int kk;
+        for (kk = 0; kk < 624 - 397; kk++) mt[kk] = mt_mix(mt[kk], mt[kk + 1], mt[kk + 397]);
+        for (; kk < 623; kk++) mt[kk] = mt_mix(mt[kk], mt[kk + 1], mt[kk - 227]);
+        mt[623] = mt_mix(mt[623], mt[0], mt[396]);
+        idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    r.c[C_MT_ORDER_IDX + stream] = idx;
+    return mt_temper(y);
+}
+
+MARO_DEV double mt_uniform01(uint32_t y0, uint32_t y1) {
+    uint32_t a = y0 >> 5, b = y1 >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
 
 // value + random.uniform(-noise, noise)   (maro/data_lib/cim/utils.py:30-42; Lib/random.py uniform)
-MARO_DEV double apply_noise(const Replica& r, int stream, double value, double noise) {
-    uint32_t a = mt_next(r, stream) >> 5, b = mt_next(r, stream) >> 6;
-    double u = ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+MARO_DEV double noised(double value, double noise, double u) {
     double lo = -noise, hi = noise;
     return value + (lo + (hi - lo) * u);
 }
+MARO_DEV double apply_noise_serial(const Replica& r, int stream, double value, double noise) {
+    uint32_t y0 = mt_next(r, stream), y1 = mt_next(r, stream);
+    return noised(value, noise, mt_uniform01(y0, y1));
+}
+
+// Cooperative twist of the whole state (all lanes of the group).
+template <int G>
+MARO_DEV void mt_twist(const Grp<G>& g, uint32_t* mt) {
+    for (int b0 = 0; b0 < 623; b0 += G) {
+        int kk = b0 + g.lane;
+        uint32_t nv = 0;
+        if (kk < 623) nv = mt_mix(mt[kk], mt[kk + 1], kk < 227 ? mt[kk + 397] : mt[kk - 227]);
+        g.sync();
+        if (kk < 623) mt[kk] = nv;
+        g.sync();
+        // a batch never straddles the 227 boundary dependency: element kk >= 227 reads mt[kk-227] written >= one
+        // batch earlier because G <= 32 < 227.
+    }
+    if (g.lane == 0) mt[623] = mt_mix(mt[623], mt[0], mt[396]);
+    g.sync();
+}
+
+// Make the next `n_out` tempered outputs of `stream` addressable by rank: output k is view.at(k).
+struct MtView {
+    const uint32_t* a;
+    int na;
+    const uint32_t* b;
+    MARO_DEV uint32_t at(int k) const { return mt_temper(k < na ? a[k] : b[k - na]); }
+};
+template <int G>
+MARO_DEV MtView mt_reserve(const CimShape& s, const Grp<G>& g, const Replica& r, int stream, int n_out) {
+    uint32_t* mt = r.mt + stream * 640;
+    int idx = r.c[C_MT_ORDER_IDX + stream];
+    MtView v;
+    if (idx + n_out <= 624) {
+        v.a = mt + idx; v.na = n_out; v.b = mt;
+        g.sync();
+        if (g.lane == 0) r.c[C_MT_ORDER_IDX + stream] = idx + n_out;
+        g.sync();
+        return v;
+    }
+    int tail = 624 - idx;
+    uint32_t* scratch = r.mt + s.mt_scratch;
+    LANE_LOOP(i, tail) scratch[i] = mt[idx + i];
+    g.sync();
+    mt_twist(g, mt);
+    v.a = scratch; v.na = tail; v.b = mt;
+    if (g.lane == 0) r.c[C_MT_ORDER_IDX + stream] = n_out - tail;
+    g.sync();
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------
-// Calendar queue of dynamic events.  Event slot = 4 words {type|a<<8|b<<16|c<<24, qty, tick, next}.
-// bucket[tick & (QH-1)] = head | tail << 16 (0xffff = nil).  FIFO per tick == the reference's insertion order.
+// Calendar queue of dynamic events.  Slot = 4 words {type|a<<8|b<<16|c<<24, qty, tick, next};
+// bucket[tick & (QH-1)] = head | tail << 16 (0xffff = nil); free slots on a stack (parallel pop / push).
+// group_push: every lane with `want` appends one event; FIFO order per bucket = lane order.
 // ------------------------------------------------------------------------------------------------
 #define Q_NIL 0xffff
 
-MARO_DEV void queue_push(const CimShape& s, const Replica& r, int tick, int type, int a, int b, int c, int qty) {
-    if (tick >= s.max_tick || tick < 0) return;  // never executed (event_buffer.py:190: only ticks the Env visits)
-    int slot = r.c[C_FREE_HEAD];
-    if (slot == Q_NIL) { r.c[C_ERR] = -2; return; }
-    int32_t* e = r.q + slot * 4;
-    r.c[C_FREE_HEAD] = e[3];
-    e[0] = type | (a << 8) | (b << 16) | (c << 24);
-    e[1] = qty;
-    e[2] = tick;
-    e[3] = Q_NIL;
-    int32_t* bk = r.q + s.QN * 4 + (tick & (s.QH - 1));
-    int hb = *bk;
-    int tail = (hb >> 16) & 0xffff;
-    if (tail == Q_NIL) *bk = slot | (slot << 16);
-    else { r.q[tail * 4 + 3] = slot; *bk = (hb & 0xffff) | (slot << 16); }
-    r.c[C_Q_COUNT] += 1;
+template <int G>
+MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, bool want, int tick, int w0, int qty) {
+    want = want && tick < s.max_tick && tick >= 0;  // later ticks are never visited by the Env (event_buffer.py:190)
+    uint32_t bal = g.ballot(want);
+    if (bal == 0) return;
+    int n = maro_popc(bal);
+    int rank = maro_popc(bal & ((1u << g.lane) - 1u));
+    int top = r.c[C_FREE_TOP];
+    if (top < n) {  // group-uniform
+        g.sync();
+        if (g.lane == 0) r.c[C_ERR] = -2;
+        g.sync();
+        return;
+    }
+    int32_t* fs = r.q + s.QN * 4 + s.QH;
+    int slot = want ? fs[top - 1 - rank] : Q_NIL;
+    int b = tick & (s.QH - 1);
+    uint32_t peers = g.match(want ? b : (0x10000 + g.lane));
+    uint32_t below = peers & ((1u << g.lane) - 1u);
+    uint32_t above = g.lane == 31 ? 0u : (peers & ~((2u << g.lane) - 1u));
+    int nxt_lane = above ? maro_ffs32(above) - 1 : g.lane;
+    int last_lane = 31 - maro_clz(peers);
+    int nxt_slot = g.shfl(slot, nxt_lane);
+    int last_slot = g.shfl(slot, want ? last_lane : g.lane);
+    g.sync();
+    if (g.lane == 0) { r.c[C_FREE_TOP] = top - n; r.c[C_Q_COUNT] += n; }
+    if (want) {
+        int32_t* e = r.q + slot * 4;
+        e[0] = w0; e[1] = qty; e[2] = tick;
+        e[3] = above ? nxt_slot : Q_NIL;
+        if (!below) {  // first lane of this bucket's run: splice the run after the current tail
+            int32_t* bk = r.q + s.QN * 4 + b;
+            int hb = *bk, tail = (hb >> 16) & 0xffff;
+            if (tail == Q_NIL) *bk = slot | (last_slot << 16);
+            else { r.q[tail * 4 + 3] = slot; *bk = (hb & 0xffff) | (last_slot << 16); }
+        }
+    }
+    g.sync();
 }
 
 // ------------------------------------------------------------------------------------------------
 // Static-table helpers (maro/data_lib/cim/vessel_*_wrapper.py, vessel_future_stops_prediction.py)
 // ------------------------------------------------------------------------------------------------
-MARO_DEV int route_len(const CimShape& s, const Replica& r, int v) {
-    int rt = TBL_I(r, s.t_vessel_route, v);
-    return TBL_I(r, s.t_route_offset, rt + 1) - TBL_I(r, s.t_route_offset, rt);
+// Vessel._update_remaining_space (vessel.py:113-120); total_space = floor(capacity / container_volume)
+MARO_DEV int total_space(const CimShape& s, int cap) { return s.vol_is_one ? cap : (int)maro_floor((double)cap / s.vol); }
+MARO_DEV void vessel_update_space(const CimShape& s, const Replica& r, int v) {
+    VA(s, r, VA_REMAINING_SPACE, v) = total_space(s, VA(s, r, VA_CAPACITY, v)) - VA(s, r, VA_FULL, v) - VA(s, r, VA_EMPTY, v);
 }
 
-// VesselFutureStopsPrediction._predict_future_stops (:49-85): k-th predicted stop after stop `last_stop_idx`.
-// Writes `n` (port, tick) pairs through the callback-free pattern: ports/ticks stored to dst arrays or plans.
-MARO_DEV void predict_to_lists(const CimShape& s, const Replica& r, int v, int last_stop_idx, int n,
-                               int32_t* dst_port, int32_t* dst_tick) {
-    int rt = TBL_I(r, s.t_vessel_route, v);
-    int rbase = TBL_I(r, s.t_route_offset, rt);
-    int rl = TBL_I(r, s.t_route_offset, rt + 1) - rbase;
-    int lbase = TBL_I(r, s.t_vessel_leg_offset, v);
-    int arrival = TBL_I(r, s.t_stop_arrival, TBL_I(r, s.t_stop_offset, v) + last_stop_idx);
-    int loc = (TBL_I(r, s.t_vessel_route_start, v) + last_stop_idx) % rl;
-    for (int k = 0; k < n; k++) {
-        arrival += TBL_I(r, s.t_vessel_leg, lbase + loc);
-        loc = loc + 1 == rl ? 0 : loc + 1;
-        dst_port[k] = TBL_I(r, s.t_route_port, rbase + loc);
-        dst_tick[k] = arrival;
-    }
-}
-
-// VesselSailingPlanWrapper (:24-28) applied to the vessel_plans row (business_engine.py:393-398, 626-632)
-MARO_DEV void update_vessel_plans(const CimShape& s, const Replica& r, int v, int stop_idx) {
-    int rt = TBL_I(r, s.t_vessel_route, v);
-    int rbase = TBL_I(r, s.t_route_offset, rt);
-    int rl = TBL_I(r, s.t_route_offset, rt + 1) - rbase;
-    int lbase = TBL_I(r, s.t_vessel_leg_offset, v);
-    int arrival = TBL_I(r, s.t_stop_arrival, TBL_I(r, s.t_stop_offset, v) + stop_idx);
-    int loc = (TBL_I(r, s.t_vessel_route_start, v) + stop_idx) % rl;
-    int32_t* plans = r.f + s.o_vp + v * s.P;
-    for (int k = 0; k < rl; k++) {
-        arrival += TBL_I(r, s.t_vessel_leg, lbase + loc);
-        loc = loc + 1 == rl ? 0 : loc + 1;
-        plans[TBL_I(r, s.t_route_port, rbase + loc)] = arrival;
-    }
-}
-
-MARO_DEV void set_future_stops(const CimShape& s, const Replica& r, int v, int last_loc_idx, int loc_idx) {
-    if (s.fut <= 0) return;
-    int last_stop_idx = loc_idx + (last_loc_idx == loc_idx ? 0 : -1);
-    predict_to_lists(s, r, v, last_stop_idx, s.fut, r.f + s.o_fut + v * s.fut, r.f + s.o_fut_tick + v * s.fut);
-}
-
-// VesselPastStopsWrapper.__getitem__ (:23-38) + Vessel.set_stop_list (vessel.py:91-111)
+// VesselPastStopsWrapper.__getitem__ (:23-38) + Vessel.set_stop_list (vessel.py:91-111) — one lane per vessel
 MARO_DEV void set_past_stops(const CimShape& s, const Replica& r, int v, int last_loc_idx, int loc_idx) {
     int n = s.past;
     if (n <= 0) return;
@@ -256,116 +418,297 @@ MARO_DEV void set_past_stops(const CimShape& s, const Replica& r, int v, int las
     }
 }
 
-// Vessel._update_remaining_space (vessel.py:113-120); total_space = floor(capacity / container_volume)
-MARO_DEV void vessel_update_space(const CimShape& s, const Replica& r, int v) {
-    int cap = VA(s, r, VA_CAPACITY, v);
-    int total_space = s.vol == 1.0 ? cap : (int)maro_floor((double)cap / s.vol);
-    VA(s, r, VA_REMAINING_SPACE, v) = total_space - VA(s, r, VA_FULL, v) - VA(s, r, VA_EMPTY, v);
-}
-
-// PortBufferTickWrapper.__getitem__ (port_buffer_tick_wrapper.py:29-35)
-MARO_DEV int buffer_ticks(const CimShape& s, const Replica& r, int off_base_d, int off_noise_d, int off_int, int port) {
-    if (!s.buffer_noise) return TBL_I(r, off_int, port);  // ceil(base) precomputed on the host
-    return (int)maro_ceil(apply_noise(r, 1, TBL_D(r, off_base_d, port), TBL_D(r, off_noise_d, port)));
-}
-
-// ------------------------------------------------------------------------------------------------
-// Event handlers (leader lane).  business_engine.py:448-748; callbacks port.py:88-97, vessel.py:113-120.
-// ------------------------------------------------------------------------------------------------
-MARO_DEV void on_full_return(const CimShape& s, const Replica& r, int src, int dst, int qty) {  // :499-522
-    PA(s, r, PA_ON_SHIPPER, src) -= qty;
-    PA(s, r, PA_FULL, src) += qty;
-    r.f[s.o_fop + src * s.P + dst] += qty;
-}
-
-MARO_DEV void on_empty_return(const CimShape& s, const Replica& r, int port, int qty) {  // :695-706
-    PA(s, r, PA_ON_CONSIGNEE, port) -= qty;
-    PA(s, r, PA_EMPTY, port) += qty;
-}
-
-MARO_DEV void on_order(const CimShape& s, const Replica& r, int tick, int src, int dst, int qty, int& nev) {  // :448-497
-    int execute_qty = qty;
-    int src_empty = PA(s, r, PA_EMPTY, src);
-    int booking = PA(s, r, PA_BOOKING, src) + qty;
-    PA(s, r, PA_BOOKING, src) = booking;
-    PA(s, r, PA_ACC_BOOKING, src) += qty;
-    int shortage = PA(s, r, PA_SHORTAGE, src);
-    if (src_empty < qty) {
-        int shortage_qty = qty - src_empty;
-        shortage += shortage_qty;
-        PA(s, r, PA_SHORTAGE, src) = shortage;
-        PA(s, r, PA_ACC_SHORTAGE, src) += shortage_qty;
-        execute_qty = src_empty;
+// VesselFutureStopsPrediction._predict_future_stops (:49-85), serial form: used by reset (one lane per vessel)
+MARO_DEV void predict_serial(const CimShape& s, const Replica& r, int v, int stop_idx, bool lists, bool plans) {
+    int rt = TBL_I(r, s.t_vessel_route, v);
+    int rbase = TBL_I(r, s.t_route_offset, rt);
+    int rl = TBL_I(r, s.t_route_offset, rt + 1) - rbase;
+    int lbase = TBL_I(r, s.t_vessel_leg_offset, v);
+    int arrival = TBL_I(r, s.t_stop_arrival, TBL_I(r, s.t_stop_offset, v) + stop_idx);
+    int loc = (TBL_I(r, s.t_vessel_route_start, v) + stop_idx) % rl;
+    int n = rl > s.fut ? rl : s.fut;
+    for (int k = 0; k < n; k++) {
+        arrival += TBL_I(r, s.t_vessel_leg, lbase + loc);
+        loc = loc + 1 == rl ? 0 : loc + 1;
+        int port = TBL_I(r, s.t_route_port, rbase + loc);
+        if (lists && k < s.fut) { r.f[s.o_fut + v * s.fut + k] = port; r.f[s.o_fut_tick + v * s.fut + k] = arrival; }
+        if (plans && k < rl) r.f[s.o_vp + v * s.P + port] = arrival;
     }
-    PA(s, r, PA_FULFILLMENT, src) = booking - shortage;  // _on_booking_changed / _on_shortage_changed
-    PA(s, r, PA_EMPTY, src) = src_empty - execute_qty;
-    PA(s, r, PA_ON_SHIPPER, src) += execute_qty;
-    int buf = buffer_ticks(s, r, s.t_frb_d, s.t_frn_d, s.t_frb_i, src);
-    if (buf == 0) { on_full_return(s, r, src, dst, execute_qty); nev++; }  // immediate event, runs right after
-    else queue_push(s, r, tick + buf, DE_RETURN_FULL, src, dst, 0, execute_qty);
 }
 
-MARO_DEV void on_discharge(const CimShape& s, const Replica& r, int tick, int v, int port, int qty, int& nev) {  // :658-693
-    VA(s, r, VA_FULL, v) -= qty;
-    vessel_update_space(s, r, v);
-    PA(s, r, PA_ON_CONSIGNEE, port) += qty;
-    r.f[s.o_fov + v * s.P + port] -= qty;
-    int buf = buffer_ticks(s, r, s.t_erb_d, s.t_ern_d, s.t_erb_i, port);
-    if (buf == 0) { on_empty_return(s, r, port, qty); nev++; }
-    else queue_push(s, r, tick + buf, DE_RETURN_EMPTY, port, 0, 0, qty);
+// ------------------------------------------------------------------------------------------------
+// Phase (b): events queued for this tick by earlier ticks.  _on_full_return (:499-522), _on_empty_return (:695-706),
+// _on_discharge (:658-693) are pure adds -> shared-memory atomics in any order; RETURN_EMPTY pushes keep lane order.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, int tick) {
+    int32_t* bk = r.q + s.QN * 4 + (tick & (s.QH - 1));
+    int head = *bk & 0xffff;
+    if (head == Q_NIL) return 0;
+    g.sync();
+    if (g.lane == 0) *bk = Q_NIL | (Q_NIL << 16);
+    int nev = 0;
+    int32_t* fs = r.q + s.QN * 4 + s.QH;
+    while (head != Q_NIL) {  // group-uniform
+        // lane i walks to the i-th event of the list (Q_NIL past the end)
+        int my = head;
+        for (int h = 0; h < g.lane && my != Q_NIL; h++) my = r.q[my * 4 + 3];
+        bool valid = my != Q_NIL;
+        int w0 = 0, qty = 0, nxt = Q_NIL;
+        if (valid) { w0 = r.q[my * 4]; qty = r.q[my * 4 + 1]; nxt = r.q[my * 4 + 3]; }
+        head = g.shfl(nxt, G - 1);  // continuation for lists longer than G
+        uint32_t vb = g.ballot(valid);
+        int n = maro_popc(vb);
+        int type = w0 & 0xff, a = (w0 >> 8) & 0xff, c = (w0 >> 24) & 0xff, b = (w0 >> 16) & 0xff;
+        bool is_dis = valid && type == DE_DISCHARGE_FULL;
+        if (valid) {
+            if (type == DE_RETURN_FULL) {
+                atomic_add(&PA(s, r, PA_ON_SHIPPER, a), -qty);
+                atomic_add(&PA(s, r, PA_FULL, a), qty);
+                atomic_add(&r.f[s.o_fop + a * s.P + b], qty);
+            } else if (type == DE_RETURN_EMPTY) {
+                atomic_add(&PA(s, r, PA_ON_CONSIGNEE, a), -qty);
+                atomic_add(&PA(s, r, PA_EMPTY, a), qty);
+            } else {  // DISCHARGE_FULL: a = vessel, b = from port, c = port
+                atomic_add(&VA(s, r, VA_FULL, a), -qty);
+                atomic_add(&VA(s, r, VA_REMAINING_SPACE, a), qty);
+                atomic_add(&PA(s, r, PA_ON_CONSIGNEE, c), qty);
+                atomic_add(&r.f[s.o_fov + a * s.P + c], -qty);
+            }
+        }
+        // empty-return buffer ticks of the discharges (port_buffer_tick_wrapper.py:29-35), drawn in event order
+        uint32_t db = g.ballot(is_dis);
+        int buf = 0;
+        if (db) {
+            if (s.buffer_noise) {
+                int nd = maro_popc(db);
+                int drank = maro_popc(db & ((1u << g.lane) - 1u));
+                MtView mv = mt_reserve(s, g, r, 1, 2 * nd);
+                if (is_dis) {
+                    double u = mt_uniform01(mv.at(2 * drank), mv.at(2 * drank + 1));
+                    buf = (int)maro_ceil(noised(TBL_D(r, s.t_erb_d, c), TBL_D(r, s.t_ern_d, c), u));
+                }
+            } else if (is_dis) {
+                buf = TBL_I(r, s.t_erb_i, c);
+            }
+            bool imm = is_dis && buf == 0;  // immediate RETURN_EMPTY right after the discharge
+            if (imm) {
+                atomic_add(&PA(s, r, PA_ON_CONSIGNEE, c), -qty);
+                atomic_add(&PA(s, r, PA_EMPTY, c), qty);
+            }
+            nev += maro_popc(g.ballot(imm));
+        }
+        // recycle this chunk's slots, then append the RETURN_EMPTY events
+        g.sync();
+        int top = r.c[C_FREE_TOP];
+        if (valid) fs[top + g.lane] = my;
+        g.sync();
+        if (g.lane == 0) { r.c[C_FREE_TOP] = top + n; r.c[C_Q_COUNT] -= n; }
+        g.sync();
+        if (db) group_push(s, g, r, is_dis && buf > 0, tick + buf, DE_RETURN_EMPTY | (c << 8), qty);
+        nev += n;
+    }
+    g.sync();
+    return nev;
 }
 
-MARO_DEV void on_arrival(const CimShape& s, const Replica& r, int v) {  // :600-632
-    int loc = VA(s, r, VA_NEXT_LOC_IDX, v);
-    VA(s, r, VA_LAST_LOC_IDX, v) = loc;
-    VA(s, r, VA_IS_PARKING, v) = 1;
-    VA(s, r, VA_LOC_PORT_IDX, v) = TBL_I(r, s.t_stop_port, TBL_I(r, s.t_stop_offset, v) + loc);
-    set_future_stops(s, r, v, loc, loc);
-    update_vessel_plans(s, r, v, loc);
+// ------------------------------------------------------------------------------------------------
+// Phase (c): this tick's ORDER events.  _on_order_generated (:448-497) for up to G orders at a time:
+// orders of one source port consume `empty` in sequence -> segmented prefix sum (orders arrive sorted by source).
+// `get(i, w, q)` yields order i as {src | dst << 8, qty}.
+// ------------------------------------------------------------------------------------------------
+template <int G, class Get>
+MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, int tick, int n_orders, Get get) {
+    int nev = 0;
+    for (int base = 0; base < n_orders; base += G) {
+        int i = base + g.lane;
+        bool valid = i < n_orders;
+        int w = 0, q = 0;
+        if (valid) get(i, w, q);
+        int src = valid ? (w & 0xff) : (0x100 + g.lane), dst = (w >> 8) & 0xff;
+        int empty0 = valid ? PA(s, r, PA_EMPTY, src) : 0;
+        int S = scan_incl_seg(g, q, src);
+        int E = S < empty0 ? S : empty0;
+        int Ep = (S - q) < empty0 ? (S - q) : empty0;
+        int exec = E - Ep;
+        int src_next = g.shfl_down(src, 1);
+        bool is_last = valid && (g.lane == G - 1 || src_next != src);
+        g.sync();
+        if (is_last) {  // one lane per source port commits the port's totals
+            int booking = PA(s, r, PA_BOOKING, src) + S;
+            int shortage = PA(s, r, PA_SHORTAGE, src) + (S - E);
+            PA(s, r, PA_BOOKING, src) = booking;
+            PA(s, r, PA_ACC_BOOKING, src) += S;
+            PA(s, r, PA_SHORTAGE, src) = shortage;
+            PA(s, r, PA_ACC_SHORTAGE, src) += S - E;
+            PA(s, r, PA_FULFILLMENT, src) = booking - shortage;  // _on_booking_changed / _on_shortage_changed
+            PA(s, r, PA_EMPTY, src) = empty0 - E;
+            PA(s, r, PA_ON_SHIPPER, src) += E;
+        }
+        g.sync();
+        // full-return buffer ticks, drawn in order (one draw per ORDER)
+        int buf = 0;
+        int nv = base + G <= n_orders ? G : n_orders - base;
+        if (s.buffer_noise) {
+            MtView mv = mt_reserve(s, g, r, 1, 2 * nv);
+            if (valid) {
+                double u = mt_uniform01(mv.at(2 * g.lane), mv.at(2 * g.lane + 1));
+                buf = (int)maro_ceil(noised(TBL_D(r, s.t_frb_d, src), TBL_D(r, s.t_frn_d, src), u));
+            }
+        } else if (valid) {
+            buf = TBL_I(r, s.t_frb_i, src);
+        }
+        bool imm = valid && buf == 0;  // immediate RETURN_FULL (_on_full_return :499-522)
+        if (imm) {
+            atomic_add(&PA(s, r, PA_ON_SHIPPER, src), -exec);
+            atomic_add(&PA(s, r, PA_FULL, src), exec);
+            atomic_add(&r.f[s.o_fop + src * s.P + dst], exec);
+        }
+        nev += nv + maro_popc(g.ballot(imm));
+        group_push(s, g, r, valid && buf > 0, tick + buf, DE_RETURN_FULL | (src << 8) | (dst << 16), exec);
+    }
+    return nev;
 }
 
-MARO_DEV void on_full_load(const CimShape& s, const Replica& r, int port, int v) {  // :524-598
-    int cap = VA(s, r, VA_CAPACITY, v);
-    int loc = VA(s, r, VA_NEXT_LOC_IDX, v);
-    VA(s, r, VA_LAST_LOC_IDX, v) = loc;
-    int full = VA(s, r, VA_FULL, v);
-    int acceptable = s.vol == 1.0 ? cap - full : (int)maro_floor(((double)cap - (double)full * s.vol) / s.vol);
-    int sb = TBL_I(r, s.t_stop_offset, v);
-    int ns = TBL_I(r, s.t_stop_offset, v + 1) - sb;
-    int rl = route_len(s, r, v);
-    int port_full = PA(s, r, PA_FULL, port);
-    for (int k = 0; k < rl; k++) {  // reachable stops: stops[loc + 1 : loc + 1 + route_len]
-        int si = loc + 1 + k;
-        if (si >= ns) break;
-        int next_port = TBL_I(r, s.t_stop_port, sb + si);
-        int pending = r.f[s.o_fop + port * s.P + next_port];
-        if (acceptable > 0 && pending > 0) {
-            int loaded = pending < acceptable ? pending : acceptable;
-            r.f[s.o_fop + port * s.P + next_port] = pending - loaded;
-            port_full -= loaded;
-            full += loaded;
-            r.f[s.o_fov + v * s.P + next_port] += loaded;
-            acceptable -= loaded;
-            queue_push(s, r, TBL_I(r, s.t_stop_arrival, sb + si), DE_DISCHARGE_FULL, v, port, next_port, loaded);
+// Noisy order generation (leader lane, float64): CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398).
+// Writes {src | dst << 8, qty} pairs to `out` and returns the count.  Scratch doubles live in the MT block.
+MARO_DEV int gen_orders_serial(const CimShape& s, const Replica& r, int tick, int total_empty, int32_t* out, double* dscr) {
+    int orders_to_gen = TBL_I(r, s.t_order_proportion, tick);
+    if (s.order_mode == 1) {
+        int delta = s.total_containers - total_empty;
+        if (orders_to_gen <= delta) return 0;
+        orders_to_gen -= delta;
+    }
+    int remaining = orders_to_gen, n = 0;
+    double* srcd = dscr;
+    double* tgtd = dscr + s.P;
+    double tot = 0.0;
+    for (int p = 0; p < s.P; p++) {
+        double x = s.order_noise ? apply_noise_serial(r, 0, TBL_D(r, s.t_sb_d, p), TBL_D(r, s.t_sn_d, p))
+                                 : TBL_D(r, s.t_sb_d, p) + 0.0;
+        srcd[p] = x;
+        tot = tot + x;
+    }
+    for (int p = 0; p < s.P; p++) {
+        if (remaining == 0) break;
+        int lo = TBL_I(r, s.t_target_offset, p), hi = TBL_I(r, s.t_target_offset, p + 1);
+        double ttot = 0.0;
+        for (int i = lo; i < hi; i++) {
+            double x = s.order_noise ? apply_noise_serial(r, 0, TBL_D(r, s.t_tb_d, i), TBL_D(r, s.t_tn_d, i))
+                                     : TBL_D(r, s.t_tb_d, i) + 0.0;
+            tgtd[i - lo] = x;
+            ttot = ttot + x;
+        }
+        double sp = srcd[p];
+        if (tot != 0.0) sp = sp / tot;
+        int cur = (int)maro_ceil((double)orders_to_gen * sp);
+        if (cur > remaining) cur = remaining;
+        remaining -= cur;
+        if (cur > 0) {
+            int trem = cur;
+            for (int i = lo; i < hi; i++) {
+                double tp = tgtd[i - lo];
+                if (ttot != 0.0) tp = tp / ttot;
+                int num = (int)maro_ceil((double)cur * tp);
+                if (num > trem) num = trem;
+                trem -= num;
+                if (num > 0) { out[2 * n] = p | (TBL_I(r, s.t_target_port, i) << 8); out[2 * n + 1] = num; n++; }
+            }
         }
     }
-    PA(s, r, PA_FULL, port) = port_full;
-    VA(s, r, VA_FULL, v) = full;
-    int empty = VA(s, r, VA_EMPTY, v);
-    int total_container = full + empty;
-    int early = 0;
-    bool over = s.vol == 1.0 ? total_container > cap : (double)total_container * s.vol > (double)cap;
-    if (over) {
-        early = total_container - (s.vol == 1.0 ? cap : (int)maro_ceil((double)cap / s.vol));
-        empty -= early;
-        VA(s, r, VA_EMPTY, v) = empty;
-        PA(s, r, PA_EMPTY, port) += early;
-    }
-    VA(s, r, VA_EARLY_DISCHARGE, v) = early;
-    vessel_update_space(s, r, v);
+    return n;
 }
 
-MARO_DEV void on_departure(const CimShape& s, const Replica& r, int v) {  // :634-656
+// ------------------------------------------------------------------------------------------------
+// Phase (d): VESSEL_ARRIVAL (:600-632) + LOAD_FULL (:524-598) of one arriving vessel, lanes over route positions.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+MARO_DEV void run_arrival(const CimShape& s, const Grp<G>& g, const Replica& r, int tick, int v) {
+    const int loc = VA(s, r, VA_NEXT_LOC_IDX, v);
+    const int sb = TBL_I(r, s.t_stop_offset, v);
+    const int ns = TBL_I(r, s.t_stop_offset, v + 1) - sb;
+    const int port = TBL_I(r, s.t_stop_port, sb + loc);
+    const int rt = TBL_I(r, s.t_vessel_route, v);
+    const int rbase = TBL_I(r, s.t_route_offset, rt);
+    const int rl = TBL_I(r, s.t_route_offset, rt + 1) - rbase;
+    const int lbase = TBL_I(r, s.t_vessel_leg_offset, v);
+    // ---- _on_arrival: future stop list + sailing plan = prefix sums of the no-noise legs after this stop
+    {
+        int pos0 = (TBL_I(r, s.t_vessel_route_start, v) + loc) % rl;
+        int arrival0 = TBL_I(r, s.t_stop_arrival, sb + loc);
+        int n = rl > s.fut ? rl : s.fut;
+        for (int b0 = 0; b0 < n; b0 += G) {  // n <= G in every shipped topology; loop keeps it general
+            int k = b0 + g.lane;
+            int pos = (pos0 + k) % rl;
+            int leg = k < n ? TBL_I(r, s.t_vessel_leg, lbase + pos) : 0;
+            int cum = scan_incl(g, leg);
+            int arr = arrival0 + cum;
+            int nport = TBL_I(r, s.t_route_port, rbase + (pos + 1 == rl ? 0 : pos + 1));
+            if (k < s.fut) { r.f[s.o_fut + v * s.fut + k] = nport; r.f[s.o_fut_tick + v * s.fut + k] = arr; }
+            // plans: a port that appears twice within one route period keeps the later arrival (dict overwrite order)
+            uint32_t same = g.match(k < rl ? nport : (0x1000 + g.lane));
+            bool last_of_port = (same >> g.lane) <= 1u;
+            if (k < rl && last_of_port) r.f[s.o_vp + v * s.P + nport] = arr;
+            arrival0 += g.shfl(cum, G - 1);
+        }
+    }
+    // ---- _on_full_load
+    const int cap = VA(s, r, VA_CAPACITY, v);
+    int full = VA(s, r, VA_FULL, v);
+    int acceptable = s.vol_is_one ? cap - full : (int)maro_floor(((double)cap - (double)full * s.vol) / s.vol);
+    if (acceptable < 0) acceptable = 0;
+    int total_loaded = 0;
+    g.sync();
+    for (int b0 = 0; b0 < rl; b0 += G) {  // reachable stops: stops[loc + 1 : loc + 1 + route_len]
+        int k = b0 + g.lane;
+        int si = loc + 1 + k;
+        bool valid = k < rl && si < ns;
+        int next_port = valid ? TBL_I(r, s.t_stop_port, sb + si) : 0;
+        // a port reachable twice: the first occurrence sees the pending cargo, later ones whatever is left (0 if
+        // the first took it all; nothing if acceptable ran out) -> only the first occurrence carries `pending`
+        uint32_t same = g.match(valid ? next_port : (0x1000 + g.lane));
+        bool first = (same & ((1u << g.lane) - 1u)) == 0;
+        int pending = valid && first ? r.f[s.o_fop + port * s.P + next_port] : 0;
+        if (pending < 0) pending = 0;
+        int A = scan_incl(g, pending);
+        int hi = A < acceptable ? A : acceptable;
+        int lo = (A - pending) < acceptable ? (A - pending) : acceptable;
+        int loaded = hi - lo;
+        if (loaded > 0) {
+            r.f[s.o_fop + port * s.P + next_port] = pending - loaded;
+            r.f[s.o_fov + v * s.P + next_port] += loaded;
+        }
+        group_push(s, g, r, loaded > 0, valid ? TBL_I(r, s.t_stop_arrival, sb + si) : 0,
+                   DE_DISCHARGE_FULL | (v << 8) | (port << 16) | (next_port << 24), loaded);
+        int chunk = g.shfl(hi, G - 1);
+        total_loaded += chunk;
+        acceptable -= chunk;
+    }
+    if (g.lane == 0) {
+        VA(s, r, VA_LAST_LOC_IDX, v) = loc;
+        VA(s, r, VA_IS_PARKING, v) = 1;
+        VA(s, r, VA_LOC_PORT_IDX, v) = port;
+        PA(s, r, PA_FULL, port) -= total_loaded;
+        full += total_loaded;
+        VA(s, r, VA_FULL, v) = full;
+        int empty = VA(s, r, VA_EMPTY, v);
+        int total_container = full + empty;
+        int early = 0;
+        bool over = s.vol_is_one ? total_container > cap : (double)total_container * s.vol > (double)cap;
+        if (over) {
+            early = total_container - (s.vol_is_one ? cap : (int)maro_ceil((double)cap / s.vol));
+            empty -= early;
+            VA(s, r, VA_EMPTY, v) = empty;
+            PA(s, r, PA_EMPTY, port) += early;
+        }
+        VA(s, r, VA_EARLY_DISCHARGE, v) = early;
+        VA(s, r, VA_REMAINING_SPACE, v) = total_space(s, cap) - full - empty;
+    }
+    g.sync();
+}
+
+// _on_departure (:634-656) — one lane per vessel
+MARO_DEV void on_departure(const CimShape& s, const Replica& r, int v) {
     int next = VA(s, r, VA_NEXT_LOC_IDX, v) + 1;
     VA(s, r, VA_NEXT_LOC_IDX, v) = next;
     VA(s, r, VA_IS_PARKING, v) = 0;
@@ -373,7 +716,7 @@ MARO_DEV void on_departure(const CimShape& s, const Replica& r, int v) {  // :63
     set_past_stops(s, r, v, VA(s, r, VA_LAST_LOC_IDX, v), next);
 }
 
-// _on_action_received (:708-748).  Returns false where the reference would raise AssertionError.
+// _on_action_received (:708-748), leader lane.  Returns false where the reference would raise AssertionError.
 MARO_DEV bool on_actions(const CimShape& s, const Replica& r, const int32_t* act, int n) {
     for (int i = 0; i < n; i++) {
         int v = act[4 * i], p = act[4 * i + 1], move = act[4 * i + 2], type = act[4 * i + 3];
@@ -400,154 +743,81 @@ MARO_DEV bool on_actions(const CimShape& s, const Replica& r, const int32_t* act
 }
 
 // ------------------------------------------------------------------------------------------------
-// Order generation + execution for one tick (leader lane).
-// CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398) fused with _on_order_generated:
-// each Order is executed as soon as it is produced — valid because order generation reads no simulation state
-// in fixed mode, its RNG stream is private, and `total_empty` (unfixed mode) is sampled at tick start.
-// ------------------------------------------------------------------------------------------------
-MARO_DEV void gen_and_run_orders(const CimShape& s, const Replica& r, int tick, int total_empty, int& nev) {
-    if (s.order_table) {
-        // noise-free fixed mode: the tick's order list is a pure function of order_proportion[tick]; the host ran the
-        // same float64 arithmetic once per distinct value (cim_host.hpp: build_order_table)
-        int slot = TBL_I(r, s.t_ord_slot, tick);
-        int lo = TBL_I(r, s.t_ord_off, slot), hi = TBL_I(r, s.t_ord_off, slot + 1);
-        for (int i = lo; i < hi; i++) {
-            int w = TBL_I(r, s.t_ord_list, 2 * i);
-            on_order(s, r, tick, w & 0xff, (w >> 8) & 0xff, TBL_I(r, s.t_ord_list, 2 * i + 1), nev);
-            nev++;
-        }
-        return;
-    }
-    int orders_to_gen = TBL_I(r, s.t_order_proportion, tick);
-    if (s.order_mode == 1) {
-        int delta = s.total_containers - total_empty;
-        if (orders_to_gen <= delta) return;
-        orders_to_gen -= delta;
-    }
-    int remaining = orders_to_gen;
-    // pass 1: noised source distribution + its python sum (left to right)
-    double tot = 0.0;
-    if (!s.order_noise) {
-        for (int p = 0; p < s.P; p++) tot = tot + (TBL_D(r, s.t_sb_d, p) + 0.0);
-    }
-    // with noise the P draws must happen before any target draw; keep the noised values in the (otherwise unused
-    // between ticks) tail of the MT block: r.mt[2*640 .. 2*640 + 2P)
-    double* srcd = s.order_noise ? reinterpret_cast<double*>(r.mt + 2 * 640) : nullptr;
-    if (s.order_noise) {
-        for (int p = 0; p < s.P; p++) {
-            double x = apply_noise(r, 0, TBL_D(r, s.t_sb_d, p), TBL_D(r, s.t_sn_d, p));
-            srcd[p] = x;
-            tot = tot + x;
-        }
-    }
-    double* tgtd = s.order_noise ? srcd + s.P : nullptr;
-    for (int p = 0; p < s.P; p++) {
-        if (remaining == 0) break;
-        int lo = TBL_I(r, s.t_target_offset, p), hi = TBL_I(r, s.t_target_offset, p + 1);
-        double ttot = 0.0;
-        if (s.order_noise) {
-            for (int i = lo; i < hi; i++) {
-                double x = apply_noise(r, 0, TBL_D(r, s.t_tb_d, i), TBL_D(r, s.t_tn_d, i));
-                tgtd[i - lo] = x;
-                ttot = ttot + x;
-            }
-        } else {
-            for (int i = lo; i < hi; i++) ttot = ttot + (TBL_D(r, s.t_tb_d, i) + 0.0);
-        }
-        double sp = s.order_noise ? srcd[p] : TBL_D(r, s.t_sb_d, p) + 0.0;
-        if (tot != 0.0) sp = sp / tot;
-        int cur = (int)maro_ceil((double)orders_to_gen * sp);
-        if (cur > remaining) cur = remaining;
-        remaining -= cur;
-        if (cur > 0) {
-            int trem = cur;
-            for (int i = lo; i < hi; i++) {
-                double tp = s.order_noise ? tgtd[i - lo] : TBL_D(r, s.t_tb_d, i) + 0.0;
-                if (ttot != 0.0) tp = tp / ttot;
-                int num = (int)maro_ceil((double)cur * tp);
-                if (num > trem) num = trem;
-                trem -= num;
-                if (num > 0) {
-                    on_order(s, r, tick, p, TBL_I(r, s.t_target_port, i), num, nev);
-                    nev++;
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Snapshot: copy the live frame into ring row (frame_index % ring_rows) with 128-bit coalesced stores
 // (FrameBase.take_snapshot -> NPSnapshotList.take_snapshot, np_backend.pyx:481-518).
 // ------------------------------------------------------------------------------------------------
-MARO_DEV void take_snapshot(const CimShape& s, const Replica& r, int lane, int frame_index) {
-    WARP_SYNC();
+template <int G>
+MARO_DEV void take_snapshot(const CimShape& s, const Grp<G>& g, const Replica& r, int frame_index) {
+    g.sync();
     int row = frame_index % s.ring_rows;
     int32_t* dst = r.snap + (int64_t)row * s.FWp;
 #ifdef MARO_HOST_EMULATION
-    memcpy(dst, r.f, sizeof(int32_t) * s.FWp);
+    LANE_LOOP(i, s.FWp) dst[i] = r.f[i];
 #else
     const int4* src4 = reinterpret_cast<const int4*>(r.f);
     int4* dst4 = reinterpret_cast<int4*>(dst);
-    for (int i = lane; i < s.FWp / 4; i += 32) dst4[i] = src4[i];
+    LANE_LOOP(i, s.FWp / 4) dst4[i] = src4[i];
 #endif
-    if (lane == 0) {
+    if (g.lane == 0) {
         r.snap_frame[row] = frame_index;
         r.c[C_LAST_FRAME] = frame_index;
         ctrl_add64(r, C_NSNAPS_LO, 1);
     }
-    WARP_SYNC();
+    g.sync();
 }
 
 MARO_DEV int frame_index_of(const CimShape& s, int tick) { return (tick - s.start_tick) / s.resolution; }
 
 // ------------------------------------------------------------------------------------------------
 // One Env.step for one replica.  `act`/`n_act` are this replica's action rows; `dec` (8 int32) and `met`
-// (3 int64) its output rows.  All lanes of the warp call this together.
+// (3 int64) its output rows.  All lanes of the group call this together.
 // ------------------------------------------------------------------------------------------------
-MARO_DEV void replica_step(const CimShape& s, const Replica& r, int lane, const int32_t* act, int n_act,
+template <int G>
+MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r, const int32_t* act, int n_act,
                            int32_t* dec, int64_t* met) {
     int state = r.c[C_STATE];
     int nev = 0;
     if (state >= ST_DONE) {  // StopIteration -> (None, None, True)   core.py:128-131
-        if (lane == 0) {
+        g.sync();
+        if (g.lane == 0) {
             if (state == ST_DONE) r.c[C_STATE] = ST_FINISHED;
             for (int i = 0; i < 8; i++) dec[i] = 0;
             dec[6] = 2;
             met[0] = met[1] = met[2] = 0;
         }
-        WARP_SYNC();
+        g.sync();
         return;
     }
-    if (lane == 0) ctrl_add64(r, C_NSTEPS_LO, 1);
     if (state == ST_AWAIT) {
         // _assign_action (core.py:301-315): the decision event finishes, TAKE_ACTION runs as its immediate event
-        bool ok = true;
-        if (lane == 0) {
-            ok = on_actions(s, r, act, n_act);
-            nev += 2;
-            if (!ok) { r.c[C_STATE] = ST_ERROR; r.c[C_ERR] = -1; }
+        g.sync();
+        if (g.lane == 0) {
+            ctrl_add64(r, C_NSTEPS_LO, 1);
+            if (!on_actions(s, r, act, n_act)) { r.c[C_STATE] = ST_ERROR; r.c[C_ERR] = -1; }
         }
-        WARP_SYNC();
+        g.sync();
+        nev += 2;
         if (r.c[C_STATE] == ST_ERROR) {
-            if (lane == 0) { for (int i = 0; i < 8; i++) dec[i] = 0; dec[6] = -1; met[0] = met[1] = met[2] = 0; }
-            WARP_SYNC();
+            if (g.lane == 0) { for (int i = 0; i < 8; i++) dec[i] = 0; dec[6] = -1; met[0] = met[1] = met[2] = 0; }
+            g.sync();
             return;
         }
         state = ST_DECISIONS;
-    } else if (state == ST_START) {
-        state = ST_TICK_BEGIN;
+    } else {
+        if (g.lane == 0) ctrl_add64(r, C_NSTEPS_LO, 1);
+        if (state == ST_START) state = ST_TICK_BEGIN;
     }
 
     int tick = r.c[C_TICK];
     uint64_t arr = ((uint64_t)(uint32_t)r.c[C_ARR_HI] << 32) | (uint32_t)r.c[C_ARR_LO];
     int dec_pos = r.c[C_DEC_POS];
-    int status = 0;
+    int status = 0, nticks = 0;
     for (;;) {
         if (state == ST_TICK_BEGIN) {
+            nticks++;
             // ---- BusinessEngine.step(tick), arrival part (business_engine.py:145-199): which vessels arrive now
             uint32_t alo = 0, ahi = 0;
-            int64_t total_empty = 0;
+            int total_empty = 0;
             LANE_LOOP(v, s.V) {
                 int loc = VA(s, r, VA_NEXT_LOC_IDX, v);
                 int si = TBL_I(r, s.t_stop_offset, v) + loc;
@@ -559,10 +829,10 @@ MARO_DEV void replica_step(const CimShape& s, const Replica& r, int lane, const 
             }
             if (s.order_mode == 1) {
                 LANE_LOOP(p, s.P) total_empty += PA(s, r, PA_EMPTY, p);
-                total_empty = warp_sum64(total_empty);
+                total_empty = g.sum(total_empty);
             }
-            alo = warp_or32(alo);
-            ahi = s.V > 32 ? warp_or32(ahi) : 0u;
+            alo = g.or32(alo);
+            ahi = s.V > 32 ? g.or32(ahi) : 0u;
             arr = ((uint64_t)ahi << 32) | alo;
             // ---- (a) departures pre-inserted at init (business_engine.py:371-379): one lane per vessel
             int ndep = 0;
@@ -576,41 +846,35 @@ MARO_DEV void replica_step(const CimShape& s, const Replica& r, int lane, const 
                     ndep++;
                 }
             }
-            nev += (int)warp_sum64(ndep);
-            WARP_SYNC();
-            if (lane == 0) {
-                ctrl_add64(r, C_NTICKS_LO, 1);
-                // ---- (b) events queued by earlier ticks, FIFO
-                int32_t* bk = r.q + s.QN * 4 + (tick & (s.QH - 1));
-                int slot = *bk & 0xffff;
-                *bk = Q_NIL | (Q_NIL << 16);
-                while (slot != Q_NIL) {
-                    int32_t* e = r.q + slot * 4;
-                    int w0 = e[0], qty = e[1], nxt = e[3];
-                    e[3] = r.c[C_FREE_HEAD];
-                    r.c[C_FREE_HEAD] = slot;
-                    r.c[C_Q_COUNT] -= 1;
-                    int type = w0 & 0xff, a = (w0 >> 8) & 0xff, b = (w0 >> 16) & 0xff, c = (w0 >> 24) & 0xff;
-                    if (type == DE_RETURN_FULL) on_full_return(s, r, a, b, qty);
-                    else if (type == DE_RETURN_EMPTY) on_empty_return(s, r, a, qty);
-                    else on_discharge(s, r, tick, a, c, qty, nev);
-                    nev++;
-                    slot = nxt;
-                }
-                // ---- (c) this tick's orders
-                gen_and_run_orders(s, r, tick, (int)total_empty, nev);
-                // ---- (d) VESSEL_ARRIVAL + LOAD_FULL per arriving vessel, vessel order
-                uint64_t m = arr;
-                while (m) {
-                    int v = maro_ffs64(m) - 1;
-                    m &= m - 1;
-                    int port = TBL_I(r, s.t_stop_port, TBL_I(r, s.t_stop_offset, v) + VA(s, r, VA_NEXT_LOC_IDX, v));
-                    on_arrival(s, r, v);
-                    on_full_load(s, r, port, v);
-                    nev += 2;
-                }
+            nev += g.sum(ndep);
+            g.sync();
+            // ---- (b) events queued by earlier ticks
+            nev += run_bucket(s, g, r, tick);
+            // ---- (c) this tick's orders
+            if (s.order_table) {
+                int slot = TBL_I(r, s.t_ord_slot, tick);
+                int lo = TBL_I(r, s.t_ord_off, slot), hi = TBL_I(r, s.t_ord_off, slot + 1);
+                const int32_t* list = r.t + s.t_ord_list + 2 * lo;
+                nev += run_orders(s, g, r, tick, hi - lo, [&](int i, int& w, int& q) { w = list[2 * i]; q = list[2 * i + 1]; });
+            } else {
+                // float64 generation on the leader lane into the replica's scratch area, then cooperative execution
+                int32_t* olist = reinterpret_cast<int32_t*>(r.mt + s.mt_scratch + 64);
+                double* dscr = reinterpret_cast<double*>(olist + 2 * ((s.max_targets + 1) & ~1));
+                g.sync();
+                if (g.lane == 0) r.c[C_N_ORDERS] = gen_orders_serial(s, r, tick, total_empty, olist, dscr);
+                g.sync();
+                int n = r.c[C_N_ORDERS];
+                nev += run_orders(s, g, r, tick, n, [&](int i, int& w, int& q) { w = olist[2 * i]; q = olist[2 * i + 1]; });
             }
-            WARP_SYNC();
+            g.sync();
+            // ---- (d) VESSEL_ARRIVAL + LOAD_FULL per arriving vessel, vessel order
+            uint64_t m = arr;
+            while (m) {
+                int v = maro_ffs64(m) - 1;
+                m &= m - 1;
+                run_arrival(s, g, r, tick, v);
+                nev += 2;
+            }
             dec_pos = 0;
             state = ST_DECISIONS;
         }
@@ -618,8 +882,8 @@ MARO_DEV void replica_step(const CimShape& s, const Replica& r, int lane, const 
         uint64_t m = dec_pos >= 64 ? 0 : (arr >> dec_pos) << dec_pos;
         if (m) {
             int v = maro_ffs64(m) - 1;
-            take_snapshot(s, r, lane, frame_index_of(s, tick));  // core.py:345
-            if (lane == 0) {
+            take_snapshot(s, g, r, frame_index_of(s, tick));  // core.py:345
+            if (g.lane == 0) {
                 int port = VA(s, r, VA_LOC_PORT_IDX, v);
                 int pe = PA(s, r, PA_EMPTY, port), sp = VA(s, r, VA_REMAINING_SPACE, v);
                 dec[0] = tick; dec[1] = port; dec[2] = v;
@@ -634,32 +898,34 @@ MARO_DEV void replica_step(const CimShape& s, const Replica& r, int lane, const 
         }
         // ---- post_step (business_engine.py:201-224)
         if ((tick + 1) % s.resolution == 0) {
+            g.sync();
             LANE_LOOP(p, s.P) PA(s, r, PA_ACC_FULFILLMENT, p) = PA(s, r, PA_ACC_BOOKING, p) - PA(s, r, PA_ACC_SHORTAGE, p);
-            take_snapshot(s, r, lane, frame_index_of(s, tick));
+            take_snapshot(s, g, r, frame_index_of(s, tick));
             LANE_LOOP(p, s.P) {
                 PA(s, r, PA_SHORTAGE, p) = 0;
                 PA(s, r, PA_BOOKING, p) = 0;
                 PA(s, r, PA_FULFILLMENT, p) = 0;
                 PA(s, r, PA_TRANSFER_COST, p) = 0;
             }
-            WARP_SYNC();
+            g.sync();
         }
         if (tick + 1 == s.max_tick) {
-            if ((tick + 1) % s.resolution != 0) take_snapshot(s, r, lane, frame_index_of(s, tick));  // core.py:376-378
+            if ((tick + 1) % s.resolution != 0) take_snapshot(s, g, r, frame_index_of(s, tick));  // core.py:376-378
             state = ST_DONE;
             status = 1;
-            if (lane == 0) { dec[0] = tick; dec[1] = dec[2] = dec[3] = dec[4] = dec[5] = 0; }
+            if (g.lane == 0) { dec[0] = tick; dec[1] = dec[2] = dec[3] = dec[4] = dec[5] = 0; }
             break;
         }
         tick += 1;
         state = ST_TICK_BEGIN;
     }
     // ---- metrics (business_engine.py:270-282) + control write-back
+    g.sync();
     int64_t bk = 0, sh = 0;
     LANE_LOOP(p, s.P) { bk += PA(s, r, PA_ACC_BOOKING, p); sh += PA(s, r, PA_ACC_SHORTAGE, p); }
-    bk = warp_sum64(bk);
-    sh = warp_sum64(sh);
-    if (lane == 0) {
+    bk = g.sum64(bk);
+    sh = g.sum64(sh);
+    if (g.lane == 0) {
         int err = r.c[C_ERR];
         if (err == -2) { state = ST_ERROR; status = -2; }
         r.c[C_STATE] = state;
@@ -667,27 +933,29 @@ MARO_DEV void replica_step(const CimShape& s, const Replica& r, int lane, const 
         r.c[C_ARR_LO] = (int32_t)(uint32_t)(arr & 0xffffffffu);
         r.c[C_ARR_HI] = (int32_t)(uint32_t)(arr >> 32);
         r.c[C_DEC_POS] = dec_pos;
-        ctrl_add64(r, C_NEVENTS_LO, nev + (status == 0 ? 0 : 0));
+        ctrl_add64(r, C_NEVENTS_LO, nev);
+        ctrl_add64(r, C_NTICKS_LO, nticks);
         dec[6] = status;
         dec[7] = nev;
         met[0] = bk; met[1] = sh; met[2] = ctrl_get64(r, C_OPNUM_LO);
     }
-    WARP_SYNC();
+    g.sync();
 }
 
 // ------------------------------------------------------------------------------------------------
 // Env.reset / initial state of one replica (core.py:143-170; business_engine.py:226-242, 314-356, 381-398).
 // ------------------------------------------------------------------------------------------------
-MARO_DEV void replica_reset(const CimShape& s, const Replica& r, int lane) {
+template <int G>
+MARO_DEV void replica_reset(const CimShape& s, const Grp<G>& g, const Replica& r) {
     LANE_LOOP(i, s.FWp) r.f[i] = 0;
     LANE_LOOP(i, s.CWp) r.c[i] = 0;
-    WARP_SYNC();
+    g.sync();
     LANE_LOOP(p, s.P) {
         PA(s, r, PA_CAPACITY, p) = TBL_I(r, s.t_port_capacity, p);
         PA(s, r, PA_EMPTY, p) = TBL_I(r, s.t_port_init_empty, p);
     }
     LANE_LOOP(i, s.V * s.P) r.f[s.o_vp + i] = -1;
-    WARP_SYNC();
+    g.sync();
     LANE_LOOP(v, s.V) {
         VA(s, r, VA_CAPACITY, v) = TBL_I(r, s.t_vessel_capacity, v);
         VA(s, r, VA_ROUTE_IDX, v) = TBL_I(r, s.t_vessel_route, v);
@@ -697,18 +965,18 @@ MARO_DEV void replica_reset(const CimShape& s, const Replica& r, int lane) {
         VA(s, r, VA_IS_PARKING, v) = 1;
         VA(s, r, VA_LOC_PORT_IDX, v) = TBL_I(r, s.t_stop_port, TBL_I(r, s.t_stop_offset, v));
         set_past_stops(s, r, v, 0, 0);
-        set_future_stops(s, r, v, 0, 0);
-        update_vessel_plans(s, r, v, 0);
+        predict_serial(s, r, v, 0, true, true);
         // departures whose leave tick precedes start_tick are never executed
         int sb = TBL_I(r, s.t_stop_offset, v), ns = TBL_I(r, s.t_stop_offset, v + 1) - sb;
         int dc = 0;
         while (dc < ns && TBL_I(r, s.t_stop_leave, sb + dc) < s.start_tick) dc++;
         r.c[C_FIXED + v] = dc;
     }
-    // queue: free list through slot word 3, empty buckets
+    // queue: all slots on the free stack (slot 0 on top so that allocation order is ascending), empty buckets
+    int32_t* fs = r.q + s.QN * 4 + s.QH;
     LANE_LOOP(i, s.QN) {
-        r.q[i * 4 + 0] = 0; r.q[i * 4 + 1] = 0; r.q[i * 4 + 2] = 0;
-        r.q[i * 4 + 3] = i + 1 < s.QN ? i + 1 : Q_NIL;
+        r.q[i * 4 + 0] = 0; r.q[i * 4 + 1] = 0; r.q[i * 4 + 2] = 0; r.q[i * 4 + 3] = Q_NIL;
+        fs[i] = s.QN - 1 - i;
     }
     LANE_LOOP(i, s.QH) r.q[s.QN * 4 + i] = Q_NIL | (Q_NIL << 16);
     LANE_LOOP(i, s.ring_rows) r.snap_frame[i] = -1;
@@ -718,15 +986,16 @@ MARO_DEV void replica_reset(const CimShape& s, const Replica& r, int lane) {
             r.mt[640 + i] = (uint32_t)TBL_I(r, s.t_mt_buffer, i);
         }
     }
-    if (lane == 0) {
+    g.sync();
+    if (g.lane == 0) {
         r.c[C_STATE] = ST_START;
         r.c[C_TICK] = s.start_tick;
-        r.c[C_FREE_HEAD] = 0;
+        r.c[C_FREE_TOP] = s.QN;
         r.c[C_MT_ORDER_IDX] = 624;
         r.c[C_MT_BUFFER_IDX] = 624;
         r.c[C_LAST_FRAME] = -1;
     }
-    WARP_SYNC();
+    g.sync();
 }
 
 }  // namespace maro

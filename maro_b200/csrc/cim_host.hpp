@@ -238,7 +238,10 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
                                      : std::max(32, max_targets * buf_full + V * max_rl * (1 + buf_empty) + 16);
     if (qn > 65000) qn = 65000;
     s.QN = round_up(qn, 4);
-    s.SW = round_up(s.FWp + s.CWp + s.QN * 4 + s.QH, 4);
+    s.SW = round_up(s.FWp + s.CWp + s.QN * 4 + s.QH + s.QN, 4);  // frame | ctrl | pool | buckets | free stack
+    s.vol_is_one = s.vol == 1.0 ? 1 : 0;
+    s.max_targets = max_targets;
+    s.mt_scratch = 2 * 640;
     // tables (stop arrays get 12.5% head-room so that re-seeded topologies of the same config still fit)
     max_stops += max_stops / 8 + 8;
     max_stops_out = max_stops;
@@ -254,6 +257,18 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
         if (build_blob(topos[k], s, tables, max_stops, max_targets, k == 0, max_distinct)) return 1;
     }
     return 0;
+}
+
+// words of one replica's MT block: 2 states | 64 tail scratch | order list | float64 scratch
+inline int mt_block_words(const CimShape& s) {
+    int mt_even = (s.max_targets + 1) & ~1;
+    return round_up(2 * 640 + 64 + 2 * mt_even + 2 * (s.P + mt_even) + 8, 4);
+}
+
+// lanes per replica: smallest power of two >= the widest cooperative phase of the topology (>= 8)
+inline int lanes_per_replica(const CimShape& s) {
+    int w = std::max(std::max(s.P, s.V), std::max(s.max_route_len, std::max(s.fut, s.past)));
+    return w <= 8 ? 8 : (w <= 16 ? 16 : 32);
 }
 
 }  // namespace maro

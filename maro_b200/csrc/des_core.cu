@@ -84,29 +84,31 @@ __device__ __forceinline__ Replica make_replica(const CimShape& s, const StepArg
     return r;
 }
 
-template <int kWarps>
+template <int kWarps, int G>
 __global__ void __launch_bounds__(kWarps * 32) cim_step_kernel(const __grid_constant__ CimShape s,
                                                                const __grid_constant__ StepArgs a) {
+    constexpr int kGroups = kWarps * 32 / G;  // replicas in flight per CTA
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per warp (first 128 B)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 128) + (size_t)warp * s.SW;
-    uint64_t* bar = bars + warp;
-    if (lane == 0) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per lane group (first 256 B)
+    const int gid = threadIdx.x / G;
+    const Grp<G> g(threadIdx.x & 31);
+    int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 256) + (size_t)gid * s.SW;
+    uint64_t* bar = bars + gid;
+    if (g.lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
     }
-    __syncwarp();
+    g.sync();
     uint32_t phase = 0;
     const uint32_t bytes = (uint32_t)s.SW * 4u;
-    for (int rep = blockIdx.x * kWarps + warp; rep < s.n_replicas; rep += gridDim.x * kWarps) {
+    for (int rep = blockIdx.x * kGroups + gid; rep < s.n_replicas; rep += gridDim.x * kGroups) {
         if (a.active && !a.active[rep]) {
-            if (lane == 0) a.decisions[rep * 8 + 6] = MARO_STATUS_INACTIVE;
+            if (g.lane == 0) a.decisions[rep * 8 + 6] = MARO_STATUS_INACTIVE;
             continue;
         }
         int32_t* gstate = a.state + (int64_t)rep * s.SW;
-        // ---- stage in: one TMA bulk copy of the whole state block, completion on the warp's mbarrier
-        if (lane == 0) {
+        // ---- stage in: one TMA bulk copy of the whole state block, completion on the group's mbarrier
+        if (g.lane == 0) {
             fence_proxy_async();  // order earlier generic-proxy accesses to this smem before the async write
             mbar_expect_tx(bar, bytes);
             bulk_g2s(st, gstate, bytes, bar);
@@ -116,22 +118,23 @@ __global__ void __launch_bounds__(kWarps * 32) cim_step_kernel(const __grid_cons
         Replica r = make_replica(s, a, rep, st);
         const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), s.max_actions) : 1) : 0;
         const int32_t* act = a.actions ? a.actions + (int64_t)rep * s.max_actions * 4 : nullptr;
-        replica_step(s, r, lane, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
+        replica_step<G>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
         // ---- write back (128-bit coalesced)
         const int4* src4 = reinterpret_cast<const int4*>(st);
         int4* dst4 = reinterpret_cast<int4*>(gstate);
-        for (int i = lane; i < s.SW / 4; i += 32) dst4[i] = src4[i];
-        __syncwarp();
+        for (int i = g.lane; i < s.SW / 4; i += G) dst4[i] = src4[i];
+        g.sync();
     }
 }
 
 __global__ void cim_reset_kernel(const __grid_constant__ CimShape s, const __grid_constant__ StepArgs a) {
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const Grp<32> g(threadIdx.x & 31);
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int rep = warp_global; rep < s.n_replicas; rep += n_warps) {
         if (a.active && !a.active[rep]) continue;
         Replica r = make_replica(s, a, rep, a.state + (int64_t)rep * s.SW);  // operate directly on global memory
-        replica_reset(s, r, lane);
+        replica_reset<32>(s, g, r);
     }
 }
 
@@ -211,7 +214,7 @@ struct AttrInfo { const char* name; int off, slots, isf, n_nodes; };
 
 struct MaroCimEnv {
     CimShape s;
-    int device = 0, B = 0, K = 0, mt_words = 0, warps_per_cta = 4, grid = 0, max_stops = 0, max_targets = 0, max_distinct = 0;
+    int device = 0, B = 0, K = 0, mt_words = 0, warps_per_cta = 4, lanes = 32, grid = 0, max_stops = 0, max_targets = 0, max_distinct = 0;
     size_t smem_bytes = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int32_t *d_state = nullptr, *d_snap = nullptr, *d_snap_frame = nullptr, *d_tables = nullptr, *d_topo = nullptr;
@@ -259,20 +262,29 @@ static StepArgs base_args(MaroCimEnv* e) {
     return a;
 }
 
-template <int W>
-static cudaError_t launch_step_w(MaroCimEnv* e, const StepArgs& a) {
-    cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+template <int W, int G>
+static cudaError_t launch_step_wg(MaroCimEnv* e, const StepArgs& a) {
+    cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
     if (err != cudaSuccess) return err;
-    cim_step_kernel<W><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+    cim_step_kernel<W, G><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_step(MaroCimEnv* e, const StepArgs& a) {
+template <int G>
+static cudaError_t launch_step_g(MaroCimEnv* e, const StepArgs& a) {
     switch (e->warps_per_cta) {
-        case 1: return launch_step_w<1>(e, a);
-        case 2: return launch_step_w<2>(e, a);
-        case 4: return launch_step_w<4>(e, a);
-        default: return launch_step_w<8>(e, a);
+        case 1: return launch_step_wg<1, G>(e, a);
+        case 2: return launch_step_wg<2, G>(e, a);
+        case 4: return launch_step_wg<4, G>(e, a);
+        default: return launch_step_wg<8, G>(e, a);
+    }
+}
+
+static cudaError_t launch_step(MaroCimEnv* e, const StepArgs& a) {
+    switch (e->lanes) {
+        case 8: return launch_step_g<8>(e, a);
+        case 16: return launch_step_g<16>(e, a);
+        default: return launch_step_g<32>(e, a);
     }
 }
 
@@ -315,23 +327,24 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
         delete e;
         return fail("maro_cim_create: inconsistent topology tables / durations must be positive");
     }
-    const int P = s.P;
-    const int max_targets = e->max_targets;
+    const int cfg_lanes = 0;
     register_attrs(e);
 
-    // launch geometry: as many warps per CTA as shared memory allows (<= 8), persistent grid over replicas
+    // launch geometry: G lanes per replica, as many warps per CTA as shared memory allows (<= 8), persistent grid
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, e->device));
-    const size_t per_warp = (size_t)s.SW * 4;
+    e->lanes = cfg_lanes > 0 ? cfg_lanes : lanes_per_replica(s);
+    const int gpw = 32 / e->lanes;  // replicas per warp
+    const size_t per_warp = (size_t)s.SW * 4 * gpw;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     int w = 8;
-    while (w > 1 && 128 + per_warp * w > std::min<size_t>(max_smem, 96 * 1024)) w >>= 1;
-    if (128 + per_warp * w > max_smem) { delete e; return fail("maro_cim_create: replica state does not fit in shared memory"); }
+    while (w > 1 && 256 + per_warp * w > std::min<size_t>(max_smem, 100 * 1024)) w >>= 1;
+    if (256 + per_warp * w > max_smem) { delete e; return fail("maro_cim_create: replica state does not fit in shared memory"); }
     // small batches: spread replicas over all SMs
-    while (w > 1 && (e->B + w - 1) / w < prop.multiProcessorCount) w >>= 1;
+    while (w > 1 && (e->B + w * gpw - 1) / (w * gpw) < prop.multiProcessorCount) w >>= 1;
     e->warps_per_cta = w;
-    e->smem_bytes = 128 + per_warp * w;
-    int ctas_needed = (e->B + w - 1) / w;
+    e->smem_bytes = 256 + per_warp * w;
+    int ctas_needed = (e->B + w * gpw - 1) / (w * gpw);
     int resident = std::max<int>(1, (int)std::min<size_t>(64 / w, max_smem / e->smem_bytes));
     e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
 
@@ -352,7 +365,7 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
         }
     CK(cudaMemcpy(e->d_topo, topo.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
     if (s.order_noise || s.buffer_noise) {
-        e->mt_words = round_up(2 * 640 + 4 * (P + max_targets) + 8, 4);
+        e->mt_words = mt_block_words(s);
         CK(cudaMalloc(&e->d_mt, (size_t)B * e->mt_words * 4));
     }
     e->in_bytes = (size_t)B * s.max_actions * 16 + (size_t)B * 4 + round_up(B, 16);

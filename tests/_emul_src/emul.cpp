@@ -1,6 +1,7 @@
-// TEST INFRASTRUCTURE ONLY — compiles maro_b200/csrc/cim_core.cuh for the host with one "lane" so that the
-// kernel's per-replica logic can be debugged against the oracle without a GPU.  Never loaded by the package.
-// Build: g++ -O1 -g -ffp-contract=off -DMARO_HOST_EMULATION -shared -fPIC emul.cpp -o ../_emul/libmaro_emul.so
+// TEST INFRASTRUCTURE ONLY — compiles maro_b200/csrc/cim_core.cuh for the host: every lane of a lane group is a
+// host thread (warp_emul.hpp), so the cooperative shuffle / ballot / match / atomic phases run as written.  Lets the
+// kernel's per-replica logic be debugged against the oracle without a GPU.  Never loaded by the package.
+// Build: g++ -O1 -g -pthread -ffp-contract=off -DMARO_HOST_EMULATION -I. -shared -fPIC emul.cpp -o ../_emul/libmaro_emul.so
 #define MARO_HOST_EMULATION 1
 #include "../../maro_b200/csrc/cim_host.hpp"
 
@@ -10,7 +11,7 @@ struct Emul {
     CimShape s;
     std::vector<int32_t> tables, state, snap, snap_frame, topo;
     std::vector<uint32_t> mt;
-    int mt_words = 0, B = 0;
+    int mt_words = 0, B = 0, lanes = 8;
 };
 
 static Replica rep_of(Emul* e, int i) {
@@ -24,34 +25,55 @@ static Replica rep_of(Emul* e, int i) {
     return r;
 }
 
+template <int G>
+static void reset_g(Emul* e, int i) {
+    Replica r = rep_of(e, i);
+    wemu::run_group(G, [&](int lane) { replica_reset<G>(e->s, Grp<G>(lane), r); });
+}
+template <int G>
+static void step_g(Emul* e, int i, const int32_t* act, int n, int32_t* dec, int64_t* met) {
+    Replica r = rep_of(e, i);
+    wemu::run_group(G, [&](int lane) { replica_step<G>(e->s, Grp<G>(lane), r, act, n, dec, met); });
+}
+static void reset_one(Emul* e, int i) {
+    switch (e->lanes) { case 1: reset_g<1>(e, i); break; case 8: reset_g<8>(e, i); break; case 16: reset_g<16>(e, i); break; default: reset_g<32>(e, i); }
+}
+
 extern "C" {
-Emul* emul_create(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg) {
+Emul* emul_create(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg, int lanes) {
     Emul* e = new Emul();
     int ms, mt, md;
     if (compute_shape_and_tables(topos, n_topos, cfg, e->s, e->tables, ms, mt, md)) { delete e; return nullptr; }
     e->B = cfg->n_replicas;
+    e->lanes = lanes > 0 ? lanes : lanes_per_replica(e->s);
     e->state.assign((size_t)e->B * e->s.SW, 0);
     e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
     e->snap_frame.assign((size_t)e->B * e->s.ring_rows, -1);
     e->topo.assign(e->B, 0);
     if (cfg->replica_topology) for (int i = 0; i < e->B; i++) e->topo[i] = cfg->replica_topology[i];
     if (e->s.order_noise || e->s.buffer_noise) {
-        e->mt_words = round_up(2 * 640 + 4 * (e->s.P + mt) + 8, 4);
+        e->mt_words = mt_block_words(e->s);
         e->mt.assign((size_t)e->B * e->mt_words, 0);
     }
-    for (int i = 0; i < e->B; i++) replica_reset(e->s, rep_of(e, i), 0);
+    for (int i = 0; i < e->B; i++) reset_one(e, i);
     return e;
 }
 void emul_destroy(Emul* e) { delete e; }
-void emul_reset(Emul* e) { for (int i = 0; i < e->B; i++) replica_reset(e->s, rep_of(e, i), 0); }
+void emul_reset(Emul* e) { for (int i = 0; i < e->B; i++) reset_one(e, i); }
 void emul_step(Emul* e, const int32_t* actions, const int32_t* n_actions, int32_t* decisions, int64_t* metrics) {
     for (int i = 0; i < e->B; i++) {
         int n = actions ? (n_actions ? n_actions[i] : 1) : 0;
-        replica_step(e->s, rep_of(e, i), 0, actions ? actions + (size_t)i * e->s.max_actions * 4 : nullptr, n,
-                     decisions + i * 8, metrics + i * 3);
+        const int32_t* act = actions ? actions + (size_t)i * e->s.max_actions * 4 : nullptr;
+        switch (e->lanes) {
+            case 1: step_g<1>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
+            case 8: step_g<8>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
+            case 16: step_g<16>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
+            default: step_g<32>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
+        }
     }
 }
 int emul_frame_words(Emul* e) { return e->s.FW; }
+int emul_lanes(Emul* e) { return e->lanes; }
 void emul_read_frame(Emul* e, int rep, int32_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW, 4 * e->s.FW); }
 int emul_read_snapshot(Emul* e, int rep, int frame, int32_t* out) {
     int row = frame % e->s.ring_rows;

@@ -20,14 +20,16 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [SRC, os.path.join(CORE, "cim_core.cuh"), os.path.join(CORE, "cim_host.hpp")]
+        deps = [SRC, os.path.join(os.path.dirname(SRC), "warp_emul.hpp"), os.path.join(CORE, "cim_core.cuh"),
+                os.path.join(CORE, "cim_host.hpp")]
         if not os.path.isfile(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
-            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-DMARO_HOST_EMULATION",
-                                   "-shared", "-fPIC", SRC, "-o", LIB])
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-ffp-contract=off",
+                                   "-DMARO_HOST_EMULATION", "-I", os.path.dirname(SRC), "-shared", "-fPIC", SRC,
+                                   "-o", LIB])
         _lib = C.CDLL(LIB)
         _lib.emul_create.restype = C.c_void_p
-        _lib.emul_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.emul_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         for name, args in [("emul_destroy", 1), ("emul_reset", 1)]:
             getattr(_lib, name).argtypes = [C.c_void_p]
         _lib.emul_step.argtypes = [C.c_void_p] * 5
@@ -41,7 +43,7 @@ def lib():
 
 class EmulEnv:
     def __init__(self, topos, n_replicas=1, start_tick=0, snapshot_resolution=1, max_snapshots=None, max_actions=2,
-                 replica_topology=None):
+                 replica_topology=None, lanes=0):
         if not isinstance(topos, (list, tuple)):
             topos = [topos]
         self._keep = []
@@ -61,7 +63,7 @@ class EmulEnv:
             self._keep.append(rt)
             cfg.replica_topology = rt.ctypes.data_as(C.POINTER(C.c_int32))
         self.B, self.A = n_replicas, max_actions
-        self._h = lib().emul_create(arr, len(topos), C.byref(cfg))
+        self._h = lib().emul_create(arr, len(topos), C.byref(cfg), lanes)
         assert self._h
         self.frame_words = lib().emul_frame_words(self._h)
 

@@ -9,12 +9,24 @@ from helpers import CASES, assert_snapshots_equal, case_topology, drive, load_go
 from oracle.cim_oracle import CimOracle
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
-def test_emulated_kernel_matches_reference_trace(name):
+def _lane_configs():
+    out = []
+    for name in sorted(CASES):
+        out.append((name, 0))  # the width the library would pick for the topology
+        if name in ("toy4p_l00_300_rand_r0", "toy4p_l08_200_rand", "toy6p_l05_120_rand", "gt22p_l08_60_rand"):
+            out += [(name, 1), (name, 32)] if not name.startswith("gt22p") else [(name, 8)]
+    return out
+
+
+@pytest.mark.parametrize("name,lanes", _lane_configs())
+def test_emulated_kernel_matches_reference_trace(name, lanes):
+    """lanes = lanes per replica (0: library default); the cooperative phases must give the same result for any
+    group width, including widths smaller than the number of events in a phase (chunk loops)."""
     spec = CASES[name]
     topo = case_topology(spec)
     gold = load_golden(name)
-    e = EmulEnv(topo, 1, spec.get("start_tick", 0), spec.get("snapshot_resolution", 1), spec.get("max_snapshots"))
+    e = EmulEnv(topo, 1, spec.get("start_tick", 0), spec.get("snapshot_resolution", 1), spec.get("max_snapshots"),
+                lanes=lanes)
     rows, final, dec, st = drive(lambda a: e.step1(a), spec)
     assert rows.shape == gold["steps"].shape
     if not np.array_equal(rows, gold["steps"]):
