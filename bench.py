@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--graph-chunk", type=int, default=32, help="steps per CUDA-graph chunk of the extra graph-mode measurement (0: off)")
     return ap.parse_args()
 
 
@@ -193,7 +194,7 @@ def cpu_baseline_port(args, topo):
             "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/cim_oracle.c, same topology/ticks/policy, 1 thread"}
 
 
-def host_policy(dec, seed, step, base, np):
+def host_policy(dec, seed, base, np):
     """numpy-vectorised twin of cim_policy_kernel (uint32 arithmetic)."""
     def h(x):
         x = x.astype(np.uint32)
@@ -203,7 +204,7 @@ def host_policy(dec, seed, step, base, np):
     B = dec.shape[0]
     rid = (np.arange(B, dtype=np.uint32) + np.uint32(base))
     with np.errstate(over="ignore"):
-        h1 = h(np.uint32(seed) ^ h(rid * np.uint32(0x9E3779B9) + np.uint32((step * 0x85EBCA6B) & 0xFFFFFFFF) + np.uint32(0x1234567)))
+        h1 = h(np.uint32(seed) ^ h(rid * np.uint32(0x9E3779B9) + dec[:, 7].astype(np.uint32) * np.uint32(0x85EBCA6B) + np.uint32(0x1234567)))
         h2 = h(h1 + np.uint32(0x68BC21EB))
     load, dis = dec[:, 3], dec[:, 4]
     to_dis = (dis > 0) & ((h1 & 1) == 1)
@@ -240,24 +241,19 @@ def run_ours(args, rank, local_rank, world):
     base = rank * B
     pos = {"i": 0}
 
-    def one_step(ev=None):
-        """policy + step (or the episode's first step / reset at an episode boundary)."""
-        i = pos["i"] % steps_per_episode
-        if flush is not None:
+    def one_step(ev=None, flush_l2=True):
+        """agent + step; Env.reset at an episode boundary (synchronous; part of the job).  The first step of an episode
+        ignores its action (generator start, core.py:128), so the agent kernel always runs."""
+        if pos["i"] > 0 and pos["i"] % steps_per_episode == 0:
+            env.reset()
+        if flush is not None and flush_l2:
             flush.fill_(1)
         if ev:
             ev[0].record(stream)
-        if i == 0:
-            if pos["i"] > 0:
-                env.reset()  # Env.reset (synchronous); part of the job
-            if ev:
-                ev[1].record(stream)
-            env.step_device(dec.data_ptr(), met.data_ptr())
-        else:
-            env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, i - 1, base)
-            if ev:
-                ev[1].record(stream)
-            env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+        env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
+        if ev:
+            ev[1].record(stream)
+        env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
         if ev:
             ev[2].record(stream)
         pos["i"] += 1
@@ -285,6 +281,44 @@ def run_ours(args, rank, local_rank, world):
     c1 = env.counters().sum(0)
     d_steps, d_ticks, d_events, d_snaps = (int(x) for x in (c1 - c0))
 
+    # ---- CUDA-graph mode (extra): chunks of `graph_chunk` (agent + step) pairs replayed from one graph; L2 flushed
+    # between chunks.  This is how a device-resident RL loop would drive the env (no per-step launch cost).
+    graph_info = None
+    if args.graph_chunk > 0:
+        env.reset()
+        pos["i"] = 0
+        n = args.graph_chunk
+        for _ in range(3):
+            one_step(flush_l2=False)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
+            for _ in range(n):
+                env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
+                env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+        env.reset()
+        done_in_ep = 0
+        n_chunks = max(1, args.steps // n)
+        gev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_chunks)]
+        torch.cuda.synchronize()
+        g0 = env.counters().sum(0)
+        for k in range(n_chunks):
+            if done_in_ep + n > steps_per_episode:  # chunks never straddle an episode end
+                env.reset()
+                done_in_ep = 0
+            if flush is not None:
+                flush.fill_(1)
+            gev[k][0].record(stream)
+            gr.replay()
+            gev[k][1].record(stream)
+            done_in_ep += n
+        torch.cuda.synchronize()
+        g1 = env.counters().sum(0)
+        gms = sum(a.elapsed_time(b) for a, b in gev)
+        graph_info = {"steps": int(g1[0] - g0[0]), "ms": gms, "chunk": n}
+        env.reset()
+        pos["i"] = 0
+
     # ---- e2e: host-buffer C-ABI path, agent on the host, one episode-aligned run of min(steps, 2000) steps
     e2e = None
     if not args.skip_e2e:
@@ -292,7 +326,7 @@ def run_ours(args, rank, local_rank, world):
         n_e2e = min(args.steps, 2000)
         d, m = env.step(None)
         for k in range(3):
-            d, m = env.step(host_policy(d, 0, k, base, np))
+            d, m = env.step(host_policy(d, 0, base, np))
         env.reset()
         torch.cuda.synchronize()
         cc0 = env.counters().sum(0)
@@ -306,7 +340,7 @@ def run_ours(args, rank, local_rank, world):
                 d, m = env.step(None)
             else:
                 ta = time.perf_counter()
-                a = host_policy(d, 0, i - 1, base, np)
+                a = host_policy(d, 0, base, np)
                 t_agent += time.perf_counter() - ta
                 d, m = env.step(a)
             i = (i + 1) % steps_per_episode
@@ -314,16 +348,18 @@ def run_ours(args, rank, local_rank, world):
         cc1 = env.counters().sum(0)
         e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt, "agent_seconds": t_agent}
 
-    t = torch.tensor([total_ms, kernel_ms, wall * 1000.0, (e2e or {}).get("seconds", 0.0) * 1000.0], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([d_steps, d_ticks, d_events, d_snaps, (e2e or {}).get("steps", 0)], dtype=torch.int64, device="cuda")
+    t = torch.tensor([total_ms, kernel_ms, wall * 1000.0, (e2e or {}).get("seconds", 0.0) * 1000.0,
+                      (graph_info or {}).get("ms", 0.0)], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([d_steps, d_ticks, d_events, d_snaps, (e2e or {}).get("steps", 0),
+                        (graph_info or {}).get("steps", 0)], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         # the path's single collective: collate per-replica episode metrics on every rank
         gathered = torch.empty((world * B, 3), dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(gathered, met)
-    total_ms, kernel_ms, wall_ms, e2e_ms = (float(x) for x in t.cpu())
-    g_steps, g_ticks, g_events, g_snaps, g_e2e_steps = (int(x) for x in cnt.cpu())
+    total_ms, kernel_ms, wall_ms, e2e_ms, graph_ms = (float(x) for x in t.cpu())
+    g_steps, g_ticks, g_events, g_snaps, g_e2e_steps, g_graph_steps = (int(x) for x in cnt.cpu())
 
     if rank == 0:
         peaks = {}
@@ -363,6 +399,10 @@ def run_ours(args, rank, local_rank, world):
                            "api": "maro_cim_step (host buffers) + numpy agent",
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
+        if graph_info:
+            line["graph_mode"] = {"value": g_graph_steps / (graph_ms / 1000.0), "unit": "env-steps/s",
+                                  "chunk_steps": graph_info["chunk"], "us_per_step": 1000.0 * graph_ms / max(1, (args.steps // graph_info["chunk"]) * graph_info["chunk"]),
+                                  "l2": "flushed between graph chunks"}
         line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
         print(json.dumps(line), flush=True)
     env.close()

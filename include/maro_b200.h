@@ -95,7 +95,7 @@ enum {
     MARO_DEC_SCOPE_DISCHARGE = 4, /* ActionScope.discharge = vessel.empty                            */
     MARO_DEC_EARLY_DISCHARGE = 5,
     MARO_DEC_STATUS = 6,          /* MARO_STATUS_*                                                   */
-    MARO_DEC_EVENTS = 7,          /* events executed by this step (for events/s accounting)          */
+    MARO_DEC_STEP = 7,            /* ordinal of this env-step inside the episode (0 = first decision)  */
     MARO_CIM_DECISION_WORDS = 8
 };
 
@@ -175,10 +175,10 @@ int maro_cim_counters(MaroCimEnv* env, int64_t* out);
 int maro_cim_snapshot_frames(MaroCimEnv* env, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out);
 
 /* Agent helper used by bench.py: the hello-world random policy (examples/hello_world/cim/hello.py:24-32)
- * as a counter-based hash of (replica_base + replica, step), evaluated on the device so the env state never
- * leaves HBM. */
+ * as a counter-based hash of (replica_base + replica, decision ordinal = decisions[r][MARO_DEC_STEP]), evaluated
+ * on the device so the env state never leaves HBM (and the step loop can be captured in a CUDA graph). */
 int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t* d_actions,
-                                  uint32_t seed, uint32_t step_index, uint32_t replica_base);
+                                  uint32_t seed, uint32_t replica_base);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ import numpy as np
 
 ABI_VERSION = 1
 
-DEC_TICK, DEC_PORT, DEC_VESSEL, DEC_SCOPE_LOAD, DEC_SCOPE_DISCHARGE, DEC_EARLY_DISCHARGE, DEC_STATUS, DEC_EVENTS = range(8)
+DEC_TICK, DEC_PORT, DEC_VESSEL, DEC_SCOPE_LOAD, DEC_SCOPE_DISCHARGE, DEC_EARLY_DISCHARGE, DEC_STATUS, DEC_STEP = range(8)
 DECISION_WORDS = 8
 ACTION_WORDS = 4
 METRIC_WORDS = 3

@@ -59,7 +59,7 @@ def lib():
     L.maro_cim_ticks.argtypes = [vp, vp]
     L.maro_cim_counters.argtypes = [vp, vp]
     L.maro_cim_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
-    L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32, u32]
+    L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32]
     if L.maro_abi_version() != _abi.ABI_VERSION:
         raise NativeLibraryError("libmaro_b200.so ABI version mismatch; rebuild")
     _lib = L

@@ -106,9 +106,8 @@ class CimBatch:
         _native.check(_native.lib().maro_cim_step_device(self._h, d_active or None, d_actions or None,
                                                          d_n_actions or None, d_decisions, d_metrics))
 
-    def random_policy_device(self, d_decisions: int, d_actions: int, seed: int, step_index: int, replica_base: int = 0):
-        _native.check(_native.lib().maro_cim_random_policy_device(self._h, d_decisions, d_actions, seed, step_index,
-                                                                  replica_base))
+    def random_policy_device(self, d_decisions: int, d_actions: int, seed: int, replica_base: int = 0):
+        _native.check(_native.lib().maro_cim_random_policy_device(self._h, d_decisions, d_actions, seed, replica_base))
 
     # -- inspection --------------------------------------------------------------------------------
     def attr_id(self, node: str, name: str) -> int:

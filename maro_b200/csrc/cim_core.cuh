@@ -189,7 +189,7 @@ enum Ctrl {
     C_STATE, C_TICK, C_ARR_LO, C_ARR_HI, C_DEC_POS, C_FREE_TOP, C_Q_COUNT, C_ERR,
     C_OPNUM_LO, C_OPNUM_HI, C_MT_ORDER_IDX, C_MT_BUFFER_IDX,
     C_NSTEPS_LO, C_NSTEPS_HI, C_NTICKS_LO, C_NTICKS_HI, C_NEVENTS_LO, C_NEVENTS_HI, C_NSNAPS_LO, C_NSNAPS_HI,
-    C_LAST_FRAME, C_N_ORDERS, C_RESERVED1, C_RESERVED2,
+    C_LAST_FRAME, C_N_ORDERS, C_EP_STEP, C_RESERVED2,
     C_FIXED  // followed by dep_cursor[V]
 };
 enum State { ST_START = 0, ST_TICK_BEGIN = 1, ST_DECISIONS = 2, ST_AWAIT = 3, ST_DONE = 4, ST_FINISHED = 5, ST_ERROR = 6 };
@@ -936,7 +936,8 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
         ctrl_add64(r, C_NEVENTS_LO, nev);
         ctrl_add64(r, C_NTICKS_LO, nticks);
         dec[6] = status;
-        dec[7] = nev;
+        dec[7] = r.c[C_EP_STEP];  // ordinal of this env-step inside the episode (0 = first decision)
+        r.c[C_EP_STEP] += 1;
         met[0] = bk; met[1] = sh; met[2] = ctrl_get64(r, C_OPNUM_LO);
     }
     g.sync();
@@ -948,7 +949,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
 template <int G>
 MARO_DEV void replica_reset(const CimShape& s, const Grp<G>& g, const Replica& r) {
     LANE_LOOP(i, s.FWp) r.f[i] = 0;
-    LANE_LOOP(i, s.CWp) r.c[i] = 0;
+    LANE_LOOP(i, s.CWp) if (i < C_NSTEPS_LO || i > C_NSNAPS_HI) r.c[i] = 0;  // cumulative work counters survive
     g.sync();
     LANE_LOOP(p, s.P) {
         PA(s, r, PA_CAPACITY, p) = TBL_I(r, s.t_port_capacity, p);

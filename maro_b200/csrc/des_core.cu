@@ -185,10 +185,11 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
 
 // hello-world random agent (examples/hello_world/cim/hello.py:24-32) as a counter hash of (replica, step)
 __global__ void cim_policy_kernel(const int32_t* __restrict__ dec, int32_t* __restrict__ act, int n, int max_actions,
-                                  uint32_t seed, uint32_t step, uint32_t replica_base) {
+                                  uint32_t seed, uint32_t replica_base) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t* d = dec + i * 8;
+    const uint32_t step = (uint32_t)d[7];
     uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + step * 0x85ebca6bu + 0x1234567u));
     uint32_t h2 = hash_u32(h1 + 0x68bc21ebu);
     int load = d[3], dis = d[4];
@@ -575,12 +576,12 @@ int maro_cim_snapshot_frames(MaroCimEnv* e, int32_t replica, int32_t* out, int32
     return 0;
 }
 
-int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t* d_actions, uint32_t seed, uint32_t step_index,
+int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t* d_actions, uint32_t seed,
                                   uint32_t replica_base) {
     if (!e || !d_decisions || !d_actions) return fail("maro_cim_random_policy_device: bad arguments");
     CK(cudaSetDevice(e->device));
     int threads = 256, blocks = (e->B + threads - 1) / threads;
-    cim_policy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.max_actions, seed, step_index, replica_base);
+    cim_policy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.max_actions, seed, replica_base);
     CK(cudaGetLastError());
     return 0;
 }

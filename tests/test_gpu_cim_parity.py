@@ -174,7 +174,7 @@ def test_cuda_full_size_properties():
     tapes = {i: [] for i in sample}
     n_total = CimOracle(topo).run_episode(0)[0]  # decisions + the final step; static for a given stop table
     for step in range(n_total - 1):
-        env.random_policy_device(dec.data_ptr(), act.data_ptr(), 5, step)
+        env.random_policy_device(dec.data_ptr(), act.data_ptr(), 5)
         a = act[sample].cpu().numpy()
         d = dec[sample].cpu().numpy()
         for k, i in enumerate(sample):
