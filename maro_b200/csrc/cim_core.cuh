@@ -200,8 +200,9 @@ struct CimShape {
     int max_tick, start_tick, resolution, ring_rows, order_mode, total_containers;
     int order_noise, buffer_noise, max_actions, n_replicas;
     int vol_is_one, max_targets;
+    int res_is_one;  // snapshot_resolution == 1 (skips the per-tick integer divisions)
     double vol;
-    // per-replica state block: [frame FWp][ctrl CWp][queue: pool QN*4 | buckets QH | free stack QN]
+    // per-replica state block: [frame FWp][ctrl CWp][queue: ev QN*2 | buckets QH | next+free u16 QN]
     int FW, FWp, CWp, QN, QH, SW;
     int o_vs, o_past, o_past_tick, o_fut, o_fut_tick, o_fop, o_fov, o_vp;  // frame offsets (ports start at 0)
     // static table blob offsets (words from the blob start); *_d are offsets of double arrays (even)
@@ -338,11 +339,15 @@ MARO_DEV MtView mt_reserve(const CimShape& s, const Grp<G>& g, const Replica& r,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Calendar queue of dynamic events.  Slot = 4 words {type|a<<8|b<<16|c<<24, qty, tick, next};
-// bucket[tick & (QH-1)] = head | tail << 16 (0xffff = nil); free slots on a stack (parallel pop / push).
+// Calendar queue of dynamic events.  Slot = 2 words {type|a<<8|b<<16|c<<24, qty} + a 16-bit next link;
+// bucket[tick & (QH-1)] = head | tail << 16 (0xffff = nil); free slots on a 16-bit stack (parallel pop / push).
+// Layout inside the replica's queue region: ev[QN][2] | bucket[QH] | nxt[QN] (u16) | free[QN] (u16).
 // group_push: every lane with `want` appends one event; FIFO order per bucket = lane order.
 // ------------------------------------------------------------------------------------------------
 #define Q_NIL 0xffff
+MARO_DEV int32_t* q_bucket(const CimShape& s, const Replica& r) { return r.q + s.QN * 2; }
+MARO_DEV uint16_t* q_next(const CimShape& s, const Replica& r) { return reinterpret_cast<uint16_t*>(r.q + s.QN * 2 + s.QH); }
+MARO_DEV uint16_t* q_free(const CimShape& s, const Replica& r) { return q_next(s, r) + s.QN; }
 
 template <int G>
 MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, bool want, int tick, int w0, int qty) {
@@ -358,7 +363,8 @@ MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, b
         g.sync();
         return;
     }
-    int32_t* fs = r.q + s.QN * 4 + s.QH;
+    uint16_t* fs = q_free(s, r);
+    uint16_t* nx = q_next(s, r);
     int slot = want ? fs[top - 1 - rank] : Q_NIL;
     int b = tick & (s.QH - 1);
     uint32_t peers = g.match(want ? b : (0x10000 + g.lane));
@@ -371,14 +377,14 @@ MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, b
     g.sync();
     if (g.lane == 0) { r.c[C_FREE_TOP] = top - n; r.c[C_Q_COUNT] += n; }
     if (want) {
-        int32_t* e = r.q + slot * 4;
-        e[0] = w0; e[1] = qty; e[2] = tick;
-        e[3] = above ? nxt_slot : Q_NIL;
+        int32_t* e = r.q + slot * 2;
+        e[0] = w0; e[1] = qty;
+        nx[slot] = (uint16_t)(above ? nxt_slot : Q_NIL);
         if (!below) {  // first lane of this bucket's run: splice the run after the current tail
-            int32_t* bk = r.q + s.QN * 4 + b;
+            int32_t* bk = q_bucket(s, r) + b;
             int hb = *bk, tail = (hb >> 16) & 0xffff;
             if (tail == Q_NIL) *bk = slot | (last_slot << 16);
-            else { r.q[tail * 4 + 3] = slot; *bk = (hb & 0xffff) | (last_slot << 16); }
+            else { nx[tail] = (uint16_t)slot; *bk = (hb & 0xffff) | (last_slot << 16); }
         }
     }
     g.sync();
@@ -440,22 +446,23 @@ MARO_DEV void predict_serial(const CimShape& s, const Replica& r, int v, int sto
 // Phase (b): events queued for this tick by earlier ticks.  _on_full_return (:499-522), _on_empty_return (:695-706),
 // _on_discharge (:658-693) are pure adds -> shared-memory atomics in any order; RETURN_EMPTY pushes keep lane order.
 // ------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool kGeneral>
 MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, int tick) {
-    int32_t* bk = r.q + s.QN * 4 + (tick & (s.QH - 1));
+    int32_t* bk = q_bucket(s, r) + (tick & (s.QH - 1));
     int head = *bk & 0xffff;
     if (head == Q_NIL) return 0;
     g.sync();
     if (g.lane == 0) *bk = Q_NIL | (Q_NIL << 16);
     int nev = 0;
-    int32_t* fs = r.q + s.QN * 4 + s.QH;
+    uint16_t* fs = q_free(s, r);
+    const uint16_t* nx = q_next(s, r);
     while (head != Q_NIL) {  // group-uniform
         // lane i walks to the i-th event of the list (Q_NIL past the end)
         int my = head;
-        for (int h = 0; h < g.lane && my != Q_NIL; h++) my = r.q[my * 4 + 3];
+        for (int h = 0; h < g.lane && my != Q_NIL; h++) my = nx[my];
         bool valid = my != Q_NIL;
         int w0 = 0, qty = 0, nxt = Q_NIL;
-        if (valid) { w0 = r.q[my * 4]; qty = r.q[my * 4 + 1]; nxt = r.q[my * 4 + 3]; }
+        if (valid) { w0 = r.q[my * 2]; qty = r.q[my * 2 + 1]; nxt = nx[my]; }
         head = g.shfl(nxt, G - 1);  // continuation for lists longer than G
         uint32_t vb = g.ballot(valid);
         int n = maro_popc(vb);
@@ -480,7 +487,7 @@ MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, in
         uint32_t db = g.ballot(is_dis);
         int buf = 0;
         if (db) {
-            if (s.buffer_noise) {
+            if (kGeneral && s.buffer_noise) {
                 int nd = maro_popc(db);
                 int drank = maro_popc(db & ((1u << g.lane) - 1u));
                 MtView mv = mt_reserve(s, g, r, 1, 2 * nd);
@@ -501,7 +508,7 @@ MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, in
         // recycle this chunk's slots, then append the RETURN_EMPTY events
         g.sync();
         int top = r.c[C_FREE_TOP];
-        if (valid) fs[top + g.lane] = my;
+        if (valid) fs[top + g.lane] = (uint16_t)my;
         g.sync();
         if (g.lane == 0) { r.c[C_FREE_TOP] = top + n; r.c[C_Q_COUNT] -= n; }
         g.sync();
@@ -517,7 +524,7 @@ MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, in
 // orders of one source port consume `empty` in sequence -> segmented prefix sum (orders arrive sorted by source).
 // `get(i, w, q)` yields order i as {src | dst << 8, qty}.
 // ------------------------------------------------------------------------------------------------
-template <int G, class Get>
+template <int G, bool kGeneral, class Get>
 MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, int tick, int n_orders, Get get) {
     int nev = 0;
     for (int base = 0; base < n_orders; base += G) {
@@ -549,7 +556,7 @@ MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, in
         // full-return buffer ticks, drawn in order (one draw per ORDER)
         int buf = 0;
         int nv = base + G <= n_orders ? G : n_orders - base;
-        if (s.buffer_noise) {
+        if (kGeneral && s.buffer_noise) {
             MtView mv = mt_reserve(s, g, r, 1, 2 * nv);
             if (valid) {
                 double u = mt_uniform01(mv.at(2 * g.lane), mv.at(2 * g.lane + 1));
@@ -749,7 +756,7 @@ MARO_DEV bool on_actions(const CimShape& s, const Replica& r, const int32_t* act
 template <int G>
 MARO_DEV void take_snapshot(const CimShape& s, const Grp<G>& g, const Replica& r, int frame_index) {
     g.sync();
-    int row = frame_index % s.ring_rows;
+    int row = frame_index < s.ring_rows ? frame_index : frame_index % s.ring_rows;
     int32_t* dst = r.snap + (int64_t)row * s.FWp;
 #ifdef MARO_HOST_EMULATION
     LANE_LOOP(i, s.FWp) dst[i] = r.f[i];
@@ -766,13 +773,16 @@ MARO_DEV void take_snapshot(const CimShape& s, const Grp<G>& g, const Replica& r
     g.sync();
 }
 
-MARO_DEV int frame_index_of(const CimShape& s, int tick) { return (tick - s.start_tick) / s.resolution; }
+MARO_DEV int frame_index_of(const CimShape& s, int tick) {
+    return s.res_is_one ? tick - s.start_tick : (tick - s.start_tick) / s.resolution;
+}
 
 // ------------------------------------------------------------------------------------------------
 // One Env.step for one replica.  `act`/`n_act` are this replica's action rows; `dec` (8 int32) and `met`
 // (3 int64) its output rows.  All lanes of the group call this together.
 // ------------------------------------------------------------------------------------------------
-template <int G>
+// kGeneral = false compiles the noise-free fast path only (static order schedule, integer buffer ticks, no MT19937).
+template <int G, bool kGeneral>
 MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r, const int32_t* act, int n_act,
                            int32_t* dec, int64_t* met) {
     int state = r.c[C_STATE];
@@ -825,9 +835,9 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
                     if (v < 32) alo |= 1u << v; else ahi |= 1u << (v - 32);
                     r.f[s.o_vp + v * s.P + TBL_I(r, s.t_stop_port, si)] = tick;
                 }
-                if (s.order_mode == 1) total_empty += VA(s, r, VA_EMPTY, v);
+                if (kGeneral && s.order_mode == 1) total_empty += VA(s, r, VA_EMPTY, v);
             }
-            if (s.order_mode == 1) {
+            if (kGeneral && s.order_mode == 1) {
                 LANE_LOOP(p, s.P) total_empty += PA(s, r, PA_EMPTY, p);
                 total_empty = g.sum(total_empty);
             }
@@ -849,13 +859,13 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             nev += g.sum(ndep);
             g.sync();
             // ---- (b) events queued by earlier ticks
-            nev += run_bucket(s, g, r, tick);
+            nev += run_bucket<G, kGeneral>(s, g, r, tick);
             // ---- (c) this tick's orders
-            if (s.order_table) {
+            if (!kGeneral || s.order_table) {
                 int slot = TBL_I(r, s.t_ord_slot, tick);
                 int lo = TBL_I(r, s.t_ord_off, slot), hi = TBL_I(r, s.t_ord_off, slot + 1);
                 const int32_t* list = r.t + s.t_ord_list + 2 * lo;
-                nev += run_orders(s, g, r, tick, hi - lo, [&](int i, int& w, int& q) { w = list[2 * i]; q = list[2 * i + 1]; });
+                nev += run_orders<G, kGeneral>(s, g, r, tick, hi - lo, [&](int i, int& w, int& q) { w = list[2 * i]; q = list[2 * i + 1]; });
             } else {
                 // float64 generation on the leader lane into the replica's scratch area, then cooperative execution
                 int32_t* olist = reinterpret_cast<int32_t*>(r.mt + s.mt_scratch + 64);
@@ -864,7 +874,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
                 if (g.lane == 0) r.c[C_N_ORDERS] = gen_orders_serial(s, r, tick, total_empty, olist, dscr);
                 g.sync();
                 int n = r.c[C_N_ORDERS];
-                nev += run_orders(s, g, r, tick, n, [&](int i, int& w, int& q) { w = olist[2 * i]; q = olist[2 * i + 1]; });
+                nev += run_orders<G, kGeneral>(s, g, r, tick, n, [&](int i, int& w, int& q) { w = olist[2 * i]; q = olist[2 * i + 1]; });
             }
             g.sync();
             // ---- (d) VESSEL_ARRIVAL + LOAD_FULL per arriving vessel, vessel order
@@ -897,7 +907,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             break;
         }
         // ---- post_step (business_engine.py:201-224)
-        if ((tick + 1) % s.resolution == 0) {
+        if (s.res_is_one || (tick + 1) % s.resolution == 0) {
             g.sync();
             LANE_LOOP(p, s.P) PA(s, r, PA_ACC_FULFILLMENT, p) = PA(s, r, PA_ACC_BOOKING, p) - PA(s, r, PA_ACC_SHORTAGE, p);
             take_snapshot(s, g, r, frame_index_of(s, tick));
@@ -910,7 +920,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             g.sync();
         }
         if (tick + 1 == s.max_tick) {
-            if ((tick + 1) % s.resolution != 0) take_snapshot(s, g, r, frame_index_of(s, tick));  // core.py:376-378
+            if (!s.res_is_one && (tick + 1) % s.resolution != 0) take_snapshot(s, g, r, frame_index_of(s, tick));  // core.py:376-378
             state = ST_DONE;
             status = 1;
             if (g.lane == 0) { dec[0] = tick; dec[1] = dec[2] = dec[3] = dec[4] = dec[5] = 0; }
@@ -974,12 +984,14 @@ MARO_DEV void replica_reset(const CimShape& s, const Grp<G>& g, const Replica& r
         r.c[C_FIXED + v] = dc;
     }
     // queue: all slots on the free stack (slot 0 on top so that allocation order is ascending), empty buckets
-    int32_t* fs = r.q + s.QN * 4 + s.QH;
+    uint16_t* fs = q_free(s, r);
+    uint16_t* nx = q_next(s, r);
     LANE_LOOP(i, s.QN) {
-        r.q[i * 4 + 0] = 0; r.q[i * 4 + 1] = 0; r.q[i * 4 + 2] = 0; r.q[i * 4 + 3] = Q_NIL;
-        fs[i] = s.QN - 1 - i;
+        r.q[i * 2 + 0] = 0; r.q[i * 2 + 1] = 0;
+        nx[i] = Q_NIL;
+        fs[i] = (uint16_t)(s.QN - 1 - i);
     }
-    LANE_LOOP(i, s.QH) r.q[s.QN * 4 + i] = Q_NIL | (Q_NIL << 16);
+    LANE_LOOP(i, s.QH) q_bucket(s, r)[i] = Q_NIL | (Q_NIL << 16);
     LANE_LOOP(i, s.ring_rows) r.snap_frame[i] = -1;
     if (r.mt) {
         LANE_LOOP(i, 624) {

@@ -235,10 +235,11 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
     s.QH = qh;
     // outstanding dynamic events: RETURN_FULL <= orders/tick x buffer, DISCHARGE_FULL <= V x route, RETURN_EMPTY
     int qn = cfg->queue_capacity > 0 ? cfg->queue_capacity
-                                     : std::max(32, max_targets * buf_full + V * max_rl * (1 + buf_empty) + 16);
+                                     : std::max(32, max_targets * buf_full + V * max_rl * (1 + buf_empty));
     if (qn > 65000) qn = 65000;
     s.QN = round_up(qn, 4);
-    s.SW = round_up(s.FWp + s.CWp + s.QN * 4 + s.QH + s.QN, 4);  // frame | ctrl | pool | buckets | free stack
+    s.SW = round_up(s.FWp + s.CWp + s.QN * 2 + s.QH + s.QN, 4);  // frame | ctrl | ev | buckets | next+free (u16)
+    s.res_is_one = s.resolution == 1 ? 1 : 0;
     s.vol_is_one = s.vol == 1.0 ? 1 : 0;
     s.max_targets = max_targets;
     s.mt_scratch = 2 * 640;

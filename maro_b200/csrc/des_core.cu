@@ -84,8 +84,8 @@ __device__ __forceinline__ Replica make_replica(const CimShape& s, const StepArg
     return r;
 }
 
-template <int kWarps, int G>
-__global__ void __launch_bounds__(kWarps * 32) cim_step_kernel(const __grid_constant__ CimShape s,
+template <int kWarps, int G, bool kGeneral>
+__global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_step_kernel(const __grid_constant__ CimShape s,
                                                                const __grid_constant__ StepArgs a) {
     constexpr int kGroups = kWarps * 32 / G;  // replicas in flight per CTA
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kWarps * 32) cim_step_kernel(const __grid_cons
         Replica r = make_replica(s, a, rep, st);
         const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), s.max_actions) : 1) : 0;
         const int32_t* act = a.actions ? a.actions + (int64_t)rep * s.max_actions * 4 : nullptr;
-        replica_step<G>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
+        replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
         // ---- write back (128-bit coalesced)
         const int4* src4 = reinterpret_cast<const int4*>(st);
         int4* dst4 = reinterpret_cast<int4*>(gstate);
@@ -263,12 +263,19 @@ static StepArgs base_args(MaroCimEnv* e) {
     return a;
 }
 
+template <int W, int G, bool kGeneral>
+static cudaError_t launch_step_wgn(MaroCimEnv* e, const StepArgs& a) {
+    cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W, G, kGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    if (err != cudaSuccess) return err;
+    cim_step_kernel<W, G, kGeneral><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+    return cudaGetLastError();
+}
+
 template <int W, int G>
 static cudaError_t launch_step_wg(MaroCimEnv* e, const StepArgs& a) {
-    cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
-    if (err != cudaSuccess) return err;
-    cim_step_kernel<W, G><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
-    return cudaGetLastError();
+    // noise-free fixed-mode topologies run the specialised kernel (no MT19937 / float64 paths compiled in)
+    const bool general = !(e->s.order_table && !e->s.buffer_noise);
+    return general ? launch_step_wgn<W, G, true>(e, a) : launch_step_wgn<W, G, false>(e, a);
 }
 
 template <int G>
@@ -338,15 +345,22 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     const int gpw = 32 / e->lanes;  // replicas per warp
     const size_t per_warp = (size_t)s.SW * 4 * gpw;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
-    int w = 8;
-    while (w > 1 && 256 + per_warp * w > std::min<size_t>(max_smem, 100 * 1024)) w >>= 1;
-    if (256 + per_warp * w > max_smem) { delete e; return fail("maro_cim_create: replica state does not fit in shared memory"); }
-    // small batches: spread replicas over all SMs
+    if (256 + per_warp > max_smem) { delete e; return fail("maro_cim_create: replica state does not fit in shared memory"); }
+    // warps per CTA: the choice that keeps the most warps resident per SM (shared memory vs the 64-register budget
+    // of the specialised kernel), then fewer for small batches so that replicas spread over all SMs
+    const size_t sm_smem = prop.sharedMemPerMultiprocessor;
+    int w = 1, best = 0;
+    for (int cand = 8; cand >= 1; cand >>= 1) {
+        size_t cta = 256 + per_warp * cand;
+        if (cta > max_smem) continue;
+        int blocks = (int)std::min<size_t>(sm_smem / (cta + 1024), (size_t)(64 / cand));
+        if (blocks * cand > best) { best = blocks * cand; w = cand; }
+    }
     while (w > 1 && (e->B + w * gpw - 1) / (w * gpw) < prop.multiProcessorCount) w >>= 1;
     e->warps_per_cta = w;
     e->smem_bytes = 256 + per_warp * w;
     int ctas_needed = (e->B + w * gpw - 1) / (w * gpw);
-    int resident = std::max<int>(1, (int)std::min<size_t>(64 / w, max_smem / e->smem_bytes));
+    int resident = std::max<int>(1, (int)std::min<size_t>(64 / w, sm_smem / (e->smem_bytes + 1024)));
     e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
 
     CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));

@@ -33,7 +33,8 @@ static void reset_g(Emul* e, int i) {
 template <int G>
 static void step_g(Emul* e, int i, const int32_t* act, int n, int32_t* dec, int64_t* met) {
     Replica r = rep_of(e, i);
-    wemu::run_group(G, [&](int lane) { replica_step<G>(e->s, Grp<G>(lane), r, act, n, dec, met); });
+    wemu::run_group(G, [&](int lane) { if (e->s.order_table && !e->s.buffer_noise) replica_step<G, false>(e->s, Grp<G>(lane), r, act, n, dec, met);
+        else replica_step<G, true>(e->s, Grp<G>(lane), r, act, n, dec, met); });
 }
 static void reset_one(Emul* e, int i) {
     switch (e->lanes) { case 1: reset_g<1>(e, i); break; case 8: reset_g<8>(e, i); break; case 16: reset_g<16>(e, i); break; default: reset_g<32>(e, i); }
