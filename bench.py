@@ -356,8 +356,10 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         # the path's single collective: collate per-replica episode metrics on every rank
-        gathered = torch.empty((world * B, 3), dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(gathered, met)
+        from maro_b200.parallel import gather_metrics
+
+        gathered = gather_metrics(met, world * B)
+        assert gathered.shape == (world * B, 3)
     total_ms, kernel_ms, wall_ms, e2e_ms, graph_ms = (float(x) for x in t.cpu())
     g_steps, g_ticks, g_events, g_snaps, g_e2e_steps, g_graph_steps = (int(x) for x in cnt.cpu())
 
