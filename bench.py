@@ -194,7 +194,22 @@ def cpu_baseline_port(args, topo):
             "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/cim_oracle.c, same topology/ticks/policy, 1 thread"}
 
 
-def host_policy(dec, seed, base, np):
+def load_host_agent():
+    """Compile (gcc) and load tools/host_agent.c — the host-side agent of the e2e leg."""
+    import ctypes
+    import subprocess
+
+    src = os.path.join(ROOT, "tools", "host_agent.c")
+    out = os.path.join(ROOT, "tools", "_build", "libhost_agent.so")
+    if not os.path.isfile(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", src, "-o", out])
+    lib = ctypes.CDLL(out)
+    lib.agent_random.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
+    return lib
+
+
+def host_policy_numpy(dec, seed, base, np):
     """numpy-vectorised twin of cim_policy_kernel (uint32 arithmetic)."""
     def h(x):
         x = x.astype(np.uint32)
@@ -322,6 +337,17 @@ def run_ours(args, rank, local_rank, world):
     # ---- e2e: host-buffer C-ABI path, agent on the host, one episode-aligned run of min(steps, 2000) steps
     e2e = None
     if not args.skip_e2e:
+        agent_lib = load_host_agent()
+        act_host = np.zeros((B, 1, 4), np.int32)
+
+        def host_policy(d, seed, base_, np_):
+            agent_lib.agent_random(d.ctypes.data, act_host.ctypes.data, B, 1, seed, base_)
+            return act_host
+
+        # the C agent and the numpy twin must agree (and both equal the device agent, tests/test_gpu_*)
+        env.reset()
+        d0, _ = env.step(None)
+        assert np.array_equal(host_policy(d0, 0, base, np), host_policy_numpy(d0, 0, base, np))
         env.reset()
         n_e2e = min(args.steps, 2000)
         d, m = env.step(None)
@@ -398,7 +424,7 @@ def run_ours(args, rank, local_rank, world):
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
                            "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * 56,
-                           "api": "maro_cim_step (host buffers) + numpy agent",
+                           "api": "maro_cim_step (host buffers, agent = tools/host_agent.c on the host)",
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
         if graph_info:

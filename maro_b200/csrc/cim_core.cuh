@@ -723,19 +723,25 @@ MARO_DEV void on_departure(const CimShape& s, const Replica& r, int v) {
     set_past_stops(s, r, v, VA(s, r, VA_LAST_LOC_IDX, v), next);
 }
 
-// _on_action_received (:708-748), leader lane.  Returns false where the reference would raise AssertionError.
-MARO_DEV bool on_actions(const CimShape& s, const Replica& r, const int32_t* act, int n) {
+struct Act4 { int32_t v, p, qty, type; };
+
+// _on_action_received (:708-748).  Lane k holds action k (loaded with one 128-bit read); the leader lane applies them in
+// order.  Returns false where the reference would raise AssertionError.
+template <int G>
+MARO_DEV bool on_actions(const CimShape& s, const Grp<G>& g, const Replica& r, const Act4& mine, int n) {
+    bool ok = true;
     for (int i = 0; i < n; i++) {
-        int v = act[4 * i], p = act[4 * i + 1], move = act[4 * i + 2], type = act[4 * i + 3];
-        if (v < 0 || v >= s.V || p < 0 || p >= s.P || move < 0) return false;
+        int v = g.shfl(mine.v, i), p = g.shfl(mine.p, i), move = g.shfl(mine.qty, i), type = g.shfl(mine.type, i);
+        if (g.lane != 0 || !ok) continue;
+        if (v < 0 || v >= s.V || p < 0 || p >= s.P || move < 0) { ok = false; continue; }
         int port_empty = PA(s, r, PA_EMPTY, p), vessel_empty = VA(s, r, VA_EMPTY, v);
         if (type == 1) {  // DISCHARGE
-            if (!(move <= vessel_empty)) return false;
+            if (!(move <= vessel_empty)) { ok = false; continue; }
             PA(s, r, PA_EMPTY, p) = port_empty + move;
             VA(s, r, VA_EMPTY, v) = vessel_empty - move;
         } else {
             int space = VA(s, r, VA_REMAINING_SPACE, v);
-            if (!(move <= (port_empty < space ? port_empty : space))) return false;
+            if (!(move <= (port_empty < space ? port_empty : space))) { ok = false; continue; }
             PA(s, r, PA_EMPTY, p) = port_empty - move;
             VA(s, r, VA_EMPTY, v) = vessel_empty + move;
         }
@@ -746,7 +752,7 @@ MARO_DEV bool on_actions(const CimShape& s, const Replica& r, const int32_t* act
         PA(s, r, PA_TRANSFER_COST, p) = maro_f2i(maro_d2f((double)tc + (double)move));
         r.f[s.o_vp + v * s.P + p] += TBL_I(r, s.t_vessel_period, v);
     }
-    return true;
+    return ok;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -773,6 +779,17 @@ MARO_DEV void take_snapshot(const CimShape& s, const Grp<G>& g, const Replica& r
     g.sync();
 }
 
+// Output rows are written with 128-bit / 64-bit stores (they may live in mapped host memory: one PCIe write each).
+MARO_DEV void store_out(int32_t* dec, int64_t* met, const int32_t* od, int64_t m0, int64_t m1, int64_t m2) {
+#ifdef MARO_HOST_EMULATION
+    for (int i = 0; i < 8; i++) dec[i] = od[i];
+#else
+    reinterpret_cast<int4*>(dec)[0] = make_int4(od[0], od[1], od[2], od[3]);
+    reinterpret_cast<int4*>(dec)[1] = make_int4(od[4], od[5], od[6], od[7]);
+#endif
+    met[0] = m0; met[1] = m1; met[2] = m2;
+}
+
 MARO_DEV int frame_index_of(const CimShape& s, int tick) {
     return s.res_is_one ? tick - s.start_tick : (tick - s.start_tick) / s.resolution;
 }
@@ -783,7 +800,7 @@ MARO_DEV int frame_index_of(const CimShape& s, int tick) {
 // ------------------------------------------------------------------------------------------------
 // kGeneral = false compiles the noise-free fast path only (static order schedule, integer buffer ticks, no MT19937).
 template <int G, bool kGeneral>
-MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r, const int32_t* act, int n_act,
+MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r, const Act4& act, int n_act,
                            int32_t* dec, int64_t* met) {
     int state = r.c[C_STATE];
     int nev = 0;
@@ -791,9 +808,8 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
         g.sync();
         if (g.lane == 0) {
             if (state == ST_DONE) r.c[C_STATE] = ST_FINISHED;
-            for (int i = 0; i < 8; i++) dec[i] = 0;
-            dec[6] = 2;
-            met[0] = met[1] = met[2] = 0;
+            int32_t od[8] = {0, 0, 0, 0, 0, 0, 2, 0};
+            store_out(dec, met, od, 0, 0, 0);
         }
         g.sync();
         return;
@@ -801,14 +817,15 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
     if (state == ST_AWAIT) {
         // _assign_action (core.py:301-315): the decision event finishes, TAKE_ACTION runs as its immediate event
         g.sync();
+        bool ok = on_actions(s, g, r, act, n_act);
         if (g.lane == 0) {
             ctrl_add64(r, C_NSTEPS_LO, 1);
-            if (!on_actions(s, r, act, n_act)) { r.c[C_STATE] = ST_ERROR; r.c[C_ERR] = -1; }
+            if (!ok) { r.c[C_STATE] = ST_ERROR; r.c[C_ERR] = -1; }
         }
         g.sync();
         nev += 2;
         if (r.c[C_STATE] == ST_ERROR) {
-            if (g.lane == 0) { for (int i = 0; i < 8; i++) dec[i] = 0; dec[6] = -1; met[0] = met[1] = met[2] = 0; }
+            if (g.lane == 0) { int32_t od[8] = {0, 0, 0, 0, 0, 0, -1, 0}; store_out(dec, met, od, 0, 0, 0); }
             g.sync();
             return;
         }
@@ -822,6 +839,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
     uint64_t arr = ((uint64_t)(uint32_t)r.c[C_ARR_HI] << 32) | (uint32_t)r.c[C_ARR_LO];
     int dec_pos = r.c[C_DEC_POS];
     int status = 0, nticks = 0;
+    int32_t od[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (;;) {
         if (state == ST_TICK_BEGIN) {
             nticks++;
@@ -896,10 +914,10 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             if (g.lane == 0) {
                 int port = VA(s, r, VA_LOC_PORT_IDX, v);
                 int pe = PA(s, r, PA_EMPTY, port), sp = VA(s, r, VA_REMAINING_SPACE, v);
-                dec[0] = tick; dec[1] = port; dec[2] = v;
-                dec[3] = pe < sp ? pe : sp;
-                dec[4] = VA(s, r, VA_EMPTY, v);
-                dec[5] = VA(s, r, VA_EARLY_DISCHARGE, v);
+                od[0] = tick; od[1] = port; od[2] = v;
+                od[3] = pe < sp ? pe : sp;
+                od[4] = VA(s, r, VA_EMPTY, v);
+                od[5] = VA(s, r, VA_EARLY_DISCHARGE, v);
             }
             dec_pos = v + 1;
             state = ST_AWAIT;
@@ -923,7 +941,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             if (!s.res_is_one && (tick + 1) % s.resolution != 0) take_snapshot(s, g, r, frame_index_of(s, tick));  // core.py:376-378
             state = ST_DONE;
             status = 1;
-            if (g.lane == 0) { dec[0] = tick; dec[1] = dec[2] = dec[3] = dec[4] = dec[5] = 0; }
+            od[0] = tick;
             break;
         }
         tick += 1;
@@ -945,10 +963,10 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
         r.c[C_DEC_POS] = dec_pos;
         ctrl_add64(r, C_NEVENTS_LO, nev);
         ctrl_add64(r, C_NTICKS_LO, nticks);
-        dec[6] = status;
-        dec[7] = r.c[C_EP_STEP];  // ordinal of this env-step inside the episode (0 = first decision)
+        od[6] = status;
+        od[7] = r.c[C_EP_STEP];  // ordinal of this env-step inside the episode (0 = first decision)
         r.c[C_EP_STEP] += 1;
-        met[0] = bk; met[1] = sh; met[2] = ctrl_get64(r, C_OPNUM_LO);
+        store_out(dec, met, od, bk, sh, ctrl_get64(r, C_OPNUM_LO));
     }
     g.sync();
 }

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -116,8 +117,12 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
         while (!mbar_try_wait(bar, phase)) {}
         phase ^= 1u;
         Replica r = make_replica(s, a, rep, st);
-        const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), s.max_actions) : 1) : 0;
-        const int32_t* act = a.actions ? a.actions + (int64_t)rep * s.max_actions * 4 : nullptr;
+        const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), min(s.max_actions, G)) : 1) : 0;
+        Act4 act = {0, 0, 0, 0};
+        if (g.lane < n_act) {  // lane k fetches action k with one 128-bit load (actions may live in mapped host memory)
+            int4 v = reinterpret_cast<const int4*>(a.actions + (int64_t)rep * s.max_actions * 4)[g.lane];
+            act.v = v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
+        }
         replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
         // ---- write back (128-bit coalesced)
         const int4* src4 = reinterpret_cast<const int4*>(st);
@@ -223,7 +228,9 @@ struct MaroCimEnv {
     // host-call staging
     uint8_t* d_in = nullptr;   // [actions B*A*4 i32][n_actions B i32][active B u8]
     uint8_t* d_out = nullptr;  // [decisions B*8 i32][metrics B*3 i64]
-    uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned mirrors
+    uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned mirrors (mapped into the device address space)
+    uint8_t *hd_in = nullptr, *hd_out = nullptr;  // device aliases of h_in / h_out for the zero-copy path
+    bool zero_copy = false;
     size_t in_bytes = 0, out_bytes = 0;
     int32_t* d_qidx = nullptr;  // query index scratch
     size_t qidx_cap = 0;
@@ -387,8 +394,16 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     e->out_bytes = (size_t)B * 32 + (size_t)B * 24;
     CK(cudaMalloc(&e->d_in, e->in_bytes));
     CK(cudaMalloc(&e->d_out, e->out_bytes));
-    CK(cudaMallocHost(&e->h_in, e->in_bytes));
-    CK(cudaMallocHost(&e->h_out, e->out_bytes));
+    CK(cudaHostAlloc(&e->h_in, e->in_bytes, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&e->h_out, e->out_bytes, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_in, e->h_in, 0));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_out, e->h_out, 0));
+    memset(e->h_out, 0, e->out_bytes);
+    {   // small batches: the kernel reads actions from / writes results to mapped pinned host memory (no copy engine
+        // round trips); large batches use bulk DMA copies.  MARO_B200_ZEROCOPY=0/1 overrides.
+        const char* z = getenv("MARO_B200_ZEROCOPY");
+        e->zero_copy = z ? atoi(z) != 0 : e->B <= 16384;
+    }
     CK(cudaMemset(e->d_out, 0, e->out_bytes));
     *out = e;
     int rc = maro_cim_reset(e, nullptr);
@@ -454,17 +469,29 @@ int maro_cim_step(MaroCimEnv* e, const uint8_t* active, const int32_t* actions, 
     CK(cudaSetDevice(e->device));
     const int B = e->B, A = e->s.max_actions;
     const size_t act_bytes = (size_t)B * A * 16, nact_off = act_bytes, active_off = act_bytes + (size_t)B * 4;
-    size_t lo = e->in_bytes, hi = 0;  // byte range of the staging buffer that must travel
-    if (actions) { memcpy(e->h_in, actions, act_bytes); lo = 0; hi = act_bytes; }
-    if (actions && n_actions) { memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4); hi = nact_off + (size_t)B * 4; }
-    if (active) { memcpy(e->h_in + active_off, active, B); lo = std::min(lo, active_off); hi = active_off + B; }
-    if (hi > lo) CK(cudaMemcpyAsync(e->d_in + lo, e->h_in + lo, hi - lo, cudaMemcpyHostToDevice, e->stream));
-    int rc = maro_cim_step_device(e, active ? e->d_in + active_off : nullptr,
+    if (actions) memcpy(e->h_in, actions, act_bytes);
+    if (actions && n_actions) memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4);
+    if (active) memcpy(e->h_in + active_off, active, B);
+    int rc;
+    if (e->zero_copy) {
+        rc = maro_cim_step_device(e, active ? e->hd_in + active_off : nullptr,
+                                  actions ? reinterpret_cast<const int32_t*>(e->hd_in) : nullptr,
+                                  actions && n_actions ? reinterpret_cast<const int32_t*>(e->hd_in + nact_off) : nullptr,
+                                  reinterpret_cast<int32_t*>(e->hd_out), reinterpret_cast<int64_t*>(e->hd_out + (size_t)B * 32));
+        if (rc) return rc;
+    } else {
+        size_t lo = e->in_bytes, hi = 0;  // byte range of the staging buffer that must travel
+        if (actions) { lo = 0; hi = act_bytes; }
+        if (actions && n_actions) hi = nact_off + (size_t)B * 4;
+        if (active) { lo = std::min(lo, active_off); hi = active_off + B; }
+        if (hi > lo) CK(cudaMemcpyAsync(e->d_in + lo, e->h_in + lo, hi - lo, cudaMemcpyHostToDevice, e->stream));
+        rc = maro_cim_step_device(e, active ? e->d_in + active_off : nullptr,
                                   actions ? reinterpret_cast<const int32_t*>(e->d_in) : nullptr,
                                   actions && n_actions ? reinterpret_cast<const int32_t*>(e->d_in + nact_off) : nullptr,
                                   reinterpret_cast<int32_t*>(e->d_out), reinterpret_cast<int64_t*>(e->d_out + (size_t)B * 32));
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    }
     CK(cudaStreamSynchronize(e->stream));
     memcpy(decisions, e->h_out, (size_t)B * 32);
     memcpy(metrics, e->h_out + (size_t)B * 32, (size_t)B * 24);

@@ -31,9 +31,13 @@ static void reset_g(Emul* e, int i) {
     wemu::run_group(G, [&](int lane) { replica_reset<G>(e->s, Grp<G>(lane), r); });
 }
 template <int G>
-static void step_g(Emul* e, int i, const int32_t* act, int n, int32_t* dec, int64_t* met) {
+static void step_g(Emul* e, int i, const int32_t* actp, int n, int32_t* dec, int64_t* met) {
     Replica r = rep_of(e, i);
-    wemu::run_group(G, [&](int lane) { if (e->s.order_table && !e->s.buffer_noise) replica_step<G, false>(e->s, Grp<G>(lane), r, act, n, dec, met);
+    if (n > G) n = G;
+    wemu::run_group(G, [&](int lane) {
+        Act4 act = {0, 0, 0, 0};
+        if (lane < n) { act.v = actp[4 * lane]; act.p = actp[4 * lane + 1]; act.qty = actp[4 * lane + 2]; act.type = actp[4 * lane + 3]; }
+        if (e->s.order_table && !e->s.buffer_noise) replica_step<G, false>(e->s, Grp<G>(lane), r, act, n, dec, met);
         else replica_step<G, true>(e->s, Grp<G>(lane), r, act, n, dec, met); });
 }
 static void reset_one(Emul* e, int i) {

@@ -1,0 +1,24 @@
+/* Bench infrastructure: the hello-world random agent (examples/hello_world/cim/hello.py:24-32) on the host, as the
+ * same counter hash of (replica, decision ordinal) that cim_policy_kernel evaluates on the device.  This is the
+ * *agent* of the end-to-end measurement (user code outside the library), compiled by bench.py with gcc. */
+#include <stdint.h>
+
+static inline uint32_t hash_u32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+void agent_random(const int32_t* dec, int32_t* act, int n, int max_actions, uint32_t seed, uint32_t replica_base) {
+    for (int i = 0; i < n; i++) {
+        const int32_t* d = dec + 8 * i;
+        uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + (uint32_t)d[7] * 0x85ebca6bu + 0x1234567u));
+        uint32_t h2 = hash_u32(h1 + 0x68bc21ebu);
+        int load = d[3], dis = d[4];
+        int to_discharge = dis > 0 && (h1 & 1u);
+        int scope = to_discharge ? dis : load;
+        int32_t* a = act + (int64_t)i * max_actions * 4;
+        a[0] = d[2]; a[1] = d[1];
+        a[2] = scope > 0 ? (int32_t)(h2 % (uint32_t)(scope + 1)) : 0;
+        a[3] = to_discharge;
+    }
+}
