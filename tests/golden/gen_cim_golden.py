@@ -34,6 +34,10 @@ CASES = {
     "gt22p_l00_60_null": dict(topology="global_trade.22p_l0.0", durations=60, policy=0),
     # the 22-port noisy topology of the reference's own CIM tests (tests/cim/test_cim_scenario.py:281-324, 391-460)
     "case22p_200_null": dict(topology=os.path.join(ROOT, "tests", "golden", "_case_cfg"), durations=200, policy=0),
+    # two episodes: Env.reset(keep_seed=False) draws a new topology seed from the route_init stream
+    # (cim_data_container_helpers.py:56-66); the recorded trace is the SECOND episode
+    "toy4p_l08_120_reset_newseed": dict(topology="toy.4p_ssdd_l0.8", durations=120, policy=1, pseed=4, replica=0,
+                                        reset_new_seed=True),
     "toy4p_l00_start5": dict(topology="toy.4p_ssdd_l0.0", durations=60, policy=1, pseed=2, replica=0, start_tick=0,
                              snapshot_resolution=3),
 }
@@ -93,6 +97,11 @@ def run_case(name, spec):
     if "topo_seed" in spec:
         env.set_seed(spec["topo_seed"])
         env.reset(keep_seed=True)
+    if spec.get("reset_new_seed"):
+        metrics, dec, done = env.step(None)
+        while not done:
+            metrics, dec, done = env.step(None)
+        env.reset(keep_seed=False)
     rows = []
     step = 0
     metrics, dec, done = env.step(None)

@@ -22,7 +22,12 @@ def case_topology(spec):
     if topo.endswith("_case_cfg"):
         topo = os.path.join(GOLDEN, "cim_case_config.json")
     max_tick = spec.get("start_tick", 0) + spec["durations"]
-    return build_topology(topo, max_tick, seed=spec.get("topo_seed"))
+    t = build_topology(topo, max_tick, seed=spec.get("topo_seed"))
+    if spec.get("reset_new_seed"):  # second episode after Env.reset(keep_seed=False)
+        from maro_b200.scenarios.cim.topology import next_topology_seed
+
+        t = build_topology(topo, max_tick, seed=next_topology_seed(t))
+    return t
 
 
 def load_golden(name):

@@ -125,3 +125,28 @@ def test_vector_env_large_batch_and_seeds():
             rows = met[g::4]
             assert (rows == rows[0]).all()
         assert len({tuple(met[g]) for g in range(4)}) > 1
+
+
+def test_env_reset_new_seed_matches_reference():
+    """Env.reset(keep_seed=False): new topology seed drawn like the reference; second episode must match its trace."""
+    from helpers import policy_random_py
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.simulator import Env
+
+    spec = CASES["toy4p_l08_120_reset_newseed"]
+    gold = load_golden("toy4p_l08_120_reset_newseed")["steps"]
+    env = Env("cim", spec["topology"], durations=spec["durations"])
+    m, ev, done = env.step(None)
+    while not done:
+        m, ev, done = env.step(None)
+    env.reset(keep_seed=False)
+    rows, step = [], 0
+    m, ev, done = env.step(None)
+    while not done:
+        d = [ev.tick, ev.port_idx, ev.vessel_idx, ev.action_scope.load, ev.action_scope.discharge, ev.early_discharge]
+        rows.append(d + [m["order_requirements"], m["container_shortage"], m["operation_number"]])
+        v, p, q, t = policy_random_py(d, spec["pseed"], spec["replica"], step)
+        m, ev, done = env.step(Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD))
+        step += 1
+    assert np.array_equal(np.asarray(rows), gold)
+    env.close()
