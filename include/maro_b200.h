@@ -180,6 +180,75 @@ int maro_cim_snapshot_frames(MaroCimEnv* env, int32_t replica, int32_t* out, int
 int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t* d_actions,
                                   uint32_t seed, uint32_t replica_base);
 
+
+/* ================================================================================================
+ * citi_bike scenario: same call shapes as the CIM entry points.
+ * Static tables come from maro_b200.scenarios.citi_bike.data.build_bike_topology(), which restates
+ * maro/data_lib/binary_reader.py (trace format + ItemTickPicker), citi_bike/business_engine.py:218-396 and
+ * decision_strategy.py:385-397.
+ * ============================================================================================== */
+typedef struct MaroBikeTopology {
+    int32_t n_stations, n_days;
+    int32_t max_tick;            /* start_tick + durations                                            */
+    int32_t resolution;          /* decision.resolution (decision_strategy.py:218-227)                */
+    int32_t extra_cost_mode;     /* 0 source, 1 target, 2 target_neighbors                            */
+    uint32_t transfer_seed;      /* np.random.seed() of the transfer_time stream (:213-216)           */
+    double time_mean, time_std;  /* effective_time_mean / _std                                        */
+    double supply_ratio, demand_ratio, scope_low, scope_high;
+    const int32_t* station_bikes;    /* [S] initial bikes                                             */
+    const int32_t* station_capacity; /* [S]                                                           */
+    const int32_t* station_id;       /* [S]                                                           */
+    const int32_t* nbr_offset;       /* [S+1] neighbours sorted by distance (distance != 0)           */
+    const int32_t* nbr_idx;
+    const int32_t* trip_offset;      /* [max_tick+1] trips of tick t = [offset[t], offset[t+1])       */
+    const int32_t* trip_src;
+    const int32_t* trip_dst;
+    const int32_t* trip_dur;         /* ticks until the bike is returned                              */
+    const int32_t* day_of_tick;      /* [max_tick] row of day_feat                                    */
+    const int32_t* day_feat;         /* [n_days][4] weekday, holiday, weather, temperature            */
+} MaroBikeTopology;
+
+/* Decision row: MARO_BIKE_DEC_HEAD int32 header + 2 * n_stations words of (station, scope) pairs in ascending
+ * station order (DecisionEvent, citi_bike/common.py:62-127; action_scope dict of decision_strategy.py:253-293). */
+enum {
+    MARO_BIKE_DEC_TICK = 0,
+    MARO_BIKE_DEC_STATION = 1,
+    MARO_BIKE_DEC_FRAME_INDEX = 2,
+    MARO_BIKE_DEC_TYPE = 3,    /* 0 = Supply, 1 = Demand */
+    MARO_BIKE_DEC_N_SCOPE = 4,
+    MARO_BIKE_DEC_STATUS = 6,  /* MARO_STATUS_*           */
+    MARO_BIKE_DEC_STEP = 7,
+    MARO_BIKE_DEC_HEAD = 8
+};
+/* Action row: 4 int32 {from_station_idx, to_station_idx, number, 0} (citi_bike/common.py:130-150).
+ * Metrics row: 3 int64 {trip_requirements, bike_shortage, operation_number} (business_engine.py:211-227). */
+enum { MARO_BIKE_NODE_STATIONS = 0, MARO_BIKE_NODE_MATRICES = 1 };
+
+typedef struct MaroBikeEnv MaroBikeEnv;
+
+int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, MaroBikeEnv** out);
+int maro_bike_destroy(MaroBikeEnv* env);
+int maro_bike_set_stream(MaroBikeEnv* env, void* cuda_stream, int32_t external);
+int32_t maro_bike_decision_words(MaroBikeEnv* env);
+/* decisions [B][decision_words] int32, metrics [B][3] int64, actions [B][max_actions][4] int32 */
+int maro_bike_step(MaroBikeEnv* env, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
+                   int32_t* decisions, int64_t* metrics);
+int maro_bike_step_device(MaroBikeEnv* env, const uint8_t* d_active, const int32_t* d_actions,
+                          const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
+int maro_bike_reset(MaroBikeEnv* env, const uint8_t* mask);
+int maro_bike_query(MaroBikeEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
+                    const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
+                    const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
+int32_t maro_bike_attr_id(MaroBikeEnv* env, int32_t node_type, const char* name);
+int32_t maro_bike_attr_slots(MaroBikeEnv* env, int32_t node_type, int32_t attr_id);
+int maro_bike_read_frame(MaroBikeEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);
+int32_t maro_bike_frame_words(MaroBikeEnv* env);
+int maro_bike_ticks(MaroBikeEnv* env, int32_t* out_ticks);
+int maro_bike_counters(MaroBikeEnv* env, int64_t* out);
+int maro_bike_snapshot_frames(MaroBikeEnv* env, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out);
+/* Agent helper for bench.py: examples/citi_bike/greedy/launcher.py:35-65 with top-1 (deterministic). */
+int maro_bike_greedy_policy_device(MaroBikeEnv* env, const int32_t* d_decisions, int32_t* d_actions);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,3 +106,54 @@ def frame_layout(P: int, V: int, past_n: int, future_n: int):
         lay["matrices"][a] = (off, 1, n)
         off += n
     return lay, off
+
+
+# ---------------------------------------------------------------------------------------------------- citi_bike
+class MaroBikeTopology(C.Structure):
+    _fields_ = [
+        ("n_stations", C.c_int32), ("n_days", C.c_int32), ("max_tick", C.c_int32), ("resolution", C.c_int32),
+        ("extra_cost_mode", C.c_int32), ("transfer_seed", C.c_uint32),
+        ("time_mean", C.c_double), ("time_std", C.c_double), ("supply_ratio", C.c_double),
+        ("demand_ratio", C.c_double), ("scope_low", C.c_double), ("scope_high", C.c_double),
+        ("station_bikes", _i32p), ("station_capacity", _i32p), ("station_id", _i32p), ("nbr_offset", _i32p),
+        ("nbr_idx", _i32p), ("trip_offset", _i32p), ("trip_src", _i32p), ("trip_dst", _i32p), ("trip_dur", _i32p),
+        ("day_of_tick", _i32p), ("day_feat", _i32p),
+    ]
+
+
+BIKE_DEC_HEAD = 8
+BIKE_STATION_ATTRS = ("bikes", "capacity", "extra_cost", "failed_return", "fulfillment", "holiday", "id", "min_bikes",
+                      "shortage", "temperature", "transfer_cost", "trip_requirement", "weather", "weekday")
+
+
+def bike_topology_struct(topo):
+    s = MaroBikeTopology()
+    keep = []
+    s.n_stations = topo.n_stations
+    s.n_days = len(topo.day_feat)
+    s.max_tick = topo.max_tick
+    s.resolution = topo.resolution
+    s.extra_cost_mode = topo.extra_cost_mode
+    s.transfer_seed = topo.transfer_seed
+    for name in ("time_mean", "time_std", "supply_ratio", "demand_ratio", "scope_low", "scope_high"):
+        setattr(s, name, float(getattr(topo, name)))
+    for field, attr in (("station_bikes", "station_bikes"), ("station_capacity", "station_capacity"),
+                        ("station_id", "station_id"), ("nbr_offset", "nbr_offset"), ("nbr_idx", "nbr_idx"),
+                        ("trip_offset", "trip_offset"), ("trip_src", "trip_src"), ("trip_dst", "trip_dst"),
+                        ("trip_dur", "trip_dur"), ("day_of_tick", "day_of_tick"), ("day_feat", "day_feat")):
+        a = np.ascontiguousarray(getattr(topo, attr), dtype=np.int32).reshape(-1)
+        if a.size == 0:
+            a = np.zeros(1, np.int32)
+        keep.append(a)
+        setattr(s, field, a.ctypes.data_as(_i32p))
+    return s, keep
+
+
+def bike_frame_layout(S: int):
+    lay = {"stations": {}, "matrices": {}}
+    off = 0
+    for a in BIKE_STATION_ATTRS:
+        lay["stations"][a] = (off, S, 1)
+        off += S
+    lay["matrices"]["trips_adj"] = (off, 1, S * S)
+    return lay, off + S * S
