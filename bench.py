@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--replicas", type=int, default=1024, help="parallel envs per GPU")
     ap.add_argument("--ticks", type=int, default=1000)
     ap.add_argument("--topology", default="toy.4p_ssdd_l0.0")
+    ap.add_argument("--scenario", default="cim", choices=["cim", "citi_bike"],
+                    help="citi_bike = BASELINE config #3 (frozen toy.3s_4t trace, greedy agent, snapshot_resolution 10)")
     ap.add_argument("--max-snapshots", type=int, default=0, help="0 = keep every frame (reference default)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
@@ -194,6 +196,21 @@ def cpu_baseline_port(args, topo):
             "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/cim_oracle.c, same topology/ticks/policy, 1 thread"}
 
 
+def cpu_baseline_bike(args, topo):
+    from oracle.bike_oracle import BikeOracle
+
+    o = BikeOracle(topo, 10)
+    env_steps, ep, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < args.cpu_seconds:
+        o.reset()
+        n, _ = o.run_episode(1)
+        env_steps += n
+        ep += 1
+    dt = time.perf_counter() - t0
+    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/bike_oracle.c, same trace/policy, 1 thread"}
+
+
 def load_host_agent():
     """Compile (gcc) and load tools/host_agent.c — the host-side agent of the e2e leg."""
     import ctypes
@@ -243,13 +260,33 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.replicas
-    topo = build_topology(args.topology, args.ticks)
-    steps_per_episode = CimOracle(topo).run_episode(0)[0]  # decisions + final step (static for a given stop table)
-    env = CimBatch(topo, B, device=local_rank, max_snapshots=args.max_snapshots or None)
+    bike = args.scenario == "citi_bike"
+    if bike:
+        from maro_b200.batch import BikeBatch
+        from oracle.bike_oracle import BikeOracle  # checker / cpu_baseline leg only
+        from tests.bike_helpers import bike_config
+        from maro_b200.scenarios.citi_bike.data import build_bike_topology
+
+        ticks = min(args.ticks, 2880) if args.ticks != 1000 else 1440
+        topo = build_bike_topology(bike_config("bike_toy"), 0, ticks, transfer_seed=128)
+        steps_per_episode = BikeOracle(topo, 10).run_episode(1)[0]
+        env = BikeBatch(topo, B, 10, args.max_snapshots or None, device=local_rank)
+        dec_words = env.dec_words
+    else:
+        topo = build_topology(args.topology, args.ticks)
+        steps_per_episode = CimOracle(topo).run_episode(0)[0]  # decisions + final step (static for a given stop table)
+        env = CimBatch(topo, B, device=local_rank, max_snapshots=args.max_snapshots or None)
+        dec_words = 8
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     env.set_stream(stream.cuda_stream)
-    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    dec = torch.zeros((B, dec_words), dtype=torch.int32, device="cuda")
+
+    def agent_device():
+        if bike:
+            env.greedy_policy_device(dec.data_ptr(), act.data_ptr())
+        else:
+            env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
     met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
     act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -265,7 +302,7 @@ def run_ours(args, rank, local_rank, world):
             flush.fill_(1)
         if ev:
             ev[0].record(stream)
-        env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
+        agent_device()
         if ev:
             ev[1].record(stream)
         env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
@@ -309,7 +346,7 @@ def run_ours(args, rank, local_rank, world):
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=stream):
             for _ in range(n):
-                env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
+                agent_device()
                 env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
         env.reset()
         done_in_ep = 0
@@ -341,13 +378,28 @@ def run_ours(args, rank, local_rank, world):
         act_host = np.zeros((B, 1, 4), np.int32)
 
         def host_policy(d, seed, base_, np_):
+            if bike:  # greedy top-1 (examples/citi_bike/greedy/launcher.py:35-65), vectorised
+                S = topo.n_stations
+                idx, val, n = d[:, 8:8 + 2 * S:2], d[:, 9:9 + 2 * S:2].astype(np.int64), d[:, 4:5]
+                ok = (np.arange(S)[None, :] < n) & (idx != d[:, 1:2])
+                key = np.where(ok, val * 4096 + idx, -1)
+                best = key.argmax(1)
+                rows = np.arange(B)
+                bi, bv = idx[rows, best], val[rows, best]
+                none = key[rows, best] < 0
+                supply = d[:, 3] == 0
+                act_host[:, 0, 0] = np.where(none, -1, np.where(supply, d[:, 1], bi))
+                act_host[:, 0, 1] = np.where(none, -1, np.where(supply, bi, d[:, 1]))
+                act_host[:, 0, 2] = np.where(none, 0, bv)
+                return act_host
             agent_lib.agent_random(d.ctypes.data, act_host.ctypes.data, B, 1, seed, base_)
             return act_host
 
         # the C agent and the numpy twin must agree (and both equal the device agent, tests/test_gpu_*)
         env.reset()
         d0, _ = env.step(None)
-        assert np.array_equal(host_policy(d0, 0, base, np), host_policy_numpy(d0, 0, base, np))
+        if not bike:
+            assert np.array_equal(host_policy(d0, 0, base, np), host_policy_numpy(d0, 0, base, np))
         env.reset()
         n_e2e = min(args.steps, 2000)
         d, m = env.step(None)
@@ -397,7 +449,7 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        F = F_DECLARED.get(args.topology, env.frame_words * 4)
+        F = 180 if bike else F_DECLARED.get(args.topology, env.frame_words * 4)  # SURVEY.md §8 frame bytes
         n_snap = g_snaps / max(1, g_steps)
         n_ev = g_events / max(1, g_steps)
         bytes_per_step = 2 * F + n_snap * F + 32 * n_ev + 64
@@ -407,15 +459,17 @@ def run_ours(args, rank, local_rank, world):
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"CIM {args.topology}, {B} parallel envs per GPU, {args.ticks} ticks, random actions "
-                                   f"(hashed hello-world agent), snapshot_resolution 1, max_snapshots "
-                                   f"{args.max_snapshots or 'all'}",
+            "config": {"workload": (f"citi_bike toy.3s_4t (frozen trace), {B} parallel envs per GPU, {topo.max_tick} ticks, greedy "
+                                    f"top-1 agent, snapshot_resolution 10, max_snapshots {args.max_snapshots or 'all'}") if bike else
+                                   (f"CIM {args.topology}, {B} parallel envs per GPU, {args.ticks} ticks, random actions "
+                                    f"(hashed hello-world agent), snapshot_resolution 1, max_snapshots "
+                                    f"{args.max_snapshots or 'all'}"),
                        "replicas_per_gpu": B, "l2": "state resident (no flush)" if args.no_flush else "flushed between timed steps (256 MiB write)",
                        "steps_per_episode": steps_per_episode},
             "ticks_per_s": g_ticks / (total_ms / 1000.0), "events_per_s": g_events / (total_ms / 1000.0),
             "wall_ms": wall_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "cim_step_kernel", "bytes_per_env_step": bytes_per_step,
+                         "traffic": None, "kernel": "bike_step_kernel" if bike else "cim_step_kernel", "bytes_per_env_step": bytes_per_step,
                          "n_snap": n_snap, "n_ev": n_ev, "kernel_us": 1000.0 * kernel_ms / args.steps,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "clocks": clocks,
@@ -423,7 +477,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
-                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * 56,
+                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + 24),
                            "api": "maro_cim_step (host buffers, agent = tools/host_agent.c on the host)",
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
@@ -431,7 +485,7 @@ def run_ours(args, rank, local_rank, world):
             line["graph_mode"] = {"value": g_graph_steps / (graph_ms / 1000.0), "unit": "env-steps/s",
                                   "chunk_steps": graph_info["chunk"], "us_per_step": 1000.0 * graph_ms / max(1, (args.steps // graph_info["chunk"]) * graph_info["chunk"]),
                                   "l2": "flushed between graph chunks"}
-        line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
+        line["cpu_baseline"] = (cpu_baseline_bike(args, topo) if bike else cpu_baseline_port(args, topo)) if world == 1 else None
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:

@@ -20,6 +20,10 @@ EXPORTS = (
     "maro_cim_query_device", "maro_cim_attr_id", "maro_cim_attr_slots", "maro_cim_read_frame",
     "maro_cim_frame_words", "maro_cim_ticks", "maro_cim_counters", "maro_cim_snapshot_frames",
     "maro_cim_random_policy_device",
+    "maro_bike_create", "maro_bike_destroy", "maro_bike_set_stream", "maro_bike_decision_words", "maro_bike_step",
+    "maro_bike_step_device", "maro_bike_reset", "maro_bike_query", "maro_bike_attr_id", "maro_bike_attr_slots",
+    "maro_bike_read_frame", "maro_bike_frame_words", "maro_bike_ticks", "maro_bike_counters", "maro_bike_snapshot_frames",
+    "maro_bike_greedy_policy_device",
 )
 
 
@@ -60,6 +64,26 @@ def lib():
     L.maro_cim_counters.argtypes = [vp, vp]
     L.maro_cim_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
     L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32]
+    L.maro_bike_create.argtypes = [vp, vp, C.POINTER(vp)]
+    L.maro_bike_destroy.argtypes = [vp]
+    L.maro_bike_set_stream.argtypes = [vp, vp, i32]
+    L.maro_bike_decision_words.argtypes = [vp]
+    L.maro_bike_decision_words.restype = i32
+    L.maro_bike_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.maro_bike_step_device.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.maro_bike_reset.argtypes = [vp, vp]
+    L.maro_bike_query.argtypes = [vp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+    L.maro_bike_attr_id.argtypes = [vp, i32, C.c_char_p]
+    L.maro_bike_attr_id.restype = i32
+    L.maro_bike_attr_slots.argtypes = [vp, i32, i32]
+    L.maro_bike_attr_slots.restype = i32
+    L.maro_bike_read_frame.argtypes = [vp, i32, vp, i32]
+    L.maro_bike_frame_words.argtypes = [vp]
+    L.maro_bike_frame_words.restype = i32
+    L.maro_bike_ticks.argtypes = [vp, vp]
+    L.maro_bike_counters.argtypes = [vp, vp]
+    L.maro_bike_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
+    L.maro_bike_greedy_policy_device.argtypes = [vp, vp, vp]
     if L.maro_abi_version() != _abi.ABI_VERSION:
         raise NativeLibraryError("libmaro_b200.so ABI version mismatch; rebuild")
     _lib = L

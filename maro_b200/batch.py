@@ -183,3 +183,132 @@ class CimBatch:
                     p += slots
             pos += 1
         return row
+
+
+class BikeBatch:
+    """Columnar wrapper over the citi_bike entry points of the C ABI (same shape as ``CimBatch``)."""
+
+    _NODE = {"stations": 0, "matrices": 1}
+
+    def __init__(self, topology, n_replicas: int, snapshot_resolution: int = 1, max_snapshots: Optional[int] = None,
+                 device: int = 0, max_actions: int = 1, queue_capacity: int = 0):
+        self.topology = topology
+        self.n_replicas, self.max_actions = int(n_replicas), int(max_actions)
+        L = _native.lib()
+        self._struct, self._keep = _abi.bike_topology_struct(topology)
+        cfg = _abi.MaroCimConfig()
+        cfg.n_replicas = self.n_replicas
+        cfg.start_tick = int(topology.start_tick)
+        cfg.snapshot_resolution = int(snapshot_resolution)
+        cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
+        cfg.device = int(device)
+        cfg.queue_capacity = int(queue_capacity)
+        cfg.max_actions = self.max_actions
+        h = C.c_void_p()
+        _native.check(L.maro_bike_create(C.byref(self._struct), C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.frame_words = L.maro_bike_frame_words(self._h)
+        self.dec_words = L.maro_bike_decision_words(self._h)
+        self.decisions = np.zeros((self.n_replicas, self.dec_words), np.int32)
+        self.metrics = np.zeros((self.n_replicas, 3), np.int64)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _native.lib().maro_bike_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        if cuda_stream_ptr is None:
+            _native.check(_native.lib().maro_bike_set_stream(self._h, None, 0))
+        else:
+            _native.check(_native.lib().maro_bike_set_stream(self._h, C.c_void_p(cuda_stream_ptr), 1))
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        _native.check(_native.lib().maro_bike_reset(self._h, None if m is None else m.ctypes.data))
+
+    def step(self, actions=None, n_actions=None, active=None):
+        a = n = m = None
+        if actions is not None:
+            a = np.ascontiguousarray(actions, np.int32)
+            assert a.size == self.n_replicas * self.max_actions * 4, a.shape
+        if n_actions is not None:
+            n = np.ascontiguousarray(n_actions, np.int32)
+        if active is not None:
+            m = np.ascontiguousarray(active, np.uint8)
+        _native.check(_native.lib().maro_bike_step(
+            self._h, None if m is None else m.ctypes.data, None if a is None else a.ctypes.data,
+            None if n is None else n.ctypes.data, self.decisions.ctypes.data, self.metrics.ctypes.data))
+        return self.decisions, self.metrics
+
+    def step_device(self, d_decisions: int, d_metrics: int, d_actions: int = 0, d_n_actions: int = 0, d_active: int = 0):
+        _native.check(_native.lib().maro_bike_step_device(self._h, d_active or None, d_actions or None,
+                                                          d_n_actions or None, d_decisions, d_metrics))
+
+    def greedy_policy_device(self, d_decisions: int, d_actions: int):
+        _native.check(_native.lib().maro_bike_greedy_policy_device(self._h, d_decisions, d_actions))
+
+    def attr_id(self, node: str, name: str) -> int:
+        i = _native.lib().maro_bike_attr_id(self._h, self._NODE[node], name.encode())
+        if i < 0:
+            raise KeyError(f"{node}.{name}")
+        return i
+
+    def attr_slots(self, node: str, attr_id: int) -> int:
+        return _native.lib().maro_bike_attr_slots(self._h, self._NODE[node], attr_id)
+
+    def query(self, node: str, frame_indices, nodes, attrs, replicas=None) -> np.ndarray:
+        reps = np.arange(self.n_replicas, dtype=np.int32) if replicas is None else np.ascontiguousarray(replicas, np.int32)
+        fr = np.ascontiguousarray(frame_indices, np.int32)
+        nd = np.ascontiguousarray(nodes, np.int32)
+        at = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id(node, a) for a in attrs], np.int32)
+        per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
+        out = np.zeros((len(reps), per), np.float64)
+        pr = C.c_int64()
+        _native.check(_native.lib().maro_bike_query(self._h, reps.ctypes.data, len(reps), self._NODE[node], fr.ctypes.data,
+                                                    len(fr), nd.ctypes.data, len(nd), at.ctypes.data, len(at),
+                                                    out.ctypes.data, C.byref(pr)))
+        return out
+
+    def read_frame(self, replica: int = 0) -> np.ndarray:
+        out = np.zeros(self.frame_words, np.int32)
+        _native.check(_native.lib().maro_bike_read_frame(self._h, replica, out.ctypes.data, out.size))
+        return out
+
+    def ticks(self) -> np.ndarray:
+        out = np.zeros(self.n_replicas, np.int32)
+        _native.check(_native.lib().maro_bike_ticks(self._h, out.ctypes.data))
+        return out
+
+    def counters(self) -> np.ndarray:
+        out = np.zeros((self.n_replicas, 4), np.int64)
+        _native.check(_native.lib().maro_bike_counters(self._h, out.ctypes.data))
+        return out
+
+    def snapshot_frames(self, replica: int = 0) -> np.ndarray:
+        cap = 1 << 16
+        out = np.zeros(cap, np.int32)
+        n = C.c_int32()
+        _native.check(_native.lib().maro_bike_snapshot_frames(self._h, replica, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def snapshot_row(self, frame_index: int, replica: int = 0):
+        if frame_index not in set(self.snapshot_frames(replica).tolist()):
+            return None
+        S = self.topology.n_stations
+        lay, fw = _abi.bike_frame_layout(S)
+        row = np.zeros(fw, np.int32)
+        names = list(lay["stations"])
+        vals = self.query("stations", [frame_index], np.arange(S), names, [replica])[0].reshape(S, len(names))
+        for k, a in enumerate(names):
+            off = lay["stations"][a][0]
+            row[off:off + S] = vals[:, k].astype(np.int64)
+        off, _, slots = lay["matrices"]["trips_adj"]
+        row[off:off + slots] = self.query("matrices", [frame_index], [0], ["trips_adj"], [replica])[0].astype(np.int64)
+        return row

@@ -24,6 +24,7 @@
 #include "../../include/maro_b200.h"
 #include "cim_core.cuh"
 #include "cim_host.hpp"
+#include "bike_host.hpp"
 
 using namespace maro;
 
@@ -218,17 +219,19 @@ static int fail(const std::string& m) { g_err = m; return 1; }
 
 struct AttrInfo { const char* name; int off, slots, isf, n_nodes; };
 
-struct MaroCimEnv {
-    CimShape s;
-    int device = 0, B = 0, K = 0, mt_words = 0, warps_per_cta = 4, lanes = 32, grid = 0, max_stops = 0, max_targets = 0, max_distinct = 0;
-    size_t smem_bytes = 0;
+// State shared by every scenario handle: device buffers of the replica blocks + snapshot ring, host-call staging,
+// query scratch, attribute registry.
+struct EnvCommon {
+    int device = 0, B = 0;
+    int ring_rows = 0, FW = 0, FWp = 0, SW = 0;
+    int off_tick = 0, off_counters = 0;  // word offsets inside a replica's state block
+    int dec_words = 8, max_actions = 1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    int32_t *d_state = nullptr, *d_snap = nullptr, *d_snap_frame = nullptr, *d_tables = nullptr, *d_topo = nullptr;
-    uint32_t* d_mt = nullptr;
+    int32_t *d_state = nullptr, *d_snap = nullptr, *d_snap_frame = nullptr;
     // host-call staging
     uint8_t* d_in = nullptr;   // [actions B*A*4 i32][n_actions B i32][active B u8]
-    uint8_t* d_out = nullptr;  // [decisions B*8 i32][metrics B*3 i64]
-    uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned mirrors (mapped into the device address space)
+    uint8_t* d_out = nullptr;  // [decisions B*dec_words i32][metrics B*3 i64]
+    uint8_t *h_in = nullptr, *h_out = nullptr;    // pinned mirrors (mapped into the device address space)
     uint8_t *hd_in = nullptr, *hd_out = nullptr;  // device aliases of h_in / h_out for the zero-copy path
     bool zero_copy = false;
     size_t in_bytes = 0, out_bytes = 0;
@@ -237,8 +240,125 @@ struct MaroCimEnv {
     double* d_qout = nullptr;
     size_t qout_cap = 0;
     std::vector<AttrInfo> attrs[3];
+    int n_node_types = 3;
+};
+
+struct MaroCimEnv : EnvCommon {
+    CimShape s;
+    int K = 0, mt_words = 0, warps_per_cta = 4, lanes = 32, grid = 0, max_stops = 0, max_targets = 0, max_distinct = 0;
+    size_t smem_bytes = 0;
+    int32_t *d_tables = nullptr, *d_topo = nullptr;
+    uint32_t* d_mt = nullptr;
     std::vector<int32_t> h_tables;
 };
+
+static void common_free(EnvCommon* e) {
+    cudaFree(e->d_state); cudaFree(e->d_snap); cudaFree(e->d_snap_frame);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_qidx); cudaFree(e->d_qout);
+    if (e->h_in) cudaFreeHost(e->h_in);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+}
+
+// stream + replica blocks + snapshot ring + host staging (sizes from B / SW / ring_rows / FWp / dec_words / max_actions)
+static int common_alloc(EnvCommon* e) {
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    const size_t B = (size_t)e->B;
+    CK(cudaMalloc(&e->d_state, B * e->SW * 4));
+    CK(cudaMalloc(&e->d_snap, B * e->ring_rows * e->FWp * 4));
+    CK(cudaMalloc(&e->d_snap_frame, B * e->ring_rows * 4));
+    e->in_bytes = B * e->max_actions * 16 + B * 4 + round_up(e->B, 16);
+    e->out_bytes = B * e->dec_words * 4 + B * 24;
+    CK(cudaMalloc(&e->d_in, e->in_bytes));
+    CK(cudaMalloc(&e->d_out, e->out_bytes));
+    CK(cudaHostAlloc(&e->h_in, e->in_bytes, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&e->h_out, e->out_bytes, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_in, e->h_in, 0));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_out, e->h_out, 0));
+    memset(e->h_out, 0, e->out_bytes);
+    CK(cudaMemset(e->d_out, 0, e->out_bytes));
+    // small batches: the kernel reads actions from / writes results to mapped pinned host memory (no copy engine
+    // round trips); large batches use bulk DMA copies.  MARO_B200_ZEROCOPY=0/1 overrides.
+    const char* z = getenv("MARO_B200_ZEROCOPY");
+    e->zero_copy = z ? atoi(z) != 0 : e->B <= 16384;
+    return 0;
+}
+
+// Host-buffer step shared by the scenarios: stage inputs, run `step_device`, fetch outputs, synchronise.
+template <class StepDevice>
+static int common_host_step(EnvCommon* e, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
+                            int32_t* decisions, int64_t* metrics, StepDevice step_device) {
+    const int B = e->B, A = e->max_actions;
+    const size_t act_bytes = (size_t)B * A * 16, nact_off = act_bytes, active_off = act_bytes + (size_t)B * 4;
+    const size_t dec_bytes = (size_t)B * e->dec_words * 4;
+    if (actions) memcpy(e->h_in, actions, act_bytes);
+    if (actions && n_actions) memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4);
+    if (active) memcpy(e->h_in + active_off, active, B);
+    uint8_t* in = e->zero_copy ? e->hd_in : e->d_in;
+    uint8_t* out = e->zero_copy ? e->hd_out : e->d_out;
+    if (!e->zero_copy) {
+        size_t lo = e->in_bytes, hi = 0;  // byte range of the staging buffer that must travel
+        if (actions) { lo = 0; hi = act_bytes; }
+        if (actions && n_actions) hi = nact_off + (size_t)B * 4;
+        if (active) { lo = std::min(lo, active_off); hi = active_off + B; }
+        if (hi > lo) CK(cudaMemcpyAsync(e->d_in + lo, e->h_in + lo, hi - lo, cudaMemcpyHostToDevice, e->stream));
+    }
+    int rc = step_device(active ? in + active_off : nullptr, actions ? reinterpret_cast<const int32_t*>(in) : nullptr,
+                         actions && n_actions ? reinterpret_cast<const int32_t*>(in + nact_off) : nullptr,
+                         reinterpret_cast<int32_t*>(out), reinterpret_cast<int64_t*>(out + dec_bytes));
+    if (rc) return rc;
+    if (!e->zero_copy) CK(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(decisions, e->h_out, dec_bytes);
+    memcpy(metrics, e->h_out + dec_bytes, (size_t)B * 24);
+    return 0;
+}
+
+static int common_read_frame(EnvCommon* e, int32_t replica, int32_t* out_words, int32_t n_words) {
+    if (!e || replica < 0 || replica >= e->B || !out_words || n_words < e->FW) return fail("read_frame: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out_words, e->d_state + (size_t)replica * e->SW, (size_t)e->FW * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int common_ticks(EnvCommon* e, int32_t* out_ticks) {
+    if (!e || !out_ticks) return fail("ticks: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy2D(out_ticks, 4, e->d_state + e->off_tick, (size_t)e->SW * 4, 4, e->B, cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int common_counters(EnvCommon* e, int64_t* out) {
+    if (!e || !out) return fail("counters: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy2D(out, 32, e->d_state + e->off_counters, (size_t)e->SW * 4, 32, e->B, cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int common_snapshot_frames(EnvCommon* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
+    if (!e || replica < 0 || replica >= e->B || !out || !n_out) return fail("snapshot_frames: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    std::vector<int32_t> rows(e->ring_rows);
+    CK(cudaMemcpy(rows.data(), e->d_snap_frame + (size_t)replica * e->ring_rows, rows.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> have;
+    for (int32_t f : rows) if (f >= 0) have.push_back(f);
+    std::sort(have.begin(), have.end());
+    *n_out = (int32_t)have.size();
+    for (int i = 0; i < (int)have.size() && i < cap; i++) out[i] = have[i];
+    return 0;
+}
+static int32_t common_attr_id(EnvCommon* e, int32_t node_type, const char* name) {
+    if (!e || node_type < 0 || node_type >= e->n_node_types || !name) return -1;
+    for (size_t i = 0; i < e->attrs[node_type].size(); i++)
+        if (!strcmp(e->attrs[node_type][i].name, name)) return (int32_t)i;
+    return -1;
+}
+static int32_t common_attr_slots(EnvCommon* e, int32_t node_type, int32_t attr_id) {
+    if (!e || node_type < 0 || node_type >= e->n_node_types || attr_id < 0 || attr_id >= (int)e->attrs[node_type].size()) return -1;
+    return e->attrs[node_type][attr_id].slots;
+}
 
 static void register_attrs(MaroCimEnv* e) {
     const CimShape& s = e->s;
@@ -311,11 +431,8 @@ int maro_abi_version(void) { return MARO_B200_ABI_VERSION; }
 int maro_cim_destroy(MaroCimEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaFree(e->d_state); cudaFree(e->d_snap); cudaFree(e->d_snap_frame); cudaFree(e->d_tables); cudaFree(e->d_topo);
-    cudaFree(e->d_mt); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_qidx); cudaFree(e->d_qout);
-    if (e->h_in) cudaFreeHost(e->h_in);
-    if (e->h_out) cudaFreeHost(e->h_out);
-    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt);
+    common_free(e);
     delete e;
     return 0;
 }
@@ -370,12 +487,11 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     int resident = std::max<int>(1, (int)std::min<size_t>(64 / w, sm_smem / (e->smem_bytes + 1024)));
     e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
 
-    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-    e->stream = e->own_stream;
+    e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
+    e->off_tick = s.FWp + C_TICK; e->off_counters = s.FWp + C_NSTEPS_LO;
+    e->dec_words = MARO_CIM_DECISION_WORDS; e->max_actions = s.max_actions;
+    if (common_alloc(e)) { maro_cim_destroy(e); return 1; }
     const int B = e->B;
-    CK(cudaMalloc(&e->d_state, (size_t)B * s.SW * 4));
-    CK(cudaMalloc(&e->d_snap, (size_t)B * s.ring_rows * s.FWp * 4));
-    CK(cudaMalloc(&e->d_snap_frame, (size_t)B * s.ring_rows * 4));
     CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
     CK(cudaMalloc(&e->d_topo, (size_t)B * 4));
     CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
@@ -390,21 +506,6 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
         e->mt_words = mt_block_words(s);
         CK(cudaMalloc(&e->d_mt, (size_t)B * e->mt_words * 4));
     }
-    e->in_bytes = (size_t)B * s.max_actions * 16 + (size_t)B * 4 + round_up(B, 16);
-    e->out_bytes = (size_t)B * 32 + (size_t)B * 24;
-    CK(cudaMalloc(&e->d_in, e->in_bytes));
-    CK(cudaMalloc(&e->d_out, e->out_bytes));
-    CK(cudaHostAlloc(&e->h_in, e->in_bytes, cudaHostAllocMapped));
-    CK(cudaHostAlloc(&e->h_out, e->out_bytes, cudaHostAllocMapped));
-    CK(cudaHostGetDevicePointer((void**)&e->hd_in, e->h_in, 0));
-    CK(cudaHostGetDevicePointer((void**)&e->hd_out, e->h_out, 0));
-    memset(e->h_out, 0, e->out_bytes);
-    {   // small batches: the kernel reads actions from / writes results to mapped pinned host memory (no copy engine
-        // round trips); large batches use bulk DMA copies.  MARO_B200_ZEROCOPY=0/1 overrides.
-        const char* z = getenv("MARO_B200_ZEROCOPY");
-        e->zero_copy = z ? atoi(z) != 0 : e->B <= 16384;
-    }
-    CK(cudaMemset(e->d_out, 0, e->out_bytes));
     *out = e;
     int rc = maro_cim_reset(e, nullptr);
     if (rc) { maro_cim_destroy(e); *out = nullptr; return rc; }
@@ -467,53 +568,18 @@ int maro_cim_step(MaroCimEnv* e, const uint8_t* active, const int32_t* actions, 
                   int32_t* decisions, int64_t* metrics) {
     if (!e || !decisions || !metrics) return fail("maro_cim_step: bad arguments");
     CK(cudaSetDevice(e->device));
-    const int B = e->B, A = e->s.max_actions;
-    const size_t act_bytes = (size_t)B * A * 16, nact_off = act_bytes, active_off = act_bytes + (size_t)B * 4;
-    if (actions) memcpy(e->h_in, actions, act_bytes);
-    if (actions && n_actions) memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4);
-    if (active) memcpy(e->h_in + active_off, active, B);
-    int rc;
-    if (e->zero_copy) {
-        rc = maro_cim_step_device(e, active ? e->hd_in + active_off : nullptr,
-                                  actions ? reinterpret_cast<const int32_t*>(e->hd_in) : nullptr,
-                                  actions && n_actions ? reinterpret_cast<const int32_t*>(e->hd_in + nact_off) : nullptr,
-                                  reinterpret_cast<int32_t*>(e->hd_out), reinterpret_cast<int64_t*>(e->hd_out + (size_t)B * 32));
-        if (rc) return rc;
-    } else {
-        size_t lo = e->in_bytes, hi = 0;  // byte range of the staging buffer that must travel
-        if (actions) { lo = 0; hi = act_bytes; }
-        if (actions && n_actions) hi = nact_off + (size_t)B * 4;
-        if (active) { lo = std::min(lo, active_off); hi = active_off + B; }
-        if (hi > lo) CK(cudaMemcpyAsync(e->d_in + lo, e->h_in + lo, hi - lo, cudaMemcpyHostToDevice, e->stream));
-        rc = maro_cim_step_device(e, active ? e->d_in + active_off : nullptr,
-                                  actions ? reinterpret_cast<const int32_t*>(e->d_in) : nullptr,
-                                  actions && n_actions ? reinterpret_cast<const int32_t*>(e->d_in + nact_off) : nullptr,
-                                  reinterpret_cast<int32_t*>(e->d_out), reinterpret_cast<int64_t*>(e->d_out + (size_t)B * 32));
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->stream));
-    }
-    CK(cudaStreamSynchronize(e->stream));
-    memcpy(decisions, e->h_out, (size_t)B * 32);
-    memcpy(metrics, e->h_out + (size_t)B * 32, (size_t)B * 24);
-    return 0;
+    return common_host_step(e, active, actions, n_actions, decisions, metrics,
+                            [&](const uint8_t* a, const int32_t* ac, const int32_t* na, int32_t* d, int64_t* m) {
+                                return maro_cim_step_device(e, a, ac, na, d, m);
+                            });
 }
 
-int32_t maro_cim_attr_id(MaroCimEnv* e, int32_t node_type, const char* name) {
-    if (!e || node_type < 0 || node_type > 2 || !name) return -1;
-    for (size_t i = 0; i < e->attrs[node_type].size(); i++)
-        if (!strcmp(e->attrs[node_type][i].name, name)) return (int32_t)i;
-    return -1;
-}
-int32_t maro_cim_attr_slots(MaroCimEnv* e, int32_t node_type, int32_t attr_id) {
-    if (!e || node_type < 0 || node_type > 2 || attr_id < 0 || attr_id >= (int)e->attrs[node_type].size()) return -1;
-    return e->attrs[node_type][attr_id].slots;
-}
 int32_t maro_cim_frame_words(MaroCimEnv* e) { return e ? e->s.FW : -1; }
 
-static int query_impl(MaroCimEnv* e, const int32_t* replicas, int32_t nr, int32_t node_type, const int32_t* frames,
+static int query_impl(EnvCommon* e, const int32_t* replicas, int32_t nr, int32_t node_type, const int32_t* frames,
                       int32_t nf, const int32_t* nodes, int32_t nn, const int32_t* attrs, int32_t na, double* d_out,
                       double* h_out, int64_t* out_per_replica) {
-    if (!e || node_type < 0 || node_type > 2 || nr < 1 || nf < 1 || nn < 1 || na < 1 || !replicas || !frames || !nodes || !attrs)
+    if (!e || node_type < 0 || node_type >= e->n_node_types || nr < 1 || nf < 1 || nn < 1 || na < 1 || !replicas || !frames || !nodes || !attrs)
         return fail("maro_cim_query: bad arguments");
     CK(cudaSetDevice(e->device));
     const auto& reg = e->attrs[node_type];
@@ -554,7 +620,7 @@ static int query_impl(MaroCimEnv* e, const int32_t* replicas, int32_t nr, int32_
     q.snap = e->d_snap; q.snap_frame = e->d_snap_frame;
     q.replicas = e->d_qidx; q.frames = q.replicas + nr; q.nodes = q.frames + nf;
     q.attr_off = q.nodes + nn; q.attr_slots = q.attr_off + na; q.attr_isf = q.attr_slots + na; q.attr_prefix = q.attr_isf + na;
-    q.nr = nr; q.nf = nf; q.nn = nn; q.na = na; q.slots_per_node = prefix; q.ring_rows = e->s.ring_rows; q.FWp = e->s.FWp;
+    q.nr = nr; q.nf = nf; q.nn = nn; q.na = na; q.slots_per_node = prefix; q.ring_rows = e->ring_rows; q.FWp = e->FWp;
     q.out = dst;
     int threads = 256;
     int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
@@ -579,42 +645,13 @@ int maro_cim_query_device(MaroCimEnv* e, const int32_t* replicas, int32_t n_repl
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, d_out, nullptr, out_per_replica);
 }
 
-int maro_cim_read_frame(MaroCimEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) {
-    if (!e || replica < 0 || replica >= e->B || !out_words || n_words < e->s.FW) return fail("maro_cim_read_frame: bad arguments");
-    CK(cudaSetDevice(e->device));
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(out_words, e->d_state + (size_t)replica * e->s.SW, (size_t)e->s.FW * 4, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-int maro_cim_ticks(MaroCimEnv* e, int32_t* out_ticks) {
-    if (!e || !out_ticks) return fail("maro_cim_ticks: bad arguments");
-    CK(cudaSetDevice(e->device));
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy2D(out_ticks, 4, e->d_state + e->s.FWp + C_TICK, (size_t)e->s.SW * 4, 4, e->B, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-int maro_cim_counters(MaroCimEnv* e, int64_t* out) {
-    if (!e || !out) return fail("maro_cim_counters: bad arguments");
-    CK(cudaSetDevice(e->device));
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy2D(out, 32, e->d_state + e->s.FWp + C_NSTEPS_LO, (size_t)e->s.SW * 4, 32, e->B, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
+int32_t maro_cim_attr_id(MaroCimEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
+int32_t maro_cim_attr_slots(MaroCimEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }
+int maro_cim_read_frame(MaroCimEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) { return common_read_frame(e, replica, out_words, n_words); }
+int maro_cim_ticks(MaroCimEnv* e, int32_t* out_ticks) { return common_ticks(e, out_ticks); }
+int maro_cim_counters(MaroCimEnv* e, int64_t* out) { return common_counters(e, out); }
 int maro_cim_snapshot_frames(MaroCimEnv* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
-    if (!e || replica < 0 || replica >= e->B || !out || !n_out) return fail("maro_cim_snapshot_frames: bad arguments");
-    CK(cudaSetDevice(e->device));
-    CK(cudaStreamSynchronize(e->stream));
-    std::vector<int32_t> rows(e->s.ring_rows);
-    CK(cudaMemcpy(rows.data(), e->d_snap_frame + (size_t)replica * e->s.ring_rows, rows.size() * 4, cudaMemcpyDeviceToHost));
-    std::vector<int32_t> have;
-    for (int32_t f : rows) if (f >= 0) have.push_back(f);
-    std::sort(have.begin(), have.end());
-    *n_out = (int32_t)have.size();
-    for (int i = 0; i < (int)have.size() && i < cap; i++) out[i] = have[i];
-    return 0;
+    return common_snapshot_frames(e, replica, out, cap, n_out);
 }
 
 int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t* d_actions, uint32_t seed,
@@ -623,6 +660,274 @@ int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int
     CK(cudaSetDevice(e->device));
     int threads = 256, blocks = (e->B + threads - 1) / threads;
     cim_policy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.max_actions, seed, replica_base);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// citi_bike scenario
+// =====================================================================================================
+struct BikeArgs {
+    int32_t* state;
+    int32_t* snap;
+    int32_t* snap_frame;
+    uint32_t* rng;
+    const int32_t* tables;
+    const uint8_t* active;
+    const int32_t* actions;
+    const int32_t* n_actions;
+    int32_t* decisions;
+    int64_t* metrics;
+};
+
+__device__ __forceinline__ BikeReplica make_bike_replica(const BikeShape& s, const BikeArgs& a, int rep, int32_t* st) {
+    BikeReplica r;
+    r.f = st;
+    r.c = st + s.FWp;
+    r.q = st + s.FWp + s.CWp;
+    r.t = a.tables;
+    r.rng = a.rng + (int64_t)rep * s.rng_words;
+    r.snap = a.snap + (int64_t)rep * s.ring_rows * s.FWp;
+    r.snap_frame = a.snap_frame + (int64_t)rep * s.ring_rows;
+    return r;
+}
+
+template <int kWarps, int G>
+__global__ void __launch_bounds__(kWarps * 32) bike_step_kernel(const __grid_constant__ BikeShape s,
+                                                                const __grid_constant__ BikeArgs a) {
+    constexpr int kGroups = kWarps * 32 / G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    const int gid = threadIdx.x / G;
+    const Grp<G> g(threadIdx.x & 31);
+    int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 256) + (size_t)gid * s.SW;
+    uint64_t* bar = bars + gid;
+    if (g.lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    g.sync();
+    uint32_t phase = 0;
+    const uint32_t bytes = (uint32_t)s.SW * 4u;
+    for (int rep = blockIdx.x * kGroups + gid; rep < s.n_replicas; rep += gridDim.x * kGroups) {
+        if (a.active && !a.active[rep]) {
+            if (g.lane == 0) a.decisions[(int64_t)rep * s.DW + 6] = MARO_STATUS_INACTIVE;
+            continue;
+        }
+        int32_t* gstate = a.state + (int64_t)rep * s.SW;
+        if (g.lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(st, gstate, bytes, bar);
+        }
+        while (!mbar_try_wait(bar, phase)) {}
+        phase ^= 1u;
+        BikeReplica r = make_bike_replica(s, a, rep, st);
+        const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), min(s.max_actions, G)) : 1) : 0;
+        Act4 act = {0, 0, 0, 0};
+        if (g.lane < n_act) {
+            int4 v = reinterpret_cast<const int4*>(a.actions + (int64_t)rep * s.max_actions * 4)[g.lane];
+            act.v = v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
+        }
+        bike_replica_step<G>(s, g, r, act, n_act, a.decisions + (int64_t)rep * s.DW, a.metrics + (int64_t)rep * 3);
+        const int4* src4 = reinterpret_cast<const int4*>(st);
+        int4* dst4 = reinterpret_cast<int4*>(gstate);
+        for (int i = g.lane; i < s.SW / 4; i += G) dst4[i] = src4[i];
+        g.sync();
+    }
+}
+
+__global__ void bike_reset_kernel(const __grid_constant__ BikeShape s, const __grid_constant__ BikeArgs a) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const Grp<32> g(threadIdx.x & 31);
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int rep = warp_global; rep < s.n_replicas; rep += n_warps) {
+        if (a.active && !a.active[rep]) continue;
+        BikeReplica r = make_bike_replica(s, a, rep, a.state + (int64_t)rep * s.SW);
+        bike_replica_reset<32>(s, g, r);
+    }
+}
+
+// greedy top-1 agent (examples/citi_bike/greedy/launcher.py:35-65 with supply_top_k = demand_top_k = 1)
+__global__ void bike_greedy_kernel(const int32_t* __restrict__ dec, int32_t* __restrict__ act, int n, int dw, int max_actions) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* d = dec + (int64_t)i * dw;
+    int station = d[1], ns = d[4], best = -1, best_v = 0;
+    for (int k = 0; k < ns; k++) {
+        int idx = d[8 + 2 * k], v = d[9 + 2 * k];
+        if (idx == station) continue;
+        if (best < 0 || v > best_v || (v == best_v && idx > best)) { best = idx; best_v = v; }
+    }
+    int4 o = best < 0 ? make_int4(-1, -1, 0, 0) : (d[3] == 0 ? make_int4(station, best, best_v, 0) : make_int4(best, station, best_v, 0));
+    *reinterpret_cast<int4*>(act + (int64_t)i * max_actions * 4) = o;
+}
+
+struct MaroBikeEnv : EnvCommon {
+    BikeShape s;
+    int warps_per_cta = 1, lanes = 8, grid = 0;
+    size_t smem_bytes = 0;
+    int32_t* d_tables = nullptr;
+    uint32_t* d_rng = nullptr;
+    std::vector<int32_t> h_tables;
+};
+
+static BikeArgs bike_base_args(MaroBikeEnv* e) {
+    BikeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.state = e->d_state; a.snap = e->d_snap; a.snap_frame = e->d_snap_frame; a.rng = e->d_rng; a.tables = e->d_tables;
+    return a;
+}
+
+template <int W, int G>
+static cudaError_t bike_launch_wg(MaroBikeEnv* e, const BikeArgs& a) {
+    cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    if (err != cudaSuccess) return err;
+    bike_step_kernel<W, G><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+    return cudaGetLastError();
+}
+template <int G>
+static cudaError_t bike_launch_g(MaroBikeEnv* e, const BikeArgs& a) {
+    switch (e->warps_per_cta) {
+        case 1: return bike_launch_wg<1, G>(e, a);
+        case 2: return bike_launch_wg<2, G>(e, a);
+        case 4: return bike_launch_wg<4, G>(e, a);
+        default: return bike_launch_wg<8, G>(e, a);
+    }
+}
+static cudaError_t bike_launch(MaroBikeEnv* e, const BikeArgs& a) {
+    switch (e->lanes) {
+        case 8: return bike_launch_g<8>(e, a);
+        case 16: return bike_launch_g<16>(e, a);
+        default: return bike_launch_g<32>(e, a);
+    }
+}
+
+extern "C" {
+
+int maro_bike_destroy(MaroBikeEnv* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_tables); cudaFree(e->d_rng);
+    common_free(e);
+    delete e;
+    return 0;
+}
+
+int maro_bike_reset(MaroBikeEnv* e, const uint8_t* mask) {
+    if (!e) return fail("null handle");
+    CK(cudaSetDevice(e->device));
+    BikeArgs a = bike_base_args(e);
+    if (mask) {
+        uint8_t* d_active = e->d_in + (size_t)e->B * e->max_actions * 16 + (size_t)e->B * 4;
+        memcpy(e->h_in, mask, e->B);
+        CK(cudaMemcpyAsync(d_active, e->h_in, e->B, cudaMemcpyHostToDevice, e->stream));
+        a.active = d_active;
+    }
+    int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
+    bike_reset_kernel<<<blocks, threads, 0, e->stream>>>(e->s, a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, MaroBikeEnv** out) {
+    if (!topo || !cfg || !out || cfg->n_replicas < 1) return fail("maro_bike_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("maro_bike_create: no CUDA device — this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("maro_bike_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    MaroBikeEnv* e = new MaroBikeEnv();
+    e->device = cfg->device;
+    e->B = cfg->n_replicas;
+    BikeShape& s = e->s;
+    if (bike_compute_shape_and_tables(*topo, cfg, s, e->h_tables)) { delete e; return fail("maro_bike_create: bad topology (1..255 stations, durations > 0)"); }
+    e->n_node_types = 2;
+    static const char* an[] = {"bikes", "capacity", "extra_cost", "failed_return", "fulfillment", "holiday", "id", "min_bikes",
+                               "shortage", "temperature", "transfer_cost", "trip_requirement", "weather", "weekday"};
+    for (int a = 0; a < BA_COUNT; a++) e->attrs[0].push_back({an[a], a * s.S, 1, 0, s.S});
+    e->attrs[1].push_back({"trips_adj", BA_COUNT * s.S, s.S * s.S, 0, 1});
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, e->device));
+    e->lanes = bike_lanes_per_replica(s);
+    const int gpw = 32 / e->lanes;
+    const size_t per_warp = (size_t)s.SW * 4 * gpw;
+    const size_t max_smem = prop.sharedMemPerBlockOptin, sm_smem = prop.sharedMemPerMultiprocessor;
+    if (256 + per_warp > max_smem) { delete e; return fail("maro_bike_create: replica state does not fit in shared memory"); }
+    int w = 1, best = 0;
+    for (int cand = 8; cand >= 1; cand >>= 1) {
+        size_t cta = 256 + per_warp * cand;
+        if (cta > max_smem) continue;
+        int blocks = (int)std::min<size_t>(sm_smem / (cta + 1024), (size_t)(32 / cand));
+        if (blocks * cand > best) { best = blocks * cand; w = cand; }
+    }
+    while (w > 1 && (e->B + w * gpw - 1) / (w * gpw) < prop.multiProcessorCount) w >>= 1;
+    e->warps_per_cta = w;
+    e->smem_bytes = 256 + per_warp * w;
+    int ctas_needed = (e->B + w * gpw - 1) / (w * gpw);
+    int resident = std::max<int>(1, (int)std::min<size_t>(32 / w, sm_smem / (e->smem_bytes + 1024)));
+    e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
+    e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
+    e->off_tick = s.FWp + BC_TICK; e->off_counters = s.FWp + BC_NSTEPS_LO;
+    e->dec_words = s.DW; e->max_actions = s.max_actions;
+    if (common_alloc(e)) { maro_bike_destroy(e); return 1; }
+    CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
+    CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&e->d_rng, (size_t)e->B * s.rng_words * 4));
+    *out = e;
+    int rc = maro_bike_reset(e, nullptr);
+    if (rc) { maro_bike_destroy(e); *out = nullptr; return rc; }
+    return 0;
+}
+
+int maro_bike_set_stream(MaroBikeEnv* e, void* cuda_stream, int32_t external) {
+    if (!e) return fail("null handle");
+    e->stream = external ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+int32_t maro_bike_decision_words(MaroBikeEnv* e) { return e ? e->s.DW : -1; }
+int32_t maro_bike_frame_words(MaroBikeEnv* e) { return e ? e->s.FW : -1; }
+
+int maro_bike_step_device(MaroBikeEnv* e, const uint8_t* d_active, const int32_t* d_actions, const int32_t* d_n_actions,
+                          int32_t* d_decisions, int64_t* d_metrics) {
+    if (!e || !d_decisions || !d_metrics) return fail("maro_bike_step_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    BikeArgs a = bike_base_args(e);
+    a.active = d_active; a.actions = d_actions; a.n_actions = d_n_actions; a.decisions = d_decisions; a.metrics = d_metrics;
+    CK(bike_launch(e, a));
+    return 0;
+}
+int maro_bike_step(MaroBikeEnv* e, const uint8_t* active, const int32_t* actions, const int32_t* n_actions, int32_t* decisions,
+                   int64_t* metrics) {
+    if (!e || !decisions || !metrics) return fail("maro_bike_step: bad arguments");
+    CK(cudaSetDevice(e->device));
+    return common_host_step(e, active, actions, n_actions, decisions, metrics,
+                            [&](const uint8_t* a, const int32_t* ac, const int32_t* na, int32_t* d, int64_t* m) {
+                                return maro_bike_step_device(e, a, ac, na, d, m);
+                            });
+}
+int maro_bike_query(MaroBikeEnv* e, const int32_t* replicas, int32_t n_replicas, int32_t node_type, const int32_t* frame_indices,
+                    int32_t n_frames, const int32_t* nodes, int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* out,
+                    int64_t* out_per_replica) {
+    if (!out) return fail("maro_bike_query: null output");
+    return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, nullptr, out, out_per_replica);
+}
+int32_t maro_bike_attr_id(MaroBikeEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
+int32_t maro_bike_attr_slots(MaroBikeEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }
+int maro_bike_read_frame(MaroBikeEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) { return common_read_frame(e, replica, out_words, n_words); }
+int maro_bike_ticks(MaroBikeEnv* e, int32_t* out_ticks) { return common_ticks(e, out_ticks); }
+int maro_bike_counters(MaroBikeEnv* e, int64_t* out) { return common_counters(e, out); }
+int maro_bike_snapshot_frames(MaroBikeEnv* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
+    return common_snapshot_frames(e, replica, out, cap, n_out);
+}
+int maro_bike_greedy_policy_device(MaroBikeEnv* e, const int32_t* d_decisions, int32_t* d_actions) {
+    if (!e || !d_decisions || !d_actions) return fail("maro_bike_greedy_policy_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    int threads = 256, blocks = (e->B + threads - 1) / threads;
+    bike_greedy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.DW, e->s.max_actions);
     CK(cudaGetLastError());
     return 0;
 }

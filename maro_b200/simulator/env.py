@@ -9,7 +9,7 @@ from typing import List, Optional
 import numpy as np
 
 from .. import _abi
-from ..batch import CimBatch
+from ..batch import BikeBatch, CimBatch
 from ..scenarios.cim.common import Action, ActionScope, ActionType, DecisionEvent, encode_action
 from ..scenarios.cim.topology import CimTopology, build_topology, load_config, next_topology_seed
 
@@ -56,12 +56,16 @@ class SnapshotNode:
 class SnapshotList:
     """Read-only façade over the device snapshot ring of one replica (frame.pyx:804-846)."""
 
-    def __init__(self, batch: CimBatch, replica: int):
+    def __init__(self, batch, replica: int):
         self._batch, self._replica = batch, replica
-        t = batch.topologies[0]
-        self._nodes = {"ports": SnapshotNode(self, "ports", t.n_ports),
-                       "vessels": SnapshotNode(self, "vessels", t.n_vessels),
-                       "matrices": SnapshotNode(self, "matrices", 1)}
+        if isinstance(batch, BikeBatch):
+            self._nodes = {"stations": SnapshotNode(self, "stations", batch.topology.n_stations),
+                           "matrices": SnapshotNode(self, "matrices", 1)}
+        else:
+            t = batch.topologies[0]
+            self._nodes = {"ports": SnapshotNode(self, "ports", t.n_ports),
+                           "vessels": SnapshotNode(self, "vessels", t.n_vessels),
+                           "matrices": SnapshotNode(self, "matrices", 1)}
 
     def __getitem__(self, name: str):
         return self._nodes.get(name)
@@ -121,8 +125,8 @@ class Env:
                  business_engine_cls: type = None, disable_finished_events: bool = False,
                  record_finished_events: bool = False, record_file_path: str = None, options: Optional[dict] = None,
                  device: int = 0):
-        if scenario != "cim":
-            raise NotImplementedError(f"scenario {scenario!r}: only 'cim' runs on the CUDA core in this build")
+        if scenario not in ("cim", "citi_bike"):
+            raise NotImplementedError(f"scenario {scenario!r}: 'cim' and 'citi_bike' run on the CUDA core in this build")
         if business_engine_cls is not None:
             raise NotImplementedError("custom business engines run on the reference Env, not on the CUDA core")
         if int(decision_mode) != int(DecisionMode.Sequential):
@@ -132,11 +136,19 @@ class Env:
         self._snapshot_resolution, self._max_snapshots = snapshot_resolution, max_snapshots
         self._device = device
         self._name = f"{scenario}:{topology}"
-        self._config = load_config(topology)
-        self._topo = build_topology(self._config, start_tick + durations)
         self._pending_seed: Optional[int] = None
-        self._batch = CimBatch(self._topo, 1, start_tick, snapshot_resolution, max_snapshots, device=device,
-                               max_actions=8)
+        if scenario == "citi_bike":
+            from ..scenarios.citi_bike.data import build_bike_topology, load_bike_config
+
+            self._config = load_bike_config(topology)
+            self._topo = build_bike_topology(self._config, start_tick, start_tick + durations,
+                                             transfer_seed=int((options or {}).get("transfer_seed", 0)))
+            self._batch = BikeBatch(self._topo, 1, snapshot_resolution, max_snapshots, device=device, max_actions=8)
+        else:
+            self._config = load_config(topology)
+            self._topo = build_topology(self._config, start_tick + durations)
+            self._batch = CimBatch(self._topo, 1, start_tick, snapshot_resolution, max_snapshots, device=device,
+                                   max_actions=8)
         self._snapshots = SnapshotList(self._batch, 0)
         self._tick = start_tick
         self._last_metrics = make_metrics((0, 0, 0))
@@ -154,7 +166,12 @@ class Env:
         if len(actions) > self._act.shape[1]:
             raise ValueError("too many actions for one decision event")
         for i, a in enumerate(actions):
-            encode_action(a, self._act[0, i])
+            if self._scenario == "citi_bike":
+                from ..scenarios.citi_bike.common import encode_bike_action
+
+                encode_bike_action(a, self._act[0, i])
+            else:
+                encode_action(a, self._act[0, i])
         self._nact[0] = len(actions)
         dec, met = self._batch.step(self._act, self._nact)
         d = dec[0]
@@ -166,6 +183,15 @@ class Env:
         if status == _abi.STATUS_FINISHED:
             return None, None, True
         self._tick = int(d[_abi.DEC_TICK])
+        if self._scenario == "citi_bike":
+            from ..scenarios.citi_bike.common import decode_bike_decision
+
+            self._last_metrics = DocableDict("citi_bike metrics", {"trip_requirements": int(met[0][0]),
+                                                                   "bike_shortage": int(met[0][1]),
+                                                                   "operation_number": int(met[0][2])})
+            if status == _abi.STATUS_DONE:
+                return self._last_metrics, None, True
+            return self._last_metrics, decode_bike_decision(d, self._snapshots), False
         self._last_metrics = make_metrics(met[0])
         if status == _abi.STATUS_DONE:
             return self._last_metrics, None, True
@@ -178,6 +204,10 @@ class Env:
     def reset(self, keep_seed: bool = False) -> None:
         """core.py:143-170 + cim_data_container_helpers.py:56-66: ``keep_seed=False`` draws a new topology seed from
         the route_init stream; a seed set with ``set_seed`` takes effect here."""
+        if self._scenario == "citi_bike":  # CitibikeBusinessEngine.set_seed is a no-op (business_engine.py:198-199)
+            self._batch.reset()
+            self._tick = self._start_tick
+            return
         seed = self._pending_seed
         if not keep_seed:
             seed = next_topology_seed(self._topo)
@@ -241,7 +271,7 @@ class Env:
 
     @property
     def agent_idx_list(self) -> List[int]:
-        return list(range(self._topo.n_ports))
+        return list(range(self._topo.n_stations if self._scenario == "citi_bike" else self._topo.n_ports))
 
     @property
     def metrics(self) -> dict:

@@ -11,7 +11,7 @@ from typing import List, Optional
 import numpy as np
 
 from .. import _abi
-from ..batch import CimBatch
+from ..batch import BikeBatch, CimBatch
 from ..scenarios.cim.common import ActionScope, DecisionEvent, encode_action
 from ..scenarios.cim.topology import build_topology, load_config
 from ..simulator.env import DecisionMode, SnapshotList, make_metrics
@@ -37,10 +37,19 @@ class VectorEnv:
                  decision_mode=DecisionMode.Sequential, business_engine_cls: type = None,
                  disable_finished_events: bool = False, options: dict = {}, device: int = 0, seeds=None):
         assert batch_num > 0
-        if scenario != "cim" or business_engine_cls is not None or int(decision_mode) != 0:
-            raise NotImplementedError("the CUDA core implements scenario='cim', Sequential mode")
+        if scenario not in ("cim", "citi_bike") or business_engine_cls is not None or int(decision_mode) != 0:
+            raise NotImplementedError("the CUDA core implements scenario='cim' / 'citi_bike', Sequential mode")
         self._batch_num = batch_num
+        self._scenario = scenario
         self._start_tick, self._resolution = start_tick, snapshot_resolution
+        if scenario == "citi_bike":
+            from ..scenarios.citi_bike.data import build_bike_topology, load_bike_config
+
+            topo = build_bike_topology(load_bike_config(topology), start_tick, start_tick + durations,
+                                       transfer_seed=int((options or {}).get("transfer_seed", 0)))
+            self._batch = BikeBatch(topo, batch_num, snapshot_resolution, max_snapshots, device=device, max_actions=4)
+            self._finish_init(batch_num, start_tick)
+            return
         conf = load_config(topology)
         if seeds is None:
             topos, rt = [build_topology(conf, start_tick + durations)], None
@@ -52,6 +61,9 @@ class VectorEnv:
             rt = np.asarray([uniq.index(s) for s in seeds], np.int32)
         self._batch = CimBatch(topos, batch_num, start_tick, snapshot_resolution, max_snapshots, device=device,
                                max_actions=4, replica_topology=rt)
+        self._finish_init(batch_num, start_tick)
+
+    def _finish_init(self, batch_num, start_tick):
         self._snapshot_wrapper = VectorEnv.SnapshotListWrapper(self)
         self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(batch_num)]
         self._done = np.zeros(batch_num, bool)
@@ -83,7 +95,12 @@ class VectorEnv:
             return
         acts = action if isinstance(action, list) else [action]
         for k, a in enumerate(acts):
-            encode_action(a, self._act[i, k])
+            if self._scenario == "citi_bike":
+                from ..scenarios.citi_bike.common import encode_bike_action
+
+                encode_bike_action(a, self._act[i, k])
+            else:
+                encode_action(a, self._act[i, k])
         self._nact[i] = len(acts)
 
     def step(self, action):
@@ -118,6 +135,17 @@ class VectorEnv:
                 events.append(None)
                 continue
             self._ticks[i] = dec[i, 0]
+            if self._scenario == "citi_bike":
+                from ..scenarios.citi_bike.common import decode_bike_decision
+
+                metrics.append({"trip_requirements": int(met[i, 0]), "bike_shortage": int(met[i, 1]),
+                                "operation_number": int(met[i, 2])})
+                if st == _abi.STATUS_DONE:
+                    self._done[i] = True
+                    events.append(None)
+                else:
+                    events.append(decode_bike_decision(dec[i], self._snapshot_lists[i]))
+                continue
             metrics.append(make_metrics(met[i]))
             if st == _abi.STATUS_DONE:
                 self._done[i] = True

@@ -89,3 +89,73 @@ int emul_read_snapshot(Emul* e, int rep, int frame, int32_t* out) {
 int emul_tick(Emul* e, int rep) { return e->state[(size_t)rep * e->s.SW + e->s.FWp + C_TICK]; }
 void emul_counters(Emul* e, int rep, int64_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW + e->s.FWp + C_NSTEPS_LO, 32); }
 }
+
+// ------------------------------------------------------------------------------------------------ citi_bike
+#include "../../maro_b200/csrc/bike_host.hpp"
+
+struct BikeEmul {
+    BikeShape s;
+    std::vector<int32_t> tables, state, snap, snap_frame;
+    std::vector<uint32_t> rng;
+    int B = 0, lanes = 8;
+};
+static BikeReplica bike_rep_of(BikeEmul* e, int i) {
+    BikeReplica r;
+    int32_t* st = e->state.data() + (size_t)i * e->s.SW;
+    r.f = st; r.c = st + e->s.FWp; r.q = st + e->s.FWp + e->s.CWp;
+    r.t = e->tables.data();
+    r.rng = e->rng.data() + (size_t)i * e->s.rng_words;
+    r.snap = e->snap.data() + (size_t)i * e->s.ring_rows * e->s.FWp;
+    r.snap_frame = e->snap_frame.data() + (size_t)i * e->s.ring_rows;
+    return r;
+}
+template <int G>
+static void bike_reset_g(BikeEmul* e, int i) {
+    BikeReplica r = bike_rep_of(e, i);
+    wemu::run_group(G, [&](int lane) { bike_replica_reset<G>(e->s, Grp<G>(lane), r); });
+}
+template <int G>
+static void bike_step_g(BikeEmul* e, int i, const int32_t* actp, int n, int32_t* dec, int64_t* met) {
+    BikeReplica r = bike_rep_of(e, i);
+    if (n > G) n = G;
+    wemu::run_group(G, [&](int lane) {
+        Act4 act = {0, 0, 0, 0};
+        if (lane < n) { act.v = actp[4 * lane]; act.p = actp[4 * lane + 1]; act.qty = actp[4 * lane + 2]; act.type = actp[4 * lane + 3]; }
+        bike_replica_step<G>(e->s, Grp<G>(lane), r, act, n, dec, met);
+    });
+}
+extern "C" {
+BikeEmul* bike_emul_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, int lanes) {
+    BikeEmul* e = new BikeEmul();
+    if (bike_compute_shape_and_tables(*topo, cfg, e->s, e->tables)) { delete e; return nullptr; }
+    e->B = cfg->n_replicas;
+    e->lanes = lanes > 0 ? lanes : bike_lanes_per_replica(e->s);
+    e->state.assign((size_t)e->B * e->s.SW, 0);
+    e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
+    e->snap_frame.assign((size_t)e->B * e->s.ring_rows, -1);
+    e->rng.assign((size_t)e->B * e->s.rng_words, 0);
+    for (int i = 0; i < e->B; i++) { if (e->lanes == 1) bike_reset_g<1>(e, i); else if (e->lanes == 8) bike_reset_g<8>(e, i); else bike_reset_g<32>(e, i); }
+    return e;
+}
+void bike_emul_destroy(BikeEmul* e) { delete e; }
+int bike_emul_dec_words(BikeEmul* e) { return e->s.DW; }
+int bike_emul_frame_words(BikeEmul* e) { return e->s.FW; }
+void bike_emul_step(BikeEmul* e, const int32_t* actions, const int32_t* n_actions, int32_t* decisions, int64_t* metrics) {
+    for (int i = 0; i < e->B; i++) {
+        int n = actions ? (n_actions ? n_actions[i] : 1) : 0;
+        const int32_t* act = actions ? actions + (size_t)i * e->s.max_actions * 4 : nullptr;
+        if (e->lanes == 1) bike_step_g<1>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3);
+        else if (e->lanes == 8) bike_step_g<8>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3);
+        else bike_step_g<32>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3);
+    }
+}
+void bike_emul_read_frame(BikeEmul* e, int rep, int32_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW, 4 * e->s.FW); }
+int bike_emul_read_snapshot(BikeEmul* e, int rep, int frame, int32_t* out) {
+    int row = frame % e->s.ring_rows;
+    if (frame < 0 || e->snap_frame[(size_t)rep * e->s.ring_rows + row] != frame) return 0;
+    memcpy(out, e->snap.data() + ((size_t)rep * e->s.ring_rows + row) * e->s.FWp, 4 * e->s.FW);
+    return 1;
+}
+int bike_emul_tick(BikeEmul* e, int rep) { return e->state[(size_t)rep * e->s.SW + e->s.FWp + BC_TICK]; }
+void bike_emul_counters(BikeEmul* e, int rep, int64_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW + e->s.FWp + BC_NSTEPS_LO, 32); }
+}

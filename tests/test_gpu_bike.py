@@ -1,0 +1,126 @@
+"""GPU (-m gpu): the citi_bike CUDA path through the C ABI against reference traces, the oracle and the reference's
+own known answers (tests/citi_bike/test_bike_scenario.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from bike_helpers import (BIKE_CASES, GOLDEN, assert_bike_snapshots_equal, bike_named_frames, bike_topology,
+                          drive_bike, greedy_py, load_bike_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(BIKE_CASES))
+def test_bike_cuda_matches_reference_trace(name):
+    from maro_b200.batch import BikeBatch
+
+    spec = BIKE_CASES[name]
+    topo = bike_topology(spec)
+    gold = load_bike_golden(name)
+    B = 5
+    env = BikeBatch(topo, B, spec["snapshot_resolution"], spec.get("max_snapshots"), max_actions=2)
+
+    def step_fn(act):
+        if act is None:
+            dec, met = env.step(None)
+        else:
+            a = np.zeros((B, 2, 4), np.int32)
+            a[:, :1] = np.asarray(act, np.int32).reshape(1, 1, 4)
+            dec, met = env.step(a, np.ones(B, np.int32))
+        assert (dec == dec[0]).all() and (met == met[0]).all()
+        return int(dec[0, 6]), dec[0].copy(), met[0].copy()
+
+    rows, scopes, final, st, dec = drive_bike(step_fn, spec, topo.n_stations)
+    assert rows.shape == gold["steps"].shape
+    if not np.array_equal(rows, gold["steps"]):
+        bad = np.argwhere(rows != gold["steps"])[0]
+        raise AssertionError(f"step {bad[0]} col {bad[1]}: got {rows[bad[0]]} want {gold['steps'][bad[0]]}")
+    assert np.array_equal(scopes, gold["scopes"])
+    assert final.tolist() == gold["final_metrics"].tolist()
+    assert env.ticks().tolist() == [int(gold["final_tick"])] * B and st == 1
+    assert step_fn(None)[0] == 2
+    assert env.snapshot_frames(B - 1).tolist() == gold["frames"].tolist()
+    assert_bike_snapshots_equal(lambda f: env.snapshot_row(f, B - 1), gold, topo.n_stations)
+    env.close()
+
+
+def test_bike_cuda_batch_matches_oracle_and_conserves_bikes():
+    """4096 replicas (BASELINE config #3 size), greedy agent on the device; replicas are identical by construction
+    (same trace, same transfer seed) -> all equal; one replayed on the oracle; bikes are conserved."""
+    import torch
+
+    from maro_b200.batch import BikeBatch
+    from oracle.bike_oracle import BikeOracle, policy_greedy
+
+    spec = BIKE_CASES["toy_1440_greedy_res10"]
+    topo = bike_topology(spec)
+    B = 4096
+    env = BikeBatch(topo, B, 10)
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    dec = torch.zeros((B, env.dec_words), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    o = BikeOracle(topo, 10)
+    n_total = o.run_episode(1)[0]
+    o.reset()
+    st, od, om = o.step(None)
+    env.step_device(dec.data_ptr(), met.data_ptr())
+    for k in range(n_total - 1):
+        d = dec.cpu().numpy()
+        assert (d == d[0]).all()
+        assert d[0].tolist() == od.tolist(), k
+        env.greedy_policy_device(dec.data_ptr(), act.data_ptr())
+        a = act[0, 0].cpu().numpy()
+        assert a.tolist() == policy_greedy(od).tolist()
+        st, od, om = o.step(a.reshape(1, 4))
+        env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+    torch.cuda.synchronize()
+    m = met.cpu().numpy()
+    assert (m == om).all() and st == 1
+    fr = bike_named_frames([env.read_frame(i) for i in (0, 77, B - 1)], topo.n_stations)
+    assert (fr["stations/bikes"] == fr["stations/bikes"][0]).all()
+    assert np.array_equal(env.read_frame(B - 1), o.frame())
+    assert env.counters()[5].tolist() == o.counters().tolist()
+    env.close()
+
+
+def test_bike_env_surface_like_reference_tests(tmp_path):
+    """Env("citi_bike", <folder>) drop-in: reference known answers of tests/citi_bike/test_bike_scenario.py
+    (case_1: bikes after ticks 0 / 1; case_2: shortage 2 / bikes 0 / trips 6 at tick 1)."""
+    import shutil
+
+    import yaml
+
+    from maro_b200.simulator import Env
+
+    for case in ("bike_case_1", "bike_case_2"):
+        src = os.path.join(GOLDEN, case)
+        folder = tmp_path / case
+        folder.mkdir()
+        with open(os.path.join(src, "decision.yml")) as fp:
+            conf = yaml.safe_load(fp)
+        conf.update(trip_data=os.path.join(src, "trips.bin"), weather_data=os.path.join(src, "weathers.bin"),
+                    stations_init_data=os.path.join(src, "stations.csv"), distance_adj_data=os.path.join(src, "distance_adj.csv"))
+        with open(folder / "config.yml", "w") as fp:
+            yaml.safe_dump(conf, fp)
+    env = Env("citi_bike", str(tmp_path / "bike_case_2"), durations=30, options={"transfer_seed": 2})
+    gold = load_bike_golden("case2_30_greedy")
+    metrics, ev, done = env.step(None)
+    k = 0
+    from maro_b200.scenarios.citi_bike.common import Action, DecisionType
+    while not done:
+        assert [ev.tick, ev.station_idx, ev.frame_index, 0 if ev.type == DecisionType.Supply else 1] == gold["steps"][k][:4].tolist()
+        assert {i: int(v) for i, v in enumerate(gold["scopes"][k]) if v >= 0} == ev.action_scope
+        assert list(ev.action_scope)[-1] == ev.station_idx
+        row = np.zeros(8 + 2 * 8, np.int32)
+        row[1], row[3], row[4] = ev.station_idx, 0 if ev.type == DecisionType.Supply else 1, len(ev.action_scope)
+        for j, (s_, v_) in enumerate(sorted(ev.action_scope.items())):
+            row[8 + 2 * j], row[9 + 2 * j] = s_, v_
+        a = greedy_py(row)
+        metrics, ev, done = env.step(Action(a[0], a[1], a[2]))
+        k += 1
+    assert dict(metrics) == {"trip_requirements": 9, "bike_shortage": 3, "operation_number": 11}
+    x = env.snapshot_list["stations"][1::["shortage", "bikes", "trip_requirement"]].reshape(-1, 3)
+    assert x[:, 0].sum() == gold["stations/shortage"][1].sum()
+    env.close()

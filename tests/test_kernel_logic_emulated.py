@@ -49,3 +49,30 @@ def test_emulated_counters_match_oracle():
     drive(lambda a: o.step(a), spec)
     assert e.counters().tolist() == o.counters().tolist()
     assert np.array_equal(e.frame(), o.frame())
+
+
+# ------------------------------------------------------------------------------------------------ citi_bike
+from bike_helpers import BIKE_CASES, assert_bike_snapshots_equal, bike_topology, drive_bike, load_bike_golden  # noqa: E402
+from emul import BikeEmulEnv  # noqa: E402
+from oracle.bike_oracle import BikeOracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name,lanes", [(n, 0) for n in sorted(BIKE_CASES)] + [("toy_600_greedy_res1", 1), ("toy_600_greedy_res1", 32)])
+def test_emulated_bike_kernel_matches_reference_trace(name, lanes):
+    spec = BIKE_CASES[name]
+    topo = bike_topology(spec)
+    gold = load_bike_golden(name)
+    e = BikeEmulEnv(topo, spec["snapshot_resolution"], spec.get("max_snapshots"), lanes=lanes)
+    rows, scopes, final, st, dec = drive_bike(lambda a: e.step1(a), spec, topo.n_stations)
+    assert rows.shape == gold["steps"].shape
+    if not np.array_equal(rows, gold["steps"]):
+        bad = np.argwhere(rows != gold["steps"])[0]
+        raise AssertionError(f"step {bad[0]} col {bad[1]}: got {rows[bad[0]]} want {gold['steps'][bad[0]]}")
+    assert np.array_equal(scopes, gold["scopes"])
+    assert final.tolist() == gold["final_metrics"].tolist()
+    assert e.tick() == int(gold["final_tick"]) and st == 1
+    assert e.step1(None)[0] == 2
+    assert_bike_snapshots_equal(e.snapshot, gold, topo.n_stations)
+    o = BikeOracle(topo, spec["snapshot_resolution"], spec.get("max_snapshots"))
+    drive_bike(lambda a: o.step(a), spec, topo.n_stations)
+    assert e.counters().tolist() == o.counters().tolist()
