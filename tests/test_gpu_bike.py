@@ -81,7 +81,9 @@ def test_bike_cuda_batch_matches_oracle_and_conserves_bikes():
     fr = bike_named_frames([env.read_frame(i) for i in (0, 77, B - 1)], topo.n_stations)
     assert (fr["stations/bikes"] == fr["stations/bikes"][0]).all()
     assert np.array_equal(env.read_frame(B - 1), o.frame())
-    assert env.counters()[5].tolist() == o.counters().tolist()
+    o2 = BikeOracle(topo, 10)
+    o2.run_episode(1)
+    assert env.counters()[5].tolist() == o2.counters().tolist()
     env.close()
 
 
