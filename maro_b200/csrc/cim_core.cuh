@@ -152,6 +152,9 @@ __device__ __forceinline__ int maro_clz(uint32_t x) { return __clz((int)x); }
 #endif
 
 #define LANE_LOOP(i, n) for (int i = g.lane; i < (n); i += G)
+// loop over a topology dimension (ports, vessels, ...): groups narrower than a warp are sized >= every such dimension
+// (lanes_per_replica), so the loop is a single predicated pass there
+#define LANE_DIM(i, n) for (int i = g.lane; i < (n); i += (G < 32 ? 0x40000000 : G))
 
 // inclusive prefix sum over the lanes of a group
 template <int G>
@@ -190,8 +193,9 @@ enum Ctrl {
     C_OPNUM_LO, C_OPNUM_HI, C_MT_ORDER_IDX, C_MT_BUFFER_IDX,
     C_NSTEPS_LO, C_NSTEPS_HI, C_NTICKS_LO, C_NTICKS_HI, C_NEVENTS_LO, C_NEVENTS_HI, C_NSNAPS_LO, C_NSNAPS_HI,
     C_LAST_FRAME, C_N_ORDERS, C_EP_STEP, C_RESERVED2,
-    C_FIXED  // followed by dep_cursor[V]
+    C_FIXED  // followed by dep_cursor[V], next_dep_tick[V], next_arr_tick[V]
 };
+#define NO_TICK 0x7fffffff
 enum State { ST_START = 0, ST_TICK_BEGIN = 1, ST_DECISIONS = 2, ST_AWAIT = 3, ST_DONE = 4, ST_FINISHED = 5, ST_ERROR = 6 };
 enum DynEv { DE_RETURN_FULL = 0, DE_DISCHARGE_FULL = 1, DE_RETURN_EMPTY = 2 };
 
@@ -843,38 +847,42 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
     for (;;) {
         if (state == ST_TICK_BEGIN) {
             nticks++;
-            // ---- BusinessEngine.step(tick), arrival part (business_engine.py:145-199): which vessels arrive now
-            uint32_t alo = 0, ahi = 0;
+            // ---- BusinessEngine.step(tick), arrival part (business_engine.py:145-199) + (a) the departures
+            // pre-inserted at init (:371-379): one lane per vessel.  The tick of each vessel's next arrival /
+            // departure is cached in the control block (updated when they fire), so an idle tick costs two
+            // shared-memory compares per vessel and no table walk.  Arrivals are tested on the state at tick start
+            // (before this tick's departures), like step().
             int total_empty = 0;
-            LANE_LOOP(v, s.V) {
-                int loc = VA(s, r, VA_NEXT_LOC_IDX, v);
-                int si = TBL_I(r, s.t_stop_offset, v) + loc;
-                if (loc > 0 && TBL_I(r, s.t_stop_arrival, si) == tick) {
-                    if (v < 32) alo |= 1u << v; else ahi |= 1u << (v - 32);
+            int ndep = 0;
+            arr = 0;
+            for (int b0 = 0; b0 < s.V; b0 += G) {
+                const int v = b0 + g.lane;
+                const bool in = v < s.V;
+                const bool arrives = in && r.c[C_FIXED + 2 * s.V + v] == tick;
+                if (arrives) {
+                    int si = TBL_I(r, s.t_stop_offset, v) + VA(s, r, VA_NEXT_LOC_IDX, v);
                     r.f[s.o_vp + v * s.P + TBL_I(r, s.t_stop_port, si)] = tick;
+                    r.c[C_FIXED + 2 * s.V + v] = NO_TICK;
                 }
-                if (kGeneral && s.order_mode == 1) total_empty += VA(s, r, VA_EMPTY, v);
+                if (kGeneral && s.order_mode == 1 && in) total_empty += VA(s, r, VA_EMPTY, v);
+                const bool departs = in && r.c[C_FIXED + s.V + v] == tick;
+                if (departs) {
+                    on_departure(s, r, v);
+                    int dc = r.c[C_FIXED + v] + 1;
+                    r.c[C_FIXED + v] = dc;
+                    int sb = TBL_I(r, s.t_stop_offset, v), ns = TBL_I(r, s.t_stop_offset, v + 1) - sb;
+                    r.c[C_FIXED + s.V + v] = dc < ns ? TBL_I(r, s.t_stop_leave, sb + dc) : NO_TICK;
+                    int nl = VA(s, r, VA_NEXT_LOC_IDX, v);
+                    r.c[C_FIXED + 2 * s.V + v] = nl < ns ? TBL_I(r, s.t_stop_arrival, sb + nl) : NO_TICK;
+                }
+                arr |= (uint64_t)g.ballot(arrives) << b0;
+                ndep += maro_popc(g.ballot(departs));
             }
             if (kGeneral && s.order_mode == 1) {
                 LANE_LOOP(p, s.P) total_empty += PA(s, r, PA_EMPTY, p);
                 total_empty = g.sum(total_empty);
             }
-            alo = g.or32(alo);
-            ahi = s.V > 32 ? g.or32(ahi) : 0u;
-            arr = ((uint64_t)ahi << 32) | alo;
-            // ---- (a) departures pre-inserted at init (business_engine.py:371-379): one lane per vessel
-            int ndep = 0;
-            LANE_LOOP(v, s.V) {
-                int dc = r.c[C_FIXED + v];
-                int sb = TBL_I(r, s.t_stop_offset, v);
-                int ns = TBL_I(r, s.t_stop_offset, v + 1) - sb;
-                if (dc < ns && TBL_I(r, s.t_stop_leave, sb + dc) == tick) {
-                    on_departure(s, r, v);
-                    r.c[C_FIXED + v] = dc + 1;
-                    ndep++;
-                }
-            }
-            nev += g.sum(ndep);
+            nev += ndep;
             g.sync();
             // ---- (b) events queued by earlier ticks
             nev += run_bucket<G, kGeneral>(s, g, r, tick);
@@ -927,9 +935,9 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
         // ---- post_step (business_engine.py:201-224)
         if (s.res_is_one || (tick + 1) % s.resolution == 0) {
             g.sync();
-            LANE_LOOP(p, s.P) PA(s, r, PA_ACC_FULFILLMENT, p) = PA(s, r, PA_ACC_BOOKING, p) - PA(s, r, PA_ACC_SHORTAGE, p);
+            LANE_DIM(p, s.P) PA(s, r, PA_ACC_FULFILLMENT, p) = PA(s, r, PA_ACC_BOOKING, p) - PA(s, r, PA_ACC_SHORTAGE, p);
             take_snapshot(s, g, r, frame_index_of(s, tick));
-            LANE_LOOP(p, s.P) {
+            LANE_DIM(p, s.P) {
                 PA(s, r, PA_SHORTAGE, p) = 0;
                 PA(s, r, PA_BOOKING, p) = 0;
                 PA(s, r, PA_FULFILLMENT, p) = 0;
@@ -950,9 +958,14 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
     // ---- metrics (business_engine.py:270-282) + control write-back
     g.sync();
     int64_t bk = 0, sh = 0;
-    LANE_LOOP(p, s.P) { bk += PA(s, r, PA_ACC_BOOKING, p); sh += PA(s, r, PA_ACC_SHORTAGE, p); }
-    bk = g.sum64(bk);
-    sh = g.sum64(sh);
+    if (s.P <= 8) {  // few ports: the leader adds them up itself (cheaper than two 64-bit shuffle reductions)
+        if (g.lane == 0)
+            for (int p = 0; p < s.P; p++) { bk += PA(s, r, PA_ACC_BOOKING, p); sh += PA(s, r, PA_ACC_SHORTAGE, p); }
+    } else {
+        LANE_LOOP(p, s.P) { bk += PA(s, r, PA_ACC_BOOKING, p); sh += PA(s, r, PA_ACC_SHORTAGE, p); }
+        bk = g.sum64(bk);
+        sh = g.sum64(sh);
+    }
     if (g.lane == 0) {
         int err = r.c[C_ERR];
         if (err == -2) { state = ST_ERROR; status = -2; }
@@ -1000,6 +1013,8 @@ MARO_DEV void replica_reset(const CimShape& s, const Grp<G>& g, const Replica& r
         int dc = 0;
         while (dc < ns && TBL_I(r, s.t_stop_leave, sb + dc) < s.start_tick) dc++;
         r.c[C_FIXED + v] = dc;
+        r.c[C_FIXED + s.V + v] = dc < ns ? TBL_I(r, s.t_stop_leave, sb + dc) : NO_TICK;
+        r.c[C_FIXED + 2 * s.V + v] = NO_TICK;  // next_loc_idx == 0: no arrival until the first departure
     }
     // queue: all slots on the free stack (slot 0 on top so that allocation order is ascending), empty buckets
     uint16_t* fs = q_free(s, r);

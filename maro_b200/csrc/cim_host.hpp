@@ -229,7 +229,7 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
     s.o_vp = s.o_fov + V * P;
     s.FW = s.o_vp + V * P;
     s.FWp = round_up(s.FW, 4);
-    s.CWp = round_up(C_FIXED + V, 4);
+    s.CWp = round_up(C_FIXED + 3 * V, 4);
     int qh = 16;
     while (qh < max_delay + 1) qh <<= 1;
     s.QH = qh;
