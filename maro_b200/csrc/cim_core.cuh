@@ -154,7 +154,11 @@ __device__ __forceinline__ int maro_clz(uint32_t x) { return __clz((int)x); }
 #define LANE_LOOP(i, n) for (int i = g.lane; i < (n); i += G)
 // loop over a topology dimension (ports, vessels, ...): groups narrower than a warp are sized >= every such dimension
 // (lanes_per_replica), so the loop is a single predicated pass there
+#ifdef MARO_HOST_EMULATION  // the tests also run widths narrower than the topology to exercise every chunk loop
+#define LANE_DIM(i, n) LANE_LOOP(i, n)
+#else
 #define LANE_DIM(i, n) for (int i = g.lane; i < (n); i += (G < 32 ? 0x40000000 : G))
+#endif
 
 // inclusive prefix sum over the lanes of a group
 template <int G>
