@@ -585,7 +585,8 @@ MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, in
     return nev;
 }
 
-// Noisy order generation (leader lane, float64): CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398).
+// Reference form of the order generator (leader lane, float64; kept as the readable statement of the algorithm that
+// gen_orders_coop distributes over the lanes): CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398).
 // Writes {src | dst << 8, qty} pairs to `out` and returns the count.  Scratch doubles live in the MT block.
 MARO_DEV int gen_orders_serial(const CimShape& s, const Replica& r, int tick, int total_empty, int32_t* out, double* dscr) {
     int orders_to_gen = TBL_I(r, s.t_order_proportion, tick);
@@ -632,6 +633,127 @@ MARO_DEV int gen_orders_serial(const CimShape& s, const Replica& r, int tick, in
         }
     }
     return n;
+}
+
+
+// Cooperative noisy order generation: the same arithmetic as gen_orders_serial, spread over the lane group.
+// Exactness notes: (i) every python `sum()` stays a left-to-right float64 chain (one lane per chain: the source total
+// on the leader, each port's target total on that port's lane); (ii) the running-remainder clamps are integer scans done
+// sequentially per chain; (iii) MT19937 draws are addressed by rank: P source draws, then the targets of every port
+// before the `remaining == 0` break — those ports are a prefix, so their targets are a prefix of the flattened target
+// table and target i is draw P + i.  Scratch layout (global, per replica): srcd[P] | tgtd[T] doubles, then ints.
+template <int G>
+MARO_DEV int gen_orders_coop(const CimShape& s, const Grp<G>& g, const Replica& r, int tick, int total_empty,
+                             int32_t* out, double* dscr) {
+    int orders_to_gen = TBL_I(r, s.t_order_proportion, tick);
+    if (s.order_mode == 1) {
+        int delta = s.total_containers - total_empty;
+        if (orders_to_gen <= delta) return 0;
+        orders_to_gen -= delta;
+    }
+    const int P = s.P;
+    double* srcd = dscr;
+    double* tgtd = dscr + P;
+    double* bcast = dscr + P + ((s.max_targets + 1) & ~1);      // one float64 broadcast slot
+    int32_t* isc = reinterpret_cast<int32_t*>(bcast + 1);       // ints: cur[P] | c2[T] | cnt[P]
+    int32_t* cur = isc;
+    int32_t* c2 = isc + P;
+    int32_t* cnt = c2 + s.max_targets;
+    // ---- 1. noised source shares (draw p = rank p)
+    for (int p0 = 0; p0 < P; p0 += G) {
+        int nv = P - p0 < G ? P - p0 : G;
+        int p = p0 + g.lane;
+        if (s.order_noise) {
+            MtView mv = mt_reserve(s, g, r, 0, 2 * nv);
+            if (p < P) srcd[p] = noised(TBL_D(r, s.t_sb_d, p), TBL_D(r, s.t_sn_d, p), mt_uniform01(mv.at(2 * g.lane), mv.at(2 * g.lane + 1)));
+        } else if (p < P) {
+            srcd[p] = TBL_D(r, s.t_sb_d, p) + 0.0;
+        }
+    }
+    g.sync();
+    // ---- 2. total (left to right) + per-port ceil, then the sequential clamp; `pb` = first port not reached (break)
+    if (g.lane == 0) {
+        double tot = 0.0;
+        for (int p = 0; p < P; p++) tot = tot + srcd[p];
+        *bcast = tot;
+    }
+    g.sync();
+    const double tot = *bcast;
+    for (int p0 = 0; p0 < P; p0 += G) {
+        int p = p0 + g.lane;
+        if (p < P) {
+            double sp = srcd[p];
+            if (tot != 0.0) sp = sp / tot;
+            cur[p] = (int)maro_ceil((double)orders_to_gen * sp);
+        }
+    }
+    g.sync();
+    if (g.lane == 0) {
+        int remaining = orders_to_gen, pb = P;
+        for (int p = 0; p < P; p++) {
+            if (remaining == 0) { pb = p; break; }
+            int c = cur[p];
+            if (c > remaining) c = remaining;
+            remaining -= c;
+            cur[p] = c;
+        }
+        r.c[C_N_ORDERS] = pb;
+    }
+    g.sync();
+    const int pb = r.c[C_N_ORDERS];
+    const int T = TBL_I(r, s.t_target_offset, pb);  // targets of ports [0, pb) are drawn
+    // ---- 3. noised target shares (draw P + i)
+    for (int i0 = 0; i0 < T; i0 += G) {
+        int nv = T - i0 < G ? T - i0 : G;
+        int i = i0 + g.lane;
+        if (s.order_noise) {
+            MtView mv = mt_reserve(s, g, r, 0, 2 * nv);
+            if (i < T) tgtd[i] = noised(TBL_D(r, s.t_tb_d, i), TBL_D(r, s.t_tn_d, i), mt_uniform01(mv.at(2 * g.lane), mv.at(2 * g.lane + 1)));
+        } else if (i < T) {
+            tgtd[i] = TBL_D(r, s.t_tb_d, i) + 0.0;
+        }
+    }
+    g.sync();
+    // ---- 4. one lane per port: target total (left to right), per-target ceil + clamp, order count
+    for (int p0 = 0; p0 < pb; p0 += G) {
+        int p = p0 + g.lane;
+        if (p < pb) {
+            int lo = TBL_I(r, s.t_target_offset, p), hi = TBL_I(r, s.t_target_offset, p + 1);
+            double ttot = 0.0;
+            for (int i = lo; i < hi; i++) ttot = ttot + tgtd[i];
+            int c = cur[p], trem = c, n = 0;
+            for (int i = lo; i < hi; i++) {
+                int num = 0;
+                if (c > 0) {
+                    double tp = tgtd[i];
+                    if (ttot != 0.0) tp = tp / ttot;
+                    num = (int)maro_ceil((double)c * tp);
+                    if (num > trem) num = trem;
+                    trem -= num;
+                }
+                c2[i] = num;
+                n += num > 0;
+            }
+            cnt[p] = n;
+        }
+    }
+    g.sync();
+    // ---- 5. compact the orders in (port, target) order
+    int base = 0;
+    for (int p0 = 0; p0 < pb; p0 += G) {
+        int p = p0 + g.lane;
+        int n = p < pb ? cnt[p] : 0;
+        int incl = scan_incl(g, n);
+        int at = base + incl - n;
+        if (p < pb && n > 0) {
+            int lo = TBL_I(r, s.t_target_offset, p), hi = TBL_I(r, s.t_target_offset, p + 1);
+            for (int i = lo; i < hi; i++)
+                if (c2[i] > 0) { out[2 * at] = p | (TBL_I(r, s.t_target_port, i) << 8); out[2 * at + 1] = c2[i]; at++; }
+        }
+        base += g.shfl(incl, G - 1);
+    }
+    g.sync();
+    return base;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -901,9 +1023,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
                 int32_t* olist = reinterpret_cast<int32_t*>(r.mt + s.mt_scratch + 64);
                 double* dscr = reinterpret_cast<double*>(olist + 2 * ((s.max_targets + 1) & ~1));
                 g.sync();
-                if (g.lane == 0) r.c[C_N_ORDERS] = gen_orders_serial(s, r, tick, total_empty, olist, dscr);
-                g.sync();
-                int n = r.c[C_N_ORDERS];
+                int n = gen_orders_coop(s, g, r, tick, total_empty, olist, dscr);
                 nev += run_orders<G, kGeneral>(s, g, r, tick, n, [&](int i, int& w, int& q) { w = olist[2 * i]; q = olist[2 * i + 1]; });
             }
             g.sync();

@@ -263,7 +263,8 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
 // words of one replica's MT block: 2 states | 64 tail scratch | order list | float64 scratch
 inline int mt_block_words(const CimShape& s) {
     int mt_even = (s.max_targets + 1) & ~1;
-    return round_up(2 * 640 + 64 + 2 * mt_even + 2 * (s.P + mt_even) + 8, 4);
+    // 2 MT states | 64 tail scratch | order list (2 words / target) | doubles srcd[P] tgtd[T] | ints cur[P] c2[T] cnt[P]
+    return round_up(2 * 640 + 64 + 2 * mt_even + 2 * (s.P + mt_even) + (2 * s.P + mt_even) + 2 + 16, 4);
 }
 
 // lanes per replica: smallest power of two >= the widest cooperative phase of the topology (>= 8)
