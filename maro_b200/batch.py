@@ -134,6 +134,24 @@ class CimBatch:
         assert pr.value == per
         return out
 
+    def query_device(self, node: str, frame_indices, nodes, attrs, replicas=None):
+        """Same gather as ``query`` but the result stays in HBM: returns a torch float64 CUDA tensor
+        [n_replicas_queried, per_replica] (state / reward shaping without a host round trip)."""
+        import torch
+
+        reps = np.arange(self.n_replicas, dtype=np.int32) if replicas is None else np.ascontiguousarray(replicas, np.int32)
+        fr = np.ascontiguousarray(frame_indices, np.int32)
+        nd = np.ascontiguousarray(nodes, np.int32)
+        at = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id(node, a) for a in attrs], np.int32)
+        per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
+        out = torch.empty((len(reps), per), dtype=torch.float64, device=f"cuda:{self.device}")
+        pr = C.c_int64()
+        _native.check(_native.lib().maro_cim_query_device(self._h, reps.ctypes.data, len(reps), _NODE_TYPE[node],
+                                                          fr.ctypes.data, len(fr), nd.ctypes.data, len(nd), at.ctypes.data,
+                                                          len(at), out.data_ptr(), C.byref(pr)))
+        assert pr.value == per
+        return out
+
     def read_frame(self, replica: int = 0) -> np.ndarray:
         out = np.zeros(self.frame_words, np.int32)
         _native.check(_native.lib().maro_cim_read_frame(self._h, replica, out.ctypes.data, out.size))

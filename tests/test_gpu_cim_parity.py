@@ -205,3 +205,26 @@ def test_cuda_full_size_properties():
         for f in (999, 980, 936):
             assert np.array_equal(env.snapshot_row(f, i), o.snapshot(f))
     env.close()
+
+
+def test_cuda_query_device_matches_host_query():
+    """snapshot_list gather left in HBM: the RL state of examples/cim/rl/config.py:10-36
+    (7 look-back ticks x ports x 7 attrs) for every replica at once equals the host query, zero padding included."""
+    import torch
+
+    from maro_b200.scenarios.cim.topology import build_topology
+
+    topo = build_topology("toy.4p_ssdd_l0.0", 120)
+    env = _batch(topo, 64, max_snapshots=16)
+    dec, met = env.step(None)
+    for _ in range(40):
+        dec, met = env.step(None)
+    tick = int(dec[0, 0])
+    frames = [max(tick - k, -1) if tick - k >= 0 else 10 ** 6 for k in (16, 8, 4, 2, 1, 0, 40)]  # includes evicted frames
+    attrs = ["empty", "full", "on_shipper", "on_consignee", "booking", "shortage", "fulfillment"]
+    host = env.query("ports", frames, [0, 1, 2, 3], attrs)
+    dev = env.query_device("ports", frames, [0, 1, 2, 3], attrs)
+    assert dev.is_cuda and dev.dtype == torch.float64
+    assert np.array_equal(dev.cpu().numpy(), host)
+    assert (host.reshape(64, 7, -1)[:, 6] == 0).all()  # frame beyond the episode -> zeros
+    env.close()
