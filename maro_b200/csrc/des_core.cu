@@ -71,6 +71,7 @@ struct StepArgs {
     const int32_t* n_actions;         // [B] or nullptr
     int32_t* decisions;               // [B][8]
     int64_t* metrics;                 // [B][3]
+    uint8_t* light;                   // [B] 1: the next step only applies an action and yields the tick's next decision
     int mt_words;
 };
 
@@ -102,14 +103,17 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
     }
     g.sync();
     uint32_t phase = 0;
-    const uint32_t bytes = (uint32_t)s.SW * 4u;
     for (int rep = blockIdx.x * kGroups + gid; rep < s.n_replicas; rep += gridDim.x * kGroups) {
         if (a.active && !a.active[rep]) {
             if (g.lane == 0) a.decisions[rep * 8 + 6] = MARO_STATUS_INACTIVE;
             continue;
         }
         int32_t* gstate = a.state + (int64_t)rep * s.SW;
-        // ---- stage in: one TMA bulk copy of the whole state block, completion on the group's mbarrier
+        // ---- stage in: one TMA bulk copy, completion on the group's mbarrier.  A step that is known to stay inside
+        // the current tick (another decision of the same tick is pending: it applies the action, snapshots and returns)
+        // never touches the event queue, so only [frame | control] travels, both ways.
+        const bool light = a.light[rep] != 0;
+        const uint32_t bytes = light ? (uint32_t)(s.FWp + s.CWp) * 4u : (uint32_t)s.SW * 4u;
         if (g.lane == 0) {
             fence_proxy_async();  // order earlier generic-proxy accesses to this smem before the async write
             mbar_expect_tx(bar, bytes);
@@ -125,10 +129,17 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
             act.v = v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
         }
         replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
-        // ---- write back (128-bit coalesced)
+        // ---- write back (128-bit coalesced) what this step could have changed
         const int4* src4 = reinterpret_cast<const int4*>(st);
         int4* dst4 = reinterpret_cast<int4*>(gstate);
-        for (int i = g.lane; i < s.SW / 4; i += G) dst4[i] = src4[i];
+        const int n4 = (int)(bytes >> 4);
+        for (int i = g.lane; i < n4; i += G) dst4[i] = src4[i];
+        if (g.lane == 0) {  // hint for the next step: awaiting an action with another arrival of this tick still to decide
+            const int32_t* c = st + s.FWp;
+            const uint64_t arr = ((uint64_t)(uint32_t)c[C_ARR_HI] << 32) | (uint32_t)c[C_ARR_LO];
+            const int dp = c[C_DEC_POS];
+            a.light[rep] = (c[C_STATE] == ST_AWAIT && dp < 64 && (arr >> dp) != 0) ? 1 : 0;
+        }
         g.sync();
     }
 }
@@ -141,6 +152,7 @@ __global__ void cim_reset_kernel(const __grid_constant__ CimShape s, const __gri
         if (a.active && !a.active[rep]) continue;
         Replica r = make_replica(s, a, rep, a.state + (int64_t)rep * s.SW);  // operate directly on global memory
         replica_reset<32>(s, g, r);
+        if (g.lane == 0) a.light[rep] = 0;
     }
 }
 
@@ -249,6 +261,7 @@ struct MaroCimEnv : EnvCommon {
     size_t smem_bytes = 0;
     int32_t *d_tables = nullptr, *d_topo = nullptr;
     uint32_t* d_mt = nullptr;
+    uint8_t* d_light = nullptr;
     std::vector<int32_t> h_tables;
 };
 
@@ -386,6 +399,7 @@ static StepArgs base_args(MaroCimEnv* e) {
     a.mt = e->d_mt;
     a.tables = e->d_tables;
     a.replica_topology = e->d_topo;
+    a.light = e->d_light;
     a.mt_words = e->mt_words;
     return a;
 }
@@ -431,7 +445,7 @@ int maro_abi_version(void) { return MARO_B200_ABI_VERSION; }
 int maro_cim_destroy(MaroCimEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt);
+    cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt); cudaFree(e->d_light);
     common_free(e);
     delete e;
     return 0;
@@ -494,6 +508,8 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     const int B = e->B;
     CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
     CK(cudaMalloc(&e->d_topo, (size_t)B * 4));
+    CK(cudaMalloc(&e->d_light, (size_t)B));
+    CK(cudaMemset(e->d_light, 0, (size_t)B));
     CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
     std::vector<int32_t> topo(B, 0);
     if (cfg->replica_topology)
