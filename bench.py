@@ -220,9 +220,10 @@ def load_host_agent():
     out = os.path.join(ROOT, "tools", "_build", "libhost_agent.so")
     if not os.path.isfile(out) or os.path.getmtime(out) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", src, "-o", out])
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", src, "-o", out])
     lib = ctypes.CDLL(out)
     lib.agent_random.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
+    lib.agent_greedy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
 
@@ -374,53 +375,45 @@ def run_ours(args, rank, local_rank, world):
     # ---- e2e: host-buffer C-ABI path, agent on the host, one episode-aligned run of min(steps, 2000) steps
     e2e = None
     if not args.skip_e2e:
+        # Host-buffer path: the agent (tools/host_agent.c, gcc -fopenmp) reads the decision rows and writes the action
+        # rows directly in the library's pinned staging buffers; maro_*_step_pinned moves them over PCIe (zero-copy
+        # mapped memory for small batches, DMA copies for large ones) and runs the step kernel; every call synchronises.
         agent_lib = load_host_agent()
-        act_host = np.zeros((B, 1, 4), np.int32)
+        p_act, p_nact, p_active, p_dec, p_met = env.pinned()
+        dec_ptr, act_ptr = p_dec.ctypes.data, p_act.ctypes.data
 
-        def host_policy(d, seed, base_, np_):
-            if bike:  # greedy top-1 (examples/citi_bike/greedy/launcher.py:35-65), vectorised
-                S = topo.n_stations
-                idx, val, n = d[:, 8:8 + 2 * S:2], d[:, 9:9 + 2 * S:2].astype(np.int64), d[:, 4:5]
-                ok = (np.arange(S)[None, :] < n) & (idx != d[:, 1:2])
-                key = np.where(ok, val * 4096 + idx, -1)
-                best = key.argmax(1)
-                rows = np.arange(B)
-                bi, bv = idx[rows, best], val[rows, best]
-                none = key[rows, best] < 0
-                supply = d[:, 3] == 0
-                act_host[:, 0, 0] = np.where(none, -1, np.where(supply, d[:, 1], bi))
-                act_host[:, 0, 1] = np.where(none, -1, np.where(supply, bi, d[:, 1]))
-                act_host[:, 0, 2] = np.where(none, 0, bv)
-                return act_host
-            agent_lib.agent_random(d.ctypes.data, act_host.ctypes.data, B, 1, seed, base_)
-            return act_host
+        def host_agent():
+            if bike:
+                agent_lib.agent_greedy(dec_ptr, act_ptr, B, 1, dec_words)
+            else:
+                agent_lib.agent_random(dec_ptr, act_ptr, B, 1, 0, base)
 
-        # the C agent and the numpy twin must agree (and both equal the device agent, tests/test_gpu_*)
+        # cross-check the host agents against their twins once (the device agents are checked in tests/test_gpu_*)
         env.reset()
-        d0, _ = env.step(None)
-        if not bike:
-            assert np.array_equal(host_policy(d0, 0, base, np), host_policy_numpy(d0, 0, base, np))
+        env.step_pinned(use_actions=False)
+        host_agent()
+        if bike:
+            from oracle.bike_oracle import policy_greedy
+            assert p_act[0, 0].tolist() == policy_greedy(p_dec[0]).tolist()
+        else:
+            assert np.array_equal(p_act, host_policy_numpy(p_dec, 0, base, np))
+        for k in range(3):
+            env.step_pinned()
+            host_agent()
         env.reset()
         n_e2e = min(args.steps, 2000)
-        d, m = env.step(None)
-        for k in range(3):
-            d, m = env.step(host_policy(d, 0, base, np))
-        env.reset()
         torch.cuda.synchronize()
         cc0 = env.counters().sum(0)
         t0 = time.perf_counter()
         i = 0
         t_agent = 0.0
         for k in range(n_e2e):
-            if i == 0:
-                if k > 0:
-                    env.reset()
-                d, m = env.step(None)
-            else:
-                ta = time.perf_counter()
-                a = host_policy(d, 0, base, np)
-                t_agent += time.perf_counter() - ta
-                d, m = env.step(a)
+            if i == 0 and k > 0:
+                env.reset()
+            ta = time.perf_counter()
+            host_agent()  # the first step of an episode ignores its action (generator start)
+            t_agent += time.perf_counter() - ta
+            env.step_pinned()
             i = (i + 1) % steps_per_episode
         dt = time.perf_counter() - t0
         cc1 = env.counters().sum(0)
@@ -478,7 +471,7 @@ def run_ours(args, rank, local_rank, world):
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
                            "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + 24),
-                           "api": "maro_cim_step (host buffers, agent = tools/host_agent.c on the host)",
+                           "api": "maro_%s_step_pinned (pinned host buffers) + tools/host_agent.c on the host" % ("bike" if bike else "cim"),
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
         if graph_info:

@@ -138,6 +138,12 @@ int maro_cim_set_stream(MaroCimEnv* env, void* cuda_stream, int32_t external);
  *   decisions   [B][8] int32 out, metrics [B][3] int64 out                                           */
 int maro_cim_step(MaroCimEnv* env, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
                   int32_t* decisions, int64_t* metrics);
+/* Zero host-copy variant: the library's own pinned (and device-mapped) staging buffers, laid out exactly like the
+ * arguments of maro_cim_step.  Fill actions / n_actions / active in place, call maro_cim_step_pinned with flags saying
+ * which inputs are present, read decisions / metrics in place.  The pointers stay valid until maro_cim_destroy. */
+int maro_cim_pinned_buffers(MaroCimEnv* env, void** actions, void** n_actions, void** active, void** decisions,
+                            void** metrics);
+int maro_cim_step_pinned(MaroCimEnv* env, int32_t use_actions, int32_t use_n_actions, int32_t use_active);
 /* Same, device pointers, asynchronous on the handle's stream (no host<->device copies). */
 int maro_cim_step_device(MaroCimEnv* env, const uint8_t* d_active, const int32_t* d_actions,
                          const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
@@ -233,6 +239,9 @@ int32_t maro_bike_decision_words(MaroBikeEnv* env);
 /* decisions [B][decision_words] int32, metrics [B][3] int64, actions [B][max_actions][4] int32 */
 int maro_bike_step(MaroBikeEnv* env, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
                    int32_t* decisions, int64_t* metrics);
+int maro_bike_pinned_buffers(MaroBikeEnv* env, void** actions, void** n_actions, void** active, void** decisions,
+                             void** metrics);
+int maro_bike_step_pinned(MaroBikeEnv* env, int32_t use_actions, int32_t use_n_actions, int32_t use_active);
 int maro_bike_step_device(MaroBikeEnv* env, const uint8_t* d_active, const int32_t* d_actions,
                           const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
 int maro_bike_reset(MaroBikeEnv* env, const uint8_t* mask);

@@ -19,7 +19,8 @@ EXPORTS = (
     "maro_cim_step", "maro_cim_step_device", "maro_cim_reset", "maro_cim_set_topology", "maro_cim_query",
     "maro_cim_query_device", "maro_cim_attr_id", "maro_cim_attr_slots", "maro_cim_read_frame",
     "maro_cim_frame_words", "maro_cim_ticks", "maro_cim_counters", "maro_cim_snapshot_frames",
-    "maro_cim_random_policy_device",
+    "maro_cim_random_policy_device", "maro_cim_pinned_buffers", "maro_cim_step_pinned",
+    "maro_bike_pinned_buffers", "maro_bike_step_pinned",
     "maro_bike_create", "maro_bike_destroy", "maro_bike_set_stream", "maro_bike_decision_words", "maro_bike_step",
     "maro_bike_step_device", "maro_bike_reset", "maro_bike_query", "maro_bike_attr_id", "maro_bike_attr_slots",
     "maro_bike_read_frame", "maro_bike_frame_words", "maro_bike_ticks", "maro_bike_counters", "maro_bike_snapshot_frames",
@@ -64,6 +65,11 @@ def lib():
     L.maro_cim_counters.argtypes = [vp, vp]
     L.maro_cim_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
     L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32]
+    pvp = C.POINTER(vp)
+    for name in ("maro_cim_pinned_buffers", "maro_bike_pinned_buffers"):
+        getattr(L, name).argtypes = [vp, pvp, pvp, pvp, pvp, pvp]
+    for name in ("maro_cim_step_pinned", "maro_bike_step_pinned"):
+        getattr(L, name).argtypes = [vp, i32, i32, i32]
     L.maro_bike_create.argtypes = [vp, vp, C.POINTER(vp)]
     L.maro_bike_destroy.argtypes = [vp]
     L.maro_bike_set_stream.argtypes = [vp, vp, i32]

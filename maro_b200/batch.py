@@ -13,6 +13,20 @@ import numpy as np
 from . import _abi, _native
 from .scenarios.cim.topology import CimTopology
 
+def _pinned_views(lib_fn, handle, B, A, dec_words):
+    """numpy views over the library's pinned staging buffers (no copies)."""
+    ptrs = [C.c_void_p() for _ in range(5)]
+    _native.check(lib_fn(handle, *[C.byref(p) for p in ptrs]))
+
+    def view(p, nbytes, dtype, shape):
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    return (view(ptrs[0], B * A * 16, np.int32, (B, A, 4)), view(ptrs[1], B * 4, np.int32, (B,)),
+            view(ptrs[2], B, np.uint8, (B,)), view(ptrs[3], B * dec_words * 4, np.int32, (B, dec_words)),
+            view(ptrs[4], B * 24, np.int64, (B, 3)))
+
+
 _NODE_TYPE = {"ports": _abi.NODE_PORTS, "vessels": _abi.NODE_VESSELS, "matrices": _abi.NODE_MATRICES}
 
 
@@ -100,6 +114,17 @@ class CimBatch:
             self._h, None if m is None else m.ctypes.data, None if a is None else a.ctypes.data,
             None if n is None else n.ctypes.data, self.decisions.ctypes.data, self.metrics.ctypes.data))
         return self.decisions, self.metrics
+
+    def pinned(self):
+        """(actions, n_actions, active, decisions, metrics) numpy views over the library's pinned staging buffers; fill
+        the inputs in place, call ``step_pinned`` and read the outputs in place — no host-side copies at all."""
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = _pinned_views(_native.lib().maro_cim_pinned_buffers, self._h, self.n_replicas,
+                                         self.max_actions, _abi.DECISION_WORDS)
+        return self._pinned
+
+    def step_pinned(self, use_actions: bool = True, use_n_actions: bool = False, use_active: bool = False):
+        _native.check(_native.lib().maro_cim_step_pinned(self._h, int(use_actions), int(use_n_actions), int(use_active)))
 
     def step_device(self, d_decisions: int, d_metrics: int, d_actions: int = 0, d_n_actions: int = 0, d_active: int = 0):
         """Asynchronous step on device pointers (ints, e.g. ``tensor.data_ptr()``)."""
@@ -264,6 +289,15 @@ class BikeBatch:
             self._h, None if m is None else m.ctypes.data, None if a is None else a.ctypes.data,
             None if n is None else n.ctypes.data, self.decisions.ctypes.data, self.metrics.ctypes.data))
         return self.decisions, self.metrics
+
+    def pinned(self):
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = _pinned_views(_native.lib().maro_bike_pinned_buffers, self._h, self.n_replicas,
+                                         self.max_actions, self.dec_words)
+        return self._pinned
+
+    def step_pinned(self, use_actions: bool = True, use_n_actions: bool = False, use_active: bool = False):
+        _native.check(_native.lib().maro_bike_step_pinned(self._h, int(use_actions), int(use_n_actions), int(use_active)))
 
     def step_device(self, d_decisions: int, d_metrics: int, d_actions: int = 0, d_n_actions: int = 0, d_active: int = 0):
         _native.check(_native.lib().maro_bike_step_device(self._h, d_active or None, d_actions or None,

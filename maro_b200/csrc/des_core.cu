@@ -299,15 +299,19 @@ static int common_alloc(EnvCommon* e) {
 }
 
 // Host-buffer step shared by the scenarios: stage inputs, run `step_device`, fetch outputs, synchronise.
+// `pinned` = the caller filled / reads the library's pinned staging buffers directly (maro_*_pinned_buffers): the
+// pointers are then only presence flags and no host-side memcpy happens.
 template <class StepDevice>
 static int common_host_step(EnvCommon* e, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
-                            int32_t* decisions, int64_t* metrics, StepDevice step_device) {
+                            int32_t* decisions, int64_t* metrics, StepDevice step_device, bool pinned = false) {
     const int B = e->B, A = e->max_actions;
     const size_t act_bytes = (size_t)B * A * 16, nact_off = act_bytes, active_off = act_bytes + (size_t)B * 4;
     const size_t dec_bytes = (size_t)B * e->dec_words * 4;
-    if (actions) memcpy(e->h_in, actions, act_bytes);
-    if (actions && n_actions) memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4);
-    if (active) memcpy(e->h_in + active_off, active, B);
+    if (!pinned) {
+        if (actions) memcpy(e->h_in, actions, act_bytes);
+        if (actions && n_actions) memcpy(e->h_in + nact_off, n_actions, (size_t)B * 4);
+        if (active) memcpy(e->h_in + active_off, active, B);
+    }
     uint8_t* in = e->zero_copy ? e->hd_in : e->d_in;
     uint8_t* out = e->zero_copy ? e->hd_out : e->d_out;
     if (!e->zero_copy) {
@@ -323,8 +327,21 @@ static int common_host_step(EnvCommon* e, const uint8_t* active, const int32_t* 
     if (rc) return rc;
     if (!e->zero_copy) CK(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    memcpy(decisions, e->h_out, dec_bytes);
-    memcpy(metrics, e->h_out + dec_bytes, (size_t)B * 24);
+    if (!pinned) {
+        memcpy(decisions, e->h_out, dec_bytes);
+        memcpy(metrics, e->h_out + dec_bytes, (size_t)B * 24);
+    }
+    return 0;
+}
+
+static int common_pinned_buffers(EnvCommon* e, void** actions, void** n_actions, void** active, void** decisions, void** metrics) {
+    if (!e) return fail("pinned_buffers: null handle");
+    const size_t B = (size_t)e->B, act_bytes = B * e->max_actions * 16;
+    if (actions) *actions = e->h_in;
+    if (n_actions) *n_actions = e->h_in + act_bytes;
+    if (active) *active = e->h_in + act_bytes + B * 4;
+    if (decisions) *decisions = e->h_out;
+    if (metrics) *metrics = e->h_out + B * e->dec_words * 4;
     return 0;
 }
 
@@ -590,6 +607,19 @@ int maro_cim_step(MaroCimEnv* e, const uint8_t* active, const int32_t* actions, 
                             });
 }
 
+int maro_cim_pinned_buffers(MaroCimEnv* e, void** actions, void** n_actions, void** active, void** decisions, void** metrics) {
+    return common_pinned_buffers(e, actions, n_actions, active, decisions, metrics);
+}
+int maro_cim_step_pinned(MaroCimEnv* e, int32_t use_actions, int32_t use_n_actions, int32_t use_active) {
+    if (!e) return fail("maro_cim_step_pinned: null handle");
+    CK(cudaSetDevice(e->device));
+    const uint8_t* f = reinterpret_cast<const uint8_t*>(1);  // presence flags only
+    return common_host_step(e, use_active ? f : nullptr, use_actions ? reinterpret_cast<const int32_t*>(f) : nullptr,
+                            use_n_actions ? reinterpret_cast<const int32_t*>(f) : nullptr, nullptr, nullptr,
+                            [&](const uint8_t* a, const int32_t* ac, const int32_t* na, int32_t* d, int64_t* m) {
+                                return maro_cim_step_device(e, a, ac, na, d, m);
+                            }, true);
+}
 int32_t maro_cim_frame_words(MaroCimEnv* e) { return e ? e->s.FW : -1; }
 
 static int query_impl(EnvCommon* e, const int32_t* replicas, int32_t nr, int32_t node_type, const int32_t* frames,
@@ -924,6 +954,19 @@ int maro_bike_step(MaroBikeEnv* e, const uint8_t* active, const int32_t* actions
                             [&](const uint8_t* a, const int32_t* ac, const int32_t* na, int32_t* d, int64_t* m) {
                                 return maro_bike_step_device(e, a, ac, na, d, m);
                             });
+}
+int maro_bike_pinned_buffers(MaroBikeEnv* e, void** actions, void** n_actions, void** active, void** decisions, void** metrics) {
+    return common_pinned_buffers(e, actions, n_actions, active, decisions, metrics);
+}
+int maro_bike_step_pinned(MaroBikeEnv* e, int32_t use_actions, int32_t use_n_actions, int32_t use_active) {
+    if (!e) return fail("maro_bike_step_pinned: null handle");
+    CK(cudaSetDevice(e->device));
+    const uint8_t* f = reinterpret_cast<const uint8_t*>(1);
+    return common_host_step(e, use_active ? f : nullptr, use_actions ? reinterpret_cast<const int32_t*>(f) : nullptr,
+                            use_n_actions ? reinterpret_cast<const int32_t*>(f) : nullptr, nullptr, nullptr,
+                            [&](const uint8_t* a, const int32_t* ac, const int32_t* na, int32_t* d, int64_t* m) {
+                                return maro_bike_step_device(e, a, ac, na, d, m);
+                            }, true);
 }
 int maro_bike_query(MaroBikeEnv* e, const int32_t* replicas, int32_t n_replicas, int32_t node_type, const int32_t* frame_indices,
                     int32_t n_frames, const int32_t* nodes, int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* out,

@@ -228,3 +228,28 @@ def test_cuda_query_device_matches_host_query():
     assert np.array_equal(dev.cpu().numpy(), host)
     assert (host.reshape(64, 7, -1)[:, 6] == 0).all()  # frame beyond the episode -> zeros
     env.close()
+
+
+def test_cuda_pinned_step_matches_copying_step():
+    """maro_cim_step_pinned (inputs / outputs in the library's pinned staging buffers) == maro_cim_step."""
+    from maro_b200.scenarios.cim.topology import build_topology
+    from oracle.cim_oracle import policy_random
+
+    topo = build_topology("toy.4p_ssdd_l0.8", 90)
+    a_env, b_env = _batch(topo, 32), _batch(topo, 32)
+    p_act, p_nact, p_active, p_dec, p_met = b_env.pinned()
+    dec, met = a_env.step(None)
+    b_env.step_pinned(use_actions=False)
+    step = 0
+    while (dec[:, 6] == 0).any():
+        assert np.array_equal(dec, p_dec) and np.array_equal(met, p_met)
+        acts = np.zeros((32, 1, 4), np.int32)
+        for i in range(32):
+            acts[i, 0] = policy_random(dec[i], 3, i, step)
+        p_act[:] = acts
+        dec, met = a_env.step(acts)
+        b_env.step_pinned()
+        step += 1
+    assert np.array_equal(dec, p_dec) and np.array_equal(met, p_met)
+    a_env.close()
+    b_env.close()

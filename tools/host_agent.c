@@ -9,6 +9,7 @@ static inline uint32_t hash_u32(uint32_t x) {
 }
 
 void agent_random(const int32_t* dec, int32_t* act, int n, int max_actions, uint32_t seed, uint32_t replica_base) {
+#pragma omp parallel for schedule(static) if (n >= 8192)
     for (int i = 0; i < n; i++) {
         const int32_t* d = dec + 8 * i;
         uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + (uint32_t)d[7] * 0x85ebca6bu + 0x1234567u));
@@ -20,5 +21,24 @@ void agent_random(const int32_t* dec, int32_t* act, int n, int max_actions, uint
         a[0] = d[2]; a[1] = d[1];
         a[2] = scope > 0 ? (int32_t)(h2 % (uint32_t)(scope + 1)) : 0;
         a[3] = to_discharge;
+    }
+}
+
+/* greedy top-1 citi_bike agent (examples/citi_bike/greedy/launcher.py:35-65): the candidate with the largest
+ * (value, station) pair; decision rows are 8 + 2 * S words */
+void agent_greedy(const int32_t* dec, int32_t* act, int n, int max_actions, int dec_words) {
+#pragma omp parallel for schedule(static) if (n >= 8192)
+    for (int i = 0; i < n; i++) {
+        const int32_t* d = dec + (int64_t)i * dec_words;
+        int station = d[1], ns = d[4], best = -1, best_v = 0;
+        for (int k = 0; k < ns; k++) {
+            int idx = d[8 + 2 * k], v = d[9 + 2 * k];
+            if (idx == station) continue;
+            if (best < 0 || v > best_v || (v == best_v && idx > best)) { best = idx; best_v = v; }
+        }
+        int32_t* a = act + (int64_t)i * max_actions * 4;
+        if (best < 0) { a[0] = a[1] = -1; a[2] = a[3] = 0; }
+        else if (d[3] == 0) { a[0] = station; a[1] = best; a[2] = best_v; a[3] = 0; }
+        else { a[0] = best; a[1] = station; a[2] = best_v; a[3] = 0; }
     }
 }
