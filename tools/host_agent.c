@@ -9,7 +9,7 @@ static inline uint32_t hash_u32(uint32_t x) {
 }
 
 void agent_random(const int32_t* dec, int32_t* act, int n, int max_actions, uint32_t seed, uint32_t replica_base) {
-#pragma omp parallel for schedule(static) if (n >= 8192)
+#pragma omp parallel for schedule(static) num_threads(16) if (n >= 4096)
     for (int i = 0; i < n; i++) {
         const int32_t* d = dec + 8 * i;
         uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + (uint32_t)d[7] * 0x85ebca6bu + 0x1234567u));
@@ -27,7 +27,7 @@ void agent_random(const int32_t* dec, int32_t* act, int n, int max_actions, uint
 /* greedy top-1 citi_bike agent (examples/citi_bike/greedy/launcher.py:35-65): the candidate with the largest
  * (value, station) pair; decision rows are 8 + 2 * S words */
 void agent_greedy(const int32_t* dec, int32_t* act, int n, int max_actions, int dec_words) {
-#pragma omp parallel for schedule(static) if (n >= 8192)
+#pragma omp parallel for schedule(static) num_threads(16) if (n >= 4096)
     for (int i = 0; i < n; i++) {
         const int32_t* d = dec + (int64_t)i * dec_words;
         int station = d[1], ns = d[4], best = -1, best_v = 0;
