@@ -258,6 +258,92 @@ int maro_bike_snapshot_frames(MaroBikeEnv* env, int32_t replica, int32_t* out, i
 /* Agent helper for bench.py: examples/citi_bike/greedy/launcher.py:35-65 with top-1 (deterministic). */
 int maro_bike_greedy_policy_device(MaroBikeEnv* env, const int32_t* d_decisions, int32_t* d_actions);
 
+/* ================================================================================================
+ * vm_scheduling scenario: same call shapes again.
+ * Static tables come from maro_b200.scenarios.vm_scheduling.data.build_vm_topology(), which restates
+ * vm_scheduling/business_engine.py:131-440 (config / hierarchy), :449-493 (request stream), cpu_reader.py:9-77 and the
+ * utilisation-series semantics of virtual_machine.py:73-90.
+ * ============================================================================================== */
+typedef struct MaroVmTopology {
+    int32_t n_pm, n_rack, n_cluster, n_dc, n_zone, n_region, n_pm_types, n_vm;
+    int32_t max_tick, delay_duration, buffer_budget, kill_all;
+    double ticks_per_hour, max_cpu_over, max_mem_over, max_util_rate, unit_energy_price, pue;
+    const int32_t* pm_attr;        /* [n_pm][8] cpu, memory, pm_type, region, zone, dc, cluster, rack           */
+    const double* pm_idle_energy;  /* [n_pm]                                                                   */
+    const double* pmtype_power;    /* [n_pm_types][3] calibration_parameter, busy_power, idle_power            */
+    const int32_t* rack_range;     /* [n_rack][2] pm lo, hi        */
+    const int32_t* rack_ids;       /* [n_rack][4] region, zone, dc, cluster */
+    const int32_t* cluster_range;  /* [n_cluster][2] rack lo, hi   */
+    const int32_t* cluster_ids;    /* [n_cluster][3] region, zone, dc */
+    const int32_t* dc_range;       /* [n_dc][2] cluster lo, hi     */
+    const int32_t* dc_ids;         /* [n_dc][2] region, zone       */
+    const int32_t* zone_range;     /* [n_zone][2] dc lo, hi        */
+    const int32_t* zone_ids;       /* [n_zone] region              */
+    const int32_t* region_range;   /* [n_region][2] zone lo, hi    */
+    const int32_t* vm_attr;        /* [n_vm][8] vm_id, sub_id, deploy_id, request tick, lifetime, category, cores, memory */
+    const double* vm_price;        /* [n_vm] unit price per tick (business_engine.py:917-920)                   */
+    const int32_t* req_offset;     /* [max_tick+1] requests of tick t = vm indices [offset[t], offset[t+1])     */
+    const int32_t* vm_sorted_ids;  /* [n_vm] vm ids ascending      */
+    const int32_t* vm_sorted_idx;  /* [n_vm] matching vm indices   */
+    const int32_t* util_offset;    /* [n_vm+1] into util_*         */
+    const double* util_val;        /* forward-filled readings from the request tick on                         */
+    const int32_t* util_has;       /* 1 where the trace holds a reading for that tick                          */
+} MaroVmTopology;
+
+/* Decision row: MARO_VM_DEC_HEAD int32 header + n_pm words of valid PM ids (DecisionEvent, vm_scheduling/common.py:66-120). */
+enum {
+    MARO_VM_DEC_TICK = 0,
+    MARO_VM_DEC_VM_ID = 1,
+    MARO_VM_DEC_FRAME_INDEX = 2,
+    MARO_VM_DEC_CPU = 3,
+    MARO_VM_DEC_MEMORY = 4,
+    MARO_VM_DEC_SUB_ID = 5,
+    MARO_VM_DEC_STATUS = 6,
+    MARO_VM_DEC_STEP = 7,
+    MARO_VM_DEC_CATEGORY = 8,
+    MARO_VM_DEC_BUFFER_TIME = 9,
+    MARO_VM_DEC_N_VALID = 10,
+    MARO_VM_DEC_HEAD = 12
+};
+/* Action row: 4 int32 {vm_id, kind, pm_id | postpone_step, 0}; kind 0 = AllocateAction, 1 = PostponeAction
+ * (common.py:9-57).  n_actions = 0 is the reference's empty action list (the pending request is dropped). */
+enum { MARO_VM_ACTION_ALLOCATE = 0, MARO_VM_ACTION_POSTPONE = 1 };
+/* Metrics row: 16 x 8 bytes (business_engine.py:539-565); float entries are IEEE doubles stored in the int64 slots. */
+enum {
+    MARO_VM_MET_TOTAL_VM_REQUESTS = 0, MARO_VM_MET_TOTAL_INCOMES_F64 = 1, MARO_VM_MET_ENERGY_COST_F64 = 2,
+    MARO_VM_MET_TOTAL_PROFIT_F64 = 3, MARO_VM_MET_TOTAL_ENERGY_F64 = 4, MARO_VM_MET_SUCCESSFUL_ALLOCATION = 5,
+    MARO_VM_MET_SUCCESSFUL_COMPLETION = 6, MARO_VM_MET_FAILED_ALLOCATION = 7, MARO_VM_MET_FAILED_COMPLETION = 8,
+    MARO_VM_MET_LATENCY_AGENT = 9, MARO_VM_MET_LATENCY_RESOURCE = 10, MARO_VM_MET_OVERSUBSCRIPTIONS = 11,
+    MARO_VM_MET_OVERLOAD_PMS = 12, MARO_VM_MET_OVERLOAD_VMS = 13, MARO_VM_METRIC_WORDS = 16
+};
+enum { MARO_VM_NODE_PMS = 0, MARO_VM_NODE_RACKS = 1, MARO_VM_NODE_CLUSTERS = 2, MARO_VM_NODE_DATA_CENTERS = 3,
+       MARO_VM_NODE_ZONES = 4, MARO_VM_NODE_REGIONS = 5 };
+
+typedef struct MaroVmEnv MaroVmEnv;
+
+int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmEnv** out);
+int maro_vm_destroy(MaroVmEnv* env);
+int maro_vm_set_stream(MaroVmEnv* env, void* cuda_stream, int32_t external);
+int32_t maro_vm_decision_words(MaroVmEnv* env);
+/* decisions [B][decision_words] int32, metrics [B][16] int64, actions [B][max_actions][4] int32 */
+int maro_vm_step(MaroVmEnv* env, const uint8_t* active, const int32_t* actions, const int32_t* n_actions,
+                 int32_t* decisions, int64_t* metrics);
+int maro_vm_step_device(MaroVmEnv* env, const uint8_t* d_active, const int32_t* d_actions, const int32_t* d_n_actions,
+                        int32_t* d_decisions, int64_t* d_metrics);
+int maro_vm_reset(MaroVmEnv* env, const uint8_t* mask);
+int maro_vm_query(MaroVmEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
+                  const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
+                  const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
+int32_t maro_vm_attr_id(MaroVmEnv* env, int32_t node_type, const char* name);
+int32_t maro_vm_attr_slots(MaroVmEnv* env, int32_t node_type, int32_t attr_id);
+int maro_vm_read_frame(MaroVmEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);
+int32_t maro_vm_frame_words(MaroVmEnv* env);
+int maro_vm_ticks(MaroVmEnv* env, int32_t* out_ticks);
+int maro_vm_counters(MaroVmEnv* env, int64_t* out);
+int maro_vm_snapshot_frames(MaroVmEnv* env, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out);
+/* Agent helper for bench.py: best fit (examples/vm_scheduling/rule_based_algorithm/best_fit.py:27-64). */
+int maro_vm_best_fit_policy_device(MaroVmEnv* env, const int32_t* d_decisions, int32_t* d_actions);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,3 +157,88 @@ def bike_frame_layout(S: int):
         off += S
     lay["matrices"]["trips_adj"] = (off, 1, S * S)
     return lay, off + S * S
+
+
+# ---------------------------------------------------------------------------------------------------- vm_scheduling
+_VM_I32 = ("pm_attr", "rack_range", "rack_ids", "cluster_range", "cluster_ids", "dc_range", "dc_ids", "zone_range", "zone_ids",
+           "region_range", "vm_attr", "req_offset", "vm_sorted_ids", "vm_sorted_idx", "util_offset", "util_has")
+_VM_F64 = ("pm_idle_energy", "pmtype_power", "vm_price", "util_val")
+
+
+class MaroVmTopology(C.Structure):
+    _fields_ = [
+        ("n_pm", C.c_int32), ("n_rack", C.c_int32), ("n_cluster", C.c_int32), ("n_dc", C.c_int32), ("n_zone", C.c_int32),
+        ("n_region", C.c_int32), ("n_pm_types", C.c_int32), ("n_vm", C.c_int32),
+        ("max_tick", C.c_int32), ("delay_duration", C.c_int32), ("buffer_budget", C.c_int32), ("kill_all", C.c_int32),
+        ("ticks_per_hour", C.c_double), ("max_cpu_over", C.c_double), ("max_mem_over", C.c_double),
+        ("max_util_rate", C.c_double), ("unit_energy_price", C.c_double), ("pue", C.c_double),
+        ("pm_attr", _i32p), ("pm_idle_energy", _f64p), ("pmtype_power", _f64p), ("rack_range", _i32p), ("rack_ids", _i32p),
+        ("cluster_range", _i32p), ("cluster_ids", _i32p), ("dc_range", _i32p), ("dc_ids", _i32p), ("zone_range", _i32p),
+        ("zone_ids", _i32p), ("region_range", _i32p), ("vm_attr", _i32p), ("vm_price", _f64p), ("req_offset", _i32p),
+        ("vm_sorted_ids", _i32p), ("vm_sorted_idx", _i32p), ("util_offset", _i32p), ("util_val", _f64p), ("util_has", _i32p),
+    ]
+
+
+VM_DEC_HEAD = 12
+VM_METRIC_WORDS = 16
+VM_METRIC_NAMES = ("total_vm_requests", "total_incomes", "energy_consumption_cost", "total_profit",
+                   "total_energy_consumption", "successful_allocation", "successful_completion", "failed_allocation",
+                   "failed_completion", "latency_due_to_agent", "latency_due_to_resource", "total_oversubscriptions",
+                   "total_overload_pms", "total_overload_vms")
+VM_METRIC_FLOAT = (1, 2, 3, 4)
+VM_NODE_ATTRS = {
+    "pms": ("cluster_id", "cpu_cores_allocated", "cpu_cores_capacity", "cpu_utilization", "data_center_id",
+            "energy_consumption", "id", "memory_allocated", "memory_capacity", "oversubscribable", "pm_type", "rack_id",
+            "region_id", "zone_id"),
+    "racks": ("cluster_id", "data_center_id", "empty_machine_num", "id", "region_id", "total_machine_num", "zone_id"),
+    "clusters": ("data_center_id", "empty_machine_num", "id", "region_id", "total_machine_num", "zone_id"),
+    "data_centers": ("empty_machine_num", "id", "region_id", "total_machine_num", "zone_id"),
+    "zones": ("empty_machine_num", "id", "region_id", "total_machine_num"),
+    "regions": ("empty_machine_num", "id", "total_machine_num"),
+}
+VM_FLOAT_ATTRS = ("cpu_utilization", "energy_consumption")
+
+
+def vm_topology_struct(topo):
+    s = MaroVmTopology()
+    keep = []
+    for name in ("n_pm", "n_rack", "n_cluster", "n_dc", "n_zone", "n_region", "max_tick", "delay_duration", "buffer_budget",
+                 "kill_all"):
+        setattr(s, name, int(getattr(topo, name)))
+    s.n_pm_types = len(topo.pmtype_power)
+    s.n_vm = topo.n_vm
+    for name in ("ticks_per_hour", "max_cpu_over", "max_mem_over", "max_util_rate", "unit_energy_price", "pue"):
+        setattr(s, name, float(getattr(topo, name)))
+    for name in _VM_I32:
+        a = np.ascontiguousarray(getattr(topo, name), dtype=np.int32).reshape(-1)
+        if a.size == 0:
+            a = np.zeros(1, np.int32)
+        keep.append(a)
+        setattr(s, name, a.ctypes.data_as(_i32p))
+    for name in _VM_F64:
+        a = np.ascontiguousarray(getattr(topo, name), dtype=np.float64).reshape(-1)
+        if a.size == 0:
+            a = np.zeros(1, np.float64)
+        keep.append(a)
+        setattr(s, name, a.ctypes.data_as(_f64p))
+    return s, keep
+
+
+def vm_frame_layout(topo):
+    counts = {"pms": topo.n_pm, "racks": topo.n_rack, "clusters": topo.n_cluster, "data_centers": topo.n_dc,
+              "zones": topo.n_zone, "regions": topo.n_region}
+    lay, off = {}, 0
+    for node, attrs in VM_NODE_ATTRS.items():
+        lay[node] = {}
+        for a in attrs:
+            lay[node][a] = (off, counts[node], 1)
+            off += counts[node]
+    return lay, off
+
+
+def vm_metrics_dict(row):
+    out = {}
+    r = np.asarray(row, np.int64)
+    for i, name in enumerate(VM_METRIC_NAMES):
+        out[name] = float(r[i:i + 1].view(np.float64)[0]) if i in VM_METRIC_FLOAT else int(r[i])
+    return out
