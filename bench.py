@@ -35,8 +35,11 @@ def parse():
     ap.add_argument("--replicas", type=int, default=1024, help="parallel envs per GPU")
     ap.add_argument("--ticks", type=int, default=1000)
     ap.add_argument("--topology", default="toy.4p_ssdd_l0.0")
-    ap.add_argument("--scenario", default="cim", choices=["cim", "citi_bike"],
-                    help="citi_bike = BASELINE config #3 (frozen toy.3s_4t trace, greedy agent, snapshot_resolution 10)")
+    ap.add_argument("--scenario", default="cim", choices=["cim", "citi_bike", "vm_scheduling"],
+                    help="citi_bike = BASELINE config #3 (frozen toy.3s_4t trace, greedy agent, snapshot_resolution 10); "
+                         "vm_scheduling = config #5 (synthetic azure.2019.10k-scale trace, best-fit agent)")
+    ap.add_argument("--vm-count", type=int, default=10000, help="vm_scheduling: VMs in the synthetic trace")
+    ap.add_argument("--vm-trace-dir", default="", help="vm_scheduling: where the synthetic trace is written (default: a temp dir)")
     ap.add_argument("--max-snapshots", type=int, default=0, help="0 = keep every frame (reference default)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
@@ -114,6 +117,8 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"CIM {args.topology}, {args.ticks} ticks, random actions", "replicas": cores}}
+    if args.scenario == "vm_scheduling":
+        return run_reference_vm(args, line, ref_root, cores)
     if os.path.isdir(os.path.join(ref_root, "maro")):
         os.environ["SKIP_DEPLOYMENT"] = "TRUE"
         os.environ.setdefault("DEFAULT_BACKEND_NAME", "dynamic")  # the Cython/C++ RawBackend the north-star names
@@ -180,6 +185,73 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_vm(args, line, ref_root, cores):
+    """vm_scheduling: the unmodified reference (VectorEnv over every host core, best-fit agent of
+    examples/vm_scheduling/rule_based_algorithm/best_fit.py) on the same synthetic trace; else the C port."""
+    import numpy as np
+
+    conf, ticks = vm_workload(args)
+    line["config"] = {"workload": f"vm_scheduling synthetic azure.2019.10k-scale trace ({args.vm_count} VMs, 100 PMs, {ticks} ticks), best-fit agent",
+                      "replicas": cores}
+    line["dtype"] = "int32+f64"
+    if os.path.isdir(os.path.join(ref_root, "maro")):
+        import yaml
+
+        os.environ["SKIP_DEPLOYMENT"] = "TRUE"
+        sys.path.insert(0, ref_root)
+        sys.path.insert(1, os.path.join(ref_root, "_stubs"))
+        from maro.simulator.scenarios.vm_scheduling import AllocateAction
+        from maro.vector_env import VectorEnv
+
+        cdir = os.path.dirname(conf["VM_TABLE"])
+        with open(os.path.join(cdir, "config.yml"), "w") as fp:
+            yaml.safe_dump(conf, fp, sort_keys=False)
+        with VectorEnv(batch_num=cores, scenario="vm_scheduling", topology=cdir, durations=ticks) as env:
+            def agent(decisions):
+                acts = {}
+                frames = env.frame_index
+                for i, d in enumerate(decisions):
+                    if d is None:
+                        continue
+                    info = env.snapshot_list["pms"][frames[i]:d.valid_pms:["cpu_cores_capacity", "cpu_cores_allocated"]][i]
+                    info = np.asarray(info).reshape(-1, 2)
+                    acts[i] = AllocateAction(vm_id=d.vm_id, pm_id=d.valid_pms[int(np.argmin(info[:, 0] - info[:, 1]))])
+                return acts
+
+            metrics, decisions, done = env.step(None)
+            env_steps = 0
+            t0 = None
+            for k in range(args.warmup + args.steps):
+                if k == args.warmup:
+                    t0, env_steps = time.perf_counter(), 0
+                if done:
+                    env.reset()
+                    metrics, decisions, done = env.step(None)
+                else:
+                    metrics, decisions, done = env.step(agent(decisions))
+                env_steps += cores
+            dt = time.perf_counter() - t0
+        kind, sample = "reference", f"VectorEnv(batch_num={cores}) x {args.steps} steps of one episode, static backend"
+    else:
+        from maro_b200.scenarios.vm_scheduling.data import build_vm_topology
+        from oracle.vm_oracle import VmOracle
+
+        o = VmOracle(build_vm_topology(conf, 0, ticks), 1, 8)
+        env_steps, ep, t0 = 0, 0, time.perf_counter()
+        while env_steps < args.steps * 1024 and time.perf_counter() - t0 < 60:
+            o.reset()
+            env_steps += o.run_episode(1)[0]
+            ep += 1
+        dt = time.perf_counter() - t0
+        kind, sample, cores = "port", f"{ep} episodes of oracle/vm_oracle.c, 1 thread", 1
+    value = env_steps / dt
+    line.update({"value": value, "ms_per_step": 1000.0 * dt / max(1, args.steps),
+                 "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def cpu_baseline_port(args, topo):
     from oracle.cim_oracle import CimOracle
@@ -224,7 +296,37 @@ def load_host_agent():
     lib = ctypes.CDLL(out)
     lib.agent_random.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
     lib.agent_greedy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.agent_best_fit.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     return lib
+
+
+def vm_workload(args):
+    """(config dict, ticks) of the vm_scheduling bench workload: tools/vm_trace_gen.py trace + azure.2019.10k topology."""
+    import tempfile
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vm_trace_gen
+
+    ticks = 8638 if args.ticks == 1000 else args.ticks
+    d = args.vm_trace_dir or os.path.join(tempfile.gettempdir(), f"maro_b200_vm_trace_{args.vm_count}_{ticks}")
+    vm_path, cpu_path = vm_trace_gen.generate(d, args.vm_count, ticks)
+    return vm_trace_gen.azure_like_config(vm_path, cpu_path), ticks
+
+
+def cpu_baseline_vm(args, topo, max_snapshots):
+    from oracle.vm_oracle import VmOracle
+
+    o = VmOracle(topo, 1, max_snapshots)
+    env_steps, ep, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < args.cpu_seconds:
+        o.reset()
+        n, _ = o.run_episode(1)
+        env_steps += n
+        ep += 1
+    dt = time.perf_counter() - t0
+    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/vm_oracle.c, same trace / best-fit policy, 1 thread"}
 
 
 def host_policy_numpy(dec, seed, base, np):
@@ -262,7 +364,22 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.replicas
     bike = args.scenario == "citi_bike"
-    if bike:
+    vm = args.scenario == "vm_scheduling"
+    met_words = 16 if vm else 3
+    if vm:
+        from maro_b200.batch import VmBatch
+        from maro_b200.scenarios.vm_scheduling.data import build_vm_topology
+        from oracle.vm_oracle import VmOracle  # checker / cpu_baseline leg only
+
+        conf, ticks = vm_workload(args)
+        topo = build_vm_topology(conf, 0, ticks)
+        vm_snaps = args.max_snapshots or 8  # the reference default (every frame) is 51 MB per replica at this size
+        steps_per_episode = VmOracle(topo, 1, vm_snaps).run_episode(1)[0]
+        env = VmBatch(topo, B, 1, vm_snaps, device=local_rank)
+        dec_words = env.dec_words
+        life = topo.vm_attr[:, 4].astype("int64")
+        vm_avg_live = float(np.minimum(np.where(life <= 0, ticks, life), ticks - topo.vm_attr[:, 3]).sum()) / ticks
+    elif bike:
         from maro_b200.batch import BikeBatch
         from oracle.bike_oracle import BikeOracle  # checker / cpu_baseline leg only
         from tests.bike_helpers import bike_config
@@ -284,11 +401,13 @@ def run_ours(args, rank, local_rank, world):
     dec = torch.zeros((B, dec_words), dtype=torch.int32, device="cuda")
 
     def agent_device():
-        if bike:
+        if vm:
+            env.best_fit_policy_device(dec.data_ptr(), act.data_ptr())
+        elif bike:
             env.greedy_policy_device(dec.data_ptr(), act.data_ptr())
         else:
             env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
-    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    met = torch.zeros((B, met_words), dtype=torch.int64, device="cuda")
     act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     base = rank * B
@@ -382,8 +501,16 @@ def run_ours(args, rank, local_rank, world):
         p_act, p_nact, p_active, p_dec, p_met = env.pinned()
         dec_ptr, act_ptr = p_dec.ctypes.data, p_act.ctypes.data
 
+        if vm:
+            pm_nodes = np.arange(topo.n_pm)
+
         def host_agent():
-            if bike:
+            if vm:  # the reference agent's snapshot query (best_fit.py:38-44), batched over the replicas, then the argmin
+                live = p_dec[:, 6] == 0
+                frames = np.unique(p_dec[live, 2]).astype(np.int32) if live.any() else np.zeros(1, np.int32)
+                q = env.query("pms", frames, pm_nodes, ["cpu_cores_capacity", "cpu_cores_allocated"])
+                agent_lib.agent_best_fit(dec_ptr, act_ptr, B, 1, dec_words, q.ctypes.data, frames.ctypes.data, len(frames), topo.n_pm)
+            elif bike:
                 agent_lib.agent_greedy(dec_ptr, act_ptr, B, 1, dec_words)
             else:
                 agent_lib.agent_random(dec_ptr, act_ptr, B, 1, 0, base)
@@ -392,7 +519,11 @@ def run_ours(args, rank, local_rank, world):
         env.reset()
         env.step_pinned(use_actions=False)
         host_agent()
-        if bike:
+        if vm:
+            chk = VmOracle(topo, 1, vm_snaps)
+            _, od, _ = chk.step(None)
+            assert p_act[0, 0].tolist() == chk.best_fit(od).tolist(), (p_act[0, 0], chk.best_fit(od))
+        elif bike:
             from oracle.bike_oracle import policy_greedy
             assert p_act[0, 0].tolist() == policy_greedy(p_dec[0]).tolist()
         else:
@@ -430,7 +561,7 @@ def run_ours(args, rank, local_rank, world):
         from maro_b200.parallel import gather_metrics
 
         gathered = gather_metrics(met, world * B)
-        assert gathered.shape == (world * B, 3)
+        assert gathered.shape == (world * B, met_words)
     total_ms, kernel_ms, wall_ms, e2e_ms, graph_ms = (float(x) for x in t.cpu())
     g_steps, g_ticks, g_events, g_snaps, g_e2e_steps, g_graph_steps = (int(x) for x in cnt.cpu())
 
@@ -446,23 +577,34 @@ def run_ours(args, rank, local_rank, world):
         n_snap = g_snaps / max(1, g_steps)
         n_ev = g_events / max(1, g_steps)
         bytes_per_step = 2 * F + n_snap * F + 32 * n_ev + 64
+        if vm:
+            # per snapshot one frame row written; per tick every live VM's list entry (16 B) + its reading
+            # (4 B + 1 B) read and the 5 dynamic PM attributes rewritten; per step the decision / metrics / action rows
+            n_tick = g_ticks / max(1, g_steps)
+            bytes_per_step = n_snap * F + n_tick * (21.0 * vm_avg_live + 20.0 * topo.n_pm) + dec_words * 4 + 128 + 16
         achieved = bytes_per_step * g_steps / world / (kernel_ms / 1000.0) / 1e9  # per GPU
         value = g_steps / (total_ms / 1000.0)
+        snaps = args.max_snapshots or "all"
+        if vm:
+            workload = (f"vm_scheduling synthetic azure.2019.10k-scale trace ({topo.n_vm} VMs, {topo.n_pm} PMs 32c/128G, {ticks} ticks; "
+                        f"tools/vm_trace_gen.py), {B} parallel envs per GPU, best-fit agent, snapshot_resolution 1, max_snapshots {vm_snaps}")
+        elif bike:
+            workload = (f"citi_bike toy.3s_4t (frozen trace), {B} parallel envs per GPU, {topo.max_tick} ticks, greedy top-1 agent, "
+                        f"snapshot_resolution 10, max_snapshots {snaps}")
+        else:
+            workload = (f"CIM {args.topology}, {B} parallel envs per GPU, {args.ticks} ticks, random actions (hashed hello-world "
+                        f"agent), snapshot_resolution 1, max_snapshots {snaps}")
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": (f"citi_bike toy.3s_4t (frozen trace), {B} parallel envs per GPU, {topo.max_tick} ticks, greedy "
-                                    f"top-1 agent, snapshot_resolution 10, max_snapshots {args.max_snapshots or 'all'}") if bike else
-                                   (f"CIM {args.topology}, {B} parallel envs per GPU, {args.ticks} ticks, random actions "
-                                    f"(hashed hello-world agent), snapshot_resolution 1, max_snapshots "
-                                    f"{args.max_snapshots or 'all'}"),
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64" if vm else "int32", "data": "synthetic",
+            "config": {"workload": workload,
                        "replicas_per_gpu": B, "l2": "state resident (no flush)" if args.no_flush else "flushed between timed steps (256 MiB write)",
                        "steps_per_episode": steps_per_episode},
             "ticks_per_s": g_ticks / (total_ms / 1000.0), "events_per_s": g_events / (total_ms / 1000.0),
             "wall_ms": wall_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "bike_step_kernel" if bike else "cim_step_kernel", "bytes_per_env_step": bytes_per_step,
+                         "traffic": None, "kernel": "vm_step_kernel" if vm else ("bike_step_kernel" if bike else "cim_step_kernel"), "bytes_per_env_step": bytes_per_step,
                          "n_snap": n_snap, "n_ev": n_ev, "kernel_us": 1000.0 * kernel_ms / args.steps,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "clocks": clocks,
@@ -470,15 +612,17 @@ def run_ours(args, rank, local_rank, world):
         }
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
-                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + 24),
-                           "api": "maro_%s_step_pinned (pinned host buffers) + tools/host_agent.c on the host" % ("bike" if bike else "cim"),
+                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + met_words * 8) + (B * topo.n_pm * 16 if vm else 0),
+                           "api": ("maro_vm_step_pinned + maro_vm_query (the agent's snapshot query) + tools/host_agent.c on the host" if vm else
+                                   "maro_%s_step_pinned (pinned host buffers) + tools/host_agent.c on the host" % ("bike" if bike else "cim")),
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
         if graph_info:
             line["graph_mode"] = {"value": g_graph_steps / (graph_ms / 1000.0), "unit": "env-steps/s",
                                   "chunk_steps": graph_info["chunk"], "us_per_step": 1000.0 * graph_ms / max(1, (args.steps // graph_info["chunk"]) * graph_info["chunk"]),
                                   "l2": "flushed between graph chunks"}
-        line["cpu_baseline"] = (cpu_baseline_bike(args, topo) if bike else cpu_baseline_port(args, topo)) if world == 1 else None
+        line["cpu_baseline"] = (cpu_baseline_vm(args, topo, vm_snaps) if vm else
+                                (cpu_baseline_bike(args, topo) if bike else cpu_baseline_port(args, topo))) if world == 1 else None
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:

@@ -290,7 +290,8 @@ typedef struct MaroVmTopology {
     const int32_t* util_has;       /* 1 where the trace holds a reading for that tick                          */
 } MaroVmTopology;
 
-/* Decision row: MARO_VM_DEC_HEAD int32 header + n_pm words of valid PM ids (DecisionEvent, vm_scheduling/common.py:66-120). */
+/* Decision row: MARO_VM_DEC_HEAD int32 header + n_pm words of valid PM ids, ascending (DecisionEvent,
+ * vm_scheduling/common.py:66-120); maro_vm_decision_words() = 12 + n_pm rounded up to a multiple of 4. */
 enum {
     MARO_VM_DEC_TICK = 0,
     MARO_VM_DEC_VM_ID = 1,
@@ -330,6 +331,10 @@ int maro_vm_step(MaroVmEnv* env, const uint8_t* active, const int32_t* actions, 
                  int32_t* decisions, int64_t* metrics);
 int maro_vm_step_device(MaroVmEnv* env, const uint8_t* d_active, const int32_t* d_actions, const int32_t* d_n_actions,
                         int32_t* d_decisions, int64_t* d_metrics);
+/* zero host-copy variant over the library's pinned staging buffers (see maro_cim_pinned_buffers) */
+int maro_vm_pinned_buffers(MaroVmEnv* env, void** actions, void** n_actions, void** active, void** decisions,
+                           void** metrics);
+int maro_vm_step_pinned(MaroVmEnv* env, int32_t use_actions, int32_t use_n_actions, int32_t use_active);
 int maro_vm_reset(MaroVmEnv* env, const uint8_t* mask);
 int maro_vm_query(MaroVmEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
                   const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,

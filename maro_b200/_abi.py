@@ -179,7 +179,10 @@ class MaroVmTopology(C.Structure):
     ]
 
 
+VM_DEC_TICK, VM_DEC_VM_ID, VM_DEC_FRAME_INDEX, VM_DEC_CPU, VM_DEC_MEMORY, VM_DEC_SUB_ID = 0, 1, 2, 3, 4, 5
+VM_DEC_STATUS, VM_DEC_STEP, VM_DEC_CATEGORY, VM_DEC_BUFFER_TIME, VM_DEC_N_VALID = 6, 7, 8, 9, 10
 VM_DEC_HEAD = 12
+VM_ACTION_ALLOCATE, VM_ACTION_POSTPONE = 0, 1
 VM_METRIC_WORDS = 16
 VM_METRIC_NAMES = ("total_vm_requests", "total_incomes", "energy_consumption_cost", "total_profit",
                    "total_energy_consumption", "successful_allocation", "successful_completion", "failed_allocation",

@@ -25,6 +25,10 @@ EXPORTS = (
     "maro_bike_step_device", "maro_bike_reset", "maro_bike_query", "maro_bike_attr_id", "maro_bike_attr_slots",
     "maro_bike_read_frame", "maro_bike_frame_words", "maro_bike_ticks", "maro_bike_counters", "maro_bike_snapshot_frames",
     "maro_bike_greedy_policy_device",
+    "maro_vm_create", "maro_vm_destroy", "maro_vm_set_stream", "maro_vm_decision_words", "maro_vm_step",
+    "maro_vm_step_device", "maro_vm_pinned_buffers", "maro_vm_step_pinned", "maro_vm_reset", "maro_vm_query",
+    "maro_vm_attr_id", "maro_vm_attr_slots", "maro_vm_read_frame", "maro_vm_frame_words", "maro_vm_ticks",
+    "maro_vm_counters", "maro_vm_snapshot_frames", "maro_vm_best_fit_policy_device",
 )
 
 
@@ -66,9 +70,9 @@ def lib():
     L.maro_cim_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
     L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32]
     pvp = C.POINTER(vp)
-    for name in ("maro_cim_pinned_buffers", "maro_bike_pinned_buffers"):
+    for name in ("maro_cim_pinned_buffers", "maro_bike_pinned_buffers", "maro_vm_pinned_buffers"):
         getattr(L, name).argtypes = [vp, pvp, pvp, pvp, pvp, pvp]
-    for name in ("maro_cim_step_pinned", "maro_bike_step_pinned"):
+    for name in ("maro_cim_step_pinned", "maro_bike_step_pinned", "maro_vm_step_pinned"):
         getattr(L, name).argtypes = [vp, i32, i32, i32]
     L.maro_bike_create.argtypes = [vp, vp, C.POINTER(vp)]
     L.maro_bike_destroy.argtypes = [vp]
@@ -90,6 +94,27 @@ def lib():
     L.maro_bike_counters.argtypes = [vp, vp]
     L.maro_bike_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
     L.maro_bike_greedy_policy_device.argtypes = [vp, vp, vp]
+    for pre in ("maro_vm",):  # same shapes as the citi_bike entry points
+        getattr(L, pre + "_create").argtypes = [vp, vp, C.POINTER(vp)]
+        getattr(L, pre + "_destroy").argtypes = [vp]
+        getattr(L, pre + "_set_stream").argtypes = [vp, vp, i32]
+        getattr(L, pre + "_decision_words").argtypes = [vp]
+        getattr(L, pre + "_decision_words").restype = i32
+        getattr(L, pre + "_step").argtypes = [vp, vp, vp, vp, vp, vp]
+        getattr(L, pre + "_step_device").argtypes = [vp, vp, vp, vp, vp, vp]
+        getattr(L, pre + "_reset").argtypes = [vp, vp]
+        getattr(L, pre + "_query").argtypes = [vp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+        getattr(L, pre + "_attr_id").argtypes = [vp, i32, C.c_char_p]
+        getattr(L, pre + "_attr_id").restype = i32
+        getattr(L, pre + "_attr_slots").argtypes = [vp, i32, i32]
+        getattr(L, pre + "_attr_slots").restype = i32
+        getattr(L, pre + "_read_frame").argtypes = [vp, i32, vp, i32]
+        getattr(L, pre + "_frame_words").argtypes = [vp]
+        getattr(L, pre + "_frame_words").restype = i32
+        getattr(L, pre + "_ticks").argtypes = [vp, vp]
+        getattr(L, pre + "_counters").argtypes = [vp, vp]
+        getattr(L, pre + "_snapshot_frames").argtypes = [vp, i32, vp, i32, vp]
+    L.maro_vm_best_fit_policy_device.argtypes = [vp, vp, vp]
     if L.maro_abi_version() != _abi.ABI_VERSION:
         raise NativeLibraryError("libmaro_b200.so ABI version mismatch; rebuild")
     _lib = L

@@ -13,7 +13,7 @@ import numpy as np
 from . import _abi, _native
 from .scenarios.cim.topology import CimTopology
 
-def _pinned_views(lib_fn, handle, B, A, dec_words):
+def _pinned_views(lib_fn, handle, B, A, dec_words, met_words=3):
     """numpy views over the library's pinned staging buffers (no copies)."""
     ptrs = [C.c_void_p() for _ in range(5)]
     _native.check(lib_fn(handle, *[C.byref(p) for p in ptrs]))
@@ -24,7 +24,7 @@ def _pinned_views(lib_fn, handle, B, A, dec_words):
 
     return (view(ptrs[0], B * A * 16, np.int32, (B, A, 4)), view(ptrs[1], B * 4, np.int32, (B,)),
             view(ptrs[2], B, np.uint8, (B,)), view(ptrs[3], B * dec_words * 4, np.int32, (B, dec_words)),
-            view(ptrs[4], B * 24, np.int64, (B, 3)))
+            view(ptrs[4], B * met_words * 8, np.int64, (B, met_words)))
 
 
 _NODE_TYPE = {"ports": _abi.NODE_PORTS, "vessels": _abi.NODE_VESSELS, "matrices": _abi.NODE_MATRICES}
@@ -232,13 +232,20 @@ class BikeBatch:
     """Columnar wrapper over the citi_bike entry points of the C ABI (same shape as ``CimBatch``)."""
 
     _NODE = {"stations": 0, "matrices": 1}
+    _PREFIX = "maro_bike"
+    _MET_WORDS = 3
+
+    def _f(self, name):
+        return getattr(_native.lib(), f"{self._PREFIX}_{name}")
+
+    def _topology_struct(self, topology):
+        return _abi.bike_topology_struct(topology)
 
     def __init__(self, topology, n_replicas: int, snapshot_resolution: int = 1, max_snapshots: Optional[int] = None,
                  device: int = 0, max_actions: int = 1, queue_capacity: int = 0):
         self.topology = topology
         self.n_replicas, self.max_actions = int(n_replicas), int(max_actions)
-        L = _native.lib()
-        self._struct, self._keep = _abi.bike_topology_struct(topology)
+        self._struct, self._keep = self._topology_struct(topology)
         cfg = _abi.MaroCimConfig()
         cfg.n_replicas = self.n_replicas
         cfg.start_tick = int(topology.start_tick)
@@ -248,16 +255,16 @@ class BikeBatch:
         cfg.queue_capacity = int(queue_capacity)
         cfg.max_actions = self.max_actions
         h = C.c_void_p()
-        _native.check(L.maro_bike_create(C.byref(self._struct), C.byref(cfg), C.byref(h)))
+        _native.check(self._f("create")(C.byref(self._struct), C.byref(cfg), C.byref(h)))
         self._h = h
-        self.frame_words = L.maro_bike_frame_words(self._h)
-        self.dec_words = L.maro_bike_decision_words(self._h)
+        self.frame_words = self._f("frame_words")(self._h)
+        self.dec_words = self._f("decision_words")(self._h)
         self.decisions = np.zeros((self.n_replicas, self.dec_words), np.int32)
-        self.metrics = np.zeros((self.n_replicas, 3), np.int64)
+        self.metrics = np.zeros((self.n_replicas, self._MET_WORDS), np.int64)
 
     def close(self):
         if getattr(self, "_h", None):
-            _native.lib().maro_bike_destroy(self._h)
+            self._f("destroy")(self._h)
             self._h = None
 
     def __del__(self):
@@ -268,13 +275,13 @@ class BikeBatch:
 
     def set_stream(self, cuda_stream_ptr: Optional[int]):
         if cuda_stream_ptr is None:
-            _native.check(_native.lib().maro_bike_set_stream(self._h, None, 0))
+            _native.check(self._f("set_stream")(self._h, None, 0))
         else:
-            _native.check(_native.lib().maro_bike_set_stream(self._h, C.c_void_p(cuda_stream_ptr), 1))
+            _native.check(self._f("set_stream")(self._h, C.c_void_p(cuda_stream_ptr), 1))
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
-        _native.check(_native.lib().maro_bike_reset(self._h, None if m is None else m.ctypes.data))
+        _native.check(self._f("reset")(self._h, None if m is None else m.ctypes.data))
 
     def step(self, actions=None, n_actions=None, active=None):
         a = n = m = None
@@ -285,35 +292,35 @@ class BikeBatch:
             n = np.ascontiguousarray(n_actions, np.int32)
         if active is not None:
             m = np.ascontiguousarray(active, np.uint8)
-        _native.check(_native.lib().maro_bike_step(
+        _native.check(self._f("step")(
             self._h, None if m is None else m.ctypes.data, None if a is None else a.ctypes.data,
             None if n is None else n.ctypes.data, self.decisions.ctypes.data, self.metrics.ctypes.data))
         return self.decisions, self.metrics
 
     def pinned(self):
         if getattr(self, "_pinned", None) is None:
-            self._pinned = _pinned_views(_native.lib().maro_bike_pinned_buffers, self._h, self.n_replicas,
-                                         self.max_actions, self.dec_words)
+            self._pinned = _pinned_views(self._f("pinned_buffers"), self._h, self.n_replicas,
+                                         self.max_actions, self.dec_words, self._MET_WORDS)
         return self._pinned
 
     def step_pinned(self, use_actions: bool = True, use_n_actions: bool = False, use_active: bool = False):
-        _native.check(_native.lib().maro_bike_step_pinned(self._h, int(use_actions), int(use_n_actions), int(use_active)))
+        _native.check(self._f("step_pinned")(self._h, int(use_actions), int(use_n_actions), int(use_active)))
 
     def step_device(self, d_decisions: int, d_metrics: int, d_actions: int = 0, d_n_actions: int = 0, d_active: int = 0):
-        _native.check(_native.lib().maro_bike_step_device(self._h, d_active or None, d_actions or None,
+        _native.check(self._f("step_device")(self._h, d_active or None, d_actions or None,
                                                           d_n_actions or None, d_decisions, d_metrics))
 
     def greedy_policy_device(self, d_decisions: int, d_actions: int):
-        _native.check(_native.lib().maro_bike_greedy_policy_device(self._h, d_decisions, d_actions))
+        _native.check(self._f("greedy_policy_device")(self._h, d_decisions, d_actions))
 
     def attr_id(self, node: str, name: str) -> int:
-        i = _native.lib().maro_bike_attr_id(self._h, self._NODE[node], name.encode())
+        i = self._f("attr_id")(self._h, self._NODE[node], name.encode())
         if i < 0:
             raise KeyError(f"{node}.{name}")
         return i
 
     def attr_slots(self, node: str, attr_id: int) -> int:
-        return _native.lib().maro_bike_attr_slots(self._h, self._NODE[node], attr_id)
+        return self._f("attr_slots")(self._h, self._NODE[node], attr_id)
 
     def query(self, node: str, frame_indices, nodes, attrs, replicas=None) -> np.ndarray:
         reps = np.arange(self.n_replicas, dtype=np.int32) if replicas is None else np.ascontiguousarray(replicas, np.int32)
@@ -323,31 +330,31 @@ class BikeBatch:
         per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
         out = np.zeros((len(reps), per), np.float64)
         pr = C.c_int64()
-        _native.check(_native.lib().maro_bike_query(self._h, reps.ctypes.data, len(reps), self._NODE[node], fr.ctypes.data,
+        _native.check(self._f("query")(self._h, reps.ctypes.data, len(reps), self._NODE[node], fr.ctypes.data,
                                                     len(fr), nd.ctypes.data, len(nd), at.ctypes.data, len(at),
                                                     out.ctypes.data, C.byref(pr)))
         return out
 
     def read_frame(self, replica: int = 0) -> np.ndarray:
         out = np.zeros(self.frame_words, np.int32)
-        _native.check(_native.lib().maro_bike_read_frame(self._h, replica, out.ctypes.data, out.size))
+        _native.check(self._f("read_frame")(self._h, replica, out.ctypes.data, out.size))
         return out
 
     def ticks(self) -> np.ndarray:
         out = np.zeros(self.n_replicas, np.int32)
-        _native.check(_native.lib().maro_bike_ticks(self._h, out.ctypes.data))
+        _native.check(self._f("ticks")(self._h, out.ctypes.data))
         return out
 
     def counters(self) -> np.ndarray:
         out = np.zeros((self.n_replicas, 4), np.int64)
-        _native.check(_native.lib().maro_bike_counters(self._h, out.ctypes.data))
+        _native.check(self._f("counters")(self._h, out.ctypes.data))
         return out
 
     def snapshot_frames(self, replica: int = 0) -> np.ndarray:
         cap = 1 << 16
         out = np.zeros(cap, np.int32)
         n = C.c_int32()
-        _native.check(_native.lib().maro_bike_snapshot_frames(self._h, replica, out.ctypes.data, cap, C.byref(n)))
+        _native.check(self._f("snapshot_frames")(self._h, replica, out.ctypes.data, cap, C.byref(n)))
         return out[:n.value].copy()
 
     def snapshot_row(self, frame_index: int, replica: int = 0):
@@ -363,4 +370,41 @@ class BikeBatch:
             row[off:off + S] = vals[:, k].astype(np.int64)
         off, _, slots = lay["matrices"]["trips_adj"]
         row[off:off + slots] = self.query("matrices", [frame_index], [0], ["trips_adj"], [replica])[0].astype(np.int64)
+        return row
+
+
+class VmBatch(BikeBatch):
+    """Columnar wrapper over the vm_scheduling entry points of the C ABI.  Decision rows: ``_abi.VM_DEC_*`` header +
+    valid PM ids; metrics rows: 16 x int64 (``_abi.vm_metrics_dict`` decodes the float64 slots)."""
+
+    _NODE = {"pms": 0, "racks": 1, "clusters": 2, "data_centers": 3, "zones": 4, "regions": 5}
+    _PREFIX = "maro_vm"
+    _MET_WORDS = 16
+
+    def _topology_struct(self, topology):
+        if getattr(topology, "error", None):
+            raise Exception(topology.error)
+        return _abi.vm_topology_struct(topology)
+
+    def greedy_policy_device(self, d_decisions: int, d_actions: int):
+        raise AttributeError("vm_scheduling has best_fit_policy_device")
+
+    def best_fit_policy_device(self, d_decisions: int, d_actions: int):
+        _native.check(self._f("best_fit_policy_device")(self._h, d_decisions, d_actions))
+
+    def snapshot_row(self, frame_index: int, replica: int = 0):
+        if frame_index not in set(self.snapshot_frames(replica).tolist()):
+            return None
+        lay, fw = _abi.vm_frame_layout(self.topology)
+        row = np.zeros(fw, np.int32)
+        for node, attrs in lay.items():
+            names = list(attrs)
+            n = attrs[names[0]][1]
+            vals = self.query(node, [frame_index], np.arange(n), names, [replica])[0].reshape(n, len(names))
+            for k, a in enumerate(names):
+                off = attrs[a][0]
+                if a in _abi.VM_FLOAT_ATTRS:
+                    row[off:off + n] = vals[:, k].astype(np.float32).view(np.int32)
+                else:
+                    row[off:off + n] = vals[:, k].astype(np.int64)
         return row

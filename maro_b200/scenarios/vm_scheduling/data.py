@@ -28,26 +28,34 @@ def _find_item(key, dictionary):
 
 
 class _TickPicker:
-    """ItemTickPicker (binary_reader.py:71-113) over an already filtered item array, time unit = seconds."""
+    """ItemTickPicker (binary_reader.py:71-113) over an already filtered item array, time unit = seconds.  Items are
+    consumed front to back: earlier timestamps are dropped, equal ones picked, the scan stops at the first later one."""
 
     def __init__(self, items, starttime):
         self.items, self.pos, self.starttime = items, 0, starttime
+        self.ts = items["timestamp"].astype(np.int64)
+        self.sorted = bool(len(self.ts) < 2 or (np.diff(self.ts) >= 0).all())
 
     def pick(self, tick):
+        """-> the picked items (a structured array slice when the timestamps are sorted)."""
         t0 = self.starttime + tick
+        if self.sorted:
+            lo = max(self.pos, int(np.searchsorted(self.ts, t0, "left")))
+            hi = max(lo, int(np.searchsorted(self.ts, t0, "right")))
+            self.pos = hi
+            return self.items[lo:hi]
         out = []
         while self.pos < len(self.items):
-            it = self.items[self.pos]
-            ts = int(it["timestamp"])
+            ts = int(self.ts[self.pos])
             if ts >= t0:
                 if ts - t0 < 1:
-                    out.append(it)
+                    out.append(self.pos)
                     self.pos += 1
                 else:
                     break
             else:
                 self.pos += 1  # unsorted leftovers are dropped
-        return out
+        return self.items[out]
 
 
 class _CpuReader:
@@ -75,25 +83,29 @@ class _CpuReader:
         self.path = self._next_name(self.path)
         self._open(first=False)
 
-    def _pick(self, cur, tick):
-        end_time = 0
-        for it in self.picker.pick(tick - self.st):
-            cur[int(it["vm_id"])] = float(it["cpu_utilization"])
-            end_time = int(it["timestamp"])
-        return cur, end_time
+    def _pick(self, tick):
+        got = self.picker.pick(tick - self.st)
+        end_time = int(got["timestamp"][-1]) if len(got) else 0
+        return got["vm_id"].astype(np.int64), got["cpu_utilization"].astype(np.float64), end_time
 
-    def items(self, tick) -> Dict[int, float]:
-        cur, end_time = self._pick({}, tick)
+    def items_arrays(self, tick):
+        """CpuReader.items(tick) as (vm ids, utilisations) in arrival order (a later row of the same id wins)."""
+        ids, vals, end_time = self._pick(tick)
         if end_time == 8638:
-            return cur
+            return ids, vals
         while end_time == self.et:
             nxt = os.path.expanduser(self._next_name(self.path))
             if not os.path.exists(nxt):
                 break
             self._switch()
             if self.st == end_time:
-                cur, _ = self._pick(cur, tick)
-        return cur
+                i2, v2, _ = self._pick(tick)
+                ids, vals = np.concatenate([ids, i2]), np.concatenate([vals, v2])
+        return ids, vals
+
+    def items(self, tick) -> Dict[int, float]:
+        ids, vals = self.items_arrays(tick)
+        return {int(i): float(v) for i, v in zip(ids, vals)}
 
 
 @dataclass
@@ -231,42 +243,57 @@ def build_vm_topology(conf: dict, start_tick: int, max_tick: int) -> VmTopology:
     req_offset = np.cumsum(req_offset).astype(np.int32)
     order = np.argsort(vm_attr[:, 0], kind="stable")
 
-    # ---- utilisation series: replay CpuReader.items(tick) for every tick, forward-fill per VM from its request tick
+    # ---- utilisation series: replay CpuReader.items(tick) for every tick, forward-fill per VM from its request tick.
+    # A VM needs its series only while it can still be pending or live: at most buffer budget + lifetime ticks after
+    # its request (a zero lifetime never matches a later deletion tick, so such a VM lives to the end).
     reader = _CpuReader(conf["CPU_READINGS"], start_tick)
-    idx_of = {int(v): i for i, v in enumerate(vm_attr[:, 0])}
-    series: List[List[float]] = [[] for _ in range(n_vm)]
-    has: List[List[int]] = [[] for _ in range(n_vm)]
-    active: List[int] = []
-    nxt = 0
+    req, life = vm_attr[:, 3].astype(np.int64), vm_attr[:, 4].astype(np.int64)
+    budget = int(conf["BUFFER_TIME_BUDGET"]) + int(conf["DELAY_DURATION"]) + 2
+    last = np.where(life <= 0, max_tick - 1, np.minimum(max_tick - 1, req + life + budget))
+    util_offset = np.zeros(n_vm + 1, np.int64)
+    np.cumsum(np.maximum(last - req + 1, 0), out=util_offset[1:])
+    util_val = np.zeros(int(util_offset[-1]), np.float64)
+    util_has = np.zeros(int(util_offset[-1]), np.int32)
+    sorted_ids, sorted_idx = vm_attr[order, 0].astype(np.int64), order
+    unique_ids = bool(n_vm < 2 or (np.diff(sorted_ids) > 0).all())
+    cur = np.zeros(n_vm, np.float64)
+    hasnow = np.zeros(n_vm, np.int32)
     error = None
     for t in range(start_tick, max_tick):
-        readings = reader.items(t)
-        while nxt < n_vm and vm_attr[nxt, 3] == t:
-            if int(vm_attr[nxt, 0]) not in readings:
-                # the reference raises this from BusinessEngine.step (:476-477); surfaced when the env is created
-                error = error or f"The VM id: '{int(vm_attr[nxt, 0])}' does not exist at this tick."
-                readings = dict(readings)
-                readings[int(vm_attr[nxt, 0])] = 0.0
-            active.append(nxt)
-            nxt += 1
-        # a VM needs its series only while it can still be pending or live: at most buffer budget + lifetime ticks
-        # after its request (a zero lifetime never matches a later deletion tick, so such a VM lives to the end)
-        budget = int(conf["BUFFER_TIME_BUDGET"]) + int(conf["DELAY_DURATION"]) + 2
-        active = [i for i in active if vm_attr[i, 4] <= 0 or t <= vm_attr[i, 3] + vm_attr[i, 4] + budget]
-        for i in active:
-            vid = int(vm_attr[i, 0])
-            if vid in readings:
-                series[i].append(readings[vid])
-                has[i].append(1)
-            else:
-                series[i].append(series[i][-1])
-                has[i].append(0)
-    util_offset = np.zeros(n_vm + 1, np.int64)
-    for i in range(n_vm):
-        util_offset[i + 1] = util_offset[i] + len(series[i])
-    util_val = np.asarray([x for s_ in series for x in s_], np.float64)
-    util_has = np.asarray([x for s_ in has for x in s_], np.int32)
-    del idx_of
+        rid, rval = reader.items_arrays(t)
+        hi = int(req_offset[t + 1])
+        if len(rid) and n_vm:
+            if unique_ids:
+                pos = np.minimum(np.searchsorted(sorted_ids, rid), n_vm - 1)
+                ok = sorted_ids[pos] == rid
+                vi, vv = sorted_idx[pos[ok]], rval[ok]
+            else:  # several table rows share a vm id: each of them sees the reading
+                lo_, hi_ = np.searchsorted(sorted_ids, rid, "left"), np.searchsorted(sorted_ids, rid, "right")
+                rep = hi_ - lo_
+                vi = sorted_idx[np.concatenate([np.arange(a_, b_) for a_, b_ in zip(lo_, hi_)])] if rep.sum() else rid[:0]
+                vv = np.repeat(rval, rep)
+            if len(vi) != len(np.unique(vi)):  # a later row of the same id wins
+                _, first_rev = np.unique(vi[::-1], return_index=True)
+                keep_ = np.sort(len(vi) - 1 - first_rev)
+                vi, vv = vi[keep_], vv[keep_]
+            cur[vi] = vv
+            hasnow[vi] = 1
+        else:
+            vi = np.zeros(0, np.int64)
+        new = np.arange(int(req_offset[t]), hi)
+        missing = new[hasnow[new] == 0]
+        if len(missing):
+            # the reference raises this from BusinessEngine.step (:476-477); surfaced when the env is created
+            error = error or f"The VM id: '{int(vm_attr[missing[0], 0])}' does not exist at this tick."
+            cur[missing] = 0.0
+            hasnow[missing] = 1
+        act = np.nonzero(last[:hi] >= t)[0]
+        if len(act):
+            p = util_offset[act] + (t - req[act])
+            util_val[p] = cur[act]
+            util_has[p] = hasnow[act]
+        hasnow[vi] = 0
+        hasnow[missing] = 0
     return VmTopology(
         config=conf, start_tick=start_tick, max_tick=max_tick, n_pm=len(pm_attr), n_rack=len(racks),
         n_cluster=len(clusters), n_dc=len(dcs), n_zone=len(zones), n_region=len(regions), pm_attr=pm_attr,

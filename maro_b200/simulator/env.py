@@ -9,7 +9,7 @@ from typing import List, Optional
 import numpy as np
 
 from .. import _abi
-from ..batch import BikeBatch, CimBatch
+from ..batch import BikeBatch, CimBatch, VmBatch
 from ..scenarios.cim.common import Action, ActionScope, ActionType, DecisionEvent, encode_action
 from ..scenarios.cim.topology import CimTopology, build_topology, load_config, next_topology_seed
 
@@ -58,7 +58,12 @@ class SnapshotList:
 
     def __init__(self, batch, replica: int):
         self._batch, self._replica = batch, replica
-        if isinstance(batch, BikeBatch):
+        if isinstance(batch, VmBatch):
+            t = batch.topology
+            self._nodes = {n: SnapshotNode(self, n, c) for n, c in (
+                ("pms", t.n_pm), ("racks", t.n_rack), ("clusters", t.n_cluster), ("data_centers", t.n_dc),
+                ("zones", t.n_zone), ("regions", t.n_region))}
+        elif isinstance(batch, BikeBatch):
             self._nodes = {"stations": SnapshotNode(self, "stations", batch.topology.n_stations),
                            "matrices": SnapshotNode(self, "matrices", 1)}
         else:
@@ -125,8 +130,8 @@ class Env:
                  business_engine_cls: type = None, disable_finished_events: bool = False,
                  record_finished_events: bool = False, record_file_path: str = None, options: Optional[dict] = None,
                  device: int = 0):
-        if scenario not in ("cim", "citi_bike"):
-            raise NotImplementedError(f"scenario {scenario!r}: 'cim' and 'citi_bike' run on the CUDA core in this build")
+        if scenario not in ("cim", "citi_bike", "vm_scheduling"):
+            raise NotImplementedError(f"scenario {scenario!r}: 'cim', 'citi_bike' and 'vm_scheduling' run on the CUDA core")
         if business_engine_cls is not None:
             raise NotImplementedError("custom business engines run on the reference Env, not on the CUDA core")
         if int(decision_mode) != int(DecisionMode.Sequential):
@@ -144,6 +149,12 @@ class Env:
             self._topo = build_bike_topology(self._config, start_tick, start_tick + durations,
                                              transfer_seed=int((options or {}).get("transfer_seed", 0)))
             self._batch = BikeBatch(self._topo, 1, snapshot_resolution, max_snapshots, device=device, max_actions=8)
+        elif scenario == "vm_scheduling":
+            from ..scenarios.vm_scheduling.data import build_vm_topology, load_vm_config
+
+            self._config = load_vm_config(topology)
+            self._topo = build_vm_topology(self._config, start_tick, start_tick + durations)
+            self._batch = VmBatch(self._topo, 1, snapshot_resolution, max_snapshots, device=device, max_actions=8)
         else:
             self._config = load_config(topology)
             self._topo = build_topology(self._config, start_tick + durations)
@@ -170,6 +181,10 @@ class Env:
                 from ..scenarios.citi_bike.common import encode_bike_action
 
                 encode_bike_action(a, self._act[0, i])
+            elif self._scenario == "vm_scheduling":
+                from ..scenarios.vm_scheduling.common import encode_vm_action
+
+                encode_vm_action(a, self._act[0, i])
             else:
                 encode_action(a, self._act[0, i])
         self._nact[0] = len(actions)
@@ -177,6 +192,8 @@ class Env:
         d = dec[0]
         status = int(d[_abi.DEC_STATUS])
         if status == _abi.STATUS_BAD_ACTION:
+            if self._scenario == "vm_scheduling":
+                raise Exception("The VM id or PM id sent by agent is invalid. (vm_scheduling/business_engine.py:842)")
             raise AssertionError("invalid action: quantity exceeds the action scope (business_engine.py:731,736)")
         if status == _abi.STATUS_QUEUE_OVERFLOW:
             raise RuntimeError("event queue overflow: recreate the Env with a larger queue_capacity")
@@ -192,6 +209,13 @@ class Env:
             if status == _abi.STATUS_DONE:
                 return self._last_metrics, None, True
             return self._last_metrics, decode_bike_decision(d, self._snapshots), False
+        if self._scenario == "vm_scheduling":
+            from ..scenarios.vm_scheduling.common import decode_vm_decision, decode_vm_metrics
+
+            self._last_metrics = DocableDict("vm_scheduling metrics", decode_vm_metrics(met[0]))
+            if status == _abi.STATUS_DONE:
+                return self._last_metrics, None, True
+            return self._last_metrics, decode_vm_decision(d), False
         self._last_metrics = make_metrics(met[0])
         if status == _abi.STATUS_DONE:
             return self._last_metrics, None, True
@@ -204,7 +228,7 @@ class Env:
     def reset(self, keep_seed: bool = False) -> None:
         """core.py:143-170 + cim_data_container_helpers.py:56-66: ``keep_seed=False`` draws a new topology seed from
         the route_init stream; a seed set with ``set_seed`` takes effect here."""
-        if self._scenario == "citi_bike":  # CitibikeBusinessEngine.set_seed is a no-op (business_engine.py:198-199)
+        if self._scenario in ("citi_bike", "vm_scheduling"):  # their set_seed is a no-op (citi_bike/business_engine.py:198-199)
             self._batch.reset()
             self._tick = self._start_tick
             return
@@ -271,6 +295,8 @@ class Env:
 
     @property
     def agent_idx_list(self) -> List[int]:
+        if self._scenario == "vm_scheduling":
+            return list(range(self._topo.n_pm))  # get_agent_idx_list (vm_scheduling/business_engine.py:531-535)
         return list(range(self._topo.n_stations if self._scenario == "citi_bike" else self._topo.n_ports))
 
     @property

@@ -11,7 +11,7 @@ from typing import List, Optional
 import numpy as np
 
 from .. import _abi
-from ..batch import BikeBatch, CimBatch
+from ..batch import BikeBatch, CimBatch, VmBatch
 from ..scenarios.cim.common import ActionScope, DecisionEvent, encode_action
 from ..scenarios.cim.topology import build_topology, load_config
 from ..simulator.env import DecisionMode, SnapshotList, make_metrics
@@ -37,8 +37,8 @@ class VectorEnv:
                  decision_mode=DecisionMode.Sequential, business_engine_cls: type = None,
                  disable_finished_events: bool = False, options: dict = {}, device: int = 0, seeds=None):
         assert batch_num > 0
-        if scenario not in ("cim", "citi_bike") or business_engine_cls is not None or int(decision_mode) != 0:
-            raise NotImplementedError("the CUDA core implements scenario='cim' / 'citi_bike', Sequential mode")
+        if scenario not in ("cim", "citi_bike", "vm_scheduling") or business_engine_cls is not None or int(decision_mode) != 0:
+            raise NotImplementedError("the CUDA core implements scenario='cim' / 'citi_bike' / 'vm_scheduling', Sequential mode")
         self._batch_num = batch_num
         self._scenario = scenario
         self._start_tick, self._resolution = start_tick, snapshot_resolution
@@ -48,6 +48,13 @@ class VectorEnv:
             topo = build_bike_topology(load_bike_config(topology), start_tick, start_tick + durations,
                                        transfer_seed=int((options or {}).get("transfer_seed", 0)))
             self._batch = BikeBatch(topo, batch_num, snapshot_resolution, max_snapshots, device=device, max_actions=4)
+            self._finish_init(batch_num, start_tick)
+            return
+        if scenario == "vm_scheduling":
+            from ..scenarios.vm_scheduling.data import build_vm_topology, load_vm_config
+
+            topo = build_vm_topology(load_vm_config(topology), start_tick, start_tick + durations)
+            self._batch = VmBatch(topo, batch_num, snapshot_resolution, max_snapshots, device=device, max_actions=4)
             self._finish_init(batch_num, start_tick)
             return
         conf = load_config(topology)
@@ -99,6 +106,10 @@ class VectorEnv:
                 from ..scenarios.citi_bike.common import encode_bike_action
 
                 encode_bike_action(a, self._act[i, k])
+            elif self._scenario == "vm_scheduling":
+                from ..scenarios.vm_scheduling.common import encode_vm_action
+
+                encode_vm_action(a, self._act[i, k])
             else:
                 encode_action(a, self._act[i, k])
         self._nact[i] = len(acts)
@@ -127,7 +138,7 @@ class VectorEnv:
                 continue
             st = int(dec[i, _abi.DEC_STATUS])
             if st == _abi.STATUS_BAD_ACTION:
-                raise AssertionError(f"env {i}: invalid action (quantity exceeds the action scope)")
+                raise AssertionError(f"env {i}: invalid action (outside the action scope / unknown VM or PM id)")
             if st == _abi.STATUS_QUEUE_OVERFLOW:
                 raise RuntimeError(f"env {i}: event queue overflow")
             if st == _abi.STATUS_FINISHED:  # env_process.py:37-40
@@ -145,6 +156,16 @@ class VectorEnv:
                     events.append(None)
                 else:
                     events.append(decode_bike_decision(dec[i], self._snapshot_lists[i]))
+                continue
+            if self._scenario == "vm_scheduling":
+                from ..scenarios.vm_scheduling.common import decode_vm_decision, decode_vm_metrics
+
+                metrics.append(decode_vm_metrics(met[i]))
+                if st == _abi.STATUS_DONE:
+                    self._done[i] = True
+                    events.append(None)
+                else:
+                    events.append(decode_vm_decision(dec[i]))
                 continue
             metrics.append(make_metrics(met[i]))
             if st == _abi.STATUS_DONE:

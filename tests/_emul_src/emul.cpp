@@ -159,3 +159,65 @@ int bike_emul_read_snapshot(BikeEmul* e, int rep, int frame, int32_t* out) {
 int bike_emul_tick(BikeEmul* e, int rep) { return e->state[(size_t)rep * e->s.SW + e->s.FWp + BC_TICK]; }
 void bike_emul_counters(BikeEmul* e, int rep, int64_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW + e->s.FWp + BC_NSTEPS_LO, 32); }
 }
+
+// ------------------------------------------------------------------------------------------------ vm_scheduling
+#include "../../maro_b200/csrc/vm_host.hpp"
+
+struct VmEmul {
+    VmShape s;
+    std::vector<int32_t> tables, state, snap, snap_frame;
+    std::vector<double> scratch;
+    int B = 0, lanes = 32;
+    std::string err;
+};
+template <int G>
+static void vm_reset_g(VmEmul* e, int i) {
+    VmReplica r = vm_replica_at(e->s, e->state.data(), e->tables.data(), e->snap.data(), e->snap_frame.data(), i);
+    wemu::run_group(G, [&](int lane) { vm_replica_reset<G>(e->s, Grp<G>(lane), r); });
+}
+template <int G>
+static void vm_step_g(VmEmul* e, int i, const int32_t* actp, int n, int32_t* dec, int64_t* met) {
+    VmReplica r = vm_replica_at(e->s, e->state.data(), e->tables.data(), e->snap.data(), e->snap_frame.data(), i);
+    wemu::run_group(G, [&](int lane) { vm_replica_step<G>(e->s, Grp<G>(lane), r, actp, n, dec, met, e->scratch.data()); });
+}
+extern "C" {
+VmEmul* vm_emul_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, int lanes) {
+    VmEmul* e = new VmEmul();
+    e->err = vm_compute_shape_and_tables(*topo, cfg, e->s, e->tables);
+    if (!e->err.empty()) { fprintf(stderr, "vm_emul_create: %s\n", e->err.c_str()); delete e; return nullptr; }
+    e->B = cfg->n_replicas;
+    e->lanes = lanes > 0 ? lanes : 32;
+    e->state.assign((size_t)e->B * e->s.SW, 0);
+    e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
+    e->snap_frame.assign((size_t)e->B * e->s.ring_rows, -1);
+    e->scratch.assign(2 * (size_t)e->s.N, 0.0);
+    for (int i = 0; i < e->B; i++) { if (e->lanes == 1) vm_reset_g<1>(e, i); else if (e->lanes == 8) vm_reset_g<8>(e, i); else vm_reset_g<32>(e, i); }
+    return e;
+}
+void vm_emul_destroy(VmEmul* e) { delete e; }
+int vm_emul_dec_words(VmEmul* e) { return e->s.DW; }
+int vm_emul_frame_words(VmEmul* e) { return e->s.FW; }
+void vm_emul_reset(VmEmul* e) {
+    for (int i = 0; i < e->B; i++) { if (e->lanes == 1) vm_reset_g<1>(e, i); else if (e->lanes == 8) vm_reset_g<8>(e, i); else vm_reset_g<32>(e, i); }
+}
+void vm_emul_step(VmEmul* e, const int32_t* actions, const int32_t* n_actions, int32_t* decisions, int64_t* metrics) {
+    for (int i = 0; i < e->B; i++) {
+        int n = actions ? (n_actions ? n_actions[i] : 1) : 0;
+        const int32_t* act = actions ? actions + (size_t)i * e->s.max_actions * 4 : nullptr;
+        int32_t* dec = decisions + (size_t)i * e->s.DW;
+        int64_t* met = metrics + (size_t)i * MARO_VM_METRIC_WORDS;
+        if (e->lanes == 1) vm_step_g<1>(e, i, act, n, dec, met);
+        else if (e->lanes == 8) vm_step_g<8>(e, i, act, n, dec, met);
+        else vm_step_g<32>(e, i, act, n, dec, met);
+    }
+}
+void vm_emul_read_frame(VmEmul* e, int rep, int32_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW, 4 * e->s.FW); }
+int vm_emul_read_snapshot(VmEmul* e, int rep, int frame, int32_t* out) {
+    int row = frame % e->s.ring_rows;
+    if (frame < 0 || e->snap_frame[(size_t)rep * e->s.ring_rows + row] != frame) return 0;
+    memcpy(out, e->snap.data() + ((size_t)rep * e->s.ring_rows + row) * e->s.FWp, 4 * e->s.FW);
+    return 1;
+}
+int vm_emul_tick(VmEmul* e, int rep) { return e->state[(size_t)rep * e->s.SW + e->s.FWp + VC_TICK]; }
+void vm_emul_counters(VmEmul* e, int rep, int64_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW + e->s.FWp + VC_NSTEPS, 32); }
+}

@@ -21,11 +21,13 @@ def lib():
     global _lib
     if _lib is None:
         deps = [SRC, os.path.join(os.path.dirname(SRC), "warp_emul.hpp"), os.path.join(CORE, "cim_core.cuh"),
-                os.path.join(CORE, "cim_host.hpp"), os.path.join(CORE, "bike_core.cuh"), os.path.join(CORE, "bike_host.hpp")]
+                os.path.join(CORE, "cim_host.hpp"), os.path.join(CORE, "bike_core.cuh"), os.path.join(CORE, "bike_host.hpp"),
+                os.path.join(CORE, "vm_core.cuh"), os.path.join(CORE, "vm_host.hpp")]
         if not os.path.isfile(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-ffp-contract=off",
-                                   "-DMARO_HOST_EMULATION", "-I", os.path.dirname(SRC), "-shared", "-fPIC", SRC,
+                                   "-DMARO_HOST_EMULATION", "-I", os.path.dirname(SRC), "-I", os.path.join(HERE, "..", "include"),
+                                   "-shared", "-fPIC", SRC,
                                    "-o", LIB])
         _lib = C.CDLL(LIB)
         _lib.emul_create.restype = C.c_void_p
@@ -48,6 +50,17 @@ def lib():
         _lib.bike_emul_read_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.bike_emul_tick.argtypes = [C.c_void_p, C.c_int]
         _lib.bike_emul_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.vm_emul_create.restype = C.c_void_p
+        _lib.vm_emul_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _lib.vm_emul_destroy.argtypes = [C.c_void_p]
+        _lib.vm_emul_reset.argtypes = [C.c_void_p]
+        _lib.vm_emul_dec_words.argtypes = [C.c_void_p]
+        _lib.vm_emul_frame_words.argtypes = [C.c_void_p]
+        _lib.vm_emul_step.argtypes = [C.c_void_p] * 5
+        _lib.vm_emul_read_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.vm_emul_read_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib.vm_emul_tick.argtypes = [C.c_void_p, C.c_int]
+        _lib.vm_emul_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -168,4 +181,61 @@ class BikeEmulEnv:
     def counters(self):
         out = np.zeros(4, np.int64)
         lib().bike_emul_counters(self._h, 0, out.ctypes.data)
+        return out
+
+
+class VmEmulEnv:
+    """vm_scheduling device logic under the thread-per-lane emulator (one replica)."""
+
+    def __init__(self, topo, snapshot_resolution=1, max_snapshots=None, max_actions=2, lanes=0):
+        self._struct, self._keep = _abi.vm_topology_struct(topo)
+        cfg = _abi.MaroCimConfig()
+        cfg.n_replicas = 1
+        cfg.start_tick = topo.start_tick
+        cfg.snapshot_resolution = snapshot_resolution
+        cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
+        cfg.max_actions = max_actions
+        self.A = max_actions
+        self._h = lib().vm_emul_create(C.byref(self._struct), C.byref(cfg), lanes)
+        assert self._h
+        self.dec_words = lib().vm_emul_dec_words(self._h)
+        self.frame_words = lib().vm_emul_frame_words(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vm_emul_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().vm_emul_reset(self._h)
+
+    def step(self, actions=None):
+        dec = np.zeros((1, self.dec_words), np.int32)
+        met = np.zeros((1, 16), np.int64)
+        if actions is None:
+            lib().vm_emul_step(self._h, None, None, dec.ctypes.data, met.ctypes.data)
+        else:
+            src = np.asarray(actions, np.int32).reshape(1, -1, 4)
+            a = np.zeros((1, max(self.A, src.shape[1]), 4), np.int32)
+            a[:, :src.shape[1]] = src
+            a = np.ascontiguousarray(a[:, :self.A])
+            n = np.full(1, src.shape[1], np.int32)
+            lib().vm_emul_step(self._h, a.ctypes.data, n.ctypes.data, dec.ctypes.data, met.ctypes.data)
+        return int(dec[0, 6]), dec[0], met[0]
+
+    def frame(self):
+        out = np.zeros(self.frame_words, np.int32)
+        lib().vm_emul_read_frame(self._h, 0, out.ctypes.data)
+        return out
+
+    def snapshot(self, frame_index):
+        out = np.zeros(self.frame_words, np.int32)
+        return out if lib().vm_emul_read_snapshot(self._h, 0, frame_index, out.ctypes.data) else None
+
+    def tick(self):
+        return lib().vm_emul_tick(self._h, 0)
+
+    def counters(self):
+        out = np.zeros(4, np.int64)
+        lib().vm_emul_counters(self._h, 0, out.ctypes.data)
         return out

@@ -1,0 +1,66 @@
+"""CPU: the vm_scheduling device code (maro_b200/csrc/vm_core.cuh) under the thread-per-lane emulator, against the
+reference traces and the C oracle.  Integers and the energy metrics are bit-exact; total_incomes / total_profit use
+a maintained live-price sum and are compared to 1e-9."""
+import numpy as np
+import pytest
+
+from emul import VmEmulEnv
+from oracle.vm_oracle import VmOracle
+from vm_helpers import VM_CASES, assert_metrics_close, assert_vm_snapshots_equal, drive_vm, load_vm_golden, vm_topology
+
+EXACT_COLS = [0, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]  # every metric except total_incomes (1) and total_profit (3)
+
+
+@pytest.mark.parametrize("lanes", [32, 8, 1])
+@pytest.mark.parametrize("name", sorted(VM_CASES))
+def test_vm_device_logic_matches_reference_trace(name, lanes):
+    spec = VM_CASES[name]
+    topo = vm_topology(spec)
+    gold = load_vm_golden(name)
+    res, ms = spec.get("snapshot_resolution", 1), spec.get("max_snapshots")
+    e = VmEmulEnv(topo, res, ms, lanes=lanes)
+    rows, valid, mets, final, st, dec = drive_vm(lambda a: e.step(a), gold, topo.n_pm)
+    assert rows.shape == gold["steps"].shape
+    if not np.array_equal(rows, gold["steps"]):
+        bad = np.argwhere(rows != gold["steps"])[0]
+        raise AssertionError(f"step {bad[0]} col {bad[1]}: got {rows[bad[0]]} want {gold['steps'][bad[0]]}")
+    assert np.array_equal(valid, gold["valid"])
+    assert_metrics_close(mets, gold["metrics"], "per-step")
+    assert_metrics_close(final, gold["final_metrics"], "final")
+    assert e.tick() == int(gold["final_tick"]) and st == 1
+    assert e.step(None)[0] == 2
+    assert_vm_snapshots_equal(e.snapshot, gold, topo)
+    # against the oracle: same counters, bit-identical frames and energy metrics
+    o = VmOracle(topo, res, ms)
+    _, _, omets, ofinal, _, _ = drive_vm(lambda a: o.step(a), gold, topo.n_pm)
+    assert np.array_equal(mets[:, EXACT_COLS], omets[:, EXACT_COLS])
+    assert np.array_equal(final[EXACT_COLS], ofinal[EXACT_COLS])
+    o.step(None)
+    assert np.array_equal(e.counters(), o.counters())
+    assert np.array_equal(e.frame(), o.frame())
+    for f in gold["frames"].tolist():
+        assert np.array_equal(e.snapshot(int(f)), o.snapshot(int(f))), f
+
+
+def test_vm_device_logic_reset_and_bad_action():
+    spec = VM_CASES["synth_160_bestfit"]
+    topo = vm_topology(spec)
+    gold = load_vm_golden("synth_160_bestfit")
+    e = VmEmulEnv(topo)
+    first = drive_vm(lambda a: e.step(a), gold, topo.n_pm)
+    e.reset()
+    again = drive_vm(lambda a: e.step(a), gold, topo.n_pm)
+    for a, b in zip(first[:4], again[:4]):
+        assert np.array_equal(a, b)
+    # an action naming a VM that is not the pending decision's -> BAD_ACTION (reference: "The VM id ... is invalid.")
+    e.reset()
+    st, dec, _ = e.step(None)
+    assert st == 0
+    st, dec, _ = e.step([[dec[1] + 12345, 0, dec[12], 0]])
+    assert st == -1
+    assert e.step(None)[0] == 2
+    # allocating to a PM id outside the cluster is rejected too
+    e.reset()
+    st, dec, _ = e.step(None)
+    st, _, _ = e.step([[dec[1], 0, topo.n_pm, 0]])
+    assert st == -1

@@ -42,3 +42,28 @@ void agent_greedy(const int32_t* dec, int32_t* act, int n, int max_actions, int 
         else { a[0] = best; a[1] = station; a[2] = best_v; a[3] = 0; }
     }
 }
+
+/* best-fit vm_scheduling agent (examples/vm_scheduling/rule_based_algorithm/best_fit.py:27-64, "remaining_cpu_cores"):
+ * `q` is the snapshot query the reference agent makes, as returned by maro_vm_query for every replica:
+ * q[replica][frame][pm][{cpu_cores_capacity, cpu_cores_allocated}] (float64), `frames` the queried frame indices.
+ * Decision rows: 12-word header (frame index at [2], status at [6], n_valid at [10]) + valid PM ids. */
+void agent_best_fit(const int32_t* dec, int32_t* act, int n, int max_actions, int dec_words, const double* q,
+                    const int32_t* frames, int n_frames, int n_pm) {
+#pragma omp parallel for schedule(static) num_threads(16) if (n >= 1024)
+    for (int i = 0; i < n; i++) {
+        const int32_t* d = dec + (int64_t)i * dec_words;
+        int32_t* a = act + (int64_t)i * max_actions * 4;
+        int nv = d[6] == 0 ? d[10] : 0, f = 0;
+        while (f < n_frames - 1 && frames[f] != d[2]) f++;
+        const double* qq = q + ((int64_t)i * n_frames + f) * n_pm * 2;
+        int best = -1;
+        double best_rem = 0;
+        for (int k = 0; k < nv; k++) {
+            int p = d[12 + k];
+            double rem = qq[2 * p] - qq[2 * p + 1];
+            if (best < 0 || rem < best_rem) { best = p; best_rem = rem; }
+        }
+        if (best < 0) { a[0] = a[1] = -1; a[2] = a[3] = 0; }
+        else { a[0] = d[1]; a[1] = 0; a[2] = best; a[3] = 0; }
+    }
+}
