@@ -1029,14 +1029,14 @@ __global__ void __launch_bounds__(kWarps * 32) vm_step_kernel(const __grid_const
     }
 }
 
-__global__ void vm_reset_kernel(const __grid_constant__ VmShape s, const __grid_constant__ VmArgs a) {
+__global__ void vm_reset_kernel(const __grid_constant__ VmShape s, const __grid_constant__ VmArgs a, int init_ring) {
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const Grp<32> g(threadIdx.x & 31);
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int rep = warp_global; rep < s.n_replicas; rep += n_warps) {
         if (a.active && !a.active[rep]) continue;
         VmReplica r = vm_replica_at(s, a.state, a.tables, a.snap, a.snap_frame, (size_t)rep);
-        vm_replica_reset<32>(s, g, r);
+        vm_replica_reset<32>(s, g, r, init_ring != 0);
     }
 }
 
@@ -1103,7 +1103,7 @@ int maro_vm_destroy(MaroVmEnv* e) {
     return 0;
 }
 
-int maro_vm_reset(MaroVmEnv* e, const uint8_t* mask) {
+static int vm_reset_impl(MaroVmEnv* e, const uint8_t* mask, int init_ring) {
     if (!e) return fail("null handle");
     CK(cudaSetDevice(e->device));
     VmArgs a = vm_base_args(e);
@@ -1114,11 +1114,12 @@ int maro_vm_reset(MaroVmEnv* e, const uint8_t* mask) {
         a.active = d_active;
     }
     int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
-    vm_reset_kernel<<<blocks, threads, 0, e->stream>>>(e->s, a);
+    vm_reset_kernel<<<blocks, threads, 0, e->stream>>>(e->s, a, init_ring);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
+int maro_vm_reset(MaroVmEnv* e, const uint8_t* mask) { return vm_reset_impl(e, mask, 0); }
 
 int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmEnv** out) {
     if (!topo || !cfg || !out || cfg->n_replicas < 1) return fail("maro_vm_create: bad arguments");
@@ -1163,7 +1164,7 @@ int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmE
     CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
     CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
     *out = e;
-    int rc = maro_vm_reset(e, nullptr);
+    int rc = vm_reset_impl(e, nullptr, 1);
     if (rc) { maro_vm_destroy(e); *out = nullptr; return rc; }
     return 0;
 }

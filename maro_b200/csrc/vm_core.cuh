@@ -8,9 +8,10 @@
 // replica, all resident in HBM / L2 (a replica of azure.2019.10k is ~70 KB, too large for shared memory at a useful
 // occupancy):
 //
-//   * PM lists.  `pm.live_vms` + `_live_vms[vm_id]` become one array of 16-byte entries {vm, creation tick, utilisation
-//     (float32 bits), deletion tick} per PM, kept in allocation order, laid out [slot][pm] so that the lanes of a group
-//     (lane = pm mod G) read consecutive entries.  The per-tick sweep (_process_finished_vm, _update_vm_workload,
+//   * PM lists.  `pm.live_vms` + `_live_vms[vm_id]` become two parallel arrays of 16-byte entries per PM, kept in
+//     allocation order and laid out [slot][pm] so that the lanes of a group (lane = pm mod G) read consecutive entries:
+//     hot {series base, deletion tick, cores | request->creation delay << 16, utilisation (float32 bits)} is everything
+//     the per-tick sweep needs (no per-VM table look-up), cold {vm, creation tick, memory, -} is read when a VM leaves.  The per-tick sweep (_process_finished_vm, _update_vm_workload,
 //     _update_pm_workload: :575-592, :640-652, :770-781) is ONE pass over these lists: each lane walks its PMs' lists
 //     in order, drops entries whose deletion tick is now, refreshes the utilisation from the trace and accumulates
 //     `cpu_utilization * cores` in list order (the order fixes the float64 sum, hence round(x, 2), hence decisions).
@@ -68,7 +69,8 @@ struct VmReplica {
     int32_t* uk;   // [N] cpu_utilization * 100 as an integer
     int32_t* len;  // [N] PM list lengths
     int32_t* q;    // [FQ][4] postponed requests {vm, remaining buffer time, due tick, 0}
-    int32_t* l;    // [K][N][4] PM lists {vm, creation, utilisation bits, deletion}
+    int32_t* l;    // [K][N][4] PM lists, hot part  {series offset - creation, deletion, cores | (creation - request) << 16, util bits}
+    int32_t* lc;   // [K][N][4] PM lists, cold part {vm, creation, memory, 0}
     const int32_t* t;
     int32_t* snap;
     int32_t* snap_frame;
@@ -84,6 +86,7 @@ MARO_DEV VmReplica vm_replica_at(const VmShape& s, int32_t* state, const int32_t
     r.len = r.uk + s.N;
     r.q = r.uk + ((2 * s.N + 3) & ~3);
     r.l = r.q + 4 * (size_t)s.FQ;
+    r.lc = r.l + 4 * (size_t)s.K * s.N;
     r.t = tables;
     r.snap = snap + i * (size_t)s.ring_rows * s.FWp;
     r.snap_frame = snap_frame + i * (size_t)s.ring_rows;
@@ -142,12 +145,30 @@ MARO_DEV void pm_store_util(const VmShape& s, const VmReplica& r, int p, int k) 
 
 MARO_DEV int vm_frame_index(const VmShape& s, int tick) { return (tick - s.start_tick) / s.snap_res; }
 
+// Snapshot rows hold the whole frame, but the static attributes are written once per row at reset (vm_replica_reset):
+// take_snapshot copies only the words that can change — five PM attributes and the empty-machine counts.
+template <int G>
+MARO_DEV void vm_copy_dynamic(const VmShape& s, const Grp<G>& g, const int32_t* src, int32_t* dst) {
+    const int N = s.N;
+    for (int i = g.lane; i < N; i += G) {
+        dst[VPA_CPU_ALLOC * N + i] = src[VPA_CPU_ALLOC * N + i];
+        dst[VPA_CPU_UTIL * N + i] = src[VPA_CPU_UTIL * N + i];
+        dst[VPA_ENERGY * N + i] = src[VPA_ENERGY * N + i];
+        dst[VPA_MEM_ALLOC * N + i] = src[VPA_MEM_ALLOC * N + i];
+        dst[VPA_OVERSUB * N + i] = src[VPA_OVERSUB * N + i];
+    }
+    for (int i = g.lane; i < s.R; i += G) dst[s.o_rack + 2 * s.R + i] = src[s.o_rack + 2 * s.R + i];
+    for (int i = g.lane; i < s.C; i += G) dst[s.o_cluster + s.C + i] = src[s.o_cluster + s.C + i];
+    for (int i = g.lane; i < s.D; i += G) dst[s.o_dc + i] = src[s.o_dc + i];
+    for (int i = g.lane; i < s.Z; i += G) dst[s.o_zone + i] = src[s.o_zone + i];
+    for (int i = g.lane; i < s.RG; i += G) dst[s.o_region + i] = src[s.o_region + i];
+}
+
 template <int G>
 MARO_DEV void vm_snapshot(const VmShape& s, const Grp<G>& g, const VmReplica& r, int frame_index) {
     g.sync();
     int row = frame_index % s.ring_rows;
-    int32_t* dst = r.snap + (size_t)row * s.FWp;
-    for (int i = g.lane * 4; i < s.FWp; i += G * 4) st4(dst + i, ld4(r.f + i));
+    vm_copy_dynamic(s, g, r.f, r.snap + (size_t)row * s.FWp);
     if (g.lane == 0) r.snap_frame[row] = frame_index;
     g.sync();
 }
@@ -214,7 +235,10 @@ MARO_DEV int vm_on_actions(const VmShape& s, const VmReplica& r, int tick, const
             int n = r.len[p];
             if (n >= s.K) return -2;
             float u = maro_i2f(r.t[s.t_val + r0.x]);  // get_utilization(cur_tick): series[0]
-            st4(r.l + 4 * ((size_t)n * s.N + p), I4{vm, tick, maro_f2i(u), tick + r0.z});
+            const int delay = tick - r0.y;  // creation - request tick (0 .. buffer budget)
+            if (delay < 0 || delay > 0x7fff || r0.w < 0 || r0.w > 0xffff) return -2;
+            st4(r.l + 4 * ((size_t)n * s.N + p), I4{r0.x - tick, tick + r0.z, r0.w | (delay << 16), maro_f2i(u)});
+            st4(r.lc + 4 * ((size_t)n * s.N + p), I4{vm, tick, r1.x, 0});
             r.len[p] = n + 1;
             r.c[VC_N_LIVE] += 1;
             if (VPM(s, r, VPA_OVERSUB, p) == 0) VPM(s, r, VPA_OVERSUB, p) = r1.w == 0 ? 1 : -1;
@@ -240,30 +264,55 @@ MARO_DEV void vm_tick_begin(const VmShape& s, const Grp<G>& g, const VmReplica& 
     const uint8_t* has = reinterpret_cast<const uint8_t*>(r.t + s.t_has);
     int fin = 0;
     double fin_price = 0.0;
+    const int32_t* val = r.t + s.t_val;
     for (int p = g.lane; p < s.N; p += G) {
         const int n = r.len[p];
         int kept = 0, ca = 0, ma = 0;
         double used = 0.0;
-        for (int k = 0; k < n; k++) {
-            int32_t* slot = r.l + 4 * ((size_t)k * s.N + p);
-            I4 e = ld4(slot);
-            I4 r0 = ld4_ro(r.t + s.t_rec0 + 4 * e.x);
-            if (e.w == tick) {  // _process_finished_vm (:770-781)
-                ca += r0.w;
-                ma += r.t[s.t_rec1 + 4 * e.x];
-                fin++;
-                fin_price += price[e.x];
-                continue;
+        // four list slots per round: their entry loads, then their trace look-ups, are issued together (the sweep is
+        // latency bound: one replica = one warp, ~14 warps per SM); the float64 sum still runs in list order
+        for (int k0 = 0; k0 < n; k0 += 4) {
+            I4 e[4];
+            int32_t nb[4];
+            uint8_t hs[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (k0 + j < n) e[j] = ld4(r.l + 4 * ((size_t)(k0 + j) * s.N + p));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                hs[j] = 0; nb[j] = 0;
+                if (k0 + j < n && e[j].y != tick) {
+                    int idx = e[j].x + tick;  // series offset + (tick - creation)
+                    hs[j] = has[idx + (e[j].z >> 16)];  // "+ (creation - request)": flags are indexed from the request tick
+                    nb[j] = val[idx];
+                }
             }
-            bool dirty = kept != k;
-            if (has[r0.x + (tick - r0.y)]) {  // _update_vm_workload: a reading exists for this VM at this tick
-                int32_t nb = r.t[s.t_val + r0.x + (tick - e.y)];
-                dirty |= nb != e.z;
-                e.z = nb;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = k0 + j;
+                if (k >= n) break;
+                if (e[j].y == tick) {  // _process_finished_vm (:770-781)
+                    I4 c = ld4(r.lc + 4 * ((size_t)k * s.N + p));
+                    ca += e[j].z & 0xffff;
+                    ma += c.z;
+                    fin++;
+                    fin_price += price[c.x];
+                    continue;
+                }
+                bool dirty = false;
+                if (hs[j]) {  // _update_vm_workload: a reading exists for this VM at this tick
+                    dirty = nb[j] != e[j].w;
+                    e[j].w = nb[j];
+                }
+                used += (double)maro_i2f(e[j].w) * (double)(e[j].z & 0xffff);
+                if (kept != k) {
+                    st4(r.l + 4 * ((size_t)kept * s.N + p), e[j]);
+                    st4(r.lc + 4 * ((size_t)kept * s.N + p), ld4(r.lc + 4 * ((size_t)k * s.N + p)));
+                } else if (dirty) {
+                    r.l[4 * ((size_t)k * s.N + p) + 3] = e[j].w;
+                }
+                kept++;
             }
-            used += (double)maro_i2f(e.z) * (double)r0.w;
-            if (dirty) st4(r.l + 4 * ((size_t)kept * s.N + p), e);
-            kept++;
         }
         if (kept != n) {
             r.len[p] = kept;
@@ -334,9 +383,9 @@ MARO_DEV void vm_tick_end(const VmShape& s, const Grp<G>& g, const VmReplica& r,
                 if (s.kill_all) {
                     double gone = 0.0;
                     for (int k = 0; k < n; k++) {
-                        I4 e = ld4(r.l + 4 * ((size_t)k * s.N + p));
-                        incomes -= price[e.x] * (double)(tick - e.y);
-                        gone += price[e.x];
+                        I4 c = ld4(r.lc + 4 * ((size_t)k * s.N + p));
+                        incomes -= price[c.x] * (double)(tick - c.y);
+                        gone += price[c.x];
                     }
                     r.len[p] = 0;
                     int live = r.c[VC_N_LIVE] - n;
@@ -483,12 +532,16 @@ MARO_DEV void vm_replica_step(const VmShape& s, const Grp<G>& g, const VmReplica
 
 // Env.reset (core.py:135-153) + BusinessEngine.reset (:527-563); the step / tick / event / snapshot counters persist
 template <int G>
-MARO_DEV void vm_replica_reset(const VmShape& s, const Grp<G>& g, const VmReplica& r) {
+MARO_DEV void vm_replica_reset(const VmShape& s, const Grp<G>& g, const VmReplica& r, bool init_ring) {
     for (int i = g.lane; i < s.FWp; i += G) r.f[i] = i < s.FW ? r.t[s.t_frame0 + i] : 0;
     for (int i = g.lane; i < s.CWp; i += G)
         if (i < VC_NSTEPS || i >= VC_M_REQ) r.c[i] = 0;
     for (int i = g.lane; i < s.N; i += G) { r.uk[i] = 0; r.len[i] = 0; }
     for (int i = g.lane; i < s.ring_rows; i += G) r.snap_frame[i] = -1;
+    // ring rows: the static attributes are written once, when the handle is created (snapshots copy only the dynamic words)
+    if (init_ring)
+        for (int row = 0; row < s.ring_rows; row++)
+            for (int i = g.lane * 4; i < s.FWp; i += G * 4) st4(r.snap + (size_t)row * s.FWp + i, ld4(r.t + s.t_frame0 + i));
     g.sync();
     if (g.lane == 0) r.c[VC_TICK] = s.start_tick;
     g.sync();

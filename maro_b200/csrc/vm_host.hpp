@@ -74,7 +74,7 @@ inline std::string vm_compute_shape_and_tables(const MaroVmTopology& t, const Ma
     }
     fq = cfg->queue_capacity > 0 ? cfg->queue_capacity : std::min(fq + 4, std::max(t.n_vm, 1) + 1);
     s.FQ = std::max(fq, 4);
-    const long long sw = (long long)s.FWp + s.CWp + round_up(2 * N, 4) + 4LL * s.FQ + 4LL * s.K * N;
+    const long long sw = (long long)s.FWp + s.CWp + round_up(2 * N, 4) + 4LL * s.FQ + 8LL * s.K * N;
     if (sw > 0x7fffffffLL) return "replica block too large";
     s.SW = (int)sw;
 

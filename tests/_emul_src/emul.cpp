@@ -171,9 +171,9 @@ struct VmEmul {
     std::string err;
 };
 template <int G>
-static void vm_reset_g(VmEmul* e, int i) {
+static void vm_reset_g(VmEmul* e, int i, bool init_ring = false) {
     VmReplica r = vm_replica_at(e->s, e->state.data(), e->tables.data(), e->snap.data(), e->snap_frame.data(), i);
-    wemu::run_group(G, [&](int lane) { vm_replica_reset<G>(e->s, Grp<G>(lane), r); });
+    wemu::run_group(G, [&](int lane) { vm_replica_reset<G>(e->s, Grp<G>(lane), r, init_ring); });
 }
 template <int G>
 static void vm_step_g(VmEmul* e, int i, const int32_t* actp, int n, int32_t* dec, int64_t* met) {
@@ -191,7 +191,7 @@ VmEmul* vm_emul_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, int
     e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
     e->snap_frame.assign((size_t)e->B * e->s.ring_rows, -1);
     e->scratch.assign(2 * (size_t)e->s.N, 0.0);
-    for (int i = 0; i < e->B; i++) { if (e->lanes == 1) vm_reset_g<1>(e, i); else if (e->lanes == 8) vm_reset_g<8>(e, i); else vm_reset_g<32>(e, i); }
+    for (int i = 0; i < e->B; i++) { if (e->lanes == 1) vm_reset_g<1>(e, i, true); else if (e->lanes == 8) vm_reset_g<8>(e, i, true); else vm_reset_g<32>(e, i, true); }
     return e;
 }
 void vm_emul_destroy(VmEmul* e) { delete e; }

@@ -33,7 +33,9 @@ def main():
         m = re.match(r"\s*/\*([0-9a-f]+)\*/", ln)
         if m and cur:
             amap[int(m.group(1), 16)] = cur
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    skip = os.environ.get("NCU_SKIP")  # NCU_SKIP=n: use the (n+1)-th launch of the report instead of the first
+    extra = ["--launch-skip", skip, "--launch-count", "1"] if skip else []
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     # first kernel block only
     hdr = rows[1]
