@@ -585,6 +585,14 @@ def run_ours(args, rank, local_rank, world):
         achieved = bytes_per_step * g_steps / world / (kernel_ms / 1000.0) / 1e9  # per GPU
         value = g_steps / (total_ms / 1000.0)
         snaps = args.max_snapshots or "all"
+        traffic = None  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this config, if any
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fp:
+                key = (f"vm_scheduling/azure-synth-{args.vm_count}/{B}" if vm else
+                       f"{args.scenario}/{'toy.3s_4t' if bike else args.topology}/{B}")
+                traffic = json.load(fp).get(key, {}).get("bytes_per_launch")
+        except Exception:
+            pass
         if vm:
             workload = (f"vm_scheduling synthetic azure.2019.10k-scale trace ({topo.n_vm} VMs, {topo.n_pm} PMs 32c/128G, {ticks} ticks; "
                         f"tools/vm_trace_gen.py), {B} parallel envs per GPU, best-fit agent, snapshot_resolution 1, max_snapshots {vm_snaps}")
@@ -604,7 +612,7 @@ def run_ours(args, rank, local_rank, world):
             "ticks_per_s": g_ticks / (total_ms / 1000.0), "events_per_s": g_events / (total_ms / 1000.0),
             "wall_ms": wall_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "vm_step_kernel" if vm else ("bike_step_kernel" if bike else "cim_step_kernel"), "bytes_per_env_step": bytes_per_step,
+                         "traffic": traffic, "kernel": "vm_step_kernel" if vm else ("bike_step_kernel" if bike else "cim_step_kernel"), "bytes_per_env_step": bytes_per_step,
                          "n_snap": n_snap, "n_ev": n_ev, "kernel_us": 1000.0 * kernel_ms / args.steps,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "clocks": clocks,
