@@ -9,7 +9,7 @@ static inline uint32_t hash_u32(uint32_t x) {
 }
 
 void agent_random(const int32_t* dec, int32_t* act, int n, int max_actions, uint32_t seed, uint32_t replica_base) {
-#pragma omp parallel for schedule(static) num_threads(16) if (n >= 4096)
+#pragma omp parallel for schedule(static) num_threads(n >= 4096 ? 16 : 4) if (n >= 1024)
     for (int i = 0; i < n; i++) {
         const int32_t* d = dec + 8 * i;
         uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + (uint32_t)d[7] * 0x85ebca6bu + 0x1234567u));
