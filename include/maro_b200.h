@@ -186,6 +186,27 @@ int maro_cim_snapshot_frames(MaroCimEnv* env, int32_t replica, int32_t* out, int
 int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t* d_actions,
                                   uint32_t seed, uint32_t replica_base);
 
+/* ---- RL state / reward shaping on the device snapshot ring -------------------------------
+ * Batched, device-resident forms of the reference's CIM example shaping (examples/cim/rl/env_sampler.py:15-36, 66-80),
+ * which issue one snapshot_list query per decision / per reward from Python.  All pointers are device pointers; work is
+ * enqueued on the handle's stream and not synchronised.
+ *
+ * State of replica i, for its decision row d (MARO_DEC_*; rows that are not MARO_STATUS_DECISION give zeros):
+ *   ticks  = [max(0, d.tick - rt) for rt in range(look_back - 1)]              (used as frame indices, like the example)
+ *   ports  = [d.port] + future_stop_list of d.vessel in the snapshot of frame d.tick
+ *   state  = concat(ports snapshot [ticks : ports : port_attrs], vessels snapshot [d.tick : d.vessel : vessel_attrs])
+ * as float64, tick -> port -> attr order, zeros for frames the ring no longer holds (np_backend.pyx:536-549).
+ * out: [n_replicas][maro_cim_rl_state_dim()] doubles.  Attribute ids come from maro_cim_attr_id (single-slot only). */
+int32_t maro_cim_rl_state_dim(MaroCimEnv* env, int32_t look_back, int32_t n_port_attrs, int32_t n_vessel_attrs);
+int maro_cim_rl_state_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
+                             int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out);
+/* Reward of replica i for the action it took at tick d_ticks[i] on port d_ports[i] (env_sampler.py:66-80):
+ *   float32(fulfillment_factor * sum_k decay[k] * fulfillment[tick+1+k, port]
+ *           - shortage_factor * sum_k decay[k] * shortage[tick+1+k, port]),   k = 0 .. time_window-1,
+ * d_decay = [time_decay ** k] (time_window doubles on the device).  out: [n_replicas] float32. */
+int maro_cim_rl_reward_device(MaroCimEnv* env, const int32_t* d_ticks, const int32_t* d_ports, const double* d_decay,
+                              int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out);
+
 
 /* ================================================================================================
  * citi_bike scenario: same call shapes as the CIM entry points.

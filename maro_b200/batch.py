@@ -134,6 +134,21 @@ class CimBatch:
     def random_policy_device(self, d_decisions: int, d_actions: int, seed: int, replica_base: int = 0):
         _native.check(_native.lib().maro_cim_random_policy_device(self._h, d_decisions, d_actions, seed, replica_base))
 
+    # -- RL shaping on the device snapshot ring (examples/cim/rl/env_sampler.py:15-36, 66-80) ---------
+    def rl_state_dim(self, look_back: int, n_port_attrs: int, n_vessel_attrs: int) -> int:
+        return _native.lib().maro_cim_rl_state_dim(self._h, look_back, n_port_attrs, n_vessel_attrs)
+
+    def rl_state_device(self, d_decisions: int, look_back: int, port_attrs, vessel_attrs, d_out: int):
+        pa = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id("ports", a) for a in port_attrs], np.int32)
+        va = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id("vessels", a) for a in vessel_attrs], np.int32)
+        _native.check(_native.lib().maro_cim_rl_state_device(self._h, d_decisions, look_back, pa.ctypes.data, len(pa),
+                                                             va.ctypes.data, len(va), d_out))
+
+    def rl_reward_device(self, d_ticks: int, d_ports: int, d_decay: int, time_window: int, fulfillment_factor: float,
+                         shortage_factor: float, d_out: int):
+        _native.check(_native.lib().maro_cim_rl_reward_device(self._h, d_ticks, d_ports, d_decay, time_window,
+                                                              float(fulfillment_factor), float(shortage_factor), d_out))
+
     # -- inspection --------------------------------------------------------------------------------
     def attr_id(self, node: str, name: str) -> int:
         i = _native.lib().maro_cim_attr_id(self._h, _NODE_TYPE[node], name.encode())

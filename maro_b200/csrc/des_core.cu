@@ -392,6 +392,99 @@ static int32_t common_attr_slots(EnvCommon* e, int32_t node_type, int32_t attr_i
     return e->attrs[node_type][attr_id].slots;
 }
 
+// =====================================================================================================
+// RL state / reward shaping on the snapshot ring (examples/cim/rl/env_sampler.py:15-36, 66-80)
+// =====================================================================================================
+struct ShapeArgs {
+    const int32_t* snap;
+    const int32_t* snap_frame;
+    int ring_rows, FWp, B;
+    // state
+    const int32_t* decisions;  // [B][8]
+    int look_back_ticks;       // look_back - 1 frames: max(0, tick - rt), rt = 0..look_back-2
+    int n_ports_per_state;     // 1 + future_stop_number
+    int npa, nva;              // attribute counts
+    int port_attr_off[16], port_attr_isf[16], vessel_attr_off[16], vessel_attr_isf[16];
+    int o_fut, fut;            // future_stop_list: word offset, slots per vessel
+    int P, V;
+    double* state_out;         // [B][look_back_ticks * n_ports_per_state * npa + nva]
+    // reward
+    const int32_t* ticks;      // [B] tick of the action
+    const int32_t* ports;      // [B] port that acted
+    const double* decay;       // [time_window] time_decay ** i
+    int time_window, off_fulfillment, off_shortage;
+    double fulfillment_factor, shortage_factor;
+    float* reward_out;         // [B]
+};
+
+// word `w` of snapshot `frame` of replica `rep`; frames not in the ring read as 0 (np_backend.pyx:543-549)
+__device__ __forceinline__ bool snap_row(const ShapeArgs& q, int rep, int frame, const int32_t*& row) {
+    if (frame < 0) return false;
+    int r = frame % q.ring_rows;
+    if (q.snap_frame[(int64_t)rep * q.ring_rows + r] != frame) return false;
+    row = q.snap + ((int64_t)rep * q.ring_rows + r) * q.FWp;
+    return true;
+}
+
+// state[rep] = concat(ports[ticks : [port] + future_stop_list : port_attrs], vessels[tick : vessel : vessel_attrs]) as float64
+__global__ void cim_rl_state_kernel(const __grid_constant__ ShapeArgs q) {
+    const int per_tick = q.n_ports_per_state * q.npa;
+    const int dim = q.look_back_ticks * per_tick + q.nva;
+    const int64_t total = (int64_t)q.B * dim;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int rep = (int)(i / dim), e = (int)(i % dim);
+        const int32_t* d = q.decisions + (int64_t)rep * 8;
+        double v = 0.0;
+        if (d[MARO_DEC_STATUS] == MARO_STATUS_DECISION) {
+            const int tick = d[MARO_DEC_TICK], vessel = d[MARO_DEC_VESSEL];
+            const int32_t* now = nullptr;
+            const bool have_now = snap_row(q, rep, tick, now);
+            if (e >= q.look_back_ticks * per_tick) {
+                const int a = e - q.look_back_ticks * per_tick;
+                if (have_now) {
+                    int w = now[q.vessel_attr_off[a] + vessel];
+                    v = q.vessel_attr_isf[a] ? (double)__int_as_float(w) : (double)w;
+                }
+            } else {
+                const int k = e / per_tick, j = (e % per_tick) / q.npa, a = e % q.npa;
+                int port = d[MARO_DEC_PORT];
+                if (j > 0) port = have_now ? now[q.o_fut + vessel * q.fut + (j - 1)] : 0;  // .astype("int") of a 0-padded query
+                const int frame = tick - k > 0 ? tick - k : 0;
+                const int32_t* row = nullptr;
+                if (port >= 0 && port < q.P && snap_row(q, rep, frame, row)) {
+                    int w = row[q.port_attr_off[a] + port];
+                    v = q.port_attr_isf[a] ? (double)__int_as_float(w) : (double)w;
+                }
+            }
+        }
+        q.state_out[i] = v;
+    }
+}
+
+// reward[rep] = float32(ff * sum_k decay[k] * fulfillment[tick+1+k, port] - sf * sum_k decay[k] * shortage[tick+1+k, port])
+__global__ void cim_rl_reward_kernel(const __grid_constant__ ShapeArgs q) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int rep = warp_global; rep < q.B; rep += n_warps) {
+        const int tick = q.ticks[rep], port = q.ports[rep];
+        double f = 0.0, sh = 0.0;
+        if (port >= 0 && port < q.P) {
+            for (int k = lane; k < q.time_window; k += 32) {
+                const int32_t* row = nullptr;
+                if (snap_row(q, rep, tick + 1 + k, row)) {
+                    f += q.decay[k] * (double)row[q.off_fulfillment + port];
+                    sh += q.decay[k] * (double)row[q.off_shortage + port];
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            f += __shfl_xor_sync(0xffffffffu, f, o);
+            sh += __shfl_xor_sync(0xffffffffu, sh, o);
+        }
+        if (lane == 0) q.reward_out[rep] = (float)(q.fulfillment_factor * f - q.shortage_factor * sh);
+    }
+}
+
 static void register_attrs(MaroCimEnv* e) {
     const CimShape& s = e->s;
     static const char* pn[] = {"acc_booking", "acc_fulfillment", "acc_shortage", "booking", "capacity", "empty",
@@ -708,6 +801,65 @@ int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int
     CK(cudaSetDevice(e->device));
     int threads = 256, blocks = (e->B + threads - 1) / threads;
     cim_policy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.max_actions, seed, replica_base);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+static int shape_common(MaroCimEnv* e, ShapeArgs& q) {
+    memset(&q, 0, sizeof(q));
+    q.snap = e->d_snap; q.snap_frame = e->d_snap_frame; q.ring_rows = e->ring_rows; q.FWp = e->FWp; q.B = e->B;
+    q.P = e->s.P; q.V = e->s.V; q.o_fut = e->s.o_fut; q.fut = e->s.fut;
+    return 0;
+}
+
+extern "C" {
+
+int32_t maro_cim_rl_state_dim(MaroCimEnv* e, int32_t look_back, int32_t n_port_attrs, int32_t n_vessel_attrs) {
+    if (!e || look_back < 2) return -1;
+    return (look_back - 1) * (1 + e->s.fut) * n_port_attrs + n_vessel_attrs;
+}
+
+int maro_cim_rl_state_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
+                             int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out) {
+    if (!e || !d_decisions || !d_out || !port_attrs || !vessel_attrs || look_back < 2 || n_port_attrs < 1 || n_port_attrs > 16 ||
+        n_vessel_attrs < 0 || n_vessel_attrs > 16)
+        return fail("maro_cim_rl_state_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    ShapeArgs q;
+    shape_common(e, q);
+    for (int i = 0; i < n_port_attrs; i++) {
+        int a = port_attrs[i];
+        if (a < 0 || a >= (int)e->attrs[0].size() || e->attrs[0][a].slots != 1) return fail("maro_cim_rl_state_device: bad port attribute");
+        q.port_attr_off[i] = e->attrs[0][a].off; q.port_attr_isf[i] = e->attrs[0][a].isf;
+    }
+    for (int i = 0; i < n_vessel_attrs; i++) {
+        int a = vessel_attrs[i];
+        if (a < 0 || a >= (int)e->attrs[1].size() || e->attrs[1][a].slots != 1) return fail("maro_cim_rl_state_device: bad vessel attribute");
+        q.vessel_attr_off[i] = e->attrs[1][a].off; q.vessel_attr_isf[i] = e->attrs[1][a].isf;
+    }
+    q.decisions = d_decisions; q.look_back_ticks = look_back - 1; q.n_ports_per_state = 1 + e->s.fut;
+    q.npa = n_port_attrs; q.nva = n_vessel_attrs; q.state_out = d_out;
+    const int64_t total = (int64_t)e->B * maro_cim_rl_state_dim(e, look_back, n_port_attrs, n_vessel_attrs);
+    int threads = 256, blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
+    cim_rl_state_kernel<<<blocks, threads, 0, e->stream>>>(q);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int maro_cim_rl_reward_device(MaroCimEnv* e, const int32_t* d_ticks, const int32_t* d_ports, const double* d_decay,
+                              int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out) {
+    if (!e || !d_ticks || !d_ports || !d_decay || !d_out || time_window < 1) return fail("maro_cim_rl_reward_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    ShapeArgs q;
+    shape_common(e, q);
+    q.ticks = d_ticks; q.ports = d_ports; q.decay = d_decay; q.time_window = time_window;
+    q.off_fulfillment = e->attrs[0][common_attr_id(e, 0, "fulfillment")].off;
+    q.off_shortage = e->attrs[0][common_attr_id(e, 0, "shortage")].off;
+    q.fulfillment_factor = fulfillment_factor; q.shortage_factor = shortage_factor; q.reward_out = d_out;
+    int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
+    cim_rl_reward_kernel<<<blocks, threads, 0, e->stream>>>(q);
     CK(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,52 @@
+"""Batched, device-resident state / reward shaping for the CIM scenario.
+
+The reference's RL example shapes one decision at a time from Python: a ``snapshot_list`` query for the look-back
+window of the acting port and the vessel's next stops, and later a 99-tick window query + a decayed dot product for
+the reward (``examples/cim/rl/env_sampler.py:15-36, 66-80``, constants in ``examples/cim/rl/config.py``).  Here both run
+as one kernel launch over all replicas on the snapshot ring in HBM and return torch CUDA tensors — nothing crosses PCIe.
+"""
+from typing import Sequence
+
+import numpy as np
+
+from .batch import CimBatch
+
+# examples/cim/rl/config.py:10-36
+PORT_ATTRIBUTES = ("empty", "full", "on_shipper", "on_consignee", "booking", "shortage", "fulfillment")
+VESSEL_ATTRIBUTES = ("empty", "full", "remaining_space")
+
+
+class CimShaper:
+    def __init__(self, batch: CimBatch, look_back: int = 7, port_attributes: Sequence[str] = PORT_ATTRIBUTES,
+                 vessel_attributes: Sequence[str] = VESSEL_ATTRIBUTES, time_window: int = 99, time_decay: float = 0.97,
+                 fulfillment_factor: float = 1.0, shortage_factor: float = 1.0):
+        import torch
+
+        self._torch = torch
+        self.batch = batch
+        self.look_back = int(look_back)
+        self._pa = [batch.attr_id("ports", a) for a in port_attributes]
+        self._va = [batch.attr_id("vessels", a) for a in vessel_attributes]
+        self.state_dim = batch.rl_state_dim(self.look_back, len(self._pa), len(self._va))
+        self.time_window = int(time_window)
+        self.fulfillment_factor, self.shortage_factor = float(fulfillment_factor), float(shortage_factor)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # decay_list = [time_decay ** i ...] evaluated on the host exactly like the example (env_sampler.py:75)
+        self._decay = torch.tensor(np.asarray([time_decay ** i for i in range(self.time_window)], np.float64), device=dev)
+        B = batch.n_replicas
+        self._state = torch.zeros((B, self.state_dim), dtype=torch.float64, device=dev)
+        self._reward = torch.zeros(B, dtype=torch.float32, device=dev)
+
+    def states(self, decisions):
+        """decisions: int32 CUDA tensor [B][8] (MARO_DEC_* rows of the last step) -> float64 CUDA tensor [B][state_dim]."""
+        assert decisions.is_cuda and decisions.dtype == self._torch.int32 and decisions.is_contiguous()
+        self.batch.rl_state_device(decisions.data_ptr(), self.look_back, self._pa, self._va, self._state.data_ptr())
+        return self._state
+
+    def rewards(self, ticks, ports):
+        """ticks, ports: int32 CUDA tensors [B] (tick at which replica i acted, acting port) -> float32 CUDA tensor [B]."""
+        for t in (ticks, ports):
+            assert t.is_cuda and t.dtype == self._torch.int32 and t.is_contiguous()
+        self.batch.rl_reward_device(ticks.data_ptr(), ports.data_ptr(), self._decay.data_ptr(), self.time_window,
+                                    self.fulfillment_factor, self.shortage_factor, self._reward.data_ptr())
+        return self._reward

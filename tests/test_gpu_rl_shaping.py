@@ -1,0 +1,83 @@
+"""GPU (-m gpu): device-resident RL state / reward shaping (maro_cim_rl_state_device / maro_cim_rl_reward_device,
+maro_b200.rl_shaping.CimShaper) against vectors recorded from the unmodified reference and the numpy restatement."""
+import numpy as np
+import pytest
+
+from rl_helpers import RL_CASES, SnapshotView, load_rl_golden, reward_numpy, state_numpy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(RL_CASES))
+def test_device_shaping_matches_reference_vectors(name):
+    import torch
+
+    from maro_b200.batch import CimBatch
+    from maro_b200.rl_shaping import CimShaper
+    from maro_b200.scenarios.cim.topology import build_topology
+
+    spec, gold = RL_CASES[name], load_rl_golden(name)
+    topo = build_topology(spec["topology"], spec["durations"])
+    B = 4
+    env = CimBatch(topo, B, max_snapshots=spec.get("max_snapshots"))
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    shaper = CimShaper(env)
+    assert shaper.state_dim == gold["states"].shape[1]
+    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    env.step_device(dec.data_ptr(), met.data_ptr())
+    for k in range(len(gold["steps"])):
+        d = dec.cpu().numpy()
+        assert d[:, 6].tolist() == [0] * B and d[0, :3].tolist() == gold["steps"][k].tolist()
+        s = shaper.states(dec).cpu().numpy()
+        assert np.array_equal(s, np.broadcast_to(gold["states"][k], s.shape)), k   # integers -> float64: exact
+        act[:, 0] = torch.tensor(gold["actions"][k], dtype=torch.int32, device="cuda")
+        env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+    assert dec.cpu().numpy()[:, 6].tolist() == [1] * B
+    assert (shaper.states(dec).cpu().numpy() == 0).all()  # no decision pending -> zero rows
+    # rewards of every decision, four at a time (replica r scores decision k + r)
+    got = np.zeros(len(gold["steps"]), np.float32)
+    for k in range(0, len(gold["steps"]), B):
+        idx = [min(k + r, len(gold["steps"]) - 1) for r in range(B)]
+        ticks = torch.tensor(gold["steps"][idx, 0], dtype=torch.int32, device="cuda")
+        ports = torch.tensor(gold["steps"][idx, 1], dtype=torch.int32, device="cuda")
+        got[idx] = shaper.rewards(ticks, ports).cpu().numpy()
+    # float rewards within 1e-6 (BASELINE north_star): float64 dot products in a different association, cast to float32
+    assert np.allclose(got, gold["rewards"], rtol=1e-6, atol=1e-3), np.abs(got - gold["rewards"]).max()
+    env.close()
+
+
+def test_device_shaping_at_batch_size_matches_restatement():
+    """1024 desynchronised replicas (hashed random agent on the device): sampled replicas against the restatement."""
+    import torch
+
+    from maro_b200.batch import CimBatch
+    from maro_b200.rl_shaping import CimShaper
+    from maro_b200.scenarios.cim.topology import build_topology
+
+    topo = build_topology("toy.4p_ssdd_l0.0", 400)
+    B = 1024
+    env = CimBatch(topo, B)
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    shaper = CimShaper(env)
+    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    env.step_device(dec.data_ptr(), met.data_ptr())
+    for _ in range(150):
+        env.random_policy_device(dec.data_ptr(), act.data_ptr(), 11, 0)
+        env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+    d = dec.cpu().numpy()
+    states = shaper.states(dec).cpu().numpy()
+    ticks = torch.tensor(np.maximum(d[:, 0] - 120, 0), dtype=torch.int32, device="cuda")
+    ports = torch.tensor(d[:, 1] % topo.n_ports, dtype=torch.int32, device="cuda")
+    rewards = shaper.rewards(ticks, ports).cpu().numpy()
+    assert len(set(d[:, 0].tolist())) > 1  # replicas are at different ticks
+    for rep in (0, 1, 511, 1023):
+        view = SnapshotView(lambda f, rep=rep: env.snapshot_row(f, rep), topo, cache=True)
+        assert d[rep, 6] == 0
+        assert np.array_equal(states[rep], state_numpy(view, int(d[rep, 0]), int(d[rep, 1]), int(d[rep, 2]))), rep
+        want = reward_numpy(view, int(ports[rep]), int(ticks[rep]))
+        assert abs(float(rewards[rep]) - float(want)) <= 1e-6 * max(1.0, abs(float(want))), (rep, rewards[rep], want)
+    env.close()
