@@ -491,6 +491,33 @@ def run_ours(args, rank, local_rank, world):
         env.reset()
         pos["i"] = 0
 
+    # ---- extra: device-resident RL state / reward shaping over the snapshot ring, not part of `value`
+    shaping = None
+    if not bike and not vm:
+        from maro_b200.rl_shaping import CimShaper
+
+        shaper = CimShaper(env)
+        t_ticks = torch.clamp(dec[:, 0] - 120, min=0).contiguous()
+        t_ports = torch.remainder(dec[:, 1], topo.n_ports).to(torch.int32).contiguous()
+        for _ in range(3):
+            shaper.states(dec); shaper.rewards(t_ticks, t_ports)
+        sev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        reps = 20
+        sev[0].record(stream)
+        for _ in range(reps):
+            shaper.states(dec)
+        sev[1].record(stream)
+        for _ in range(reps):
+            shaper.rewards(t_ticks, t_ports)
+        sev[2].record(stream)
+        torch.cuda.synchronize()
+        s_us, r_us = 1000.0 * sev[0].elapsed_time(sev[1]) / reps, 1000.0 * sev[1].elapsed_time(sev[2]) / reps
+        shaping = {"state_dim": shaper.state_dim, "states_us": s_us, "states_per_s": B / (s_us * 1e-6),
+                   "state_gbs": B * shaper.state_dim * 12 / (s_us * 1e-6) / 1e9,  # 8 B written + 4 B gathered per element
+                   "rewards_us": r_us, "rewards_per_s": B / (r_us * 1e-6),
+                   "reward_gbs": B * (shaper.time_window * 2 * 4 + 4) / (r_us * 1e-6) / 1e9,
+                   "what": "examples/cim/rl shaping (look_back 7, 99-tick decayed reward) for all replicas, L2 warm"}
+
     # ---- e2e: host-buffer C-ABI path, agent on the host, one episode-aligned run of min(steps, 2000) steps
     e2e = None
     if not args.skip_e2e:
@@ -625,6 +652,8 @@ def run_ours(args, rank, local_rank, world):
                                    "maro_%s_step_pinned (pinned host buffers) + tools/host_agent.c on the host" % ("bike" if bike else "cim")),
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}
+        if shaping:
+            line["rl_shaping"] = shaping
         if graph_info:
             line["graph_mode"] = {"value": g_graph_steps / (graph_ms / 1000.0), "unit": "env-steps/s",
                                   "chunk_steps": graph_info["chunk"], "us_per_step": 1000.0 * graph_ms / max(1, (args.steps // graph_info["chunk"]) * graph_info["chunk"]),

@@ -49,7 +49,8 @@ def test_device_shaping_matches_reference_vectors(name):
 
 
 def test_device_shaping_at_batch_size_matches_restatement():
-    """1024 desynchronised replicas (hashed random agent on the device): sampled replicas against the restatement."""
+    """1024 replicas with different action histories (hashed random agent on the device; the noise-free schedule keeps
+    them at the same tick, their container counts differ): sampled replicas against the restatement."""
     import torch
 
     from maro_b200.batch import CimBatch
@@ -73,7 +74,7 @@ def test_device_shaping_at_batch_size_matches_restatement():
     ticks = torch.tensor(np.maximum(d[:, 0] - 120, 0), dtype=torch.int32, device="cuda")
     ports = torch.tensor(d[:, 1] % topo.n_ports, dtype=torch.int32, device="cuda")
     rewards = shaper.rewards(ticks, ports).cpu().numpy()
-    assert len(set(d[:, 0].tolist())) > 1  # replicas are at different ticks
+    assert len({states[r].tobytes() for r in range(B)}) > B // 2  # the replicas' states differ
     for rep in (0, 1, 511, 1023):
         view = SnapshotView(lambda f, rep=rep: env.snapshot_row(f, rep), topo, cache=True)
         assert d[rep, 6] == 0
