@@ -309,7 +309,8 @@ def vm_workload(args):
     import vm_trace_gen
 
     ticks = 8638 if args.ticks == 1000 else args.ticks
-    d = args.vm_trace_dir or os.path.join(tempfile.gettempdir(), f"maro_b200_vm_trace_{args.vm_count}_{ticks}")
+    rank = os.environ.get("RANK", "0")  # one copy per rank: the ranks of a torchrun job generate it concurrently
+    d = args.vm_trace_dir or os.path.join(tempfile.gettempdir(), f"maro_b200_vm_trace_{args.vm_count}_{ticks}_r{rank}")
     vm_path, cpu_path = vm_trace_gen.generate(d, args.vm_count, ticks)
     return vm_trace_gen.azure_like_config(vm_path, cpu_path), ticks
 
