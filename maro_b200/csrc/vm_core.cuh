@@ -124,11 +124,7 @@ __device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(
 __device__ __forceinline__ void atomic_min_i32(int32_t* p, int32_t v) { atomicMin(p, v); }
 #endif
 // doubles of per-group scratch the step needs (vm_tick_begin: sum[N] + 5 N + 1 ints; vm_tick_end: 2 N doubles)
-#ifdef MARO_HOST_EMULATION
-inline int vm_scratch_doubles(int n_pm) { return 4 * n_pm + 2; }
-#else
-__host__ __device__ inline int vm_scratch_doubles(int n_pm) { return 4 * n_pm + 2; }
-#endif
+MARO_DEV int vm_scratch_doubles(int n_pm) { return 4 * n_pm + 2; }
 MARO_DEV int64_t vctrl_get64(const VmReplica& r, int i) { return *reinterpret_cast<const int64_t*>(r.c + i); }
 MARO_DEV void vctrl_add64(const VmReplica& r, int i, int64_t d) { *reinterpret_cast<int64_t*>(r.c + i) += d; }
 MARO_DEV double& vctrl_f64(const VmReplica& r, int i) { return *reinterpret_cast<double*>(r.c + i); }
