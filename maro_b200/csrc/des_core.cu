@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(kWarps * 32) vm_step_kernel(const __grid_const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
     const Grp<32> g(threadIdx.x & 31);
-    double* scratch = reinterpret_cast<double*>(smem_raw) + (size_t)wid * vm_scratch_doubles(s.N);
+    double* scratch = reinterpret_cast<double*>(smem_raw) + (size_t)wid * 2 * s.N;
     for (int rep = blockIdx.x * kWarps + wid; rep < s.n_replicas; rep += gridDim.x * kWarps) {
         if (a.active && !a.active[rep]) {
             if (g.lane == 0) a.decisions[(int64_t)rep * s.DW + MARO_VM_DEC_STATUS] = MARO_STATUS_INACTIVE;
@@ -1306,7 +1306,7 @@ int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmE
     int w = 4;
     while (w > 1 && (e->B + w - 1) / w < prop.multiProcessorCount) w >>= 1;
     e->warps_per_cta = w;
-    e->smem_bytes = (size_t)w * vm_scratch_doubles(s.N) * sizeof(double);
+    e->smem_bytes = (size_t)w * 2 * s.N * sizeof(double);
     if (e->smem_bytes > 48 * 1024) { delete e; return fail("maro_vm_create: too many PMs for the per-warp scratch"); }
     e->grid = std::min((e->B + w - 1) / w, prop.multiProcessorCount * (48 / w));
     e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;

@@ -107,24 +107,6 @@ __device__ __forceinline__ double maro_rint(double x) { return rint(x); }
 #endif
 
 MARO_DEV int32_t& VPM(const VmShape& s, const VmReplica& r, int attr, int p) { return r.f[attr * s.N + p]; }
-// word offset of list slot k of PM p (lists are contiguous per PM: a lane that walks a list reads consecutive entries)
-MARO_DEV size_t vm_slot(const VmShape& s, int p, int k) { return 4 * ((size_t)p * s.K + k); }
-#ifdef MARO_HOST_EMULATION
-static inline void atomic_add_f64(double* p, double v) {
-    uint64_t* q = reinterpret_cast<uint64_t*>(p);
-    uint64_t old = __atomic_load_n(q, __ATOMIC_RELAXED), nw;
-    do { double d; memcpy(&d, &old, 8); d += v; memcpy(&nw, &d, 8); } while (!__atomic_compare_exchange_n(q, &old, nw, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
-}
-static inline void atomic_min_i32(int32_t* p, int32_t v) {
-    int32_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
-    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-}
-#else
-__device__ __forceinline__ void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
-__device__ __forceinline__ void atomic_min_i32(int32_t* p, int32_t v) { atomicMin(p, v); }
-#endif
-// doubles of per-group scratch the step needs (vm_tick_begin: sum[N] + 5 N + 1 ints; vm_tick_end: 2 N doubles)
-MARO_DEV int vm_scratch_doubles(int n_pm) { return 4 * n_pm + 2; }
 MARO_DEV int64_t vctrl_get64(const VmReplica& r, int i) { return *reinterpret_cast<const int64_t*>(r.c + i); }
 MARO_DEV void vctrl_add64(const VmReplica& r, int i, int64_t d) { *reinterpret_cast<int64_t*>(r.c + i) += d; }
 MARO_DEV double& vctrl_f64(const VmReplica& r, int i) { return *reinterpret_cast<double*>(r.c + i); }
@@ -255,8 +237,8 @@ MARO_DEV int vm_on_actions(const VmShape& s, const VmReplica& r, int tick, const
             float u = maro_i2f(r.t[s.t_val + r0.x]);  // get_utilization(cur_tick): series[0]
             const int delay = tick - r0.y;  // creation - request tick (0 .. buffer budget)
             if (delay < 0 || delay > 0x7fff || r0.w < 0 || r0.w > 0xffff) return -2;
-            st4(r.l + vm_slot(s, p, n), I4{r0.x - tick, tick + r0.z, r0.w | (delay << 16), maro_f2i(u)});
-            st4(r.lc + vm_slot(s, p, n), I4{vm, tick, r1.x, 0});
+            st4(r.l + 4 * ((size_t)n * s.N + p), I4{r0.x - tick, tick + r0.z, r0.w | (delay << 16), maro_f2i(u)});
+            st4(r.lc + 4 * ((size_t)n * s.N + p), I4{vm, tick, r1.x, 0});
             r.len[p] = n + 1;
             r.c[VC_N_LIVE] += 1;
             if (VPM(s, r, VPA_OVERSUB, p) == 0) VPM(s, r, VPA_OVERSUB, p) = r1.w == 0 ? 1 : -1;
@@ -275,134 +257,68 @@ MARO_DEV int vm_on_actions(const VmShape& s, const VmReplica& r, int tick, const
     return 0;
 }
 
-// BusinessEngine.step (:449-493) minus the request insertion: finished VMs, VM / PM workloads, roll-ups.
-//
-// The sweep over the live VMs is flat: the T list entries of the replica are cut into G equal chunks, one per lane,
-// regardless of how they spread over the PMs (one lane per PM would leave most lanes idle: list lengths range 0..K).
-// That changes the order in which a PM's `utilisation * cores` terms are added, which is admissible because the sum is
-// order-free whenever it is exact: every term is an integer multiple of q = ulp(smallest non-zero float32 utilisation
-// of the PM), so if the total stays below 2^52 q every partial sum of every order is representable and all orders give
-// the exact sum — the one the reference's sequential loop produces.  Each PM tracks the smallest exponent field next
-// to its sum; a PM that fails the test (a reading below ~1e-5 %) is re-summed in list order.
+// BusinessEngine.step (:449-493) minus the request insertion: finished VMs, VM / PM workloads, roll-ups
 template <int G>
-MARO_DEV void vm_tick_begin(const VmShape& s, const Grp<G>& g, const VmReplica& r, int tick, double* scratch) {
-    const int N = s.N;
+MARO_DEV void vm_tick_begin(const VmShape& s, const Grp<G>& g, const VmReplica& r, int tick) {
     const double* price = vm_tab_f64(r, s.t_price);
     const uint8_t* has = reinterpret_cast<const uint8_t*>(r.t + s.t_has);
+    int fin = 0;
+    double fin_price = 0.0;
     const int32_t* val = r.t + s.t_val;
-    double* sum = scratch;                                           // [N]
-    int32_t* start = reinterpret_cast<int32_t*>(scratch + N);        // [N+1] exclusive prefix of the list lengths
-    int32_t* min_e = start + N + 1;                                  // [N] smallest exponent field of a non-zero term
-    int32_t* dca = min_e + N;                                        // [N] cores released by VMs finishing now
-    int32_t* nfin = dca + N;                                         // [N] finished entries
-    int carry = 0;
-    for (int b0 = 0; b0 < N; b0 += G) {
-        const int p = b0 + g.lane;
-        const int n = p < N ? r.len[p] : 0;
-        const int incl = scan_incl(g, n);
-        if (p < N) { start[p] = carry + incl - n; sum[p] = 0.0; min_e[p] = 255; dca[p] = 0; nfin[p] = 0; }
-        carry += g.shfl(incl, G - 1);
-    }
-    if (g.lane == 0) start[N] = carry;
-    g.sync();
-    const int T = carry;
-    int f = (int)((long long)g.lane * T / G);
-    const int f1 = (int)((long long)(g.lane + 1) * T / G);
-    if (f < f1) {
-        int lo = 0, hi = N;  // start[lo] <= f < start[hi]
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (start[mid] <= f) lo = mid; else hi = mid;
-        }
-        int p = lo, k = f - start[lo], end = start[lo + 1] - start[lo];
-        int cur_p = p, acc_e = 255;
-        double acc = 0.0;
-        while (f < f1) {
-            // four entries per round: their loads, then their trace look-ups, are issued together
-            int pp[4], kk[4];
+    for (int p = g.lane; p < s.N; p += G) {
+        const int n = r.len[p];
+        int kept = 0, ca = 0, ma = 0;
+        double used = 0.0;
+        // four list slots per round: their entry loads, then their trace look-ups, are issued together (the sweep is
+        // latency bound: one replica = one warp, ~14 warps per SM); the float64 sum still runs in list order
+        for (int k0 = 0; k0 < n; k0 += 4) {
             I4 e[4];
             int32_t nb[4];
             uint8_t hs[4];
-            const int nj = f1 - f < 4 ? f1 - f : 4;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                pp[j] = p; kk[j] = k;
-                if (j < nj) {
-                    if (++k == end) {
-                        do { p++; } while (p < N && start[p + 1] == start[p]);
-                        k = 0;
-                        end = p < N ? start[p + 1] - start[p] : 0;
-                    }
-                }
-            }
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (j < nj) e[j] = ld4(r.l + vm_slot(s, pp[j], kk[j]));
+                if (k0 + j < n) e[j] = ld4(r.l + 4 * ((size_t)(k0 + j) * s.N + p));
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 hs[j] = 0; nb[j] = 0;
-                if (j < nj && e[j].y != tick) {
-                    int idx = e[j].x + tick;            // series offset + (tick - creation)
-                    hs[j] = has[idx + (e[j].z >> 16)];  // flags are indexed from the request tick: + (creation - request)
+                if (k0 + j < n && e[j].y != tick) {
+                    int idx = e[j].x + tick;  // series offset + (tick - creation)
+                    hs[j] = has[idx + (e[j].z >> 16)];  // "+ (creation - request)": flags are indexed from the request tick
                     nb[j] = val[idx];
                 }
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (j >= nj) break;
-                if (pp[j] != cur_p) {
-                    atomic_add_f64(&sum[cur_p], acc);
-                    atomic_min_i32(&min_e[cur_p], acc_e);
-                    cur_p = pp[j]; acc = 0.0; acc_e = 255;
-                }
-                if (e[j].y == tick) {  // _process_finished_vm (:770-781): removed from the list in the second pass
-                    atomic_add(&nfin[cur_p], 1);
-                    atomic_add(&dca[cur_p], e[j].z & 0xffff);
+                const int k = k0 + j;
+                if (k >= n) break;
+                if (e[j].y == tick) {  // _process_finished_vm (:770-781)
+                    I4 c = ld4(r.lc + 4 * ((size_t)k * s.N + p));
+                    ca += e[j].z & 0xffff;
+                    ma += c.z;
+                    fin++;
+                    fin_price += price[c.x];
                     continue;
                 }
-                if (hs[j] && nb[j] != e[j].w) {  // _update_vm_workload: a reading exists for this VM at this tick
+                bool dirty = false;
+                if (hs[j]) {  // _update_vm_workload: a reading exists for this VM at this tick
+                    dirty = nb[j] != e[j].w;
                     e[j].w = nb[j];
-                    r.l[vm_slot(s, pp[j], kk[j]) + 3] = nb[j];
                 }
-                acc += (double)maro_i2f(e[j].w) * (double)(e[j].z & 0xffff);
-                if (e[j].w != 0) { int ex = (e[j].w >> 23) & 0xff; acc_e = ex < acc_e ? ex : acc_e; }
-            }
-            f += nj;
-        }
-        atomic_add_f64(&sum[cur_p], acc);
-        atomic_min_i32(&min_e[cur_p], acc_e);
-    }
-    g.sync();
-    int fin = 0;
-    double fin_price = 0.0;
-    for (int p = g.lane; p < N; p += G) {
-        int n = r.len[p];
-        if (nfin[p]) {  // stable compaction of the lists that lost entries
-            int kept = 0, ma = 0;
-            for (int k = 0; k < n; k++) {
-                I4 h = ld4(r.l + vm_slot(s, p, k));
-                I4 c = ld4(r.lc + vm_slot(s, p, k));
-                if (h.y == tick) { ma += c.z; fin++; fin_price += price[c.x]; continue; }
-                if (kept != k) { st4(r.l + vm_slot(s, p, kept), h); st4(r.lc + vm_slot(s, p, kept), c); }
+                used += (double)maro_i2f(e[j].w) * (double)(e[j].z & 0xffff);
+                if (kept != k) {
+                    st4(r.l + 4 * ((size_t)kept * s.N + p), e[j]);
+                    st4(r.lc + 4 * ((size_t)kept * s.N + p), ld4(r.lc + 4 * ((size_t)k * s.N + p)));
+                } else if (dirty) {
+                    r.l[4 * ((size_t)k * s.N + p) + 3] = e[j].w;
+                }
                 kept++;
             }
-            r.len[p] = n = kept;
-            VPM(s, r, VPA_CPU_ALLOC, p) -= dca[p];
+        }
+        if (kept != n) {
+            r.len[p] = kept;
+            VPM(s, r, VPA_CPU_ALLOC, p) -= ca;
             VPM(s, r, VPA_MEM_ALLOC, p) -= ma;
             if (kept == 0) VPM(s, r, VPA_OVERSUB, p) = 0;
-        }
-        double used = sum[p];
-        if (min_e[p] != 255 && used > 0.0) {
-            int64_t bits;
-            memcpy(&bits, &used, 8);
-            const int e_sum = (int)((bits >> 52) & 0x7ff) - 1023, e_min = min_e[p] > 1 ? min_e[p] : 1;
-            if (e_sum > e_min - 99) {  // used >= 2^52 ulp(smallest term): not provably exact -> the reference's order
-                used = 0.0;
-                for (int k = 0; k < n; k++) {
-                    I4 h = ld4(r.l + vm_slot(s, p, k));
-                    used += (double)maro_i2f(h.w) * (double)(h.z & 0xffff);
-                }
-            }
         }
         int k100 = util_to_k(used / (double)VPM(s, r, VPA_CPU_CAP, p));  // _update_pm_workload (:640-652)
         if (k100 != r.uk[p]) pm_store_util(s, r, p, k100);
@@ -437,7 +353,7 @@ MARO_DEV void vm_tick_begin(const VmShape& s, const Grp<G>& g, const VmReplica& 
     g.sync();
 }
 
-// post_step (:495-525) up to the snapshot; `scratch` = vm_scratch_doubles(N) doubles private to the group
+// post_step (:495-525) up to the snapshot; `scratch` = 2 N doubles private to the group
 template <int G>
 MARO_DEV void vm_tick_end(const VmShape& s, const Grp<G>& g, const VmReplica& r, int tick, double* scratch) {
     const double* price = vm_tab_f64(r, s.t_price);
@@ -467,7 +383,7 @@ MARO_DEV void vm_tick_end(const VmShape& s, const Grp<G>& g, const VmReplica& r,
                 if (s.kill_all) {
                     double gone = 0.0;
                     for (int k = 0; k < n; k++) {
-                        I4 c = ld4(r.lc + vm_slot(s, p, k));
+                        I4 c = ld4(r.lc + 4 * ((size_t)k * s.N + p));
                         incomes -= price[c.x] * (double)(tick - c.y);
                         gone += price[c.x];
                     }
@@ -529,7 +445,7 @@ MARO_DEV void vm_replica_step(const VmShape& s, const Grp<G>& g, const VmReplica
     int status = MARO_STATUS_DONE, cur_vm = -1, cur_budget = 0;
     while (!err) {
         if (!resume) {
-            vm_tick_begin(s, g, r, tick, scratch);
+            vm_tick_begin(s, g, r, tick);
             nticks++;
             req_cur = r.t[s.t_req_offset + tick];
             req_end = r.t[s.t_req_offset + tick + 1];

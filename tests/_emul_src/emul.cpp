@@ -190,7 +190,7 @@ VmEmul* vm_emul_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, int
     e->state.assign((size_t)e->B * e->s.SW, 0);
     e->snap.assign((size_t)e->B * e->s.ring_rows * e->s.FWp, 0);
     e->snap_frame.assign((size_t)e->B * e->s.ring_rows, -1);
-    e->scratch.assign((size_t)vm_scratch_doubles(e->s.N), 0.0);
+    e->scratch.assign(2 * (size_t)e->s.N, 0.0);
     for (int i = 0; i < e->B; i++) { if (e->lanes == 1) vm_reset_g<1>(e, i, true); else if (e->lanes == 8) vm_reset_g<8>(e, i, true); else vm_reset_g<32>(e, i, true); }
     return e;
 }
