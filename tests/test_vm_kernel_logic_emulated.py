@@ -64,3 +64,29 @@ def test_vm_device_logic_reset_and_bad_action():
     st, dec, _ = e.step(None)
     st, _, _ = e.step([[dec[1], 0, topo.n_pm, 0]])
     assert st == -1
+
+
+@pytest.mark.parametrize("lanes", [32, 8])
+def test_vm_device_logic_tiny_and_denormal_utilisations(lanes):
+    """30 % of the readings replaced by tiny / denormal float32 values: decisions, frames and energy metrics stay
+    bit-identical to the oracle (the float64 utilisation sums run in the reference's list order)."""
+    spec = VM_CASES["synth_120_oversub_mixed"]
+    topo = vm_topology(spec)
+    rng = np.random.default_rng(5)
+    v = topo.util_val.copy()
+    pick = rng.random(len(v)) < 0.3
+    tiny = np.asarray([1e-12, 3e-20, 1e-40, 7.5e-6, 2e-9], np.float32).astype(np.float64)
+    v[pick] = tiny[rng.integers(0, len(tiny), int(pick.sum()))]
+    topo.util_val = v
+    e, o = VmEmulEnv(topo, lanes=lanes), VmOracle(topo)
+    (st, dec, met), (ost, odec, omet) = e.step(None), o.step(None)
+    n = 0
+    while ost == 0:
+        assert st == 0 and dec[:12 + odec[10]].tolist() == odec[:12 + odec[10]].tolist(), n
+        assert np.array_equal(met[EXACT_COLS], omet[EXACT_COLS]), n
+        a = o.best_fit(odec)
+        (st, dec, met), (ost, odec, omet) = e.step(a.reshape(1, 4)), o.step(a.reshape(1, 4))
+        n += 1
+    assert st == 1 and n > 50
+    assert np.array_equal(met[EXACT_COLS], omet[EXACT_COLS])
+    assert np.array_equal(e.frame(), o.frame()) and np.array_equal(e.counters(), o.counters())
