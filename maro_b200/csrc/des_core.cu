@@ -89,13 +89,17 @@ __device__ __forceinline__ Replica make_replica(const CimShape& s, const StepArg
     return r;
 }
 
-template <int kWarps, int G, bool kGeneral>
+// kSpread (small batches, G < 32): one replica per WARP, only its first G lanes work.  Packing 32/G replicas into a warp
+// makes the warp issue the union of their control paths; with fewer replicas than the GPU has warp slots it is faster to
+// give every replica its own warp (same lane-group code, the other lanes exit).
+template <int kWarps, int G, bool kGeneral, bool kSpread = false>
 __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_step_kernel(const __grid_constant__ CimShape s,
                                                                const __grid_constant__ StepArgs a) {
-    constexpr int kGroups = kWarps * 32 / G;  // replicas in flight per CTA
+    constexpr int kGroups = kSpread ? kWarps : kWarps * 32 / G;  // replicas in flight per CTA
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // one mbarrier per lane group (first 256 B)
-    const int gid = threadIdx.x / G;
+    if (kSpread && (threadIdx.x & 31) >= G) return;
+    const int gid = kSpread ? threadIdx.x >> 5 : threadIdx.x / G;
     const Grp<G> g(threadIdx.x & 31);
     int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 256) + (size_t)gid * s.SW;
     uint64_t* bar = bars + gid;
@@ -260,6 +264,7 @@ struct EnvCommon {
 struct MaroCimEnv : EnvCommon {
     CimShape s;
     int K = 0, mt_words = 0, warps_per_cta = 4, lanes = 32, grid = 0, max_stops = 0, max_targets = 0, max_distinct = 0;
+    bool spread = false;  // one replica per warp (cim_step_kernel kSpread)
     size_t smem_bytes = 0;
     int32_t *d_tables = nullptr, *d_topo = nullptr;
     uint32_t* d_mt = nullptr;
@@ -518,6 +523,12 @@ static StepArgs base_args(MaroCimEnv* e) {
 
 template <int W, int G, bool kGeneral>
 static cudaError_t launch_step_wgn(MaroCimEnv* e, const StepArgs& a) {
+    if (G < 32 && W == 4 && e->spread) {  // one replica per warp (small batches), instantiated for 4 warps per CTA only
+        cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W, G, kGeneral, (G < 32 && W == 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+        if (err != cudaSuccess) return err;
+        cim_step_kernel<W, G, kGeneral, (G < 32 && W == 4)><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+        return cudaGetLastError();
+    }
     cudaError_t err = cudaFuncSetAttribute(cim_step_kernel<W, G, kGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
     if (err != cudaSuccess) return err;
     cim_step_kernel<W, G, kGeneral><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
@@ -612,6 +623,15 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     int ctas_needed = (e->B + w * gpw - 1) / (w * gpw);
     int resident = std::max<int>(1, (int)std::min<size_t>(64 / w, sm_smem / (e->smem_bytes + 1024)));
     e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
+    // small batch, sub-warp groups: one replica per warp while the replicas fit the resident warp slots (<= 32 per SM)
+    const char* sp = getenv("MARO_B200_SPREAD");
+    const bool want_spread = sp ? atoi(sp) != 0 : e->B <= prop.multiProcessorCount * 32;  // measured crossover 4 k .. 8 k replicas
+    if (gpw > 1 && want_spread && 256 + (size_t)s.SW * 4 * 4 <= max_smem) {
+        e->spread = true;
+        e->warps_per_cta = 4;
+        e->smem_bytes = 256 + (size_t)s.SW * 4 * 4;
+        e->grid = (e->B + 3) / 4;
+    }
 
     e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
     e->off_tick = s.FWp + C_TICK; e->off_counters = s.FWp + C_NSTEPS_LO;
@@ -894,13 +914,14 @@ __device__ __forceinline__ BikeReplica make_bike_replica(const BikeShape& s, con
     return r;
 }
 
-template <int kWarps, int G>
+template <int kWarps, int G, bool kSpread = false>  // kSpread: one replica per warp, see cim_step_kernel
 __global__ void __launch_bounds__(kWarps * 32) bike_step_kernel(const __grid_constant__ BikeShape s,
                                                                 const __grid_constant__ BikeArgs a) {
-    constexpr int kGroups = kWarps * 32 / G;
+    constexpr int kGroups = kSpread ? kWarps : kWarps * 32 / G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-    const int gid = threadIdx.x / G;
+    if (kSpread && (threadIdx.x & 31) >= G) return;
+    const int gid = kSpread ? threadIdx.x >> 5 : threadIdx.x / G;
     const Grp<G> g(threadIdx.x & 31);
     int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 256) + (size_t)gid * s.SW;
     uint64_t* bar = bars + gid;
@@ -968,6 +989,7 @@ __global__ void bike_greedy_kernel(const int32_t* __restrict__ dec, int32_t* __r
 struct MaroBikeEnv : EnvCommon {
     BikeShape s;
     int warps_per_cta = 1, lanes = 8, grid = 0;
+    bool spread = false;
     size_t smem_bytes = 0;
     int32_t* d_tables = nullptr;
     uint32_t* d_rng = nullptr;
@@ -983,6 +1005,12 @@ static BikeArgs bike_base_args(MaroBikeEnv* e) {
 
 template <int W, int G>
 static cudaError_t bike_launch_wg(MaroBikeEnv* e, const BikeArgs& a) {
+    if (G < 32 && W == 4 && e->spread) {
+        cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G, (G < 32 && W == 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+        if (err != cudaSuccess) return err;
+        bike_step_kernel<W, G, (G < 32 && W == 4)><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+        return cudaGetLastError();
+    }
     cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
     if (err != cudaSuccess) return err;
     bike_step_kernel<W, G><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
@@ -1070,6 +1098,16 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
     int ctas_needed = (e->B + w * gpw - 1) / (w * gpw);
     int resident = std::max<int>(1, (int)std::min<size_t>(32 / w, sm_smem / (e->smem_bytes + 1024)));
     e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
+    {   // the tick chain runs on each group's leader lane: packed groups serialise their leaders, so spread when possible
+        const char* sp = getenv("MARO_B200_SPREAD");
+        const bool want_spread = sp ? atoi(sp) != 0 : e->B <= prop.multiProcessorCount * 32;
+        if (gpw > 1 && want_spread && 256 + (size_t)s.SW * 4 * 4 <= max_smem) {
+            e->spread = true;
+            e->warps_per_cta = 4;
+            e->smem_bytes = 256 + (size_t)s.SW * 4 * 4;
+            e->grid = (e->B + 3) / 4;
+        }
+    }
     e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
     e->off_tick = s.FWp + BC_TICK; e->off_counters = s.FWp + BC_NSTEPS_LO;
     e->dec_words = s.DW; e->max_actions = s.max_actions;
