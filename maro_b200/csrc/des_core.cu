@@ -1100,7 +1100,7 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
     e->grid = std::min(ctas_needed, prop.multiProcessorCount * resident);
     {   // the tick chain runs on each group's leader lane: packed groups serialise their leaders, so spread when possible
         const char* sp = getenv("MARO_B200_SPREAD");
-        const bool want_spread = sp ? atoi(sp) != 0 : e->B <= prop.multiProcessorCount * 32;
+        const bool want_spread = sp ? atoi(sp) != 0 : e->B <= prop.multiProcessorCount * 128;  // measured: +25..45 % up to 16 k
         if (gpw > 1 && want_spread && 256 + (size_t)s.SW * 4 * 4 <= max_smem) {
             e->spread = true;
             e->warps_per_cta = 4;
