@@ -596,7 +596,8 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
         delete e;
         return fail("maro_cim_create: inconsistent topology tables / durations must be positive");
     }
-    const int cfg_lanes = 0;
+    const char* ln = getenv("MARO_B200_LANES");  // tuning override: lanes per replica (8 / 16 / 32, >= the topology's minimum)
+    const int cfg_lanes = ln ? std::max(atoi(ln), lanes_per_replica(s)) : 0;
     register_attrs(e);
 
     // launch geometry: G lanes per replica, as many warps per CTA as shared memory allows (<= 8), persistent grid
