@@ -43,11 +43,31 @@ def config(data, pms, pm_per_rack, racks, **over):
     return conf
 
 
+def config_multi(data, **over):
+    """two regions / three zones / four data centres, two cluster types, two rack types, two PM types (the shape of the
+    reference's own test config tests/data/vm_scheduling/config.yml, scaled down)"""
+    conf = config(data, [(32, 128, 185, 120), (16, 112, 100, 60)], 1, 1, **over)
+    conf["components"]["rack"] = [{"type": "a", "pm": [{"pm_type": 0, "pm_amount": 2}, {"pm_type": 1, "pm_amount": 1}]},
+                                  {"type": "b", "pm": [{"pm_type": 1, "pm_amount": 2}]}]
+    conf["components"]["cluster"] = [{"type": "C1", "rack": [{"rack_type": "a", "rack_amount": 2}, {"rack_type": "b", "rack_amount": 1}]},
+                                     {"type": "C2", "rack": [{"rack_type": "b", "rack_amount": 2}]}]
+    conf["architecture"] = {"region": [
+        {"name": "R1", "zone": [{"name": "Z1", "data_center": [{"name": "D1", "cluster": [{"type": "C1", "cluster_amount": 1}]},
+                                                                {"name": "D2", "cluster": [{"type": "C2", "cluster_amount": 2}]}]},
+                                {"name": "Z2", "data_center": [{"name": "D3", "cluster": [{"type": "C1", "cluster_amount": 1}]}]}]},
+        {"name": "R2", "zone": [{"name": "Z3", "data_center": [{"name": "D4", "cluster": [{"type": "C2", "cluster_amount": 1},
+                                                                                          {"type": "C1", "cluster_amount": 1}]}]}]}]}
+    return conf
+
+
 CASES = {
     "toy_5_first": dict(conf=config("vm_toy", [(32, 128, 185, 120)], 10, 10, MAX_CPU_OVERSUBSCRIPTION_RATE=1), durations=5, agent="first"),
     "synth_160_bestfit": dict(conf=config("vm_synth", [(32, 128, 185, 120), (16, 112, 100, 60)], 3, 2), durations=160, agent="best"),
     "synth_160_tight_budget": dict(conf=config("vm_synth", [(32, 64, 185, 120)], 2, 2, BUFFER_TIME_BUDGET=6, DELAY_DURATION=2),
                                    durations=160, agent="best", snapshot_resolution=4, max_snapshots=16),
+    "synth_140_multi_region": dict(conf=config_multi("vm_synth", BUFFER_TIME_BUDGET=3, MAX_CPU_OVERSUBSCRIPTION_RATE=1.5,
+                                                      MAX_UTILIZATION_RATE=1.2), durations=140, agent="mixed",
+                                   snapshot_resolution=2, max_snapshots=30),
     "synth_120_oversub_mixed": dict(conf=config("vm_synth", [(16, 96, 150, 90)], 4, 2, MAX_CPU_OVERSUBSCRIPTION_RATE=2.5,
                                                  MAX_UTILIZATION_RATE=3, BUFFER_TIME_BUDGET=4), durations=120, agent="mixed"),
 }
