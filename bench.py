@@ -504,7 +504,9 @@ def run_ours(args, rank, local_rank, world):
         t_ports = torch.remainder(dec[:, 1], topo.n_ports).to(torch.int32).contiguous()
         for _ in range(3):
             shaper.states(dec); shaper.rewards(t_ticks, t_ports)
-        sev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_model = torch.remainder(dec[:, 7], 21).to(torch.int32).contiguous()
+        shaper.env_actions(dec, t_model)
+        sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         reps = 20
         sev[0].record(stream)
         for _ in range(reps):
@@ -513,11 +515,15 @@ def run_ours(args, rank, local_rank, world):
         for _ in range(reps):
             shaper.rewards(t_ticks, t_ports)
         sev[2].record(stream)
+        for _ in range(reps):
+            shaper.env_actions(dec, t_model)
+        sev[3].record(stream)
         torch.cuda.synchronize()
+        a_us = 1000.0 * sev[2].elapsed_time(sev[3]) / reps
         s_us, r_us = 1000.0 * sev[0].elapsed_time(sev[1]) / reps, 1000.0 * sev[1].elapsed_time(sev[2]) / reps
         shaping = {"state_dim": shaper.state_dim, "states_us": s_us, "states_per_s": B / (s_us * 1e-6),
                    "state_gbs": B * shaper.state_dim * 12 / (s_us * 1e-6) / 1e9,  # 8 B written + 4 B gathered per element
-                   "rewards_us": r_us, "rewards_per_s": B / (r_us * 1e-6),
+                   "actions_us": a_us, "rewards_us": r_us, "rewards_per_s": B / (r_us * 1e-6),
                    "reward_gbs": B * (shaper.time_window * 2 * 4 + 4) / (r_us * 1e-6) / 1e9,
                    "what": "examples/cim/rl shaping (look_back 7, 99-tick decayed reward) for all replicas, L2 warm"}
 

@@ -200,6 +200,16 @@ int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, i
 int32_t maro_cim_rl_state_dim(MaroCimEnv* env, int32_t look_back, int32_t n_port_attrs, int32_t n_vessel_attrs);
 int maro_cim_rl_state_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
                              int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out);
+/* Action translation (env_sampler.py:38-64) for every replica: model action index m (into d_action_space, n doubles; the
+ * example uses [(i - 10) / 10 for i in range(21)]) and the decision row -> action row {vessel, port, quantity, type}:
+ *   m < n / 2:  LOAD       min(round(|space[m]| * scope.load), vessel.remaining_space if finite_vessel_space)
+ *   else:       DISCHARGE  plan = |space[m]| * (scope.discharge + early) - early, early = vessel.early_discharge if
+ *               has_early_discharge else 0; round(plan) if plan > 0 else round(|space[m]| * scope.discharge)
+ * with Python's round (half to even); the vessel attributes are read from the decision's snapshot like the example does.
+ * out: [n_replicas][max_actions][4] int32 (row 0 written), directly usable as the `actions` of maro_cim_step_device. */
+int maro_cim_rl_action_device(MaroCimEnv* env, const int32_t* d_decisions, const int32_t* d_model_actions,
+                              const double* d_action_space, int32_t n_action_space, int32_t finite_vessel_space,
+                              int32_t has_early_discharge, int32_t* d_actions);
 /* Reward of replica i for the action it took at tick d_ticks[i] on port d_ports[i] (env_sampler.py:66-80):
  *   float32(fulfillment_factor * sum_k decay[k] * fulfillment[tick+1+k, port]
  *           - shortage_factor * sum_k decay[k] * shortage[tick+1+k, port]),   k = 0 .. time_window-1,

@@ -144,6 +144,12 @@ class CimBatch:
         _native.check(_native.lib().maro_cim_rl_state_device(self._h, d_decisions, look_back, pa.ctypes.data, len(pa),
                                                              va.ctypes.data, len(va), d_out))
 
+    def rl_action_device(self, d_decisions: int, d_model_actions: int, d_action_space: int, n_action_space: int,
+                         finite_vessel_space: bool, has_early_discharge: bool, d_actions: int):
+        _native.check(_native.lib().maro_cim_rl_action_device(self._h, d_decisions, d_model_actions, d_action_space,
+                                                              n_action_space, int(finite_vessel_space),
+                                                              int(has_early_discharge), d_actions))
+
     def rl_reward_device(self, d_ticks: int, d_ports: int, d_decay: int, time_window: int, fulfillment_factor: float,
                          shortage_factor: float, d_out: int):
         _native.check(_native.lib().maro_cim_rl_reward_device(self._h, d_ticks, d_ports, d_decay, time_window,

@@ -420,6 +420,11 @@ struct ShapeArgs {
     int time_window, off_fulfillment, off_shortage;
     double fulfillment_factor, shortage_factor;
     float* reward_out;         // [B]
+    // action translation
+    const int32_t* model_actions;  // [B] index into action_space
+    const double* action_space;    // [n_action_space]
+    int n_action_space, finite_vessel_space, has_early_discharge, max_actions, off_remaining_space, off_early_discharge;
+    int32_t* actions_out;          // [B][max_actions][4]
 };
 
 // word `w` of snapshot `frame` of replica `rep`; frames not in the ring read as 0 (np_backend.pyx:543-549)
@@ -828,6 +833,40 @@ int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int
 
 }  // extern "C"
 
+// _translate_to_env_action (examples/cim/rl/env_sampler.py:38-64): model action index -> {vessel, port, quantity, type}
+__global__ void cim_rl_action_kernel(const __grid_constant__ ShapeArgs q) {
+    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= q.B) return;
+    const int32_t* d = q.decisions + (int64_t)rep * 8;
+    int4 out = make_int4(0, 0, 0, 0);
+    if (d[MARO_DEC_STATUS] == MARO_STATUS_DECISION) {
+        const int tick = d[MARO_DEC_TICK], vessel = d[MARO_DEC_VESSEL];
+        int m = q.model_actions[rep];
+        m = m < 0 ? 0 : (m >= q.n_action_space ? q.n_action_space - 1 : m);
+        const int32_t* now = nullptr;
+        const bool have_now = snap_row(q, rep, tick, now);
+        const double percent = fabs(q.action_space[m]);
+        const double zero_action_idx = (double)q.n_action_space / 2.0;
+        double quantity;
+        int type;
+        if ((double)m < zero_action_idx) {
+            type = 0;  // ActionType.LOAD
+            quantity = rint(percent * (double)d[MARO_DEC_SCOPE_LOAD]);  // python round(): half to even
+            if (q.finite_vessel_space) {
+                const double space = have_now ? (double)now[q.off_remaining_space + vessel] : 0.0;
+                quantity = quantity <= space ? quantity : space;
+            }
+        } else {
+            type = 1;  // ActionType.DISCHARGE ((double)m == zero_action_idx cannot happen for an odd-sized space either way)
+            const double early = q.has_early_discharge && have_now ? (double)now[q.off_early_discharge + vessel] : 0.0;
+            const double plan = percent * ((double)d[MARO_DEC_SCOPE_DISCHARGE] + early) - early;
+            quantity = plan > 0 ? rint(plan) : rint(percent * (double)d[MARO_DEC_SCOPE_DISCHARGE]);
+        }
+        out = make_int4(vessel, d[MARO_DEC_PORT], (int)quantity, type);
+    }
+    *reinterpret_cast<int4*>(q.actions_out + (int64_t)rep * q.max_actions * 4) = out;
+}
+
 static int shape_common(MaroCimEnv* e, ShapeArgs& q) {
     memset(&q, 0, sizeof(q));
     q.snap = e->d_snap; q.snap_frame = e->d_snap_frame; q.ring_rows = e->ring_rows; q.FWp = e->FWp; q.B = e->B;
@@ -865,6 +904,24 @@ int maro_cim_rl_state_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t 
     const int64_t total = (int64_t)e->B * maro_cim_rl_state_dim(e, look_back, n_port_attrs, n_vessel_attrs);
     int threads = 256, blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
     cim_rl_state_kernel<<<blocks, threads, 0, e->stream>>>(q);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const int32_t* d_model_actions, const double* d_action_space,
+                              int32_t n_action_space, int32_t finite_vessel_space, int32_t has_early_discharge, int32_t* d_actions) {
+    if (!e || !d_decisions || !d_model_actions || !d_action_space || !d_actions || n_action_space < 1)
+        return fail("maro_cim_rl_action_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    ShapeArgs q;
+    shape_common(e, q);
+    q.decisions = d_decisions; q.model_actions = d_model_actions; q.action_space = d_action_space; q.n_action_space = n_action_space;
+    q.finite_vessel_space = finite_vessel_space; q.has_early_discharge = has_early_discharge; q.max_actions = e->s.max_actions;
+    q.off_remaining_space = e->attrs[1][common_attr_id(e, 1, "remaining_space")].off;
+    q.off_early_discharge = e->attrs[1][common_attr_id(e, 1, "early_discharge")].off;
+    q.actions_out = d_actions;
+    int threads = 256, blocks = (e->B + threads - 1) / threads;
+    cim_rl_action_kernel<<<blocks, threads, 0, e->stream>>>(q);
     CK(cudaGetLastError());
     return 0;
 }

@@ -14,12 +14,14 @@ from .batch import CimBatch
 # examples/cim/rl/config.py:10-36
 PORT_ATTRIBUTES = ("empty", "full", "on_shipper", "on_consignee", "booking", "shortage", "fulfillment")
 VESSEL_ATTRIBUTES = ("empty", "full", "remaining_space")
+ACTION_SPACE = tuple((i - 10) / 10 for i in range(21))
 
 
 class CimShaper:
     def __init__(self, batch: CimBatch, look_back: int = 7, port_attributes: Sequence[str] = PORT_ATTRIBUTES,
                  vessel_attributes: Sequence[str] = VESSEL_ATTRIBUTES, time_window: int = 99, time_decay: float = 0.97,
-                 fulfillment_factor: float = 1.0, shortage_factor: float = 1.0):
+                 fulfillment_factor: float = 1.0, shortage_factor: float = 1.0, action_space: Sequence[float] = ACTION_SPACE,
+                 finite_vessel_space: bool = True, has_early_discharge: bool = True):
         import torch
 
         self._torch = torch
@@ -36,6 +38,9 @@ class CimShaper:
         B = batch.n_replicas
         self._state = torch.zeros((B, self.state_dim), dtype=torch.float64, device=dev)
         self._reward = torch.zeros(B, dtype=torch.float32, device=dev)
+        self._space = torch.tensor(np.asarray(action_space, np.float64), device=dev)
+        self.finite_vessel_space, self.has_early_discharge = bool(finite_vessel_space), bool(has_early_discharge)
+        self._actions = torch.zeros((B, batch.max_actions, 4), dtype=torch.int32, device=dev)
 
     def states(self, decisions):
         """decisions: int32 CUDA tensor [B][8] (MARO_DEC_* rows of the last step) -> float64 CUDA tensor [B][state_dim]."""
@@ -50,3 +55,11 @@ class CimShaper:
         self.batch.rl_reward_device(ticks.data_ptr(), ports.data_ptr(), self._decay.data_ptr(), self.time_window,
                                     self.fulfillment_factor, self.shortage_factor, self._reward.data_ptr())
         return self._reward
+
+    def env_actions(self, decisions, model_actions):
+        """decisions int32 [B][8], model_actions int32 [B] (indices into the action space) -> int32 CUDA tensor
+        [B][max_actions][4], the `actions` argument of ``CimBatch.step_device`` (env_sampler.py:38-64)."""
+        assert model_actions.is_cuda and model_actions.dtype == self._torch.int32 and model_actions.is_contiguous()
+        self.batch.rl_action_device(decisions.data_ptr(), model_actions.data_ptr(), self._space.data_ptr(), self._space.numel(),
+                                    self.finite_vessel_space, self.has_early_discharge, self._actions.data_ptr())
+        return self._actions

@@ -62,3 +62,16 @@ def reward_numpy(view, port, tick):
     fs = np.asarray([view.get("ports", t, port, "shortage")[0] for t in ticks])
     decay = [R["time_decay"] ** i for i in range(R["time_window"])]
     return np.float32(R["fulfillment_factor"] * np.dot(ff, decay) - R["shortage_factor"] * np.dot(fs, decay))
+
+
+def action_numpy(view, dec, model_action):
+    """env_sampler.py:38-64 over a decision row [tick, port, vessel, scope.load, scope.discharge, early_discharge]"""
+    tick, port, vessel, load, discharge = (int(x) for x in dec[:5])
+    space = rl_gen.ACTION_SPACE
+    vsl_space = view.get("vessels", tick, vessel, "remaining_space")[0] if rl_gen.FINITE_VESSEL_SPACE else float("inf")
+    percent = abs(space[model_action])
+    if model_action < len(space) / 2:
+        return [vessel, port, int(min(round(percent * load), vsl_space)), 0]
+    early = view.get("vessels", tick, vessel, "early_discharge")[0] if rl_gen.HAS_EARLY_DISCHARGE else 0
+    plan = percent * (discharge + early) - early
+    return [vessel, port, int(round(plan) if plan > 0 else round(percent * discharge)), 1]

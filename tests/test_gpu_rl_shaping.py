@@ -32,7 +32,9 @@ def test_device_shaping_matches_reference_vectors(name):
         assert d[:, 6].tolist() == [0] * B and d[0, :3].tolist() == gold["steps"][k].tolist()
         s = shaper.states(dec).cpu().numpy()
         assert np.array_equal(s, np.broadcast_to(gold["states"][k], s.shape)), k   # integers -> float64: exact
-        act[:, 0] = torch.tensor(gold["actions"][k], dtype=torch.int32, device="cuda")
+        model = torch.full((B,), int(gold["model_actions"][k]), dtype=torch.int32, device="cuda")
+        act = shaper.env_actions(dec, model)  # the example's action translation, on the device
+        assert act.cpu().numpy()[:, 0].tolist() == [gold["actions"][k].tolist()] * B, k
         env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
     assert dec.cpu().numpy()[:, 6].tolist() == [1] * B
     assert (shaper.states(dec).cpu().numpy() == 0).all()  # no decision pending -> zero rows

@@ -5,7 +5,7 @@ import pytest
 
 from maro_b200.scenarios.cim.topology import build_topology
 from oracle.cim_oracle import CimOracle
-from rl_helpers import RL_CASES, SnapshotView, load_rl_golden, reward_numpy, state_numpy
+from rl_helpers import RL_CASES, SnapshotView, action_numpy, load_rl_golden, reward_numpy, state_numpy
 
 
 @pytest.mark.parametrize("name", sorted(RL_CASES))
@@ -20,6 +20,7 @@ def test_rl_shaping_restatement_matches_reference(name):
         assert [int(dec[0]), int(dec[1]), int(dec[2])] == gold["steps"][k].tolist()
         s = state_numpy(view, int(dec[0]), int(dec[1]), int(dec[2]))
         assert s.shape == gold["states"][k].shape and np.array_equal(s, gold["states"][k]), k
+        assert action_numpy(view, dec, int(gold["model_actions"][k])) == gold["actions"][k].tolist(), k
         st, dec, _ = o.step(gold["actions"][k].reshape(1, 4))
         k += 1
     assert k == len(gold["steps"])
