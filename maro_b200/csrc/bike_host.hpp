@@ -1,5 +1,5 @@
 // bike_host.hpp — host-side (plain C++) shape + static-table serialisation for the citi_bike scenario, shared by
-// des_core.cu and the test-only host-emulation harness.  No CUDA here.
+// bike_env.cu and the test-only host-emulation harness.  No CUDA here.
 #pragma once
 #include "bike_core.cuh"
 #include "cim_host.hpp"

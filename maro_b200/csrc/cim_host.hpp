@@ -1,4 +1,4 @@
-// cim_host.hpp — host-side (plain C++) shape + static-table serialisation shared by des_core.cu and the
+// cim_host.hpp — host-side (plain C++) shape + static-table serialisation shared by cim_env.cu and the
 // test-only host-emulation harness (tests/_emul).  No CUDA here.
 #pragma once
 #include <math.h>

@@ -1,5 +1,5 @@
 // vm_host.hpp — host-side (plain C++) shape + static-table serialisation for the vm_scheduling scenario, shared by
-// des_core.cu and the test-only host-emulation harness.  No CUDA here.
+// vm_env.cu and the test-only host-emulation harness.  No CUDA here.
 #pragma once
 #include <string>
 
