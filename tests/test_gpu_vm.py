@@ -183,3 +183,51 @@ def test_vm_vector_env_two_envs_and_pinned_api():
         actions[:, 0] = np.stack([[decisions[i, 1], 0, decisions[i, 12], 0] for i in range(2)])
         b.step_pinned(use_actions=True)
         assert decisions[0, 1] == int(gold["steps"][1][1]) and mets.shape == (2, 16)
+
+
+def test_vm_cuda_full_size_episode_matches_oracle():
+    """BASELINE config #5 size: 2 048 replicas, 10 000 VMs, 100 PMs, 8 638 ticks (synthetic azure.2019.10k-scale trace,
+    tools/vm_trace_gen.py), best-fit agent kernel, the whole episode device-resident.  All replicas must agree, the
+    request bookkeeping must balance, and the final metrics / frame / counters must equal the oracle's."""
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import vm_trace_gen
+
+    from maro_b200.batch import VmBatch
+    from maro_b200.scenarios.vm_scheduling.data import build_vm_topology
+    from oracle.vm_oracle import VmOracle
+
+    ticks = 8638
+    vm_path, cpu_path = vm_trace_gen.generate(os.path.join(tempfile.gettempdir(), "maro_b200_vm_trace_test"), 10000, ticks)
+    topo = build_vm_topology(vm_trace_gen.azure_like_config(vm_path, cpu_path), 0, ticks)
+    assert topo.n_vm == 10000 and topo.n_pm == 100 and topo.error is None
+    o = VmOracle(topo, 1, 8)
+    n_steps, omet = o.run_episode(1)
+    B = 2048
+    env = VmBatch(topo, B, 1, 8)
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    dec = torch.zeros((B, env.dec_words), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    env.step_device(dec.data_ptr(), met.data_ptr())
+    for k in range(n_steps - 1):
+        env.best_fit_policy_device(dec.data_ptr(), act.data_ptr())
+        env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+        if k % 2500 == 0:
+            d = dec.cpu().numpy()
+            assert (d[:, 6] == 0).all() and (d == d[0]).all(), k
+    torch.cuda.synchronize()
+    d, m = dec.cpu().numpy(), met.cpu().numpy()
+    assert d[:, 6].tolist() == [1] * B and (m == m[0]).all()
+    assert np.array_equal(m[0][EXACT_COLS], omet[EXACT_COLS])
+    fm, fo = m[0].view(np.float64), omet.view(np.float64)
+    assert abs(fm[1] - fo[1]) <= 1e-9 * abs(fo[1]) and abs(fm[3] - fo[3]) <= 1e-9 * abs(fo[3])
+    # every request ends up allocated or failed (none pending at the end of this trace); completions <= allocations
+    assert m[0][0] == 10000 and m[0][5] + m[0][7] == m[0][0] and m[0][6] + m[0][8] <= m[0][5]
+    c = env.counters()
+    assert (c == c[0]).all() and c[0].tolist() == o.counters().tolist() and c[0, 0] == n_steps
+    assert np.array_equal(env.read_frame(B - 1), o.frame())
+    env.close()
