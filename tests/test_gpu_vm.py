@@ -174,6 +174,14 @@ def test_vm_vector_env_two_envs_and_pinned_api():
         assert n == len(gold["steps"])
         assert_metrics_close([metrics[0][k] for k in ("total_vm_requests", "total_incomes", "energy_consumption_cost", "total_profit")],
                              gold["final_metrics"][:4])
+        # dict stepping: only the named envs advance (vector_env.py:131-140)
+        venv.reset()
+        metrics, events, done = venv.step(None)
+        first = [e.vm_id for e in events]
+        metrics, events, done = venv.step({1: AllocateAction(events[1].vm_id, events[1].valid_pms[0])})
+        assert len(events) == 1 and events[0].vm_id == int(gold["steps"][1][1])  # env 1 moved on, env 0 did not
+        metrics, events, done = venv.step({0: AllocateAction(first[0], 0)})
+        assert len(events) == 1 and events[0].vm_id == int(gold["steps"][1][1])
         # zero-copy pinned staging buffers
         venv.reset()
         b = venv.batch
