@@ -122,8 +122,27 @@ class FrameView:
         self.matrix = [{a: words[off: off + slots].copy() for a, (off, _, slots) in lay["matrices"].items()}]
 
 
+class GenericFrameView:
+    """``env.current_frame`` for the scenarios whose nodes only have single-slot attributes plus matrices: attribute
+    access by node list, e.g. ``.stations[i].bikes`` / ``.pms[i].cpu_cores_allocated``, ``.matrices[0].trips_adj``."""
+
+    def __init__(self, words: np.ndarray, layout: dict, float_attrs=()):
+        for node, attrs in layout.items():
+            n = next(iter(attrs.values()))[1]
+            views = []
+            for i in range(n):
+                vals = {}
+                for a, (off, _, slots) in attrs.items():
+                    w = words[off + i * slots: off + (i + 1) * slots]
+                    if a in float_attrs:
+                        w = w.view(np.float32)
+                    vals[a] = w[0] if slots == 1 else w.copy()
+                views.append(_NodeView(vals, i))
+            setattr(self, node, views)
+
+
 class Env:
-    """Same constructor and members as ``maro.simulator.Env``; only ``scenario="cim"`` is implemented on the GPU."""
+    """Same constructor and members as ``maro.simulator.Env`` for the cim, citi_bike and vm_scheduling scenarios."""
 
     def __init__(self, scenario: str = None, topology: str = None, start_tick: int = 0, durations: int = 100,
                  snapshot_resolution: int = 1, max_snapshots: int = None, decision_mode=DecisionMode.Sequential,
@@ -254,6 +273,25 @@ class Env:
 
     @property
     def summary(self) -> dict:
+        if self._scenario == "citi_bike":  # citi_bike/business_engine.py:149-163
+            lay, _ = _abi.bike_frame_layout(self._topo.n_stations)
+            from ..scenarios.citi_bike.common import DecisionEvent as BikeDecisionEvent
+
+            return {"node_mapping": {i: int(sid) for i, sid in enumerate(self._topo.station_id)},
+                    "node_detail": {n: {"number": next(iter(a.values()))[1], "attributes": {k: {"slots": v[2]} for k, v in a.items()}}
+                                    for n, a in lay.items()},
+                    "event_payload": {"RequireBike": ["timestamp", "durations", "src_station", "dest_station"],
+                                      "ReturnBike": ["from_station_idx", "to_station_idx", "number"],
+                                      "RebalanceBike": BikeDecisionEvent.summary_key,
+                                      "DeliverBike": ["from_station_idx", "to_station_idx", "number"]}}
+        if self._scenario == "vm_scheduling":  # vm_scheduling/business_engine.py:527-545
+            lay, _ = _abi.vm_frame_layout(self._topo)
+            from ..scenarios.vm_scheduling.common import DecisionEvent as VmDecisionEvent
+
+            return {"node_mapping": {},
+                    "node_detail": {n: {"number": next(iter(a.values()))[1], "attributes": {k: {"slots": v[2]} for k, v in a.items()}}
+                                    for n, a in lay.items()},
+                    "event_payload": {"REQUEST": ["vm_info", "remaining_buffer_time"], "PENDING_DECISION": VmDecisionEvent.summary_key}}
         t = self._topo
         lay, _ = _abi.frame_layout(t.n_ports, t.n_vessels, t.past_stop_number, t.future_stop_number)
         detail = {}
@@ -278,7 +316,11 @@ class Env:
         return self._name
 
     @property
-    def current_frame(self) -> FrameView:
+    def current_frame(self):
+        if self._scenario == "citi_bike":
+            return GenericFrameView(self._batch.read_frame(0), _abi.bike_frame_layout(self._topo.n_stations)[0])
+        if self._scenario == "vm_scheduling":
+            return GenericFrameView(self._batch.read_frame(0), _abi.vm_frame_layout(self._topo)[0], _abi.VM_FLOAT_ATTRS)
         return FrameView(self._batch.read_frame(0), self._topo)
 
     @property

@@ -125,4 +125,7 @@ def test_bike_env_surface_like_reference_tests(tmp_path):
     assert dict(metrics) == {"trip_requirements": 9, "bike_shortage": 3, "operation_number": 11}
     x = env.snapshot_list["stations"][1::["shortage", "bikes", "trip_requirement"]].reshape(-1, 3)
     assert x[:, 0].sum() == gold["stations/shortage"][1].sum()
+    fr = env.current_frame
+    assert [st.capacity for st in fr.stations] == env.snapshot_list["stations"][0::"capacity"].astype(int).tolist()
+    assert fr.matrices[0].trips_adj.shape == (len(fr.stations) ** 2,) and env.summary["node_detail"]["stations"]["number"] == len(fr.stations)
     env.close()

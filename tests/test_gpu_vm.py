@@ -119,6 +119,8 @@ def test_vm_env_surface_replays_reference_trace():
     spec, gold = VM_CASES[name], load_vm_golden(name)
     env = Env("vm_scheduling", _config_dir(spec), durations=spec["durations"])
     assert env.agent_idx_list == list(range(8))
+    assert env.summary["node_detail"]["pms"]["number"] == 8 and "cpu_utilization" in env.summary["node_detail"]["pms"]["attributes"]
+    assert [p.cpu_cores_capacity for p in env.current_frame.pms] == [16] * 8 and env.current_frame.regions[0].total_machine_num == 8
     metrics, dec, done = env.step(None)
     k = 0
     while not done:
