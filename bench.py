@@ -362,8 +362,7 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs (version banner) off stdout: rank 0 prints one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.replicas
     bike = args.scenario == "citi_bike"
