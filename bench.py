@@ -10,8 +10,13 @@ Workload (config.workload): BASELINE.json configs[1] — CIM toy.4p_ssdd_l0.0, 1
 
 Printed JSON (rank 0, one line): see the keys at the bottom.  `value` = whole-job env-steps/s with state resident
 in HBM, L2 flushed between timed steps, device-timed per step with CUDA events, max over ranks.  `e2e` = the same
-metric through the host-buffer C-ABI call (maro_cim_step: pinned H2D of the actions, kernel, D2H of decisions +
-metrics every step) with the agent evaluated on the host.
+metric through the host-buffer C-ABI call (maro_cim_step_pinned: actions in / decisions + metrics out through pinned
+host buffers every step) with the agent evaluated on the host (tools/host_agent.c).  Extras on the same line:
+`graph_mode` (agent + step pairs replayed from CUDA graphs), `rl_shaping` (device-side RL state / action / reward
+shaping), `roofline`, `cpu_baseline`, `clocks`.
+
+Other workloads (not the headline): --scenario citi_bike (BASELINE config #3), --scenario vm_scheduling (config #5 on the
+synthetic azure.2019.10k-scale trace of tools/vm_trace_gen.py), --topology global_trade.22p_l0.8 --ticks 500 (config #4).
 """
 import argparse
 import json
