@@ -84,3 +84,50 @@ def test_device_shaping_at_batch_size_matches_restatement():
         want = reward_numpy(view, int(ports[rep]), int(ticks[rep]))
         assert abs(float(rewards[rep]) - float(want)) <= 1e-6 * max(1.0, abs(float(want))), (rep, rewards[rep], want)
     env.close()
+
+
+def test_device_rollout_loop_matches_oracle_replay():
+    """CimDeviceRollout (state -> torch policy -> action translation -> step, all on the device) for 256 replicas;
+    replica 3's trajectory is replayed on the C oracle with the numpy restatement of the same shaping and policy."""
+    import torch
+
+    from maro_b200.batch import CimBatch
+    from maro_b200.rl_rollout import CimDeviceRollout
+    from maro_b200.scenarios.cim.topology import build_topology
+    from oracle.cim_oracle import CimOracle
+    from rl_helpers import action_numpy
+
+    topo = build_topology("toy.4p_ssdd_l0.0", 300)
+    B = 256
+    env = CimBatch(topo, B)
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    w = torch.linspace(-1.0, 1.0, 171, device="cuda", dtype=torch.float32)
+    rid = torch.arange(B, device="cuda", dtype=torch.float32)
+
+    def policy(states):  # deterministic, replica dependent, exactly representable in float32 and float64
+        score = torch.floor((states * w).sum(1).abs() / 64.0) + rid
+        return torch.remainder(score, 21).to(torch.int32)
+
+    out = CimDeviceRollout(env, policy).run_episode()
+    T = out["ticks"].shape[0]
+    assert out["valid"].all() and out["states"].shape == (T, B, 171)   # noise-free schedule: every replica decides every step
+    rep = 3
+    o = CimOracle(topo)
+    view = SnapshotView(o.snapshot, topo)
+    st, dec, met = o.step(None)
+    wn = np.linspace(-1.0, 1.0, 171, dtype=np.float32)
+    for t in range(T):
+        assert st == 0 and [int(dec[0]), int(dec[1]), int(dec[2])] == [int(out["ticks"][t, rep]), int(out["ports"][t, rep]), int(out["vessels"][t, rep])]
+        s = state_numpy(view, int(dec[0]), int(dec[1]), int(dec[2])).astype(np.float32)
+        assert np.array_equal(s, out["states"][t, rep].cpu().numpy())
+        m = int(out["model_actions"][t, rep])
+        assert 0 <= m < 21
+        st, dec, met = o.step(np.asarray(action_numpy(view, dec, m), np.int32).reshape(1, 4))
+    assert st == 1 and met.tolist() == out["metrics"][rep].cpu().tolist()
+    view = SnapshotView(o.snapshot, topo, cache=True)
+    for t in (0, T // 2, T - 1):
+        want = reward_numpy(view, int(out["ports"][t, rep]), int(out["ticks"][t, rep]))
+        got = float(out["rewards"][t, rep])
+        assert abs(got - float(want)) <= 1e-6 * max(1.0, abs(float(want))), (t, got, want)
+    assert len({out["model_actions"][:, r].cpu().numpy().tobytes() for r in range(B)}) > B // 2
+    env.close()
