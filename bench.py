@@ -531,6 +531,23 @@ def run_ours(args, rank, local_rank, world):
                    "reward_gbs": B * (shaper.time_window * 2 * 4 + 4) / (r_us * 1e-6) / 1e9,
                    "what": "examples/cim/rl shaping (look_back 7, 99-tick decayed reward) for all replicas, L2 warm"}
 
+        # device-resident rollout with a small MLP policy (state -> 171x256x21 MLP -> argmax -> action -> step; rewards after)
+        from maro_b200.rl_rollout import CimDeviceRollout
+
+        torch.manual_seed(0)
+        mlp = torch.nn.Sequential(torch.nn.Linear(shaper.state_dim, 256), torch.nn.ReLU(), torch.nn.Linear(256, 21)).cuda()
+        ro = CimDeviceRollout(env, lambda st: mlp(st * 1e-4).argmax(1), shaper, store_states=False)
+        ro.run_episode(max_steps=50)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        traj = ro.run_episode()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        shaping["rollout"] = {"env_steps_per_s": float(traj["valid"].sum().item()) / dt, "steps": int(traj["valid"].shape[0]),
+                              "seconds": dt, "what": "CimDeviceRollout: one episode, MLP policy on the same GPU, rewards included (wall clock)"}
+        env.reset()
+        pos["i"] = 0
+
     # ---- e2e: host-buffer C-ABI path, agent on the host, one episode-aligned run of min(steps, 2000) steps
     e2e = None
     if not args.skip_e2e:
