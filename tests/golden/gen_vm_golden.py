@@ -68,6 +68,9 @@ CASES = {
     "synth_140_multi_region": dict(conf=config_multi("vm_synth", BUFFER_TIME_BUDGET=3, MAX_CPU_OVERSUBSCRIPTION_RATE=1.5,
                                                       MAX_UTILIZATION_RATE=1.2), durations=140, agent="mixed",
                                    snapshot_resolution=2, max_snapshots=30),
+    # start_tick > 0: the VM table and the readings are entered mid-trace (second readings file: the reader switches at init)
+    "synth_start90_60_bestfit": dict(conf=config("vm_synth", [(32, 128, 185, 120)], 3, 2, BUFFER_TIME_BUDGET=2), start_tick=90,
+                                     durations=60, agent="best", snapshot_resolution=3),
     "synth_120_oversub_mixed": dict(conf=config("vm_synth", [(16, 96, 150, 90)], 4, 2, MAX_CPU_OVERSUBSCRIPTION_RATE=2.5,
                                                  MAX_UTILIZATION_RATE=3, BUFFER_TIME_BUDGET=4), durations=120, agent="mixed"),
 }
@@ -110,7 +113,8 @@ def run_case(name, spec):
     d = tempfile.mkdtemp()
     with open(os.path.join(d, "config.yml"), "w") as fp:
         yaml.safe_dump(spec["conf"], fp, sort_keys=False)
-    env = Env("vm_scheduling", d, durations=spec["durations"], snapshot_resolution=spec.get("snapshot_resolution", 1),
+    env = Env("vm_scheduling", d, start_tick=spec.get("start_tick", 0), durations=spec["durations"],
+              snapshot_resolution=spec.get("snapshot_resolution", 1),
               max_snapshots=spec.get("max_snapshots"))
     n_pm = len(env.snapshot_list["pms"])
     rows, valid, mets, acts = [], [], [], []

@@ -17,7 +17,8 @@ VM_CASES = gen.CASES
 
 
 def vm_topology(spec):
-    return build_vm_topology(dict(spec["conf"]), 0, spec["durations"])
+    st = spec.get("start_tick", 0)
+    return build_vm_topology(dict(spec["conf"]), st, st + spec["durations"])
 
 
 def load_vm_golden(name):
