@@ -34,7 +34,8 @@ def bike_config(data_name):
 
 
 def bike_topology(spec):
-    return build_bike_topology(bike_config(spec["data"]), 0, spec["durations"], transfer_seed=spec["np_seed"])
+    st = spec.get("start_tick", 0)
+    return build_bike_topology(bike_config(spec["data"]), st, st + spec["durations"], transfer_seed=spec["np_seed"])
 
 
 def load_bike_golden(name):

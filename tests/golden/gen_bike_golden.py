@@ -48,6 +48,8 @@ CASES = {
     "toy_600_greedy_res1": dict(data="bike_toy", durations=600, policy=1, snapshot_resolution=1, np_seed=5),
     "toy_2000_greedy_res7_ring12": dict(data="bike_toy", durations=2000, policy=1, snapshot_resolution=7, max_snapshots=12,
                                         np_seed=77),
+    # start_tick > 0: mid-day entry into the trace (trip picker skips ahead, day features of the entry day)
+    "toy_start700_500_greedy_res5": dict(data="bike_toy", start_tick=700, durations=500, policy=1, snapshot_resolution=5, np_seed=9),
     "case1_30_null": dict(data="bike_case_1", durations=30, policy=0, snapshot_resolution=1, np_seed=1),
     "case2_30_greedy": dict(data="bike_case_2", durations=30, policy=1, snapshot_resolution=1, np_seed=2),
 }
@@ -127,7 +129,7 @@ def run_case(name, spec):
     from maro.simulator.scenarios.citi_bike.common import Action, DecisionType
 
     np.random.seed(spec["np_seed"])
-    env = Env("citi_bike", data_config_dir(spec["data"]), durations=spec["durations"],
+    env = Env("citi_bike", data_config_dir(spec["data"]), start_tick=spec.get("start_tick", 0), durations=spec["durations"],
               snapshot_resolution=spec["snapshot_resolution"], max_snapshots=spec.get("max_snapshots"))
     S = len(env.snapshot_list["stations"])
     rows, scopes = [], []
