@@ -38,6 +38,8 @@ CASES = {
     # (cim_data_container_helpers.py:56-66); the recorded trace is the SECOND episode
     "toy4p_l08_120_reset_newseed": dict(topology="toy.4p_ssdd_l0.8", durations=120, policy=1, pseed=4, replica=0,
                                         reset_new_seed=True),
+    "toy4p_l03_start7_90": dict(topology="toy.4p_ssdd_l0.3", durations=90, policy=1, pseed=6, replica=1, start_tick=7,
+                                snapshot_resolution=2),
     "toy4p_l00_start5": dict(topology="toy.4p_ssdd_l0.0", durations=60, policy=1, pseed=2, replica=0, start_tick=0,
                              snapshot_resolution=3),
 }
