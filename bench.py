@@ -31,6 +31,19 @@ sys.path.insert(0, ROOT)
 F_DECLARED = {"toy.4p_ssdd_l0.0": 886}  # frame bytes per replica in the reference's declared dtypes
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,7 +200,7 @@ def run_reference(args, rank, world):
                  "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_reference_vm(args, line, ref_root, cores):
@@ -254,7 +267,7 @@ def run_reference_vm(args, line, ref_root, cores):
                  "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -367,7 +380,6 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs (version banner) off stdout: rank 0 prints one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.replicas
     bike = args.scenario == "citi_bike"
@@ -690,13 +702,19 @@ def run_ours(args, rank, local_rank, world):
                                   "l2": "flushed between graph chunks"}
         line["cpu_baseline"] = (cpu_baseline_vm(args, topo, vm_snaps) if vm else
                                 (cpu_baseline_bike(args, topo) if bike else cpu_baseline_port(args, topo))) if world == 1 else None
-        print(json.dumps(line), flush=True)
+        emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # Native libraries (NCCL's version banner, ...) write to file descriptor 1 behind Python's back.  Keep the original
+    # stdout for the JSON line only and send everything else that targets fd 1 to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
