@@ -160,9 +160,14 @@ int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmE
     CK(cudaGetDeviceProperties(&prop, e->device));
     int w = 4;
     while (w > 1 && (e->B + w - 1) / w < prop.multiProcessorCount) w >>= 1;
+    // per-warp scratch of 2 N doubles: fewer warps per CTA for big clusters, then the opt-in shared-memory carve-out
+    while (w > 1 && (size_t)w * 2 * s.N * sizeof(double) > 48 * 1024) w >>= 1;
     e->warps_per_cta = w;
     e->smem_bytes = (size_t)w * 2 * s.N * sizeof(double);
-    if (e->smem_bytes > 48 * 1024) { delete e; return fail("maro_vm_create: too many PMs for the per-warp scratch"); }
+    if (e->smem_bytes > 48 * 1024) {
+        if (e->smem_bytes > prop.sharedMemPerBlockOptin) { delete e; return fail("maro_vm_create: too many PMs for the per-warp scratch"); }
+        CK(cudaFuncSetAttribute(vm_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    }
     e->grid = std::min((e->B + w - 1) / w, prop.multiProcessorCount * (48 / w));
     e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
     e->off_tick = s.FWp + VC_TICK; e->off_counters = s.FWp + VC_NSTEPS;

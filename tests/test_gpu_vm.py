@@ -241,3 +241,36 @@ def test_vm_cuda_full_size_episode_matches_oracle():
     assert (c == c[0]).all() and c[0].tolist() == o.counters().tolist() and c[0, 0] == n_steps
     assert np.array_equal(env.read_frame(B - 1), o.frame())
     env.close()
+
+
+def test_vm_cuda_large_hierarchy_of_the_reference_test_config():
+    """The reference's own test topology (tests/data/vm_scheduling/config.yml shape: 2 regions / 2 zones / 3 data centres /
+    8 clusters / 75 racks / 1130 PMs of two types) on the toy trace: CUDA path against the oracle, first-valid agent."""
+    import yaml
+
+    from maro_b200.batch import VmBatch
+    from maro_b200.scenarios.vm_scheduling.data import build_vm_topology
+    from oracle.vm_oracle import VmOracle
+    from test_vm_oracle_golden import CONFIG_1130
+
+    conf = yaml.safe_load(CONFIG_1130)
+    conf["VM_TABLE"] = VM_CASES["toy_5_first"]["conf"]["VM_TABLE"]
+    conf["CPU_READINGS"] = VM_CASES["toy_5_first"]["conf"]["CPU_READINGS"]
+    topo = build_vm_topology(conf, 0, 5)
+    assert topo.n_pm == 1130 and topo.error is None
+    B = 6
+    env, o = VmBatch(topo, B, 1, None), VmOracle(topo)
+    (dec, met), (ost, odec, omet) = env.step(None), o.step(None)
+    n = 0
+    while ost == 0:
+        assert (dec == dec[0]).all() and dec[0, :12 + odec[10]].tolist() == odec[:12 + odec[10]].tolist(), n
+        a = np.zeros((B, 1, 4), np.int32)
+        a[:, 0] = [odec[1], 0, odec[12], 0]
+        (dec, met), (ost, odec, omet) = env.step(a, np.ones(B, np.int32)), o.step(a[0])
+        n += 1
+    assert n > 0 and dec[:, 6].tolist() == [1] * B
+    assert np.array_equal(met[0][EXACT_COLS], omet[EXACT_COLS])
+    assert np.array_equal(env.read_frame(B - 1), o.frame())
+    q = env.query("regions", [0], [0, 1], ["total_machine_num", "empty_machine_num"])[0].reshape(2, 2)
+    assert q[:, 0].sum() == 1130
+    env.close()
