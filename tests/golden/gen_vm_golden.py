@@ -102,7 +102,7 @@ def agent_action(kind, dec, env, step, n_pm):
     return [dec.vm_id, 0, dec.valid_pms[(step + dec.vm_id) % len(dec.valid_pms)], 0]
 
 
-def run_case(name, spec):
+def run_case(name, spec, out_dir=None):
     os.environ["SKIP_DEPLOYMENT"] = "TRUE"
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
     sys.path.insert(1, os.path.join(ROOT, "oracle", "_ref", "_stubs"))
@@ -154,7 +154,7 @@ def run_case(name, spec):
         n = len(sl[node])
         for a in attrs:
             out[f"{node}/{a}"] = sl[node][frames::a].reshape(len(frames), n).astype(np.int32)
-    np.savez_compressed(os.path.join(HERE, f"vm_{name}.npz"), **out)
+    np.savez_compressed(os.path.join(out_dir or HERE, f"vm_{name}.npz"), **out)
     print(name, "steps", len(rows), "final", [round(x, 4) for x in final], "tick", env.tick, flush=True)
 
 
