@@ -195,7 +195,9 @@ MARO_DEV void bike_on_actions(const BikeShape& s, const Grp<G>& g, const BikeRep
             // transfer_time = round(np.random.normal(mean, scale=std))   (decision_strategy.py:213-216)
             double x = s.time_mean + s.time_std * bike_gauss(r);
             int tt = (int)rint(x);  // python round(): half to even
-            bike_push(s, r, tick + tt, BE_DELIVER, from, to, executed);
+            // a negative transfer time (normal(20, 5) can produce one) files the event under a tick that has already
+            // been executed: the reference never runs it and the bikes are lost (event_buffer.py:166-175)
+            if (tt >= 0) bike_push(s, r, tick + tt, BE_DELIVER, from, to, executed);
         }
     }
 }

@@ -587,6 +587,20 @@ MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, in
 
 // Reference form of the order generator (leader lane, float64; kept as the readable statement of the algorithm that
 // gen_orders_coop distributes over the lanes): CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398).
+// builtin sum() of floats as CPython >= 3.12 evaluates it (bltinmodule.c builtin_sum_impl: first item + int 0, then
+// Neumaier's compensated summation, compensation added at the end) — list_sum_normalize (data_lib/cim/utils.py:44-56).
+MARO_DEV double py_sum(const double* x, int n) {
+    if (n <= 0) return 0.0;
+    double f = 0.0 + x[0], c = 0.0;
+    for (int i = 1; i < n; i++) {
+        double v = x[i], t = f + v;
+        if (fabs(f) >= fabs(v)) c += (f - t) + v; else c += (v - t) + f;
+        f = t;
+    }
+    if (c != 0.0 && isfinite(c)) f += c;
+    return f;
+}
+
 // Writes {src | dst << 8, qty} pairs to `out` and returns the count.  Scratch doubles live in the MT block.
 MARO_DEV int gen_orders_serial(const CimShape& s, const Replica& r, int tick, int total_empty, int32_t* out, double* dscr) {
     int orders_to_gen = TBL_I(r, s.t_order_proportion, tick);
@@ -598,23 +612,17 @@ MARO_DEV int gen_orders_serial(const CimShape& s, const Replica& r, int tick, in
     int remaining = orders_to_gen, n = 0;
     double* srcd = dscr;
     double* tgtd = dscr + s.P;
-    double tot = 0.0;
-    for (int p = 0; p < s.P; p++) {
-        double x = s.order_noise ? apply_noise_serial(r, 0, TBL_D(r, s.t_sb_d, p), TBL_D(r, s.t_sn_d, p))
-                                 : TBL_D(r, s.t_sb_d, p) + 0.0;
-        srcd[p] = x;
-        tot = tot + x;
-    }
+    for (int p = 0; p < s.P; p++)
+        srcd[p] = s.order_noise ? apply_noise_serial(r, 0, TBL_D(r, s.t_sb_d, p), TBL_D(r, s.t_sn_d, p))
+                                : TBL_D(r, s.t_sb_d, p) + 0.0;
+    const double tot = py_sum(srcd, s.P);
     for (int p = 0; p < s.P; p++) {
         if (remaining == 0) break;
         int lo = TBL_I(r, s.t_target_offset, p), hi = TBL_I(r, s.t_target_offset, p + 1);
-        double ttot = 0.0;
-        for (int i = lo; i < hi; i++) {
-            double x = s.order_noise ? apply_noise_serial(r, 0, TBL_D(r, s.t_tb_d, i), TBL_D(r, s.t_tn_d, i))
-                                     : TBL_D(r, s.t_tb_d, i) + 0.0;
-            tgtd[i - lo] = x;
-            ttot = ttot + x;
-        }
+        for (int i = lo; i < hi; i++)
+            tgtd[i - lo] = s.order_noise ? apply_noise_serial(r, 0, TBL_D(r, s.t_tb_d, i), TBL_D(r, s.t_tn_d, i))
+                                         : TBL_D(r, s.t_tb_d, i) + 0.0;
+        const double ttot = py_sum(tgtd, hi - lo);
         double sp = srcd[p];
         if (tot != 0.0) sp = sp / tot;
         int cur = (int)maro_ceil((double)orders_to_gen * sp);
@@ -637,7 +645,7 @@ MARO_DEV int gen_orders_serial(const CimShape& s, const Replica& r, int tick, in
 
 
 // Cooperative noisy order generation: the same arithmetic as gen_orders_serial, spread over the lane group.
-// Exactness notes: (i) every python `sum()` stays a left-to-right float64 chain (one lane per chain: the source total
+// Exactness notes: (i) every python `sum()` stays one sequential float64 chain (py_sum; one lane per chain: the source total
 // on the leader, each port's target total on that port's lane); (ii) the running-remainder clamps are integer scans done
 // sequentially per chain; (iii) MT19937 draws are addressed by rank: P source draws, then the targets of every port
 // before the `remaining == 0` break — those ports are a prefix, so their targets are a prefix of the flattened target
@@ -673,9 +681,7 @@ MARO_DEV int gen_orders_coop(const CimShape& s, const Grp<G>& g, const Replica& 
     g.sync();
     // ---- 2. total (left to right) + per-port ceil, then the sequential clamp; `pb` = first port not reached (break)
     if (g.lane == 0) {
-        double tot = 0.0;
-        for (int p = 0; p < P; p++) tot = tot + srcd[p];
-        *bcast = tot;
+        *bcast = py_sum(srcd, P);
     }
     g.sync();
     const double tot = *bcast;
@@ -719,8 +725,7 @@ MARO_DEV int gen_orders_coop(const CimShape& s, const Grp<G>& g, const Replica& 
         int p = p0 + g.lane;
         if (p < pb) {
             int lo = TBL_I(r, s.t_target_offset, p), hi = TBL_I(r, s.t_target_offset, p + 1);
-            double ttot = 0.0;
-            for (int i = lo; i < hi; i++) ttot = ttot + tgtd[i];
+            const double ttot = py_sum(tgtd + lo, hi - lo);
             int c = cur[p], trem = c, n = 0;
             for (int i = lo; i < hi; i++) {
                 int num = 0;

@@ -2,6 +2,7 @@
 // test-only host-emulation harness (tests/_emul).  No CUDA here.
 #pragma once
 #include <math.h>
+#include <cmath>
 #include <stdint.h>
 #include <string.h>
 
@@ -51,18 +52,33 @@ struct BlobBuilder {
     }
 };
 
+// builtin sum() of floats as CPython >= 3.12 evaluates it (Neumaier compensated; see py_sum in cim_core.cuh)
+inline double py_sum_host(const std::vector<double>& x) {
+    if (x.empty()) return 0.0;
+    double f = 0.0 + x[0], c = 0.0;
+    for (size_t i = 1; i < x.size(); i++) {
+        double v = x[i], t = f + v;
+        if (fabs(f) >= fabs(v)) c += (f - t) + v; else c += (v - t) + f;
+        f = t;
+    }
+    if (c != 0.0 && std::isfinite(c)) f += c;
+    return f;
+}
+
 // Order list of one tick for a noise-free, fixed-mode topology: the arithmetic of
 // CimSyntheticDataContainer._gen_orders (cim_data_container.py:310-398) with every noise term == 0.
 inline void gen_orders_noise_free(const MaroCimTopology& t, int orders_to_gen, std::vector<int32_t>& out) {
     const int P = t.n_ports;
     int remaining = orders_to_gen;
-    double tot = 0.0;
-    for (int p = 0; p < P; p++) tot = tot + (t.source_base[p] + 0.0);
+    std::vector<double> tmp;
+    for (int p = 0; p < P; p++) tmp.push_back(t.source_base[p] + 0.0);
+    const double tot = py_sum_host(tmp);
     for (int p = 0; p < P; p++) {
         if (remaining == 0) break;
         int lo = t.target_offset[p], hi = t.target_offset[p + 1];
-        double ttot = 0.0;
-        for (int i = lo; i < hi; i++) ttot = ttot + (t.target_base[i] + 0.0);
+        tmp.clear();
+        for (int i = lo; i < hi; i++) tmp.push_back(t.target_base[i] + 0.0);
+        const double ttot = py_sum_host(tmp);
         double sp = t.source_base[p] + 0.0;
         if (tot != 0.0) sp = sp / tot;
         int cur = (int)ceil((double)orders_to_gen * sp);

@@ -27,8 +27,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.isfile(_LIB_PATH):
-            build()
+        build()  # rebuilds when the C source is newer than the library
         _lib = C.CDLL(_LIB_PATH)
         _lib.cim_oracle_create.restype = C.c_void_p
         _lib.cim_oracle_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]

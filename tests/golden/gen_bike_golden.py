@@ -50,6 +50,10 @@ CASES = {
                                         np_seed=77),
     # start_tick > 0: mid-day entry into the trace (trip picker skips ahead, day features of the entry day)
     "toy_start700_500_greedy_res5": dict(data="bike_toy", start_tick=700, durations=500, policy=1, snapshot_resolution=5, np_seed=9),
+    # found by tools/fuzz_cim_bike_parity.py: this seed draws a transfer time of -2 -> the DeliverBike event is filed under a
+    # tick that has already run and never executes (3 bikes vanish), event_buffer.py:166-175
+    "toy_start300_773_negative_transfer": dict(data="bike_toy", start_tick=300, durations=773, policy=1, snapshot_resolution=20,
+                                               np_seed=41130),
     "case1_30_null": dict(data="bike_case_1", durations=30, policy=0, snapshot_resolution=1, np_seed=1),
     "case2_30_greedy": dict(data="bike_case_2", durations=30, policy=1, snapshot_resolution=1, np_seed=2),
 }
@@ -121,7 +125,7 @@ def prepare_reference_cases():
             yaml.safe_dump({"decision": conf["decision"], "time_zone": conf["time_zone"]}, fp, sort_keys=False)
 
 
-def run_case(name, spec):
+def run_case(name, spec, out_dir=None):
     os.environ["SKIP_DEPLOYMENT"] = "TRUE"
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
     sys.path.insert(1, os.path.join(ROOT, "oracle", "_ref", "_stubs"))
@@ -157,7 +161,7 @@ def run_case(name, spec):
     for a in STATION_ATTRS:
         out["stations/" + a] = sl["stations"][frames::a].reshape(len(frames), S).astype(np.int32)
     out["matrices/trips_adj"] = sl["matrices"][frames::"trips_adj"].reshape(len(frames), S * S).astype(np.int32)
-    np.savez_compressed(os.path.join(HERE, f"bike_{name}.npz"), **out)
+    np.savez_compressed(os.path.join(out_dir or HERE, f"bike_{name}.npz"), **out)
     print(name, "steps", len(rows), "final", out["final_metrics"].tolist(), "tick", env.tick, flush=True)
 
 

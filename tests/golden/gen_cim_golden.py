@@ -73,7 +73,7 @@ def policy_random(dec, seed, replica, step):
     return dec[2], dec[1], int(qty), 1 if to_discharge else 0
 
 
-def run_case(name, spec):
+def run_case(name, spec, out_dir=None):
     os.environ["SKIP_DEPLOYMENT"] = "TRUE"
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
     sys.path.insert(1, os.path.join(ROOT, "oracle", "_ref", "_stubs"))
@@ -140,7 +140,7 @@ def run_case(name, spec):
         for a in MATRIX_ATTRS:
             x = sl["matrices"][frames::a].reshape(nf, -1)
             out["matrices/" + a] = x.astype(np.int32)
-    np.savez_compressed(os.path.join(HERE, f"cim_{name}.npz"), **out)
+    np.savez_compressed(os.path.join(out_dir or HERE, f"cim_{name}.npz"), **out)
     print(name, "steps", len(rows), "final", out["final_metrics"].tolist(), "tick", env.tick, flush=True)
 
 

@@ -89,3 +89,24 @@ def test_policy_hash_matches_python():
         a = policy_random(dec, seed, rep, step)
         b = policy_random_py([int(x) for x in dec[:6]], seed, rep, step)
         assert a.tolist() == list(b)
+
+
+def test_py_sum_restatement_matches_cpython_sum():
+    """list_sum_normalize calls builtin sum(); since CPython 3.12 that is Neumaier-compensated (bltinmodule.c).  The
+    restatement used by the oracle / host tables / device code must agree bit for bit with this interpreter."""
+    import ctypes as C
+    import random
+    import sys
+
+    from oracle import cim_oracle
+
+    assert sys.version_info >= (3, 12), "golden traces were recorded on python >= 3.12 (compensated sum)"
+    L = cim_oracle.lib()
+    L.cim_oracle_py_sum.restype = C.c_double
+    L.cim_oracle_py_sum.argtypes = [C.c_void_p, C.c_int]
+    rnd = random.Random(1)
+    for trial in range(2000):
+        n = rnd.randint(1, 40)
+        xs = [rnd.uniform(0, 1) * 10 ** rnd.randint(-6, 3) for _ in range(n)]
+        a = np.asarray(xs, np.float64)
+        assert L.cim_oracle_py_sum(a.ctypes.data, n) == sum(xs), (trial, xs)
