@@ -73,6 +73,15 @@ def policy_random(dec, seed, replica, step):
     return dec[2], dec[1], int(qty), 1 if to_discharge else 0
 
 
+def policy_pair(d, spec, step):
+    """policy 2: a LOAD followed by a DISCHARGE in one step (both inside the decision's scope: the load only adds empties
+    to the vessel, so the discharge bound of the original scope still holds) — exercises action lists."""
+    h = hash_u32(spec.get("pseed", 0) * 0x9E3779B9 + step * 0x85EBCA6B + 77)
+    load = h % (d[3] + 1) if d[3] > 0 else 0
+    dis = (h >> 11) % (d[4] + 1) if d[4] > 0 else 0
+    return [(d[2], d[1], int(load), 0), (d[2], d[1], int(dis), 1)]
+
+
 def run_case(name, spec, out_dir=None):
     os.environ["SKIP_DEPLOYMENT"] = "TRUE"
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
@@ -115,6 +124,10 @@ def run_case(name, spec, out_dir=None):
         if spec["policy"] == 1:
             v, p, q, t = policy_random(d, spec.get("pseed", 0), spec.get("replica", 0), step)
             action = Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD)
+        elif spec["policy"] == 2:
+            action = [Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD) for v, p, q, t in policy_pair(d, spec, step)]
+            if step % 7 == 3:
+                action = None
         else:
             action = None
         step += 1

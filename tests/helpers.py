@@ -44,6 +44,8 @@ def drive(step_fn, spec, max_steps=100000):
         if spec["policy"] == 1:
             act = np.asarray([policy_random_py([int(x) for x in dec[:6]], spec.get("pseed", 0),
                                                spec.get("replica", 0), step)], np.int32)
+        elif spec["policy"] == 2:  # action list (LOAD then DISCHARGE), every 7th step none
+            act = None if step % 7 == 3 else np.asarray(gen.policy_pair([int(x) for x in dec[:6]], spec, step), np.int32)
         else:
             act = None
         step += 1

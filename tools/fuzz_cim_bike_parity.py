@@ -25,7 +25,7 @@ def cim_spec(seed):
     rng = np.random.default_rng(seed)
     topo = str(rng.choice(CIM_TOPOLOGIES))
     big = topo.startswith("global")
-    spec = dict(topology=topo, durations=int(rng.integers(30, 70 if big else 260)), policy=int(rng.integers(0, 2)),
+    spec = dict(topology=topo, durations=int(rng.integers(30, 70 if big else 260)), policy=int(rng.integers(0, 3)),
                 pseed=int(rng.integers(0, 1000)), replica=int(rng.integers(0, 64)),
                 snapshot_resolution=int(rng.choice([1, 1, 2, 5])))
     if rng.random() < 0.5:
