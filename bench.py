@@ -137,6 +137,8 @@ def run_reference(args, rank, world):
             "config": {"workload": f"CIM {args.topology}, {args.ticks} ticks, random actions", "replicas": cores}}
     if args.scenario == "vm_scheduling":
         return run_reference_vm(args, line, ref_root, cores)
+    if args.scenario == "citi_bike":
+        return run_reference_bike(args, line, ref_root, cores)
     if os.path.isdir(os.path.join(ref_root, "maro")):
         os.environ["SKIP_DEPLOYMENT"] = "TRUE"
         os.environ.setdefault("DEFAULT_BACKEND_NAME", "dynamic")  # the Cython/C++ RawBackend the north-star names
@@ -196,6 +198,66 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
         kind, sample, cores = "port", f"{ep} episodes of the C restatement, 1 thread", 1
         value = env_steps / dt
+    line.update({"value": value, "ms_per_step": 1000.0 * dt / max(1, args.steps),
+                 "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    emit(line)
+
+
+def run_reference_bike(args, line, ref_root, cores):
+    """citi_bike: the unmodified reference (VectorEnv over every host core, greedy top-1 agent of
+    examples/citi_bike/greedy/launcher.py) on the frozen toy.3s_4t trace; else the C port."""
+    ticks = min(args.ticks, 2880) if args.ticks != 1000 else 1440
+    line["config"] = {"workload": f"citi_bike toy.3s_4t (frozen trace), {ticks} ticks, greedy top-1 agent, snapshot_resolution 10",
+                      "replicas": cores}
+    if os.path.isdir(os.path.join(ref_root, "maro")):
+        os.environ["SKIP_DEPLOYMENT"] = "TRUE"
+        sys.path.insert(0, ref_root)
+        sys.path.insert(1, os.path.join(ref_root, "_stubs"))
+        from maro.simulator.scenarios.citi_bike.common import Action, DecisionType
+        from maro.vector_env import VectorEnv
+
+        from tests.golden.gen_bike_golden import data_config_dir, greedy
+
+        with VectorEnv(batch_num=cores, scenario="citi_bike", topology=data_config_dir("bike_toy"), durations=ticks,
+                       snapshot_resolution=10) as env:
+            def agent(decisions):
+                acts = {}
+                for i, d in enumerate(decisions):
+                    if d is None:
+                        continue
+                    v, cand = greedy(d)
+                    acts[i] = (Action(d.station_idx, cand, int(v)) if d.type == DecisionType.Supply else Action(cand, d.station_idx, int(v)))
+                return acts
+
+            metrics, decisions, done = env.step(None)
+            env_steps, t0 = 0, None
+            for k in range(args.warmup + args.steps):
+                if k == args.warmup:
+                    t0, env_steps = time.perf_counter(), 0
+                if done:
+                    env.reset()
+                    metrics, decisions, done = env.step(None)
+                else:
+                    metrics, decisions, done = env.step(agent(decisions))
+                env_steps += cores
+            dt = time.perf_counter() - t0
+        kind, sample = "reference", f"VectorEnv(batch_num={cores}) x {args.steps} steps, static backend"
+    else:
+        from maro_b200.scenarios.citi_bike.data import build_bike_topology
+        from oracle.bike_oracle import BikeOracle
+        from tests.bike_helpers import bike_config
+
+        o = BikeOracle(build_bike_topology(bike_config("bike_toy"), 0, ticks, transfer_seed=128), 10)
+        env_steps, ep, t0 = 0, 0, time.perf_counter()
+        while env_steps < args.steps * 1024 and time.perf_counter() - t0 < 60:
+            o.reset()
+            env_steps += o.run_episode(1)[0]
+            ep += 1
+        dt = time.perf_counter() - t0
+        kind, sample, cores = "port", f"{ep} episodes of oracle/bike_oracle.c, 1 thread", 1
+    value = env_steps / dt
     line.update({"value": value, "ms_per_step": 1000.0 * dt / max(1, args.steps),
                  "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
