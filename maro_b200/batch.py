@@ -156,6 +156,11 @@ class CimBatch:
                                                               float(fulfillment_factor), float(shortage_factor), d_out))
 
     # -- inspection --------------------------------------------------------------------------------
+    def node_counts(self) -> dict:
+        """node type name -> number of nodes (what ``len(env.snapshot_list[name])`` reports)"""
+        t = self.topologies[0]
+        return {"ports": t.n_ports, "vessels": t.n_vessels, "matrices": 1}
+
     def attr_id(self, node: str, name: str) -> int:
         i = _native.lib().maro_cim_attr_id(self._h, _NODE_TYPE[node], name.encode())
         if i < 0:
@@ -261,6 +266,9 @@ class BikeBatch:
 
     def _topology_struct(self, topology):
         return _abi.bike_topology_struct(topology)
+
+    def node_counts(self) -> dict:
+        return {"stations": self.topology.n_stations, "matrices": 1}
 
     def __init__(self, topology, n_replicas: int, snapshot_resolution: int = 1, max_snapshots: Optional[int] = None,
                  device: int = 0, max_actions: int = 1, queue_capacity: int = 0):
@@ -406,6 +414,11 @@ class VmBatch(BikeBatch):
         if getattr(topology, "error", None):
             raise Exception(topology.error)
         return _abi.vm_topology_struct(topology)
+
+    def node_counts(self) -> dict:
+        t = self.topology
+        return {"pms": t.n_pm, "racks": t.n_rack, "clusters": t.n_cluster, "data_centers": t.n_dc, "zones": t.n_zone,
+                "regions": t.n_region}
 
     def greedy_policy_device(self, d_decisions: int, d_actions: int):
         raise AttributeError("vm_scheduling has best_fit_policy_device")

@@ -58,19 +58,7 @@ class SnapshotList:
 
     def __init__(self, batch, replica: int):
         self._batch, self._replica = batch, replica
-        if isinstance(batch, VmBatch):
-            t = batch.topology
-            self._nodes = {n: SnapshotNode(self, n, c) for n, c in (
-                ("pms", t.n_pm), ("racks", t.n_rack), ("clusters", t.n_cluster), ("data_centers", t.n_dc),
-                ("zones", t.n_zone), ("regions", t.n_region))}
-        elif isinstance(batch, BikeBatch):
-            self._nodes = {"stations": SnapshotNode(self, "stations", batch.topology.n_stations),
-                           "matrices": SnapshotNode(self, "matrices", 1)}
-        else:
-            t = batch.topologies[0]
-            self._nodes = {"ports": SnapshotNode(self, "ports", t.n_ports),
-                           "vessels": SnapshotNode(self, "vessels", t.n_vessels),
-                           "matrices": SnapshotNode(self, "matrices", 1)}
+        self._nodes = {name: SnapshotNode(self, name, count) for name, count in batch.node_counts().items()}
 
     def __getitem__(self, name: str):
         return self._nodes.get(name)
