@@ -8,7 +8,14 @@ from emul import VmEmulEnv
 from oracle.vm_oracle import VmOracle
 from vm_helpers import VM_CASES, assert_metrics_close, assert_vm_snapshots_equal, drive_vm, load_vm_golden, vm_topology
 
-EXACT_COLS = [0, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]  # every metric except total_incomes (1) and total_profit (3)
+EXACT_COLS = [0, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]
+
+
+def _abi_metrics(row):
+    from maro_b200 import _abi
+
+    return _abi.vm_metrics_dict(row)
+  # every metric except total_incomes (1) and total_profit (3)
 
 
 @pytest.mark.parametrize("lanes", [32, 8, 1])
@@ -90,3 +97,32 @@ def test_vm_device_logic_tiny_and_denormal_utilisations(lanes):
     assert st == 1 and n > 50
     assert np.array_equal(met[EXACT_COLS], omet[EXACT_COLS])
     assert np.array_equal(e.frame(), o.frame()) and np.array_equal(e.counters(), o.counters())
+
+
+def test_vm_trace_generator_loads_and_kernel_matches_oracle(tmp_path):
+    """tools/vm_trace_gen.py (the synthetic azure-scale trace of BASELINE config #5) at a small size: the .bin files load
+    through the host loader, and a best-fit episode of the device logic equals the oracle's."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import vm_trace_gen
+
+    from maro_b200.scenarios.vm_scheduling.data import build_vm_topology
+
+    vm_path, cpu_path = vm_trace_gen.generate(str(tmp_path), n_vm=400, ticks=300, seed=3, mean_concurrent_cores=250.0)
+    topo = build_vm_topology(vm_trace_gen.azure_like_config(vm_path, cpu_path, n_pm=10), 0, 300)
+    assert topo.n_vm == 400 and topo.n_pm == 10 and topo.error is None
+    e, o = VmEmulEnv(topo, 1, 8), VmOracle(topo, 1, 8)
+    (st, dec, met), (ost, odec, omet) = e.step(None), o.step(None)
+    n = 0
+    while ost == 0:
+        assert st == 0 and dec[:12 + odec[10]].tolist() == odec[:12 + odec[10]].tolist(), n
+        a = o.best_fit(odec)
+        (st, dec, met), (ost, odec, omet) = e.step(a.reshape(1, 4)), o.step(a.reshape(1, 4))
+        n += 1
+    assert st == 1 and n >= 300
+    assert np.array_equal(met[EXACT_COLS], omet[EXACT_COLS])
+    assert np.array_equal(e.frame(), o.frame()) and np.array_equal(e.counters(), o.counters())
+    m = _abi_metrics(met)
+    assert m["total_vm_requests"] == 400 and m["successful_allocation"] + m["failed_allocation"] == 400
