@@ -8,11 +8,25 @@ from oracle.cim_oracle import CimOracle
 from rl_helpers import RL_CASES, SnapshotView, action_numpy, load_rl_golden, reward_numpy, state_numpy
 
 
+class _EmulAsOracle:
+    """the device logic under the host emulator behind the oracle's step / snapshot interface"""
+
+    def __init__(self, topo, max_snapshots=None):
+        from emul import EmulEnv
+
+        self._e = EmulEnv(topo, 1, 0, 1, max_snapshots)
+        self.snapshot = self._e.snapshot
+
+    def step(self, actions):
+        return self._e.step1(actions)
+
+
+@pytest.mark.parametrize("backend", ["oracle", "emulated-kernel"])
 @pytest.mark.parametrize("name", sorted(RL_CASES))
-def test_rl_shaping_restatement_matches_reference(name):
+def test_rl_shaping_restatement_matches_reference(name, backend):
     spec, gold = RL_CASES[name], load_rl_golden(name)
     topo = build_topology(spec["topology"], spec["durations"])
-    o = CimOracle(topo, max_snapshots=spec.get("max_snapshots"))
+    o = (CimOracle if backend == "oracle" else _EmulAsOracle)(topo, max_snapshots=spec.get("max_snapshots"))
     view = SnapshotView(o.snapshot, topo)
     st, dec, _ = o.step(None)
     k = 0
