@@ -420,6 +420,42 @@ class VmBatch(BikeBatch):
         return {"pms": t.n_pm, "racks": t.n_rack, "clusters": t.n_cluster, "data_centers": t.n_dc, "zones": t.n_zone,
                 "regions": t.n_region}
 
+    # The reference's static backend keeps cpu_utilization / energy_consumption as float64, in the live frame and in the
+    # snapshots alike (np_backend.pyx:143-148, 293: the dtype comes from the decoded type NAME "float").  The device ring
+    # stores them as float32 words; both are exact functions of the integer k = 100 * cpu_utilization, so the query
+    # result is lifted back to the float64 values the reference returns: k / 100 and the energy model evaluated at k.
+    def _energy_f64(self, pm_type: int, k: int) -> float:
+        cache = self.__dict__.setdefault("_energy_cache", {})
+        key = (pm_type, min(k, 10000))
+        if key not in cache:
+            calibration, busy, idle = (float(x) for x in self.topology.pmtype_power[pm_type])
+            u = min(1, (key[1] / 100.0) / 100)
+            cache[key] = ((idle + (busy - idle) * (2 * u - pow(u, calibration))) / self.topology.ticks_per_hour) / 1000
+        return cache[key]
+
+    def query(self, node: str, frame_indices, nodes, attrs, replicas=None) -> np.ndarray:
+        out = super().query(node, frame_indices, nodes, attrs, replicas)
+        if node != "pms":
+            return out
+        names = [a if isinstance(a, str) else _abi.VM_NODE_ATTRS["pms"][int(a)] for a in attrs]
+        if not any(n in _abi.VM_FLOAT_ATTRS for n in names):
+            return out
+        nodes = np.ascontiguousarray(nodes, np.int32)
+        view = out.reshape(out.shape[0], len(frame_indices), len(nodes), len(names))
+        if "cpu_utilization" in names:
+            k = np.rint(view[..., names.index("cpu_utilization")] * 100.0)
+        else:
+            k = np.rint(super().query(node, frame_indices, nodes, ["cpu_utilization"], replicas).reshape(view.shape[:3]) * 100.0)
+        if "cpu_utilization" in names:
+            view[..., names.index("cpu_utilization")] = k / 100.0
+        if "energy_consumption" in names:
+            e = view[..., names.index("energy_consumption")]
+            types = self.topology.pm_attr[nodes, 2]
+            held = e != 0.0  # frames the ring no longer holds read as zeros and stay zeros
+            for idx in np.argwhere(held):
+                e[tuple(idx)] = self._energy_f64(int(types[idx[2]]), int(k[tuple(idx)]))
+        return out
+
     def greedy_policy_device(self, d_decisions: int, d_actions: int):
         raise AttributeError("vm_scheduling has best_fit_policy_device")
 

@@ -324,9 +324,9 @@ class Env:
         return self._snapshots
 
     @property
-    def agent_idx_list(self) -> List[int]:
+    def agent_idx_list(self) -> Optional[List[int]]:
         if self._scenario == "vm_scheduling":
-            return list(range(self._topo.n_pm))  # get_agent_idx_list (vm_scheduling/business_engine.py:531-535)
+            return None  # the reference's get_agent_idx_list is a docstring only (vm_scheduling/business_engine.py:534-535)
         return list(range(self._topo.n_stations if self._scenario == "citi_bike" else self._topo.n_ports))
 
     @property

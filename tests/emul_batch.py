@@ -212,6 +212,29 @@ class EmulBikeBatch(_EmulScenarioBatch):
 class EmulVmBatch(_EmulScenarioBatch):
     _FLOAT = _abi.VM_FLOAT_ATTRS
 
+    # the float64 lift of the product wrapper (maro_b200.batch.VmBatch.query) on top of the emulated raw query
+    def query(self, node, frame_indices, nodes, attrs, replicas=None):
+        from maro_b200.batch import BikeBatch, VmBatch
+
+        class _Raw(BikeBatch):  # stand-in for `super().query` inside VmBatch.query
+            pass
+
+        raw = _EmulScenarioBatch.query
+        outer = self
+
+        class _Shim(VmBatch):
+            def __init__(self):
+                self.topology = outer.topology
+
+        shim = _Shim()
+        # VmBatch.query calls super().query (BikeBatch.query): route that to the emulated raw query
+        orig = BikeBatch.query
+        BikeBatch.query = lambda _self, n, f, nd, a, r=None: raw(outer, n, f, nd, a, r)
+        try:
+            return VmBatch.query(shim, node, frame_indices, nodes, attrs, replicas)
+        finally:
+            BikeBatch.query = orig
+
     def __init__(self, topology, n_replicas, snapshot_resolution=1, max_snapshots=None, device=0, max_actions=1, queue_capacity=0):
         from emul import VmEmulEnv
 

@@ -22,21 +22,74 @@ TOPOLOGIES = ["toy.4p_ssdd_l0.0", "toy.4p_ssdd_l0.6", "toy.5p_ssddd_l0.2", "toy.
 
 def spec_of(seed):
     rng = np.random.default_rng(seed)
+    kind = ["cim", "cim", "citi_bike", "vm_scheduling"][int(rng.integers(0, 4))]
+    if kind != "cim":
+        return dict(scenario=kind, durations=int(rng.integers(60, 500) if kind == "citi_bike" else rng.integers(30, 150)),
+                    snapshot_resolution=int(rng.choice([1, 2, 5, 10])),
+                    max_snapshots=(None if rng.random() < 0.5 else int(rng.integers(2, 25))),
+                    stop_after=(None if rng.random() < 0.6 else int(rng.integers(1, 12))))
     t = str(rng.choice(TOPOLOGIES))
-    return dict(topology=t, durations=int(rng.integers(20, 45 if t.startswith("global") else 130)),
+    return dict(scenario="cim", topology=t, durations=int(rng.integers(20, 45 if t.startswith("global") else 130)),
                 snapshot_resolution=int(rng.choice([1, 1, 2, 3, 7])),
                 max_snapshots=(None if rng.random() < 0.5 else int(rng.integers(2, 25))),
                 stop_after=(None if rng.random() < 0.6 else int(rng.integers(1, 12))))
 
 
-def observe(env, spec):
+def topology_dir(spec):
+    """config folder of the non-CIM scenarios (the committed test fixtures)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    if spec["scenario"] == "citi_bike":
+        import gen_bike_golden
+
+        return gen_bike_golden.data_config_dir("bike_toy")
+    import tempfile
+
+    import gen_vm_golden
+    import yaml
+
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, "config.yml"), "w") as fp:
+        yaml.safe_dump(gen_vm_golden.CASES["synth_160_bestfit"]["conf"], fp, sort_keys=False)
+    return d
+
+
+def first_action(spec, dec, mod):
+    """answer every decision with the simplest valid action of the scenario (None for citi_bike / cim)"""
+    if spec["scenario"] == "vm_scheduling" and dec is not None:
+        return mod.AllocateAction(vm_id=dec.vm_id, pm_id=dec.valid_pms[0])
+    return None
+
+
+def observe(env, spec, mod=None):
     """run (optionally stop early) and collect every observable of the façade"""
     out = {}
     metrics, dec, done = env.step(None)
     n = 0
     while not done and (spec["stop_after"] is None or n < spec["stop_after"]):
-        metrics, dec, done = env.step(None)
+        metrics, dec, done = env.step(first_action(spec, dec, mod))
         n += 1
+    if spec["scenario"] != "cim":
+        sl = env.snapshot_list
+        frames = [int(f) for f in sl.get_frame_index_list()]
+        out["tick"], out["frame_index"], out["done"], out["steps"] = int(env.tick), int(env.frame_index), bool(done), n
+        out["frames"], out["len"] = frames, len(sl)
+        out["mapping"] = sorted((int(k), int(v)) for k, v in env.get_ticks_frame_index_mapping().items())
+        out["agents"] = None if env.agent_idx_list is None else [int(a) for a in env.agent_idx_list]
+        if spec["scenario"] == "citi_bike":
+            out["metrics"] = {k: int(v) for k, v in dict(metrics).items()}
+            qs = [sl["stations"][frames[-2:]::["bikes", "shortage", "trip_requirement"]], sl["stations"][:1:"fulfillment"],
+                  sl["matrices"][frames[-1]::"trips_adj"], sl["stations"][[10 ** 6]:0:"bikes"]]
+            out["n_nodes"] = [len(sl["stations"])]
+        else:
+            out["metrics"] = {k: (round(float(v), 9) if isinstance(v, float) or hasattr(v, "dtype") else
+                                  ([int(v.due_to_agent), int(v.due_to_resource)] if hasattr(v, "due_to_agent") else int(v)))
+                              for k, v in dict(metrics).items()}
+            qs = [sl["pms"][frames[-2:]::["cpu_cores_allocated", "cpu_utilization", "energy_consumption"]],
+                  sl["racks"][:0:"empty_machine_num"], sl["regions"][frames[-1]::["total_machine_num", "empty_machine_num"]],
+                  sl["pms"][[10 ** 6]:0:"cpu_cores_capacity"]]
+            out["n_nodes"] = [len(sl[k]) for k in ("pms", "racks", "clusters", "data_centers", "zones", "regions")]
+        out["queries"] = [np.asarray(q, np.float64).tolist() for q in qs]  # exact float64 values
+        return out
     sl = env.snapshot_list
     frames = [int(f) for f in sl.get_frame_index_list()]
     out["tick"], out["frame_index"], out["done"], out["steps"] = int(env.tick), int(env.frame_index), bool(done), n
@@ -60,19 +113,26 @@ def ref_run(spec, q):
     sys.path.insert(1, os.path.join(ROOT, "oracle", "_ref", "_stubs"))
     from maro.simulator import Env
 
-    env = Env("cim", spec["topology"], durations=spec["durations"], snapshot_resolution=spec["snapshot_resolution"],
-              max_snapshots=spec["max_snapshots"])
-    q.put(json.dumps(observe(env, spec), default=int, sort_keys=True))
+    mod = None
+    if spec["scenario"] == "citi_bike":
+        np.random.seed(5)
+    if spec["scenario"] == "vm_scheduling":
+        import maro.simulator.scenarios.vm_scheduling as mod
+    env = Env(spec["scenario"], spec.get("topology") or topology_dir(spec), durations=spec["durations"],
+              snapshot_resolution=spec["snapshot_resolution"], max_snapshots=spec["max_snapshots"])
+    q.put(json.dumps(observe(env, spec, mod), default=int, sort_keys=True))
 
 
 def ours(spec):
+    import maro_b200.scenarios.vm_scheduling as vm_mod
     import maro_b200.simulator.env as env_mod
-    from emul_batch import EmulCimBatch
+    from emul_batch import EmulBikeBatch, EmulCimBatch, EmulVmBatch
 
-    env_mod.CimBatch = EmulCimBatch
-    env = env_mod.Env("cim", spec["topology"], durations=spec["durations"], snapshot_resolution=spec["snapshot_resolution"],
-                      max_snapshots=spec["max_snapshots"])
-    return json.dumps(observe(env, spec), default=int, sort_keys=True)
+    env_mod.CimBatch, env_mod.BikeBatch, env_mod.VmBatch = EmulCimBatch, EmulBikeBatch, EmulVmBatch
+    env = env_mod.Env(spec["scenario"], spec.get("topology") or topology_dir(spec), durations=spec["durations"],
+                      snapshot_resolution=spec["snapshot_resolution"], max_snapshots=spec["max_snapshots"],
+                      options={"transfer_seed": 5})
+    return json.dumps(observe(env, spec, vm_mod), default=int, sort_keys=True)
 
 
 def main():
@@ -84,7 +144,12 @@ def main():
         q = ctx.Queue()
         p = ctx.Process(target=ref_run, args=(spec, q))
         p.start()
-        ref = q.get()
+        try:
+            ref = q.get(timeout=180)
+        except Exception:
+            p.terminate()
+            print(seed, "reference failed (skipped)", spec, flush=True)
+            continue
         p.join()
         got = ours(spec)
         if ref != got:
