@@ -72,8 +72,9 @@ static void* dup_arr(const void* p, size_t bytes) { void* q = malloc(bytes ? byt
 /*
  * Scalar types.  The reference's default ("static") backend builds its structured dtype from the decoded attribute
  * type NAME (np_backend.pyx:177, :143-148, :293): "float" -> float64, "short" -> int16.  So the live frame keeps
- * cpu_utilization / energy_consumption in DOUBLE precision and hands them back as np.float64; only snapshot queries cast
- * to float32 (np_backend.pyx:547-560).  Every expression below is therefore plain double arithmetic, and
+ * cpu_utilization / energy_consumption in DOUBLE precision (live row and snapshot rows alike) and hands them back as
+ * np.float64.  Every expression below is therefore plain double arithmetic (the exported frame words carry the two
+ * attributes as float32, the device ring's storage format; maro_b200.batch.VmBatch.query lifts them back), and
  * round(np.float64, 2) is numpy's around: rint(x * 100) / 100.
  */
 static double np_round2(double x) { return rint(x * 100.0) / 100.0; }
