@@ -45,3 +45,33 @@ def test_bike_env_surface_like_reference_tests_emulated(tmp_path):
 
 def test_vm_env_surface_replays_reference_trace_emulated():
     vm_surfaces.test_vm_env_surface_replays_reference_trace()
+
+
+def test_vm_float_queries_are_lifted_to_the_reference_float64_values():
+    """VmBatch.query: cpu_utilization / energy_consumption come back as the float64 values the reference's static backend
+    holds (k / 100 and the energy model at k), not as the float32 words of the ring; unknown frames stay zero."""
+    import numpy as np
+
+    from vm_helpers import VM_CASES, load_vm_golden, vm_topology
+
+    spec, gold = VM_CASES["synth_160_bestfit"], load_vm_golden("synth_160_bestfit")
+    topo = vm_topology(spec)
+    b = EmulVmBatch(topo, 1)
+    b.step(None)
+    for k in range(40):
+        a = np.zeros((1, 1, 4), np.int32)
+        a[0, 0] = gold["actions"][k]
+        b.step(a, np.ones(1, np.int32))
+    frames = b.snapshot_frames(0).tolist()[-3:]
+    n = topo.n_pm
+    q = b.query("pms", frames + [10 ** 6], np.arange(n), ["cpu_utilization", "pm_type", "energy_consumption"])[0].reshape(4, n, 3)
+    assert (q[3] == 0).all()                                   # unknown frame -> zeros
+    u = q[:3, :, 0]
+    assert np.array_equal(u, np.rint(u * 100) / 100.0) and (u > 0).any()   # exact multiples of 0.01 in float64
+    for f in range(3):
+        for p in range(n):
+            calib, busy, idle = topo.pmtype_power[int(q[f, p, 1])]
+            x = min(1, u[f, p] / 100)
+            assert q[f, p, 2] == ((idle + (busy - idle) * (2 * x - pow(x, calib))) / topo.ticks_per_hour) / 1000
+    only_e = b.query("pms", frames, np.arange(n), ["energy_consumption"])[0].reshape(3, n)
+    assert np.array_equal(only_e, q[:3, :, 2])                 # energy alone: utilisation fetched behind the scenes
