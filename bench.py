@@ -431,6 +431,55 @@ def host_policy_numpy(dec, seed, base, np):
     return act
 
 
+def _rl_extras(torch, env, dec, topo, B, stream):
+    """device-resident RL shaping kernels + rollout loop timings (extras of the CIM line; not part of `value`)"""
+    from maro_b200.rl_shaping import CimShaper
+
+    shaper = CimShaper(env)
+    t_ticks = torch.clamp(dec[:, 0] - 120, min=0).contiguous()
+    t_ports = torch.remainder(dec[:, 1], topo.n_ports).to(torch.int32).contiguous()
+    for _ in range(3):
+        shaper.states(dec); shaper.rewards(t_ticks, t_ports)
+    t_model = torch.remainder(dec[:, 7], 21).to(torch.int32).contiguous()
+    shaper.env_actions(dec, t_model)
+    sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    reps = 20
+    sev[0].record(stream)
+    for _ in range(reps):
+        shaper.states(dec)
+    sev[1].record(stream)
+    for _ in range(reps):
+        shaper.rewards(t_ticks, t_ports)
+    sev[2].record(stream)
+    for _ in range(reps):
+        shaper.env_actions(dec, t_model)
+    sev[3].record(stream)
+    torch.cuda.synchronize()
+    a_us = 1000.0 * sev[2].elapsed_time(sev[3]) / reps
+    s_us, r_us = 1000.0 * sev[0].elapsed_time(sev[1]) / reps, 1000.0 * sev[1].elapsed_time(sev[2]) / reps
+    shaping = {"state_dim": shaper.state_dim, "states_us": s_us, "states_per_s": B / (s_us * 1e-6),
+               "state_gbs": B * shaper.state_dim * 12 / (s_us * 1e-6) / 1e9,  # 8 B written + 4 B gathered per element
+               "actions_us": a_us, "rewards_us": r_us, "rewards_per_s": B / (r_us * 1e-6),
+               "reward_gbs": B * (shaper.time_window * 2 * 4 + 4) / (r_us * 1e-6) / 1e9,
+               "what": "examples/cim/rl shaping (look_back 7, 99-tick decayed reward) for all replicas, L2 warm"}
+
+    # device-resident rollout with a small MLP policy (state -> 171x256x21 MLP -> argmax -> action -> step; rewards after)
+    from maro_b200.rl_rollout import CimDeviceRollout
+
+    torch.manual_seed(0)
+    mlp = torch.nn.Sequential(torch.nn.Linear(shaper.state_dim, 256), torch.nn.ReLU(), torch.nn.Linear(256, 21)).cuda()
+    ro = CimDeviceRollout(env, lambda st: mlp(st * 1e-4).argmax(1), shaper, store_states=False)
+    ro.run_episode(max_steps=50)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    traj = ro.run_episode()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    shaping["rollout"] = {"env_steps_per_s": float(traj["valid"].sum().item()) / dt, "steps": int(traj["valid"].shape[0]),
+                          "seconds": dt, "what": "CimDeviceRollout: one episode, MLP policy on the same GPU, rewards included (wall clock)"}
+    return shaping
+
+
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -575,50 +624,10 @@ def run_ours(args, rank, local_rank, world):
     # ---- extra: device-resident RL state / reward shaping over the snapshot ring, not part of `value`
     shaping = None
     if not bike and not vm:
-        from maro_b200.rl_shaping import CimShaper
-
-        shaper = CimShaper(env)
-        t_ticks = torch.clamp(dec[:, 0] - 120, min=0).contiguous()
-        t_ports = torch.remainder(dec[:, 1], topo.n_ports).to(torch.int32).contiguous()
-        for _ in range(3):
-            shaper.states(dec); shaper.rewards(t_ticks, t_ports)
-        t_model = torch.remainder(dec[:, 7], 21).to(torch.int32).contiguous()
-        shaper.env_actions(dec, t_model)
-        sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        reps = 20
-        sev[0].record(stream)
-        for _ in range(reps):
-            shaper.states(dec)
-        sev[1].record(stream)
-        for _ in range(reps):
-            shaper.rewards(t_ticks, t_ports)
-        sev[2].record(stream)
-        for _ in range(reps):
-            shaper.env_actions(dec, t_model)
-        sev[3].record(stream)
-        torch.cuda.synchronize()
-        a_us = 1000.0 * sev[2].elapsed_time(sev[3]) / reps
-        s_us, r_us = 1000.0 * sev[0].elapsed_time(sev[1]) / reps, 1000.0 * sev[1].elapsed_time(sev[2]) / reps
-        shaping = {"state_dim": shaper.state_dim, "states_us": s_us, "states_per_s": B / (s_us * 1e-6),
-                   "state_gbs": B * shaper.state_dim * 12 / (s_us * 1e-6) / 1e9,  # 8 B written + 4 B gathered per element
-                   "actions_us": a_us, "rewards_us": r_us, "rewards_per_s": B / (r_us * 1e-6),
-                   "reward_gbs": B * (shaper.time_window * 2 * 4 + 4) / (r_us * 1e-6) / 1e9,
-                   "what": "examples/cim/rl shaping (look_back 7, 99-tick decayed reward) for all replicas, L2 warm"}
-
-        # device-resident rollout with a small MLP policy (state -> 171x256x21 MLP -> argmax -> action -> step; rewards after)
-        from maro_b200.rl_rollout import CimDeviceRollout
-
-        torch.manual_seed(0)
-        mlp = torch.nn.Sequential(torch.nn.Linear(shaper.state_dim, 256), torch.nn.ReLU(), torch.nn.Linear(256, 21)).cuda()
-        ro = CimDeviceRollout(env, lambda st: mlp(st * 1e-4).argmax(1), shaper, store_states=False)
-        ro.run_episode(max_steps=50)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        traj = ro.run_episode()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        shaping["rollout"] = {"env_steps_per_s": float(traj["valid"].sum().item()) / dt, "steps": int(traj["valid"].shape[0]),
-                              "seconds": dt, "what": "CimDeviceRollout: one episode, MLP policy on the same GPU, rewards included (wall clock)"}
+        try:  # extras never take the contract line down with them
+            shaping = _rl_extras(torch, env, dec, topo, B, stream)
+        except Exception as ex:  # pragma: no cover
+            shaping = {"error": repr(ex)}
         env.reset()
         pos["i"] = 0
 
