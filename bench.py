@@ -63,6 +63,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--graph-chunk", type=int, default=32, help="steps per CUDA-graph chunk of the extra graph-mode measurement (0: off)")
+    ap.add_argument("--chunk", type=int, default=64, help="cim: env-steps fused into one resident-kernel launch (maro_cim_rollout_device)")
+    ap.add_argument("--seeds", type=int, default=1, help="cim: distinct topology seeds in the batch (replica r runs seed 4096 + r %% seeds; "
+                    "only noisy topologies differ by seed)")
+    ap.add_argument("--launch-per-step", action="store_true", help="cim: time the one-launch-per-Env.step path as `value` instead of fused rollouts")
+    ap.add_argument("--skip-extras", action="store_true", help="cim: only the contract keys (value, e2e, roofline, cpu_baseline, clocks)")
     return ap.parse_args()
 
 
@@ -147,7 +152,7 @@ def run_reference(args, rank, world):
         from maro.simulator.scenarios.cim.common import Action, ActionType
         from maro.vector_env import VectorEnv
 
-        from tests.golden.gen_cim_golden import policy_random
+        from tools.workloads import cim_policy_random as policy_random
 
         with VectorEnv(batch_num=cores, scenario="cim", topology=args.topology, durations=args.ticks) as env:
             def agent(decisions, step):
@@ -218,9 +223,9 @@ def run_reference_bike(args, line, ref_root, cores):
         from maro.simulator.scenarios.citi_bike.common import Action, DecisionType
         from maro.vector_env import VectorEnv
 
-        from tests.golden.gen_bike_golden import data_config_dir, greedy
+        from tools.workloads import bike_greedy as greedy, bike_toy_config_dir
 
-        with VectorEnv(batch_num=cores, scenario="citi_bike", topology=data_config_dir("bike_toy"), durations=ticks,
+        with VectorEnv(batch_num=cores, scenario="citi_bike", topology=bike_toy_config_dir(), durations=ticks,
                        snapshot_resolution=10) as env:
             def agent(decisions):
                 acts = {}
@@ -247,9 +252,9 @@ def run_reference_bike(args, line, ref_root, cores):
     else:
         from maro_b200.scenarios.citi_bike.data import build_bike_topology
         from oracle.bike_oracle import BikeOracle
-        from tests.bike_helpers import bike_config
+        from tools.workloads import bike_toy_config
 
-        o = BikeOracle(build_bike_topology(bike_config("bike_toy"), 0, ticks, transfer_seed=128), 10)
+        o = BikeOracle(build_bike_topology(bike_toy_config(), 0, ticks, transfer_seed=128), 10)
         env_steps, ep, t0 = 0, 0, time.perf_counter()
         while env_steps < args.steps * 1024 and time.perf_counter() - t0 < 60:
             o.reset()
@@ -480,6 +485,266 @@ def _rl_extras(torch, env, dec, topo, B, stream):
     return shaping
 
 
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
+            return json.load(fp)
+    except Exception:
+        return {}
+
+
+def _traffic(key):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this config, if any"""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fp:
+                t = json.load(fp).get(key)
+            if t:
+                return t.get("bytes_per_launch"), name
+        except Exception:
+            pass
+    return None, None
+
+
+def run_cim(args, rank, local_rank, world):
+    """CIM arm.  `value`: resident rollouts — maro_cim_rollout_device fuses `chunk` env-steps per launch with the hashed
+    hello-world agent as a device callback (replica blocks stay in shared memory; snapshot rows stream to the HBM ring).
+    `e2e`: the host-buffer call maro_cim_step_pinned (resident session: command rows / decision rows through mapped
+    pinned memory) with the agent on the host.  Episode ends are detected from the DONE status column the device returns."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from maro_b200.batch import CimBatch
+    from maro_b200.scenarios.cim.topology import build_topology, load_config
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.replicas
+    conf = load_config(args.topology)
+    n_seeds = max(1, min(args.seeds, B))
+    topos = [build_topology(conf, args.ticks, seed=int(conf["seed"]) + k) for k in range(n_seeds)]
+    rt = (np.arange(B) % n_seeds).astype(np.int32) if n_seeds > 1 else None
+    env = CimBatch(topos, B, device=local_rank, max_snapshots=args.max_snapshots or None, replica_topology=rt)
+    topo = topos[0]
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    env.set_stream(stream.cuda_stream)
+    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    base = rank * B
+    status = dec[:, 6]
+
+    def all_done():  # the `done` the reference's step returns: every replica answered DONE / FINISHED
+        return bool((status != 0).all().item())
+
+    # ------------------------------------------------------------------ value: fused resident rollouts
+    def timed_rollouts(total_steps, chunk, timed):
+        """runs `total_steps` batched env-steps in launches of <= chunk; returns (device ms incl. resets, kernel ms, launches)"""
+        evs, launches, left, done = [], 0, total_steps, False
+        while left > 0:
+            n = min(chunk, left)
+            if flush is not None and timed:
+                flush.fill_(1)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(stream)
+            if done:
+                env.reset()
+                launches += 1
+            e[1].record(stream)
+            env.rollout_device(dec.data_ptr(), met.data_ptr(), n, 1, 0, base)
+            e[2].record(stream)
+            launches += 1
+            evs.append(e)
+            left -= n
+            done = all_done()
+        torch.cuda.synchronize()
+        return (sum(e[0].elapsed_time(e[2]) for e in evs), sum(e[1].elapsed_time(e[2]) for e in evs), launches, done)
+
+    def timed_launch_per_step(total_steps, timed):
+        evs, launches, done = [], 0, False
+        for k in range(total_steps):
+            if flush is not None and timed:
+                flush.fill_(1)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(stream)
+            if done:
+                env.reset()
+                launches += 1
+            env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0, base)
+            e[1].record(stream)
+            env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+            e[2].record(stream)
+            launches += 2
+            evs.append(e)
+            done = (k % 16 == 15) and all_done()  # the status column is read back every 16 steps
+        torch.cuda.synchronize()
+        return (sum(e[0].elapsed_time(e[2]) for e in evs), sum(e[1].elapsed_time(e[2]) for e in evs), launches, done)
+
+    chunk = max(1, min(args.chunk, args.steps))
+    warm = max(args.warmup, 3)
+    primary = (lambda n, t: timed_launch_per_step(n, t)) if args.launch_per_step else (lambda n, t: timed_rollouts(n, chunk, t))
+    primary(warm, False)
+    c0 = env.counters().sum(0)
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    wall0 = time.perf_counter()
+    total_ms, kernel_ms, launches, _ = primary(args.steps, True)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    c1 = env.counters().sum(0)
+    d_steps, d_ticks, d_events, d_snaps = (int(x) for x in (c1 - c0))
+
+    extras = {}
+    if not args.skip_extras and not args.launch_per_step:  # the one-launch-per-Env.step path, for comparison
+        env.reset()
+        dec.zero_()
+        n = min(args.steps, 500)
+        timed_launch_per_step(warm, False)
+        k0 = env.counters().sum(0)
+        ms, kms, _, _ = timed_launch_per_step(n, True)
+        k1 = env.counters().sum(0)
+        extras["launch_per_step"] = {"value": float(k1[0] - k0[0]) / (ms / 1000.0), "unit": "env-steps/s", "steps": n,
+                                     "us_per_step": 1000.0 * ms / n, "kernel_us": 1000.0 * kms / n,
+                                     "what": "cim_policy_kernel + cim_step_kernel per Env.step (stage-in / write-back every step)"}
+    if not args.skip_extras:
+        try:  # extras never take the contract line down with them
+            env.reset()
+            dec.zero_()
+            env.step_device(dec.data_ptr(), met.data_ptr())
+            extras["rl_shaping"] = _rl_extras(torch, env, dec, topo, B, stream)
+        except Exception as ex:  # pragma: no cover
+            extras["rl_shaping"] = {"error": repr(ex)}
+
+    # ------------------------------------------------------------------ e2e: host buffers, agent on the host
+    # The loop is user code in C on top of the C ABI (tools/host_agent.c:e2e_loop_cim): per sub-batch wait for the decision
+    # rows, run the agent, submit the actions.  n_sub = 1 is the lock-step loop (one maro_cim_step_pinned per step); with more
+    # sub-batches the agent's work on one overlaps the device's work and the PCIe latency of the others.
+    e2e, e2e_variants = None, {}
+    if not args.skip_e2e:
+        import ctypes as C
+
+        from maro_b200 import _native
+
+        agent_lib = load_host_agent()
+        L = _native.lib()
+        env.reset()
+        p_act, p_nact, p_active, p_dec, p_met = env.pinned()
+        dec_ptr, act_ptr = p_dec.ctypes.data, p_act.ctypes.data
+        env.step_pinned(use_actions=False)
+        agent_lib.agent_random(dec_ptr, act_ptr, B, 1, 0, base)
+        assert np.array_equal(p_act, host_policy_numpy(p_dec, 0, base, np))  # host agent == device agent
+        gran = env.pinned_granularity()
+        n_e2e = min(max(args.steps, 200), 3000)
+        fptr = lambda f: C.cast(f, C.c_void_p)
+        agent_lib.e2e_loop_cim.argtypes = [C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_uint32, C.c_uint32, C.c_void_p]
+        out3 = (C.c_double * 3)()
+
+        def run_loop(n_sub, n_steps):
+            env.reset()
+            k0 = env.counters().sum(0)
+            rc = agent_lib.e2e_loop_cim(env._h, fptr(L.maro_cim_submit_pinned), fptr(L.maro_cim_wait_pinned), fptr(L.maro_cim_reset),
+                                        dec_ptr, act_ptr, p_active.ctypes.data, B, gran, n_sub, n_steps, 0, base, out3)
+            if rc:
+                raise RuntimeError(L.maro_last_error().decode())
+            k1 = env.counters().sum(0)
+            return {"steps": int(k1[0] - k0[0]), "seconds": out3[0], "agent_seconds": out3[1], "resets": int(out3[2]),
+                    "calls": n_steps, "n_sub": n_sub}
+
+        if gran > 0:
+            run_loop(1, 50)  # warm-up
+            subs = [n for n in (1, 2, 4, 8) if n == 1 or B // gran >= 2 * n]
+            for n_sub in subs:
+                r = run_loop(n_sub, min(n_e2e, 600))
+                e2e_variants[n_sub] = r["steps"] / r["seconds"]
+            best = max(e2e_variants, key=e2e_variants.get)
+            e2e = run_loop(best, n_e2e)
+        else:  # batch too large to stay resident: lock-step calls of maro_cim_step_pinned from Python
+            env.reset()
+            cc0 = env.counters().sum(0)
+            st_col = p_dec[:, 6]
+            t_agent, resets = 0.0, 0
+            t0 = time.perf_counter()
+            for k in range(n_e2e):
+                ta = time.perf_counter()
+                agent_lib.agent_random(dec_ptr, act_ptr, B, 1, 0, base)  # the first step of an episode ignores its action
+                t_agent += time.perf_counter() - ta
+                env.step_pinned()
+                if st_col[0] != 0 and (st_col != 0).all():
+                    env.reset()
+                    resets += 1
+            dt = time.perf_counter() - t0
+            cc1 = env.counters().sum(0)
+            e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt, "agent_seconds": t_agent, "calls": n_e2e, "resets": resets, "n_sub": 0}
+
+    t = torch.tensor([total_ms, kernel_ms, wall * 1000.0, (e2e or {}).get("seconds", 0.0) * 1000.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([d_steps, d_ticks, d_events, d_snaps, (e2e or {}).get("steps", 0)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        from maro_b200.parallel import gather_metrics  # the path's single collective (SURVEY.md §8e)
+
+        gathered = gather_metrics(met, world * B)
+        assert gathered.shape == (world * B, 3)
+    total_ms, kernel_ms, wall_ms, e2e_ms = (float(x) for x in t.cpu())
+    g_steps, g_ticks, g_events, g_snaps, g_e2e_steps = (int(x) for x in cnt.cpu())
+
+    if rank == 0:
+        peaks = _peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        F = F_DECLARED.get(args.topology, env.frame_words * 4)  # SURVEY.md §8 frame bytes
+        n_snap, n_ev = g_snaps / max(1, g_steps), g_events / max(1, g_steps)
+        bytes_per_step = 2 * F + n_snap * F + 32 * n_ev + 64
+        achieved = bytes_per_step * g_steps / world / (kernel_ms / 1000.0) / 1e9  # per GPU
+        value = g_steps / (total_ms / 1000.0)
+        snaps = args.max_snapshots or "all"
+        kname = "cim_step_kernel" if args.launch_per_step else "cim_resident_kernel"
+        traffic, traffic_src = _traffic(f"cim/{args.topology}/{B}/{kname}")
+        mode = ("one launch per Env.step" if args.launch_per_step else
+                f"resident rollouts, {chunk} env-steps fused per launch, agent as a device callback")
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": (f"CIM {args.topology}, {B} parallel envs per GPU, {args.ticks} ticks, random actions (hashed "
+                                    f"hello-world agent), snapshot_resolution 1, max_snapshots {snaps}"),
+                       "replicas_per_gpu": B, "distinct_seeds": n_seeds, "mode": mode,
+                       "l2": "state resident (no flush)" if args.no_flush else "flushed between timed launches (256 MiB write)"},
+            "ticks_per_s": g_ticks / (total_ms / 1000.0), "events_per_s": g_events / (total_ms / 1000.0), "wall_ms": wall_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": kname,
+                         "bytes_per_env_step": bytes_per_step, "n_snap": n_snap, "n_ev": n_ev,
+                         "kernel_us_per_step": 1000.0 * kernel_ms / args.steps,
+                         "launch_us": 1000.0 * kernel_ms / max(1, launches),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if e2e:
+            line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
+                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (8 * 4 + 3 * 8),
+                           "api": ("maro_cim_submit_pinned / maro_cim_wait_pinned (pinned host buffers; resident session) driven by the C "
+                                   "host loop tools/host_agent.c:e2e_loop_cim, agent on the host" if e2e["n_sub"] else
+                                   "maro_cim_step_pinned (pinned host buffers) + tools/host_agent.c on the host"),
+                           "sub_batches": e2e["n_sub"], "us_per_batch_step": 1000.0 * e2e_ms / e2e["calls"],
+                           "agent_us_per_batch_step": 1e6 * e2e["agent_seconds"] / e2e["calls"],
+                           "batch_steps": e2e["calls"], "resets": e2e["resets"],
+                           "by_sub_batches": {str(k): v for k, v in e2e_variants.items()}}
+        line.update(extras)
+        line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
+        emit(line)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -512,11 +777,11 @@ def run_ours(args, rank, local_rank, world):
     elif bike:
         from maro_b200.batch import BikeBatch
         from oracle.bike_oracle import BikeOracle  # checker / cpu_baseline leg only
-        from tests.bike_helpers import bike_config
+        from tools.workloads import bike_toy_config
         from maro_b200.scenarios.citi_bike.data import build_bike_topology
 
         ticks = min(args.ticks, 2880) if args.ticks != 1000 else 1440
-        topo = build_bike_topology(bike_config("bike_toy"), 0, ticks, transfer_seed=128)
+        topo = build_bike_topology(bike_toy_config(), 0, ticks, transfer_seed=128)
         steps_per_episode = BikeOracle(topo, 10).run_episode(1)[0]
         env = BikeBatch(topo, B, 10, args.max_snapshots or None, device=local_rank)
         dec_words = env.dec_words
@@ -792,6 +1057,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.scenario == "cim":
+        run_cim(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

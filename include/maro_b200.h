@@ -144,6 +144,22 @@ int maro_cim_step(MaroCimEnv* env, const uint8_t* active, const int32_t* actions
 int maro_cim_pinned_buffers(MaroCimEnv* env, void** actions, void** n_actions, void** active, void** decisions,
                             void** metrics);
 int maro_cim_step_pinned(MaroCimEnv* env, int32_t use_actions, int32_t use_n_actions, int32_t use_active);
+/* Resident mode, host agents: when every replica block of the handle fits on the chip at once, maro_cim_step and
+ * maro_cim_step_pinned drive a kernel that STAYS resident between calls (replica blocks in shared memory): per call the
+ * host writes one 16-byte command row per replica into mapped pinned memory, the replica's warp picks it up, steps and
+ * writes its decision / metrics rows back; no launch, no stage-in / write-back, no stream synchronisation per step.  The
+ * kernel leaves on its own after MARO_B200_IDLE_US (default 200) microseconds without a command and whenever another
+ * entry point needs the state in device memory.  MARO_B200_SESSION=0 disables it (one launch per call, as for large
+ * batches).
+ * Asynchronous halves of maro_cim_step_pinned for a contiguous replica range (what VectorEnv's dict stepping gives the
+ * reference, vector_env.py:131-144, without blocking): submit sends the step to replicas [first, first + count) and returns
+ * at once, wait blocks until their decision / metrics rows are in the pinned buffers.  Ranges are whole blocks of
+ * maro_cim_pinned_granularity() replicas (0: the batch is not resident, only maro_cim_step_pinned is available); a host
+ * agent overlaps its own work on one range with the device's work on the others. */
+int32_t maro_cim_pinned_granularity(MaroCimEnv* env);
+int maro_cim_submit_pinned(MaroCimEnv* env, int32_t first, int32_t count, int32_t use_actions, int32_t use_n_actions,
+                           int32_t use_active);
+int maro_cim_wait_pinned(MaroCimEnv* env, int32_t first, int32_t count);
 /* Same, device pointers, asynchronous on the handle's stream (no host<->device copies). */
 int maro_cim_step_device(MaroCimEnv* env, const uint8_t* d_active, const int32_t* d_actions,
                          const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
@@ -185,6 +201,18 @@ int maro_cim_snapshot_frames(MaroCimEnv* env, int32_t replica, int32_t* out, int
  * on the device so the env state never leaves HBM (and the step loop can be captured in a CUDA graph). */
 int maro_cim_random_policy_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t* d_actions,
                                   uint32_t seed, uint32_t replica_base);
+
+/* Resident mode, device agents: `n_steps` fused Env.step calls per replica in ONE launch.  The replica block is staged
+ * into shared memory once, the agent is a device callback evaluated between the steps (policy 0 = step(None) every
+ * time, 1 = the hashed hello-world agent of maro_cim_random_policy_device with the same seed / replica_base), the block
+ * is written back once.  Equivalent, row for row, to n_steps x {policy kernel; maro_cim_step_device}:
+ *   d_decisions [B][8] in/out — in: the rows the previous call returned (they feed the agent), out: the last rows
+ *   d_metrics   [B][3] out
+ *   d_trace     [n_steps][B][8] out or NULL — the decision row of every fused step (replicas that finish early repeat
+ *               their MARO_STATUS_FINISHED row)
+ * Replaces the loop of examples/hello_world/cim/hello.py:21-35 around Env.step (core.py:92-133). */
+int maro_cim_rollout_device(MaroCimEnv* env, int32_t policy, uint32_t seed, uint32_t replica_base, int32_t n_steps,
+                            int32_t* d_decisions, int64_t* d_metrics, int32_t* d_trace);
 
 /* ---- RL state / reward shaping on the device snapshot ring -------------------------------
  * Batched, device-resident forms of the reference's CIM example shaping (examples/cim/rl/env_sampler.py:15-36, 66-80),

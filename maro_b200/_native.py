@@ -19,7 +19,7 @@ EXPORTS = (
     "maro_cim_step", "maro_cim_step_device", "maro_cim_reset", "maro_cim_set_topology", "maro_cim_query",
     "maro_cim_query_device", "maro_cim_attr_id", "maro_cim_attr_slots", "maro_cim_read_frame",
     "maro_cim_frame_words", "maro_cim_ticks", "maro_cim_counters", "maro_cim_snapshot_frames",
-    "maro_cim_random_policy_device", "maro_cim_pinned_buffers", "maro_cim_step_pinned",
+    "maro_cim_random_policy_device", "maro_cim_pinned_buffers", "maro_cim_step_pinned", "maro_cim_rollout_device", "maro_cim_pinned_granularity", "maro_cim_submit_pinned", "maro_cim_wait_pinned",
     "maro_cim_rl_state_dim", "maro_cim_rl_state_device", "maro_cim_rl_reward_device", "maro_cim_rl_action_device",
     "maro_bike_pinned_buffers", "maro_bike_step_pinned",
     "maro_bike_create", "maro_bike_destroy", "maro_bike_set_stream", "maro_bike_decision_words", "maro_bike_step",
@@ -70,6 +70,11 @@ def lib():
     L.maro_cim_counters.argtypes = [vp, vp]
     L.maro_cim_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
     L.maro_cim_random_policy_device.argtypes = [vp, vp, vp, u32, u32]
+    L.maro_cim_pinned_granularity.argtypes = [vp]
+    L.maro_cim_pinned_granularity.restype = i32
+    L.maro_cim_submit_pinned.argtypes = [vp, i32, i32, i32, i32, i32]
+    L.maro_cim_wait_pinned.argtypes = [vp, i32, i32]
+    L.maro_cim_rollout_device.argtypes = [vp, i32, u32, u32, i32, vp, vp, vp]
     L.maro_cim_rl_state_dim.argtypes = [vp, i32, i32, i32]
     L.maro_cim_rl_state_dim.restype = i32
     L.maro_cim_rl_state_device.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp]

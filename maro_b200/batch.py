@@ -126,10 +126,28 @@ class CimBatch:
     def step_pinned(self, use_actions: bool = True, use_n_actions: bool = False, use_active: bool = False):
         _native.check(_native.lib().maro_cim_step_pinned(self._h, int(use_actions), int(use_n_actions), int(use_active)))
 
+    def pinned_granularity(self) -> int:
+        """replicas per independently steppable block of ``submit_pinned`` / ``wait_pinned`` (0: not available)"""
+        return _native.lib().maro_cim_pinned_granularity(self._h)
+
+    def submit_pinned(self, first: int, count: int, use_actions: bool = True, use_n_actions: bool = False, use_active: bool = False):
+        """asynchronous half of ``step_pinned`` for the replicas [first, first + count)"""
+        _native.check(_native.lib().maro_cim_submit_pinned(self._h, first, count, int(use_actions), int(use_n_actions), int(use_active)))
+
+    def wait_pinned(self, first: int, count: int):
+        _native.check(_native.lib().maro_cim_wait_pinned(self._h, first, count))
+
     def step_device(self, d_decisions: int, d_metrics: int, d_actions: int = 0, d_n_actions: int = 0, d_active: int = 0):
         """Asynchronous step on device pointers (ints, e.g. ``tensor.data_ptr()``)."""
         _native.check(_native.lib().maro_cim_step_device(self._h, d_active or None, d_actions or None,
                                                          d_n_actions or None, d_decisions, d_metrics))
+
+    def rollout_device(self, d_decisions: int, d_metrics: int, n_steps: int, policy: int = 1, seed: int = 0,
+                       replica_base: int = 0, d_trace: int = 0):
+        """Resident mode: ``n_steps`` fused env-steps per replica in one launch, agent on the device (policy 0 = None
+        actions, 1 = hashed hello-world agent).  ``d_decisions`` is in/out; ``d_trace`` ([n_steps][B][8] int32) optional."""
+        _native.check(_native.lib().maro_cim_rollout_device(self._h, policy, seed, replica_base, n_steps, d_decisions,
+                                                            d_metrics, d_trace or None))
 
     def random_policy_device(self, d_decisions: int, d_actions: int, seed: int, replica_base: int = 0):
         _native.check(_native.lib().maro_cim_random_policy_device(self._h, d_decisions, d_actions, seed, replica_base))

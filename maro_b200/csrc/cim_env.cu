@@ -13,6 +13,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 //   (-fmad=false: CPython never contracts a*b+c; order generation must round like the reference.)
 #include "env_common.cuh"
+#include <time.h>
 
 // =====================================================================================================
 // Kernels
@@ -84,11 +85,13 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
         while (!mbar_try_wait(bar, phase)) {}
         phase ^= 1u;
         Replica r = make_replica(s, a, rep, st);
-        const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), min(s.max_actions, G)) : 1) : 0;
+        const int n_raw = a.actions ? (a.n_actions ? a.n_actions[rep] : 1) : 0;
+        const bool too_many = n_raw > s.max_actions;  // more actions than the handle's rows hold: MARO_STATUS_BAD_ACTION
+        const int n_act = too_many ? 1 : min(max(n_raw, 0), min(s.max_actions, G));
         Act4 act = {0, 0, 0, 0};
         if (g.lane < n_act) {  // lane k fetches action k with one 128-bit load (actions may live in mapped host memory)
             int4 v = reinterpret_cast<const int4*>(a.actions + (int64_t)rep * s.max_actions * 4)[g.lane];
-            act.v = v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
+            act.v = too_many ? -1 : v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
         }
         replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
         // ---- write back (128-bit coalesced) what this step could have changed
@@ -124,20 +127,207 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
 }
 
 // hello-world random agent (examples/hello_world/cim/hello.py:24-32) as a counter hash of (replica, step)
-__global__ void cim_policy_kernel(const int32_t* __restrict__ dec, int32_t* __restrict__ act, int n, int max_actions,
-                                  uint32_t seed, uint32_t replica_base) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t* d = dec + i * 8;
+__device__ __forceinline__ int4 policy_random_row(const int32_t* d, uint32_t seed, uint32_t rid) {
     const uint32_t step = (uint32_t)d[7];
-    uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + step * 0x85ebca6bu + 0x1234567u));
+    uint32_t h1 = hash_u32(seed ^ hash_u32(rid * 0x9e3779b9u + step * 0x85ebca6bu + 0x1234567u));
     uint32_t h2 = hash_u32(h1 + 0x68bc21ebu);
     int load = d[3], dis = d[4];
     bool to_discharge = dis > 0 && (h1 & 1u);
     int scope = to_discharge ? dis : load;
     int qty = scope > 0 ? (int)(h2 % (uint32_t)(scope + 1)) : 0;
-    int4 o = make_int4(d[2], d[1], qty, to_discharge ? 1 : 0);
-    *reinterpret_cast<int4*>(act + (int64_t)i * max_actions * 4) = o;
+    return make_int4(d[2], d[1], qty, to_discharge ? 1 : 0);
+}
+
+__global__ void cim_policy_kernel(const int32_t* __restrict__ dec, int32_t* __restrict__ act, int n, int max_actions,
+                                  uint32_t seed, uint32_t replica_base) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<int4*>(act + (int64_t)i * max_actions * 4) = policy_random_row(dec + i * 8, seed, (uint32_t)i + replica_base);
+}
+
+// =====================================================================================================
+// Resident kernel: the replica block stays in shared memory for MANY env-steps (DESIGN.md §5 "resident mode").
+//   mode RES_ROLLOUT  K fused env-steps per launch, the agent is a device callback evaluated between the steps
+//                     (null / hashed hello-world agent); per step only the snapshot rows (and an optional 32-byte
+//                     trace row) leave the SM.  No co-residency requirement: any batch size.
+//   mode RES_SESSION  host-driven: the kernel stays resident between Env.step calls; per step the host writes one
+//                     16-byte command row per replica {seq, flags, vessel|port<<16, qty} into mapped pinned memory,
+//                     the replica's lane group polls it over PCIe, steps, writes its decision + metrics rows to mapped
+//                     pinned memory and bumps a device counter; the last group publishes `seq` to a host flag.
+//                     Groups that see no command for `idle_cycles` write back and exit (the host relaunches).
+// Stage-in (one TMA bulk copy) and write-back happen once per launch instead of once per env-step.
+// =====================================================================================================
+enum { RES_ROLLOUT = 0, RES_SESSION = 1 };
+enum { RES_POLICY_NULL = 0, RES_POLICY_RANDOM = 1 };
+enum { RES_CMD_STEP = 0, RES_CMD_EXIT = 1 };
+struct ResidentArgs {
+    int mode, spread;
+    int n_steps, policy;
+    uint32_t seed, replica_base;
+    int32_t* trace;                 // [n_steps][B][8] decision rows of every fused step, or nullptr
+    const uint32_t* cmd;            // [B][4] command rows (mapped host memory)
+    uint32_t* done_flags;           // mapped host [gridDim.x]: last seq every replica of that CTA has completed
+    uint32_t poll_ns, wait_ns;      // back-off of the command poll (PCIe) and of the shared-memory relay wait
+    uint32_t* seq_state;            // device [B]: last seq each replica has completed (survives launches and resets)
+    long long idle_cycles;
+};
+
+__device__ __forceinline__ uint4 ld_sys_v4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+template <int G, bool kGeneral>
+__global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_constant__ CimShape s, const __grid_constant__ StepArgs a,
+                                                           const __grid_constant__ ResidentArgs ra) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n_groups = ra.spread ? (int)(blockDim.x >> 5) : (int)(blockDim.x / G);
+    if (ra.spread && (threadIdx.x & 31) >= G) return;
+    const int gid = ra.spread ? (int)(threadIdx.x >> 5) : (int)(threadIdx.x / G);
+    const int rep = blockIdx.x * n_groups + gid;
+    if (rep >= s.n_replicas) return;
+    const Grp<G> g(threadIdx.x & 31);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + gid;                  // [32] mbarriers
+    int32_t* dslot = reinterpret_cast<int32_t*>(smem_raw + 256) + gid * 16;      // 8 decision words + 3 int64 metrics
+    int64_t* mslot = reinterpret_cast<int64_t*>(dslot + 8);
+    int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 256 + (size_t)n_groups * 64) + (size_t)gid * s.SW;
+    int32_t* gstate = a.state + (int64_t)rep * s.SW;
+    if (g.lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)s.SW * 4u);
+        bulk_g2s(st, gstate, (uint32_t)s.SW * 4u, bar);
+    }
+    g.sync();
+    while (!mbar_try_wait(bar, 0)) {}
+    Replica r = make_replica(s, a, rep, st);
+    int32_t* gdec = a.decisions + (int64_t)rep * 8;
+    int64_t* gmet = a.metrics + (int64_t)rep * 3;
+
+    if (ra.mode == RES_ROLLOUT) {
+        if (g.lane < 8) dslot[g.lane] = gdec[g.lane];  // the decision the previous launch returned (feeds the agent)
+        g.sync();
+        int k = 0;
+        for (; k < ra.n_steps; k++) {
+            Act4 act = {0, 0, 0, 0};
+            int n_act = 0;
+            if (ra.policy == RES_POLICY_RANDOM) {
+                n_act = 1;
+                if (g.lane == 0) {
+                    int4 o = policy_random_row(dslot, ra.seed, (uint32_t)rep + ra.replica_base);
+                    act.v = o.x; act.p = o.y; act.qty = o.z; act.type = o.w;
+                }
+            }
+            replica_step<G, kGeneral>(s, g, r, act, n_act, dslot, mslot);
+            if (ra.trace && g.lane < 2)
+                reinterpret_cast<int4*>(ra.trace + ((int64_t)k * s.n_replicas + rep) * 8)[g.lane] = reinterpret_cast<const int4*>(dslot)[g.lane];
+            const int status = dslot[MARO_DEC_STATUS];
+            if (status == MARO_STATUS_FINISHED) { k++; break; }  // every further step would return the same row
+        }
+        if (ra.trace)
+            for (; k < ra.n_steps; k++)
+                if (g.lane < 2)
+                    reinterpret_cast<int4*>(ra.trace + ((int64_t)k * s.n_replicas + rep) * 8)[g.lane] = reinterpret_cast<const int4*>(dslot)[g.lane];
+        if (g.lane < 2) reinterpret_cast<int4*>(gdec)[g.lane] = reinterpret_cast<const int4*>(dslot)[g.lane];
+        if (g.lane < 3) gmet[g.lane] = mslot[g.lane];
+    } else {
+        // ---- host session.  Per CTA: group 0 polls the CTA's command rows (one coalesced PCIe read for all of them) and
+        // relays them through shared memory; every group steps its replica into its output slot; the group that finishes
+        // last copies all slots to the mapped host rows (coalesced), fences once and bumps the completion counter.
+        uint32_t* cmd_s = reinterpret_cast<uint32_t*>(smem_raw + 256 + (size_t)n_groups * 64 + (size_t)n_groups * s.SW * 4);  // [n_groups][4]
+        volatile uint32_t* seq_s = cmd_s + n_groups * 4;
+        uint32_t* done_s = cmd_s + n_groups * 4 + 1;
+        const int rep0 = blockIdx.x * n_groups;
+        const int n_live = min(n_groups, s.n_replicas - rep0);
+        uint32_t expect = ra.seq_state[rep0] + 1u;
+        if (threadIdx.x == 0) { *seq_s = expect - 1u; *done_s = 0; }
+        __syncthreads();  // (threads that left above do not take part in CTA barriers)
+        if (g.lane < 8) dslot[g.lane] = gdec[g.lane];  // rows of inactive replicas keep their previous contents
+        if (g.lane < 3) mslot[g.lane] = gmet[g.lane];
+        g.sync();
+        for (;;) {
+            if (gid == 0) {
+                const long long t0 = clock64();
+                bool stop = false;
+                for (;;) {
+                    bool ok = true;
+                    for (int b0 = 0; b0 < n_live; b0 += G) {
+                        const int i = b0 + g.lane;
+                        uint4 c = make_uint4(expect, 0, 0, 0);
+                        if (i < n_live) c = ld_sys_v4(ra.cmd + (int64_t)(rep0 + i) * 4);
+                        ok = ok && g.ballot(c.x != expect) == 0;
+                        if (i < n_live) *reinterpret_cast<uint4*>(cmd_s + i * 4) = c;
+                    }
+                    if (ok) break;
+                    if (clock64() - t0 > ra.idle_cycles) { stop = true; break; }
+                    if (ra.poll_ns) __nanosleep(ra.poll_ns);
+                }
+                if (stop)  // idle: every group of the CTA leaves together
+                    for (int i = g.lane; i < n_live; i += G) cmd_s[i * 4 + 1] = (uint32_t)RES_CMD_EXIT << 16;
+                g.sync();
+                __threadfence_block();
+                if (g.lane == 0) *seq_s = expect;
+            }
+            if (g.lane == 0) while (*seq_s != expect) if (ra.wait_ns) __nanosleep(ra.wait_ns);
+            g.sync();
+            __threadfence_block();
+            const uint4 c = *reinterpret_cast<const uint4*>(cmd_s + gid * 4);
+            const uint32_t flags = c.y;
+            if (((flags >> 16) & 0xff) == RES_CMD_EXIT) break;
+            const int n_act = min((int)(flags & 0xff), min(s.max_actions, G));
+            const bool active = (flags >> 8) & 1u, bad = (flags >> 9) & 1u;
+            if (active) {
+                Act4 act = {0, 0, 0, 0};
+                if (g.lane == 0) {
+                    act.v = bad ? -1 : (int)(c.z & 0xffffu); act.p = (int)(c.z >> 16); act.qty = (int)c.w; act.type = (int)((flags >> 24) & 1u);
+                } else if (g.lane < n_act) {  // further actions of an action list: full rows in the pinned action buffer
+                    __threadfence_system();  // (acquire side of the host's release store of the command row)
+                    uint4 v = ld_sys_v4(reinterpret_cast<const uint32_t*>(a.actions + ((int64_t)rep * s.max_actions + g.lane) * 4));
+                    act.v = (int)v.x; act.p = (int)v.y; act.qty = (int)v.z; act.type = (int)v.w;
+                }
+                replica_step<G, kGeneral>(s, g, r, act, n_act, dslot, mslot);
+            } else if (g.lane == 0) {
+                dslot[MARO_DEC_STATUS] = MARO_STATUS_INACTIVE;
+            }
+            g.sync();
+            int last = 0;
+            if (g.lane == 0) {
+                __threadfence_block();
+                last = atomicAdd_block(done_s, 1u) + 1u == (uint32_t)n_live;
+            }
+            last = g.shfl(last, 0);
+            if (last) {
+                __threadfence_block();
+                const int4* slots4 = reinterpret_cast<const int4*>(smem_raw + 256);  // 4 int4 per group: 2 decision, 1.5 metrics
+                const int64_t* slots8 = reinterpret_cast<const int64_t*>(smem_raw + 256);
+                int4* od = reinterpret_cast<int4*>(a.decisions + (int64_t)rep0 * 8);
+                int64_t* om = a.metrics + (int64_t)rep0 * 3;
+                for (int j = g.lane; j < n_live * 2; j += G) od[j] = slots4[(j >> 1) * 4 + (j & 1)];
+                for (int j = g.lane; j < n_live * 3; j += G) om[j] = slots8[(j / 3) * 8 + 4 + j % 3];
+                __threadfence_system();  // the rows are visible to the host before the CTA's flag is
+                g.sync();
+                if (g.lane == 0) {
+                    *done_s = 0;
+                    *reinterpret_cast<volatile uint32_t*>(ra.done_flags + blockIdx.x) = expect;
+                }
+            }
+            expect++;
+        }
+        if (g.lane == 0) ra.seq_state[rep] = expect - 1u;
+    }
+    // ---- write back the block + the light-step hint of the per-step kernel
+    g.sync();
+    const int4* src4 = reinterpret_cast<const int4*>(st);
+    int4* dst4 = reinterpret_cast<int4*>(gstate);
+    for (int i = g.lane; i < s.SW / 4; i += G) dst4[i] = src4[i];
+    if (g.lane == 0) {
+        const int32_t* c = st + s.FWp;
+        const uint64_t arr = ((uint64_t)(uint32_t)c[C_ARR_HI] << 32) | (uint32_t)c[C_ARR_LO];
+        const int dp = c[C_DEC_POS];
+        a.light[rep] = (c[C_STATE] == ST_AWAIT && dp < 64 && (arr >> dp) != 0) ? 1 : 0;
+    }
 }
 
 struct MaroCimEnv : EnvCommon {
@@ -149,6 +339,19 @@ struct MaroCimEnv : EnvCommon {
     uint32_t* d_mt = nullptr;
     uint8_t* d_light = nullptr;
     std::vector<int32_t> h_tables;
+    // resident mode (cim_resident_kernel)
+    int res_threads = 0, res_grid = 0, res_spread = 0;
+    size_t res_smem = 0;
+    bool session_ok = false, session_live = false;  // session_ok: the whole grid is co-resident (required to spin-wait)
+    int res_groups = 0;                              // replicas per CTA of the resident kernel
+    std::vector<uint32_t> cta_seq;                   // per CTA: last step completed (the kernel's seq_state mirrors it)
+    std::vector<uint8_t> cta_pending;                // per CTA: a step has been sent and not collected yet
+    int n_pending = 0;
+    uint32_t *h_cmd = nullptr, *hd_cmd = nullptr;    // [B][4] command rows, mapped pinned
+    uint32_t *h_flag = nullptr, *hd_flag = nullptr;  // [res_grid] completion flags (one per CTA), mapped pinned
+    uint32_t* d_seq = nullptr;
+    long long idle_cycles = 400000;
+    uint32_t poll_ns = 0, wait_ns = 20;
 };
 
 // =====================================================================================================
@@ -319,6 +522,197 @@ static cudaError_t launch_step(MaroCimEnv* e, const StepArgs& a) {
     }
 }
 
+template <int G>
+static cudaError_t launch_resident_g(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, bool query_only, int* blocks_per_sm) {
+    const bool general = !(e->s.order_table && !e->s.buffer_noise);
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->res_smem);
+        if (err != cudaSuccess) return err;
+        if (query_only) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, e->res_threads, e->res_smem);
+        kernel<<<e->res_grid, e->res_threads, e->res_smem, e->stream>>>(e->s, a, ra);
+        return cudaGetLastError();
+    };
+    return general ? go(cim_resident_kernel<G, true>) : go(cim_resident_kernel<G, false>);
+}
+
+static cudaError_t launch_resident(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, bool query_only = false, int* blocks_per_sm = nullptr) {
+    switch (e->lanes) {
+        case 8: return launch_resident_g<8>(e, a, ra, query_only, blocks_per_sm);
+        case 16: return launch_resident_g<16>(e, a, ra, query_only, blocks_per_sm);
+        default: return launch_resident_g<32>(e, a, ra, query_only, blocks_per_sm);
+    }
+}
+
+// ---- host session (RES_SESSION) ---------------------------------------------------------------------
+static int session_launch(MaroCimEnv* e) {
+    StepArgs a = base_args(e);
+    a.actions = reinterpret_cast<const int32_t*>(e->hd_in);
+    a.decisions = reinterpret_cast<int32_t*>(e->hd_out);
+    a.metrics = reinterpret_cast<int64_t*>(e->hd_out + (size_t)e->B * e->dec_words * 4);
+    ResidentArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.mode = RES_SESSION; ra.spread = e->res_spread;
+    ra.cmd = e->hd_cmd; ra.done_flags = e->hd_flag; ra.seq_state = e->d_seq; ra.poll_ns = e->poll_ns; ra.wait_ns = e->wait_ns;
+    ra.idle_cycles = e->idle_cycles;
+    CK(launch_resident(e, a, ra));
+    e->session_live = true;
+    return 0;
+}
+
+// Wait until the CTAs [c0, c1) have published the step they were last sent (their decision / metrics rows are then in
+// h_out).  The resident kernel may have left meanwhile (idle limit): relaunch it, the command rows are still in place.
+static int session_wait_ctas(MaroCimEnv* e, int c0, int c1) {
+    volatile uint32_t* flags = e->h_flag;
+    timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    int cta = c0;
+    auto advance = [&]() {
+        while (cta < c1 && (!e->cta_pending[cta] || flags[cta] == e->cta_seq[cta] + 1u)) {
+            if (e->cta_pending[cta]) { e->cta_pending[cta] = 0; e->cta_seq[cta] += 1u; e->n_pending--; }
+            cta++;
+        }
+        return cta == c1;
+    };
+    for (uint64_t spins = 1;; spins++) {
+        if (advance()) return 0;
+        __builtin_ia32_pause();
+        if ((spins & 0xfff) == 0) {  // every ~100 us: did the kernel leave (idle limit) or fail?
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            if (ts.tv_sec - ts0.tv_sec > 30) return fail("resident kernel: no completion after 30 s");  // never spin forever
+            cudaError_t q = cudaStreamQuery(e->stream);
+            if (q == cudaSuccess) {
+                if (advance()) return 0;
+                if (session_launch(e)) return 1;
+            } else if (q != cudaErrorNotReady) {
+                e->session_live = false;
+                return fail(std::string("resident kernel: ") + cudaGetErrorString(q));
+            }
+        }
+    }
+}
+
+// Ask the resident kernel (if any) to write the replica blocks back and exit; afterwards device memory is authoritative.
+static int session_end(MaroCimEnv* e) {
+    if (!e->session_live) return 0;
+    if (e->n_pending && session_wait_ctas(e, 0, e->res_grid)) return 1;
+    const int gpc = e->res_groups;
+    for (int i = 0; i < e->B; i++) {
+        volatile uint32_t* row = e->h_cmd + (size_t)i * 4;
+        row[1] = (uint32_t)RES_CMD_EXIT << 16;
+        __atomic_store_n(&row[0], e->cta_seq[i / gpc] + 1u, __ATOMIC_RELEASE);
+    }
+    e->session_live = false;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+#define END_SESSION(e) do { if ((e)->session_live && session_end(e)) return 1; } while (0)
+
+// Send one Env.step to the replicas [first, first + count) (whole CTAs): one 16-byte command row per replica, built from
+// the pinned staging buffers (h_in).  Returns at once; session_wait_ctas collects the rows.
+static int session_submit(MaroCimEnv* e, int first, int count, bool use_actions, bool use_n_actions, bool use_active) {
+    const int B = e->B, A = e->s.max_actions, gpc = e->res_groups;
+    if (first < 0 || count < 1 || first + count > B || first % gpc || ((first + count) % gpc && first + count != B))
+        return fail("submit: the replica range must cover whole blocks of maro_cim_pinned_granularity() replicas");
+    const int c0 = first / gpc, c1 = (first + count + gpc - 1) / gpc;
+    for (int c = c0; c < c1; c++)
+        if (e->cta_pending[c]) { if (session_wait_ctas(e, c0, c1)) return 1; break; }
+    const int32_t* act = reinterpret_cast<const int32_t*>(e->h_in);
+    const int32_t* nact = reinterpret_cast<const int32_t*>(e->h_in + (size_t)B * A * 16);
+    const uint8_t* active = e->h_in + (size_t)B * A * 16 + (size_t)B * 4;
+    for (int i = first; i < first + count; i++) {
+        int n = use_actions ? (use_n_actions ? nact[i] : 1) : 0;
+        if (n < 0) n = 0;
+        const int32_t* r0 = act + (size_t)i * A * 4;
+        uint32_t flags = (use_active ? (active[i] ? 1u : 0u) : 1u) << 8, w2 = 0, w3 = 0;
+        if (n > 0) {
+            const bool bad = n > A || r0[0] < 0 || r0[0] > 0xffff || r0[1] < 0 || r0[1] > 0xffff;
+            flags |= (uint32_t)std::min(n, 255) | (bad ? 1u << 9 : 0u) | (r0[3] == 1 ? 1u << 24 : 0u);
+            w2 = ((uint32_t)r0[0] & 0xffffu) | ((uint32_t)r0[1] << 16);
+            w3 = (uint32_t)r0[2];
+        }
+        volatile uint32_t* row = e->h_cmd + (size_t)i * 4;
+        row[1] = flags; row[2] = w2; row[3] = w3;
+        __atomic_store_n(&row[0], e->cta_seq[i / gpc] + 1u, __ATOMIC_RELEASE);  // x86 TSO: a reader that sees the seq sees the row
+    }
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    for (int c = c0; c < c1; c++) { e->cta_pending[c] = 1; e->n_pending++; }
+    if (!e->session_live && session_launch(e)) return 1;
+    return 0;
+}
+
+// One Env.step of every replica through the resident kernel (inputs in h_in, outputs in h_out, both mapped).
+static int session_step(MaroCimEnv* e, bool use_actions, bool use_n_actions, bool use_active) {
+    if (session_submit(e, 0, e->B, use_actions, use_n_actions, use_active)) return 1;
+    return session_wait_ctas(e, 0, e->res_grid);
+}
+
+extern "C" int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask);
+
+// device buffers + resident-mode geometry of a new handle; any failure leaves the handle for the caller to destroy
+static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32_t n_topos, const MaroCimConfig* cfg, const cudaDeviceProp& prop) {
+    (void)topos;
+    const CimShape& s = e->s;
+    const int B = e->B;
+    CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
+    CK(cudaMalloc(&e->d_topo, (size_t)B * 4));
+    CK(cudaMalloc(&e->d_light, (size_t)B));
+    CK(cudaMemset(e->d_light, 0, (size_t)B));
+    CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int32_t> topo(B, 0);
+    if (cfg->replica_topology)
+        for (int i = 0; i < B; i++) {
+            if (cfg->replica_topology[i] < 0 || cfg->replica_topology[i] >= n_topos) return fail("maro_cim_create: replica_topology out of range");
+            topo[i] = cfg->replica_topology[i];
+        }
+    CK(cudaMemcpy(e->d_topo, topo.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+    if (s.order_noise || s.buffer_noise) {
+        e->mt_words = mt_block_words(s);
+        CK(cudaMalloc(&e->d_mt, (size_t)B * e->mt_words * 4));
+    }
+    // ---- resident mode: one replica per warp while the batch is small (spread), packed lane groups otherwise
+    CK(cudaHostAlloc(&e->h_cmd, (size_t)B * 16, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&e->h_flag, (size_t)B * 4 + 64, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_cmd, e->h_cmd, 0));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_flag, e->h_flag, 0));
+    memset(e->h_cmd, 0, (size_t)B * 16);
+    memset(e->h_flag, 0, (size_t)B * 4 + 64);
+    CK(cudaMalloc(&e->d_seq, (size_t)B * 4));
+    CK(cudaMemset(e->d_seq, 0, (size_t)B * 4));
+    const int nsm = prop.multiProcessorCount;
+    const int gpw = 32 / e->lanes;
+    const size_t per_group = (size_t)s.SW * 4 + 64 + 16, max_smem = prop.sharedMemPerBlockOptin;  // block + output slot + command row
+    const char* rs = getenv("MARO_B200_RES_SPREAD");
+    e->res_spread = rs ? atoi(rs) != 0 : (B <= nsm * 32);
+    const int groups_per_warp = e->res_spread ? 1 : gpw;
+    int w = 8;
+    if (e->res_spread) {  // smallest power of two >= replicas per SM (command blocks of a CTA stay 64 / 128-byte aligned)
+        w = 1;
+        while (w < 8 && w * nsm < B) w <<= 1;
+    }
+    if (const char* rw = getenv("MARO_B200_RES_WARPS")) w = std::min(8, std::max(1, atoi(rw)));
+    while (w > 1 && 256 + 16 + per_group * w * groups_per_warp > max_smem) w--;
+    if (256 + 16 + per_group * w * groups_per_warp <= max_smem) {
+        e->res_threads = w * 32;
+        e->res_smem = 256 + 16 + per_group * w * groups_per_warp;
+        e->res_grid = (B + w * groups_per_warp - 1) / (w * groups_per_warp);
+        e->res_groups = w * groups_per_warp;
+        e->cta_seq.assign(e->res_grid, 0);
+        e->cta_pending.assign(e->res_grid, 0);
+        int per_sm = 0;
+        StepArgs a = base_args(e);
+        ResidentArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        CK(launch_resident(e, a, ra, true, &per_sm));
+        const char* se = getenv("MARO_B200_SESSION");
+        e->session_ok = (se ? atoi(se) != 0 : true) && (int64_t)per_sm * nsm >= e->res_grid;
+    }
+    if (const char* v = getenv("MARO_B200_POLL_NS")) e->poll_ns = (uint32_t)atoi(v);
+    if (const char* v = getenv("MARO_B200_WAIT_NS")) e->wait_ns = (uint32_t)atoi(v);
+    if (const char* iu = getenv("MARO_B200_IDLE_US")) e->idle_cycles = (long long)(atof(iu) * 1e-6 * prop.clockRate * 1e3);
+    return maro_cim_reset(e, nullptr);
+}
+
 extern "C" {
 
 const char* maro_last_error(void) { return g_err.c_str(); }
@@ -327,7 +721,11 @@ int maro_abi_version(void) { return MARO_B200_ABI_VERSION; }
 int maro_cim_destroy(MaroCimEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
+    if (e->session_live) session_end(e);
     cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt); cudaFree(e->d_light);
+    cudaFree(e->d_seq);
+    if (e->h_cmd) cudaFreeHost(e->h_cmd);
+    if (e->h_flag) cudaFreeHost(e->h_flag);
     common_free(e);
     delete e;
     return 0;
@@ -361,7 +759,7 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
 
     // launch geometry: G lanes per replica, as many warps per CTA as shared memory allows (<= 8), persistent grid
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, e->device));
+    if (cudaGetDeviceProperties(&prop, e->device) != cudaSuccess) { delete e; return fail("maro_cim_create: cudaGetDeviceProperties failed"); }
     e->lanes = cfg_lanes > 0 ? cfg_lanes : lanes_per_replica(s);
     const int gpw = 32 / e->lanes;  // replicas per warp
     const size_t per_warp = (size_t)s.SW * 4 * gpw;
@@ -397,31 +795,15 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
     e->off_tick = s.FWp + C_TICK; e->off_counters = s.FWp + C_NSTEPS_LO;
     e->dec_words = MARO_CIM_DECISION_WORDS; e->max_actions = s.max_actions;
     if (common_alloc(e)) { maro_cim_destroy(e); return 1; }
-    const int B = e->B;
-    CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
-    CK(cudaMalloc(&e->d_topo, (size_t)B * 4));
-    CK(cudaMalloc(&e->d_light, (size_t)B));
-    CK(cudaMemset(e->d_light, 0, (size_t)B));
-    CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
-    std::vector<int32_t> topo(B, 0);
-    if (cfg->replica_topology)
-        for (int i = 0; i < B; i++) {
-            if (cfg->replica_topology[i] < 0 || cfg->replica_topology[i] >= n_topos) { maro_cim_destroy(e); return fail("maro_cim_create: replica_topology out of range"); }
-            topo[i] = cfg->replica_topology[i];
-        }
-    CK(cudaMemcpy(e->d_topo, topo.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
-    if (s.order_noise || s.buffer_noise) {
-        e->mt_words = mt_block_words(s);
-        CK(cudaMalloc(&e->d_mt, (size_t)B * e->mt_words * 4));
-    }
+    int rc = create_device_side(e, topos, n_topos, cfg, prop);
+    if (rc) { maro_cim_destroy(e); return rc; }
     *out = e;
-    int rc = maro_cim_reset(e, nullptr);
-    if (rc) { maro_cim_destroy(e); *out = nullptr; return rc; }
     return 0;
 }
 
 int maro_cim_set_stream(MaroCimEnv* e, void* cuda_stream, int32_t external) {
     if (!e) return fail("null handle");
+    END_SESSION(e);
     e->stream = external ? (cudaStream_t)cuda_stream : e->own_stream;
     return 0;
 }
@@ -429,11 +811,13 @@ int maro_cim_set_stream(MaroCimEnv* e, void* cuda_stream, int32_t external) {
 int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask) {
     if (!e) return fail("null handle");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     StepArgs a = base_args(e);
-    if (mask) {
-        uint8_t* d_active = e->d_in + (size_t)e->B * e->s.max_actions * 16 + (size_t)e->B * 4;
-        memcpy(e->h_in, mask, e->B);
-        CK(cudaMemcpyAsync(d_active, e->h_in, e->B, cudaMemcpyHostToDevice, e->stream));
+    if (mask) {  // staged through the pinned `active` region (never through the caller-visible action rows)
+        const size_t active_off = (size_t)e->B * e->s.max_actions * 16 + (size_t)e->B * 4;
+        uint8_t* d_active = e->d_in + active_off;
+        if (mask != e->h_in + active_off) memcpy(e->h_in + active_off, mask, e->B);
+        CK(cudaMemcpyAsync(d_active, e->h_in + active_off, e->B, cudaMemcpyHostToDevice, e->stream));
         a.active = d_active;
     }
     int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
@@ -446,6 +830,7 @@ int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask) {
 int maro_cim_set_topology(MaroCimEnv* e, int32_t index, const MaroCimTopology* topo) {
     if (!e || !topo || index < 0 || index >= e->K) return fail("maro_cim_set_topology: bad arguments");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     std::vector<int32_t> blob;
     if (topo->n_ports != e->s.P || topo->n_vessels != e->s.V || topo->max_tick != e->s.max_tick)
         return fail("maro_cim_set_topology: shape differs from the handle's");
@@ -465,6 +850,7 @@ int maro_cim_step_device(MaroCimEnv* e, const uint8_t* d_active, const int32_t* 
                          int32_t* d_decisions, int64_t* d_metrics) {
     if (!e || !d_decisions || !d_metrics) return fail("maro_cim_step_device: bad arguments");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     StepArgs a = base_args(e);
     a.active = d_active; a.actions = d_actions; a.n_actions = d_n_actions;
     a.decisions = d_decisions; a.metrics = d_metrics;
@@ -476,6 +862,17 @@ int maro_cim_step(MaroCimEnv* e, const uint8_t* active, const int32_t* actions, 
                   int32_t* decisions, int64_t* metrics) {
     if (!e || !decisions || !metrics) return fail("maro_cim_step: bad arguments");
     CK(cudaSetDevice(e->device));
+    if (e->session_ok) {  // resident kernel: stage through the pinned buffers, command rows out, decision rows back
+        const int B = e->B, A = e->s.max_actions;
+        const size_t act_bytes = (size_t)B * A * 16, dec_bytes = (size_t)B * e->dec_words * 4;
+        if (actions) memcpy(e->h_in, actions, act_bytes);
+        if (actions && n_actions) memcpy(e->h_in + act_bytes, n_actions, (size_t)B * 4);
+        if (active) memcpy(e->h_in + act_bytes + (size_t)B * 4, active, B);
+        if (session_step(e, actions != nullptr, actions && n_actions, active != nullptr)) return 1;
+        memcpy(decisions, e->h_out, dec_bytes);
+        memcpy(metrics, e->h_out + dec_bytes, (size_t)B * e->met_words * 8);
+        return 0;
+    }
     return common_host_step(e, active, actions, n_actions, decisions, metrics,
                             [&](const uint8_t* a, const int32_t* ac, const int32_t* na, int32_t* d, int64_t* m) {
                                 return maro_cim_step_device(e, a, ac, na, d, m);
@@ -488,6 +885,7 @@ int maro_cim_pinned_buffers(MaroCimEnv* e, void** actions, void** n_actions, voi
 int maro_cim_step_pinned(MaroCimEnv* e, int32_t use_actions, int32_t use_n_actions, int32_t use_active) {
     if (!e) return fail("maro_cim_step_pinned: null handle");
     CK(cudaSetDevice(e->device));
+    if (e->session_ok) return session_step(e, use_actions != 0, use_actions && use_n_actions, use_active != 0);
     const uint8_t* f = reinterpret_cast<const uint8_t*>(1);  // presence flags only
     return common_host_step(e, use_active ? f : nullptr, use_actions ? reinterpret_cast<const int32_t*>(f) : nullptr,
                             use_n_actions ? reinterpret_cast<const int32_t*>(f) : nullptr, nullptr, nullptr,
@@ -495,12 +893,25 @@ int maro_cim_step_pinned(MaroCimEnv* e, int32_t use_actions, int32_t use_n_actio
                                 return maro_cim_step_device(e, a, ac, na, d, m);
                             }, true);
 }
+int32_t maro_cim_pinned_granularity(MaroCimEnv* e) { return e && e->session_ok ? e->res_groups : 0; }
+int maro_cim_submit_pinned(MaroCimEnv* e, int32_t first, int32_t count, int32_t use_actions, int32_t use_n_actions, int32_t use_active) {
+    if (!e) return fail("maro_cim_submit_pinned: null handle");
+    if (!e->session_ok) return fail("maro_cim_submit_pinned: the batch is not resident (maro_cim_pinned_granularity() == 0); use maro_cim_step_pinned");
+    CK(cudaSetDevice(e->device));
+    return session_submit(e, first, count, use_actions != 0, use_actions && use_n_actions, use_active != 0);
+}
+int maro_cim_wait_pinned(MaroCimEnv* e, int32_t first, int32_t count) {
+    if (!e || !e->session_ok || first < 0 || count < 1 || first + count > e->B) return fail("maro_cim_wait_pinned: bad arguments");
+    CK(cudaSetDevice(e->device));
+    return session_wait_ctas(e, first / e->res_groups, (first + count + e->res_groups - 1) / e->res_groups);
+}
 int32_t maro_cim_frame_words(MaroCimEnv* e) { return e ? e->s.FW : -1; }
 
 int maro_cim_query(MaroCimEnv* e, const int32_t* replicas, int32_t n_replicas, int32_t node_type, const int32_t* frame_indices,
                    int32_t n_frames, const int32_t* nodes, int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* out,
                    int64_t* out_per_replica) {
     if (!out) return fail("maro_cim_query: null output");
+    if (e) END_SESSION(e);
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, nullptr, out, out_per_replica);
 }
 
@@ -508,22 +919,52 @@ int maro_cim_query_device(MaroCimEnv* e, const int32_t* replicas, int32_t n_repl
                           int32_t n_frames, const int32_t* nodes, int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* d_out,
                           int64_t* out_per_replica) {
     if (!d_out) return fail("maro_cim_query_device: null output");
+    if (e) END_SESSION(e);
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, d_out, nullptr, out_per_replica);
 }
 
 int32_t maro_cim_attr_id(MaroCimEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
 int32_t maro_cim_attr_slots(MaroCimEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }
-int maro_cim_read_frame(MaroCimEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) { return common_read_frame(e, replica, out_words, n_words); }
-int maro_cim_ticks(MaroCimEnv* e, int32_t* out_ticks) { return common_ticks(e, out_ticks); }
-int maro_cim_counters(MaroCimEnv* e, int64_t* out) { return common_counters(e, out); }
+int maro_cim_read_frame(MaroCimEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) {
+    if (e) END_SESSION(e);
+    return common_read_frame(e, replica, out_words, n_words);
+}
+int maro_cim_ticks(MaroCimEnv* e, int32_t* out_ticks) {
+    if (e) END_SESSION(e);
+    return common_ticks(e, out_ticks);
+}
+int maro_cim_counters(MaroCimEnv* e, int64_t* out) {
+    if (e) END_SESSION(e);
+    return common_counters(e, out);
+}
 int maro_cim_snapshot_frames(MaroCimEnv* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
+    if (e) END_SESSION(e);
     return common_snapshot_frames(e, replica, out, cap, n_out);
+}
+
+/* K fused env-steps per replica in ONE launch, the agent evaluated on the device between the steps. */
+int maro_cim_rollout_device(MaroCimEnv* e, int32_t policy, uint32_t seed, uint32_t replica_base, int32_t n_steps,
+                            int32_t* d_decisions, int64_t* d_metrics, int32_t* d_trace) {
+    if (!e || !d_decisions || !d_metrics || n_steps < 1 || (policy != RES_POLICY_NULL && policy != RES_POLICY_RANDOM))
+        return fail("maro_cim_rollout_device: bad arguments");
+    if (!e->res_threads) return fail("maro_cim_rollout_device: replica state does not fit the resident kernel");
+    CK(cudaSetDevice(e->device));
+    END_SESSION(e);
+    StepArgs a = base_args(e);
+    a.decisions = d_decisions; a.metrics = d_metrics;
+    ResidentArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.mode = RES_ROLLOUT; ra.spread = e->res_spread; ra.n_steps = n_steps; ra.policy = policy; ra.seed = seed;
+    ra.replica_base = replica_base; ra.trace = d_trace;
+    CK(launch_resident(e, a, ra));
+    return 0;
 }
 
 int maro_cim_random_policy_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t* d_actions, uint32_t seed,
                                   uint32_t replica_base) {
     if (!e || !d_decisions || !d_actions) return fail("maro_cim_random_policy_device: bad arguments");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     int threads = 256, blocks = (e->B + threads - 1) / threads;
     cim_policy_kernel<<<blocks, threads, 0, e->stream>>>(d_decisions, d_actions, e->B, e->s.max_actions, seed, replica_base);
     CK(cudaGetLastError());
@@ -586,6 +1027,7 @@ int maro_cim_rl_state_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t 
         n_vessel_attrs < 0 || n_vessel_attrs > 16)
         return fail("maro_cim_rl_state_device: bad arguments");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     ShapeArgs q;
     shape_common(e, q);
     for (int i = 0; i < n_port_attrs; i++) {
@@ -612,6 +1054,7 @@ int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const i
     if (!e || !d_decisions || !d_model_actions || !d_action_space || !d_actions || n_action_space < 1)
         return fail("maro_cim_rl_action_device: bad arguments");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     ShapeArgs q;
     shape_common(e, q);
     q.decisions = d_decisions; q.model_actions = d_model_actions; q.action_space = d_action_space; q.n_action_space = n_action_space;
@@ -629,6 +1072,7 @@ int maro_cim_rl_reward_device(MaroCimEnv* e, const int32_t* d_ticks, const int32
                               int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out) {
     if (!e || !d_ticks || !d_ports || !d_decay || !d_out || time_window < 1) return fail("maro_cim_rl_reward_device: bad arguments");
     CK(cudaSetDevice(e->device));
+    END_SESSION(e);
     ShapeArgs q;
     shape_common(e, q);
     q.ticks = d_ticks; q.ports = d_ports; q.decay = d_decay; q.time_window = time_window;

@@ -1,0 +1,257 @@
+"""GPU (-m gpu): the resident kernel (replica blocks stay in shared memory across env-steps) against the per-step
+kernel and the oracle.  Two modes: fused K-step rollouts with a device agent (maro_cim_rollout_device) and the
+host-driven session behind maro_cim_step / maro_cim_step_pinned (command rows in mapped pinned memory)."""
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _topo(name, ticks):
+    from maro_b200.scenarios.cim.topology import build_topology
+
+    return build_topology(name, ticks)
+
+
+def _batch(*a, **k):
+    from maro_b200.batch import CimBatch
+
+    return CimBatch(*a, **k)
+
+
+def _ring_rows(env, replica, topo):
+    """every snapshot row the ring holds for one replica, as raw frame words"""
+    return {int(f): env.snapshot_row(int(f), replica) for f in env.snapshot_frames(replica)}
+
+
+@pytest.mark.parametrize("topology,ticks,B,chunks", [
+    ("toy.4p_ssdd_l0.0", 200, 256, [1, 1, 7, 50, 3, 1000]),
+    ("toy.4p_ssdd_l0.8", 120, 96, [5, 40, 1000]),          # general kernel: MT19937 order / buffer noise
+    ("global_trade.22p_l0.8", 40, 24, [3, 1000]),           # one warp = one replica, 30 KB blocks
+])
+def test_rollout_matches_step_loop_and_oracle(topology, ticks, B, chunks):
+    import torch
+
+    from oracle.cim_oracle import CimOracle, policy_random
+
+    topo = _topo(topology, ticks)
+    seed, base = 11, 5
+    # ---- reference run on the device: policy kernel + per-step kernel
+    a = _batch(topo, B)
+    s = torch.cuda.current_stream().cuda_stream
+    a.set_stream(s)
+    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    rows, mets = [], []
+    for _ in range(100000):
+        a.random_policy_device(dec.data_ptr(), act.data_ptr(), seed, base)
+        a.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+        rows.append(dec.cpu().numpy().copy())
+        mets.append(met.cpu().numpy().copy())
+        if (rows[-1][:, 6] == 2).all():
+            break
+    want = np.stack(rows)
+    want_met = mets[-1]
+    # ---- fused rollouts on a second handle, uneven chunk sizes
+    b = _batch(topo, B)
+    b.set_stream(s)
+    dec2 = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met2 = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    got, done = [], 0
+    for n in chunks:
+        n = min(n, len(want) - done)
+        if n <= 0:
+            break
+        trace = torch.full((n, B, 8), -7, dtype=torch.int32, device="cuda")
+        b.rollout_device(dec2.data_ptr(), met2.data_ptr(), n, 1, seed, base, trace.data_ptr())
+        got.append(trace.cpu().numpy())
+        done += n
+    got = np.concatenate(got)
+    assert done == len(want)
+    if not np.array_equal(got, want):
+        bad = np.argwhere(got != want)[0]
+        raise AssertionError(f"step {bad[0]} replica {bad[1]}: got {got[bad[0], bad[1]]} want {want[bad[0], bad[1]]}")
+    assert np.array_equal(dec2.cpu().numpy(), want[-1])
+    assert np.array_equal(met2.cpu().numpy(), want_met)
+    assert np.array_equal(a.counters(), b.counters())
+    assert np.array_equal(a.ticks(), b.ticks())
+    for i in sorted({0, 1, B // 2, B - 1}):
+        assert np.array_equal(a.read_frame(i), b.read_frame(i))
+        ra, rb = _ring_rows(a, i, topo), _ring_rows(b, i, topo)
+        assert ra.keys() == rb.keys()
+        for f in ra:
+            assert np.array_equal(ra[f], rb[f]), (i, f)
+    # ---- and the oracle on sampled replicas, replaying the traced decisions
+    for i in sorted({0, B // 3, B - 1}):
+        o = CimOracle(topo)
+        st, d, m = o.step(None)
+        k = 0
+        while st == 0:
+            assert d[:7].tolist() == got[k, i, :7].tolist(), (i, k, d, got[k, i])
+            st, d, m = o.step(np.asarray([policy_random(got[k, i], seed, i + base, int(got[k, i, 7]))], np.int32))
+            k += 1
+        assert st == 1 and got[k, i, 6] == 1 and m.tolist() == mets[k][i].tolist()
+        assert np.array_equal(b.read_frame(i), o.frame())
+    a.close()
+    b.close()
+
+
+def _host_policy(dec, seed, base, step):
+    from oracle.cim_oracle import policy_random
+
+    B = dec.shape[0]
+    acts = np.zeros((B, 2, 4), np.int32)
+    for i in range(B):
+        acts[i, 0] = policy_random(dec[i], seed, i + base, step)
+    return acts
+
+
+@pytest.mark.parametrize("topology,ticks,B", [("toy.4p_ssdd_l0.0", 150, 64), ("toy.4p_ssdd_l0.8", 90, 40),
+                                               ("global_trade.22p_l0.8", 30, 12)])
+def test_session_matches_launch_per_step(topology, ticks, B, monkeypatch):
+    """maro_cim_step through the resident session == through one launch per call: decisions, metrics, frames, rings;
+    with action lists, None actions, subset (dict) stepping and interleaved inspection calls (which end the session)."""
+    topo = _topo(topology, ticks)
+    monkeypatch.setenv("MARO_B200_SESSION", "0")
+    ref = _batch(topo, B, max_actions=2)
+    monkeypatch.setenv("MARO_B200_SESSION", "1")
+    ses = _batch(topo, B, max_actions=2)
+    rng = np.random.default_rng(3)
+    d0, m0 = (x.copy() for x in ref.step(None))
+    d1, m1 = (x.copy() for x in ses.step(None))
+    step = 0
+    while True:
+        assert np.array_equal(d0, d1) and np.array_equal(m0, m1), step
+        if step % 4 != 2 and (d0[:, 6] == 2).all():  # (a step without a mask: every row is a real answer)
+            break
+        acts = _host_policy(d0, 4, 0, step)
+        nact = np.ones(B, np.int32)
+        if step % 5 == 2:  # action lists: LOAD part then a DISCHARGE of 0; every 5th step a few None actions
+            acts[:, 1] = acts[:, 0]
+            acts[:, 1, 2] = 0
+            acts[:, 1, 3] = 1
+            nact[:] = 2
+            nact[::7] = 0
+        active = None
+        if step % 4 == 1:
+            active = (rng.random(B) < 0.7).astype(np.uint8)
+        d0, m0 = (x.copy() for x in ref.step(acts, nact, active))
+        d1, m1 = (x.copy() for x in ses.step(acts, nact, active))
+        if step % 9 == 4:  # inspection in the middle of a session: the kernel writes back, the next step relaunches
+            assert np.array_equal(ref.ticks(), ses.ticks())
+            assert np.array_equal(ref.read_frame(B - 1), ses.read_frame(B - 1))
+        step += 1
+        assert step < 100000
+    assert np.array_equal(ref.counters(), ses.counters())
+    for i in (0, B - 1):
+        assert np.array_equal(ref.read_frame(i), ses.read_frame(i))
+        assert np.array_equal(ref.snapshot_frames(i), ses.snapshot_frames(i))
+        f = int(ref.snapshot_frames(i)[-1])
+        assert np.array_equal(ref.snapshot_row(f, i), ses.snapshot_row(f, i))
+    # a finished env keeps answering FINISHED through the session as well
+    assert (ses.step(None)[0][:, 6] == 2).all()
+    ref.close()
+    ses.close()
+
+
+def test_session_survives_idle_timeout_and_reset(monkeypatch):
+    """The resident kernel leaves after MARO_B200_IDLE_US without a command; the next call relaunches it.  Reset in the
+    middle of a session; bad actions are reported per replica."""
+    from oracle.cim_oracle import CimOracle, policy_random
+
+    monkeypatch.setenv("MARO_B200_IDLE_US", "50")
+    topo = _topo("toy.4p_ssdd_l0.0", 80)
+    B = 32
+    env = _batch(topo, B)
+    pa, pn, pact, pd, pm = env.pinned()
+    for episode in range(2):
+        o = CimOracle(topo)
+        env.step_pinned(use_actions=False)
+        st, d, m = o.step(None)
+        step = 0
+        while st == 0:
+            assert d[:7].tolist() == pd[3, :7].tolist() and m.tolist() == pm[3].tolist(), (episode, step)
+            for i in range(B):
+                pa[i, 0] = policy_random(pd[i], 9, i, step)
+            a3 = pa[3].copy()
+            if step in (5, 6, 17):
+                time.sleep(0.003)  # far beyond the idle limit: the kernel has left
+            env.step_pinned()
+            st, d, m = o.step(a3)
+            step += 1
+        assert st == 1 and pd[3, 6] == 1 and m.tolist() == pm[3].tolist()
+        assert np.array_equal(env.read_frame(3), o.frame())
+        env.reset()
+    # bad action on one replica only
+    env.step_pinned(use_actions=False)
+    pa[:, 0] = 0
+    pa[:, 0, 0] = pd[:, 2]
+    pa[:, 0, 1] = pd[:, 1]
+    pa[7, 0, 2] = 10 ** 7
+    env.step_pinned()
+    assert pd[7, 6] == -1 and (np.delete(pd[:, 6], 7) == 0).all()
+    pa[:, 0, 2] = 0
+    pn[:] = 1
+    pn[5] = 2  # more actions than the handle's rows hold
+    env.step_pinned(use_n_actions=True)
+    assert pd[5, 6] == -1 and pd[7, 6] == 2
+    env.close()
+
+
+def test_too_many_actions_is_a_bad_action_without_session(monkeypatch):
+    monkeypatch.setenv("MARO_B200_SESSION", "0")
+    topo = _topo("toy.4p_ssdd_l0.0", 40)
+    env = _batch(topo, 4)
+    dec, _ = env.step(None)
+    acts = np.zeros((4, 1, 4), np.int32)
+    acts[:, 0, 0] = dec[:, 2]
+    acts[:, 0, 1] = dec[:, 1]
+    dec, _ = env.step(acts, np.asarray([1, 2, 1, 0], np.int32))
+    assert dec[:, 6].tolist() == [0, -1, 0, 0]
+    env.close()
+
+
+def test_async_submit_wait_pipelines_sub_batches():
+    """maro_cim_submit_pinned / maro_cim_wait_pinned: two halves of the batch advance independently (one is always a
+    step ahead of the other); both follow the oracle."""
+    from oracle.cim_oracle import CimOracle, policy_random
+
+    topo = _topo("toy.4p_ssdd_l0.0", 70)
+    B = 64
+    env = _batch(topo, B)
+    g = env.pinned_granularity()
+    assert g > 0 and B % g == 0
+    half = (B // g // 2) * g
+    ranges = [(0, half), (half, B - half)]
+    pa, pn, pact, pd, pm = env.pinned()
+    probes = [1, half + 2]
+    oracles = [CimOracle(topo) for _ in probes]
+    outs = [o.step(None) for o in oracles]
+    steps = [0, 0]
+    for f, c in ranges:
+        env.submit_pinned(f, c, use_actions=False)
+    env.wait_pinned(*ranges[0])
+    live = [True, True]
+    while any(live):
+        for k, (f, c) in enumerate(ranges):
+            if not live[k]:
+                continue
+            env.wait_pinned(f, c)
+            st, d, m = outs[k]
+            i = probes[k]
+            assert d[:7].tolist() == pd[i, :7].tolist() and m.tolist() == pm[i].tolist(), (k, steps[k])
+            if st != 0:
+                assert pd[i, 6] == 1
+                live[k] = False
+                continue
+            for r in range(f, f + c):
+                pa[r, 0] = policy_random(pd[r], 3, r, steps[k])
+            outs[k] = oracles[k].step(pa[i].copy())
+            env.submit_pinned(f, c)
+            steps[k] += 1
+    for k, i in enumerate(probes):
+        assert np.array_equal(env.read_frame(i), oracles[k].frame())
+    env.close()

@@ -67,3 +67,79 @@ void agent_best_fit(const int32_t* dec, int32_t* act, int n, int max_actions, in
         else { a[0] = d[1]; a[1] = 0; a[2] = best; a[3] = 0; }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * End-to-end host loop of the CIM bench (user code on top of the C ABI, include/maro_b200.h): the batch is cut into
+ * `n_sub` contiguous sub-batches; for each one the loop waits for its decision rows, runs the agent on them and submits
+ * the actions (maro_cim_wait_pinned / maro_cim_submit_pinned), so the agent's work on one sub-batch overlaps the
+ * device's work and the PCIe latency of the others.  n_sub = 1 is the plain lock-step loop.  Episodes restart
+ * (maro_cim_reset with a mask) when every replica of a sub-batch reports DONE.
+ * `dec` / `act` / `mask` are the library's pinned buffers (maro_cim_pinned_buffers). */
+#include <time.h>
+
+typedef int (*submit_fn)(void*, int32_t, int32_t, int32_t, int32_t, int32_t);
+typedef int (*wait_fn)(void*, int32_t, int32_t);
+typedef int (*reset_fn)(void*, const uint8_t*);
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void agent_random_range(const int32_t* dec, int32_t* act, int first, int count, uint32_t seed, uint32_t replica_base) {
+    for (int i = first; i < first + count; i++) {
+        const int32_t* d = dec + 8 * i;
+        uint32_t h1 = hash_u32(seed ^ hash_u32((uint32_t)(i + replica_base) * 0x9e3779b9u + (uint32_t)d[7] * 0x85ebca6bu + 0x1234567u));
+        uint32_t h2 = hash_u32(h1 + 0x68bc21ebu);
+        int load = d[3], dis = d[4];
+        int to_discharge = dis > 0 && (h1 & 1u);
+        int scope = to_discharge ? dis : load;
+        int32_t* a = act + (int64_t)i * 4;
+        a[0] = d[2]; a[1] = d[1];
+        a[2] = scope > 0 ? (int32_t)(h2 % (uint32_t)(scope + 1)) : 0;
+        a[3] = to_discharge;
+    }
+}
+
+/* returns 0 on success; out[0] = seconds of the timed loop, out[1] = seconds inside the agent, out[2] = resets */
+int e2e_loop_cim(void* env, void* submit_p, void* wait_p, void* reset_p, const int32_t* dec, int32_t* act, uint8_t* mask,
+                 int B, int gran, int n_sub, int n_steps, uint32_t seed, uint32_t replica_base, double* out) {
+    submit_fn submit = (submit_fn)submit_p;
+    wait_fn wait = (wait_fn)wait_p;
+    reset_fn reset = (reset_fn)reset_p;
+    int first[65], n = 0;
+    if (n_sub < 1) n_sub = 1;
+    if (n_sub > 64) n_sub = 64;
+    int blocks = (B + gran - 1) / gran, per = (blocks + n_sub - 1) / n_sub;
+    for (int b = 0; b < blocks; b += per) first[n++] = b * gran;
+    first[n] = B;
+    double t_agent = 0.0, resets = 0.0;
+    const double t0 = now_s();
+    for (int k = 0; k < n; k++)  /* generator start: the first step of an episode takes no action */
+        if (submit(env, first[k], first[k + 1] - first[k], 0, 0, 0)) return 1;
+    for (int step = 0; step < n_steps; step++) {
+        for (int k = 0; k < n; k++) {
+            const int f = first[k], c = first[k + 1] - first[k];
+            if (wait(env, f, c)) return 1;
+            if (step == n_steps - 1) continue;
+            int done = 1;
+            for (int i = f; i < f + c; i++) done &= dec[8 * i + 6] != 0;
+            if (done) {  /* Env.reset for this sub-batch, then the episode's first step */
+                for (int i = 0; i < B; i++) mask[i] = (uint8_t)(i >= f && i < f + c);
+                if (reset(env, mask)) return 1;
+                resets += 1.0;
+                if (submit(env, f, c, 0, 0, 0)) return 1;
+                continue;
+            }
+            const double ta = now_s();
+            agent_random_range(dec, act, f, c, seed, replica_base);
+            t_agent += now_s() - ta;
+            if (submit(env, f, c, 1, 0, 0)) return 1;
+        }
+    }
+    out[0] = now_s() - t0;
+    out[1] = t_agent;
+    out[2] = resets;
+    return 0;
+}
