@@ -10,7 +10,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmaro_b200.so")
+LIB_PATH = os.environ.get("MARO_B200_LIB") or os.path.join(_HERE, "libmaro_b200.so")  # (override: A/B builds of tools/build_variant.py)
 _lib = None
 
 #: every symbol ``include/maro_b200.h`` declares

@@ -149,6 +149,14 @@ static cudaError_t bike_launch(MaroBikeEnv* e, const BikeArgs& a) {
     }
 }
 
+
+// inside *_create, after the handle exists: a failing CUDA call frees it before returning
+#define CKD(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) { maro_bike_destroy(e); return fail(std::string(#call) + ": " + cudaGetErrorString(e__)); } \
+    } while (0)
+extern "C" int maro_bike_destroy(MaroBikeEnv* e);
 extern "C" {
 
 int maro_bike_destroy(MaroBikeEnv* e) {
@@ -195,7 +203,7 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
     for (int a = 0; a < BA_COUNT; a++) e->attrs[0].push_back({an[a], a * s.S, 1, 0, s.S});
     e->attrs[1].push_back({"trips_adj", BA_COUNT * s.S, s.S * s.S, 0, 1});
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, e->device));
+    CKD(cudaGetDeviceProperties(&prop, e->device));
     e->lanes = bike_lanes_per_replica(s);
     const int gpw = 32 / e->lanes;
     const size_t per_warp = (size_t)s.SW * 4 * gpw;
@@ -228,9 +236,9 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
     e->off_tick = s.FWp + BC_TICK; e->off_counters = s.FWp + BC_NSTEPS_LO;
     e->dec_words = s.DW; e->max_actions = s.max_actions;
     if (common_alloc(e)) { maro_bike_destroy(e); return 1; }
-    CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
-    CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&e->d_rng, (size_t)e->B * s.rng_words * 4));
+    CKD(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
+    CKD(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
+    CKD(cudaMalloc(&e->d_rng, (size_t)e->B * s.rng_words * 4));
     *out = e;
     int rc = maro_bike_reset(e, nullptr);
     if (rc) { maro_bike_destroy(e); *out = nullptr; return rc; }

@@ -243,13 +243,9 @@ struct Replica {
 MARO_DEV int32_t& PA(const CimShape& s, const Replica& r, int attr, int p) { return r.f[attr * s.P + p]; }
 MARO_DEV int32_t& VA(const CimShape& s, const Replica& r, int attr, int v) { return r.f[s.o_vs + attr * s.V + v]; }
 
-MARO_DEV int64_t ctrl_get64(const Replica& r, int lo) {
-    return (int64_t)(((uint64_t)(uint32_t)r.c[lo + 1] << 32) | (uint32_t)r.c[lo]);
-}
-MARO_DEV void ctrl_set64(const Replica& r, int lo, int64_t v) {
-    r.c[lo] = (int32_t)(uint32_t)((uint64_t)v & 0xffffffffu);
-    r.c[lo + 1] = (int32_t)(uint32_t)((uint64_t)v >> 32);
-}
+// 64-bit control words sit on even word indices of a 16-byte aligned block: one 64-bit access each
+MARO_DEV int64_t ctrl_get64(const Replica& r, int lo) { return *reinterpret_cast<const int64_t*>(r.c + lo); }
+MARO_DEV void ctrl_set64(const Replica& r, int lo, int64_t v) { *reinterpret_cast<int64_t*>(r.c + lo) = v; }
 MARO_DEV void ctrl_add64(const Replica& r, int lo, int64_t d) { ctrl_set64(r, lo, ctrl_get64(r, lo) + d); }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,10 +354,16 @@ MARO_DEV uint16_t* q_next(const CimShape& s, const Replica& r) { return reinterp
 MARO_DEV uint16_t* q_free(const CimShape& s, const Replica& r) { return q_next(s, r) + s.QN; }
 
 template <int G>
-MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, bool want, int tick, int w0, int qty) {
+MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, bool want, int now, int tick, int w0, int qty) {
     want = want && tick < s.max_tick && tick >= 0;  // later ticks are never visited by the Env (event_buffer.py:190)
     uint32_t bal = g.ballot(want);
     if (bal == 0) return;
+    if (g.ballot(want && tick - now >= s.QH)) {  // beyond the calendar horizon the bucket would alias: never silently
+        g.sync();
+        if (g.lane == 0) r.c[C_ERR] = -2;
+        g.sync();
+        return;
+    }
     int n = maro_popc(bal);
     int rank = maro_popc(bal & ((1u << g.lane) - 1u));
     int top = r.c[C_FREE_TOP];
@@ -520,7 +522,7 @@ MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, in
         g.sync();
         if (g.lane == 0) { r.c[C_FREE_TOP] = top + n; r.c[C_Q_COUNT] -= n; }
         g.sync();
-        if (db) group_push(s, g, r, is_dis && buf > 0, tick + buf, DE_RETURN_EMPTY | (c << 8), qty);
+        if (db) group_push(s, g, r, is_dis && buf > 0, tick, tick + buf, DE_RETURN_EMPTY | (c << 8), qty);
         nev += n;
     }
     g.sync();
@@ -580,7 +582,7 @@ MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, in
             atomic_add(&r.f[s.o_fop + src * s.P + dst], exec);
         }
         nev += nv + maro_popc(g.ballot(imm));
-        group_push(s, g, r, valid && buf > 0, tick + buf, DE_RETURN_FULL | (src << 8) | (dst << 16), exec);
+        group_push(s, g, r, valid && buf > 0, tick, tick + buf, DE_RETURN_FULL | (src << 8) | (dst << 16), exec);
     }
     return nev;
 }
@@ -781,7 +783,8 @@ MARO_DEV void run_arrival(const CimShape& s, const Grp<G>& g, const Replica& r, 
         int n = rl > s.fut ? rl : s.fut;
         for (int b0 = 0; b0 < n; b0 += G) {  // n <= G in every shipped topology; loop keeps it general
             int k = b0 + g.lane;
-            int pos = (pos0 + k) % rl;
+            int pos = pos0 + k;  // pos0 < rl and k < max(rl, fut): a few conditional subtractions instead of a division
+            while (pos >= rl) pos -= rl;
             int leg = k < n ? TBL_I(r, s.t_vessel_leg, lbase + pos) : 0;
             int cum = scan_incl(g, leg);
             int arr = arrival0 + cum;
@@ -820,7 +823,7 @@ MARO_DEV void run_arrival(const CimShape& s, const Grp<G>& g, const Replica& r, 
             r.f[s.o_fop + port * s.P + next_port] = pending - loaded;
             r.f[s.o_fov + v * s.P + next_port] += loaded;
         }
-        group_push(s, g, r, loaded > 0, valid ? TBL_I(r, s.t_stop_arrival, sb + si) : 0,
+        group_push(s, g, r, loaded > 0, tick, valid ? TBL_I(r, s.t_stop_arrival, sb + si) : 0,
                    DE_DISCHARGE_FULL | (v << 8) | (port << 16) | (next_port << 24), loaded);
         int chunk = g.shfl(hi, G - 1);
         total_loaded += chunk;
@@ -891,27 +894,52 @@ MARO_DEV bool on_actions(const CimShape& s, const Grp<G>& g, const Replica& r, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Snapshot: copy the live frame into ring row (frame_index % ring_rows) with 128-bit coalesced stores
+// Snapshot: copy the live frame into ring row (frame_index % ring_rows)
 // (FrameBase.take_snapshot -> NPSnapshotList.take_snapshot, np_backend.pyx:481-518).
+// On the device the row leaves shared memory as ONE TMA bulk store (cp.async.bulk shared -> global) issued by the leader
+// lane; snapshot_wait() must run before the frame is modified again (the engine has then read the source: ~200 cycles
+// for a 900-byte row, measured with tools/microbench/tma_s2g_latency.cu, against ~850 for an 8-lane 128-bit copy loop).
 // ------------------------------------------------------------------------------------------------
+#ifndef MARO_HOST_EMULATION
+__device__ __forceinline__ void snapshot_wait_lane() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk stores of this thread have been written (not merely read): once, before the kernel ends (the full wait
+// compiles to DEPBAR + CCTL.IVALL, an L1 invalidation — far too expensive per snapshot)
+__device__ __forceinline__ void snapshot_drain_lane() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
+template <int G>
+MARO_DEV void snapshot_wait(const Grp<G>& g) {
+#ifndef MARO_HOST_EMULATION
+    if (g.lane == 0) snapshot_wait_lane();
+#endif
+    g.sync();
+}
+
 template <int G>
 MARO_DEV void take_snapshot(const CimShape& s, const Grp<G>& g, const Replica& r, int frame_index) {
-    g.sync();
     int row = frame_index < s.ring_rows ? frame_index : frame_index % s.ring_rows;
     int32_t* dst = r.snap + (int64_t)row * s.FWp;
 #ifdef MARO_HOST_EMULATION
+    g.sync();
     LANE_LOOP(i, s.FWp) dst[i] = r.f[i];
 #else
-    const int4* src4 = reinterpret_cast<const int4*>(r.f);
-    int4* dst4 = reinterpret_cast<int4*>(dst);
-    LANE_LOOP(i, s.FWp / 4) dst4[i] = src4[i];
+    // every lane's generic-proxy writes to the frame become visible to the async proxy, then the leader issues the copy.
+    // Bulk stores of one thread are carried out in issue order (tools/microbench/tma_s2g_cold.cu: 2.4 M back-to-back pairs
+    // to one row, never reordered), so the several snapshots of a decision tick (they share a ring row) need no full
+    // wait_group between them — which would cost a CCTL.IVALL (L1 invalidation) each time.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    g.sync();
+    if (g.lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(r.f)),
+                     "r"((uint32_t)s.FWp * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
 #endif
     if (g.lane == 0) {
         r.snap_frame[row] = frame_index;
         r.c[C_LAST_FRAME] = frame_index;
         ctrl_add64(r, C_NSNAPS_LO, 1);
     }
-    g.sync();
 }
 
 // Output rows are written with 128-bit / 64-bit stores (they may live in mapped host memory: one PCIe write each).
@@ -1066,6 +1094,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             g.sync();
             LANE_DIM(p, s.P) PA(s, r, PA_ACC_FULFILLMENT, p) = PA(s, r, PA_ACC_BOOKING, p) - PA(s, r, PA_ACC_SHORTAGE, p);
             take_snapshot(s, g, r, frame_index_of(s, tick));
+            snapshot_wait(g);  // the row has left the frame: the per-tick resets may overwrite it
             LANE_DIM(p, s.P) {
                 PA(s, r, PA_SHORTAGE, p) = 0;
                 PA(s, r, PA_BOOKING, p) = 0;
@@ -1075,7 +1104,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             g.sync();
         }
         if (tick + 1 == s.max_tick) {
-            if (!s.res_is_one && (tick + 1) % s.resolution != 0) take_snapshot(s, g, r, frame_index_of(s, tick));  // core.py:376-378
+            if (!s.res_is_one && (tick + 1) % s.resolution != 0) { take_snapshot(s, g, r, frame_index_of(s, tick)); snapshot_wait(g); }  // core.py:376-378
             state = ST_DONE;
             status = 1;
             od[0] = tick;
@@ -1110,7 +1139,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
         r.c[C_EP_STEP] += 1;
         store_out(dec, met, od, bk, sh, ctrl_get64(r, C_OPNUM_LO));
     }
-    g.sync();
+    snapshot_wait(g);  // the pre-decision snapshot (if any) has been read: the caller may touch the frame again
 }
 
 // ------------------------------------------------------------------------------------------------

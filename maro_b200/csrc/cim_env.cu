@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
         }
         replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
         // ---- write back (128-bit coalesced) what this step could have changed
+        if (g.lane == 0) snapshot_drain_lane();
         const int4* src4 = reinterpret_cast<const int4*>(st);
         int4* dst4 = reinterpret_cast<int4*>(gstate);
         const int n4 = (int)(bytes >> 4);
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
         if (g.lane == 0) ra.seq_state[rep] = expect - 1u;
     }
     // ---- write back the block + the light-step hint of the per-step kernel
+    if (g.lane == 0) snapshot_drain_lane();
     g.sync();
     const int4* src4 = reinterpret_cast<const int4*>(st);
     int4* dst4 = reinterpret_cast<int4*>(gstate);
@@ -343,6 +345,7 @@ struct MaroCimEnv : EnvCommon {
     int res_threads = 0, res_grid = 0, res_spread = 0;
     size_t res_smem = 0;
     bool session_ok = false, session_live = false;  // session_ok: the whole grid is co-resident (required to spin-wait)
+    int buf_full_cap = 1, buf_empty_cap = 1;         // buffer ticks the event pool was sized for (set_topology re-validation)
     int res_groups = 0;                              // replicas per CTA of the resident kernel
     std::vector<uint32_t> cta_seq;                   // per CTA: last step completed (the kernel's seq_state mirrors it)
     std::vector<uint8_t> cta_pending;                // per CTA: a step has been sent and not collected yet
@@ -753,6 +756,12 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
         delete e;
         return fail("maro_cim_create: inconsistent topology tables / durations must be positive");
     }
+    for (int k = 0; k < n_topos; k++) {
+        const CimTopoNeeds n = topology_needs(topos[k]);
+        e->buf_full_cap = std::max(e->buf_full_cap, n.buf_full);
+        e->buf_empty_cap = std::max(e->buf_empty_cap, n.buf_empty);
+    }
+    if (cfg->queue_capacity > 0) e->buf_full_cap = e->buf_empty_cap = 1 << 30;  // explicit pool size: the caller's responsibility
     const char* ln = getenv("MARO_B200_LANES");  // tuning override: lanes per replica (8 / 16 / 32, >= the topology's minimum)
     const int cfg_lanes = ln ? std::max(atoi(ln), lanes_per_replica(s)) : 0;
     register_attrs(e);
@@ -836,6 +845,17 @@ int maro_cim_set_topology(MaroCimEnv* e, int32_t index, const MaroCimTopology* t
         return fail("maro_cim_set_topology: shape differs from the handle's");
     if (topo->stop_offset[topo->n_vessels] > e->max_stops || topo->target_offset[topo->n_ports] > e->max_targets)
         return fail("maro_cim_set_topology: more stops/targets than the handle was sized for");
+    {   // the handle's calendar-queue horizon, default queue capacity and RNG paths were sized from the create-time
+        // topologies: a replacement has to fit them (an event beyond the horizon would alias into an earlier bucket)
+        const CimTopoNeeds n = topology_needs(*topo);
+        if (n.max_delay + 1 > e->s.QH)
+            return fail("maro_cim_set_topology: the new instance needs an event horizon of " + std::to_string(n.max_delay + 1) +
+                        " ticks, the handle was created with " + std::to_string(e->s.QH) + " (create the handle with this instance among its topologies)");
+        if ((n.order_noise && !e->s.order_noise) || (n.buffer_noise && !e->s.buffer_noise))
+            return fail("maro_cim_set_topology: the new instance draws order / buffer noise, the handle was created without those streams");
+        if (n.buf_full > e->buf_full_cap || n.buf_empty > e->buf_empty_cap)
+            return fail("maro_cim_set_topology: longer container buffer times than the handle's event pool was sized for");
+    }
     CimShape probe = e->s;  // rebuild with identical padding; offsets must come out the same
     if ((e->s.order_table && count_distinct_orders(*topo) > e->max_distinct) ||
         build_blob(*topo, probe, blob, e->max_stops, e->max_targets, true, e->max_distinct) || probe.table_words != e->s.table_words ||

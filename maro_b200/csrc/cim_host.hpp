@@ -195,6 +195,32 @@ inline int check_same_shape(const MaroCimTopology& a, const MaroCimTopology& b) 
 
 
 // Fill `s` (layout, queue sizing) and serialise every topology into `tables`.  Returns non-zero on mismatch.
+// What one topology instance asks of a handle's sizing: the longest event delay (calendar-queue horizon), the buffer
+// ticks behind the default queue capacity, and which MT19937 streams it draws from.
+struct CimTopoNeeds { int max_delay = 2, buf_full = 1, buf_empty = 1, max_stops = 0; bool order_noise = false, buffer_noise = false; };
+inline CimTopoNeeds topology_needs(const MaroCimTopology& t) {
+    CimTopoNeeds n;
+    const int P = t.n_ports, V = t.n_vessels;
+    n.max_stops = t.stop_offset[V];
+    for (int p = 0; p < P; p++) {
+        if (t.source_noise[p] != 0) n.order_noise = true;
+        if (t.full_return_noise[p] != 0 || t.empty_return_noise[p] != 0) n.buffer_noise = true;
+        n.buf_full = std::max(n.buf_full, (int)ceil(t.full_return_base[p] + fabs(t.full_return_noise[p])));
+        n.buf_empty = std::max(n.buf_empty, (int)ceil(t.empty_return_base[p] + fabs(t.empty_return_noise[p])));
+    }
+    for (int i = 0; i < t.target_offset[P]; i++)
+        if (t.target_noise[i] != 0) n.order_noise = true;
+    for (int v = 0; v < V; v++) {
+        int rl = t.route_offset[t.vessel_route[v] + 1] - t.route_offset[t.vessel_route[v]];
+        for (int i = t.stop_offset[v]; i < t.stop_offset[v + 1]; i++) {
+            int j = std::min(i + rl, t.stop_offset[v + 1] - 1);
+            n.max_delay = std::max(n.max_delay, t.stop_arrival[j] - t.stop_arrival[i] + 1);
+        }
+    }
+    n.max_delay = std::max(n.max_delay, std::max(n.buf_full, n.buf_empty) + 1);
+    return n;
+}
+
 inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, const MaroCimConfig* cfg, CimShape& s,
                                     std::vector<int32_t>& tables, int& max_stops_out, int& max_targets_out,
                                     int& max_distinct_out) {
@@ -215,25 +241,17 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
     for (int r = 0; r < t0.n_routes; r++) max_rl = std::max(max_rl, t0.route_offset[r + 1] - t0.route_offset[r]);
     s.max_route_len = max_rl;
     for (int k = 0; k < n_topos; k++) {
-        const MaroCimTopology& t = topos[k];
-        max_stops = std::max(max_stops, t.stop_offset[V]);
-        for (int p = 0; p < P; p++) {
-            if (t.source_noise[p] != 0) s.order_noise = 1;
-            if (t.full_return_noise[p] != 0 || t.empty_return_noise[p] != 0) s.buffer_noise = 1;
-            buf_full = std::max(buf_full, (int)ceil(t.full_return_base[p] + fabs(t.full_return_noise[p])));
-            buf_empty = std::max(buf_empty, (int)ceil(t.empty_return_base[p] + fabs(t.empty_return_noise[p])));
-        }
-        for (int i = 0; i < t.target_offset[P]; i++)
-            if (t.target_noise[i] != 0) s.order_noise = 1;
-        for (int v = 0; v < V; v++) {
-            int rl = t.route_offset[t.vessel_route[v] + 1] - t.route_offset[t.vessel_route[v]];
-            for (int i = t.stop_offset[v]; i < t.stop_offset[v + 1]; i++) {
-                int j = std::min(i + rl, t.stop_offset[v + 1] - 1);
-                max_delay = std::max(max_delay, t.stop_arrival[j] - t.stop_arrival[i] + 1);
-            }
-        }
+        const CimTopoNeeds n = topology_needs(topos[k]);
+        max_stops = std::max(max_stops, n.max_stops);
+        if (n.order_noise) s.order_noise = 1;
+        if (n.buffer_noise) s.buffer_noise = 1;
+        buf_full = std::max(buf_full, n.buf_full);
+        buf_empty = std::max(buf_empty, n.buf_empty);
+        max_delay = std::max(max_delay, n.max_delay);
     }
-    max_delay = std::max(max_delay, std::max(buf_full, buf_empty) + 1);
+    // re-seeded instances of the same config (Env.reset(keep_seed=False), set_seed) draw other vessel speeds / parking
+    // times: 25 % head-room on the horizon; maro_cim_set_topology re-validates every replacement against it
+    max_delay += max_delay / 4 + 8;
     // frame layout (DESIGN.md "Frame layout")
     s.o_vs = 12 * P;
     s.o_past = s.o_vs + 10 * V;

@@ -99,6 +99,14 @@ static cudaError_t vm_launch(MaroVmEnv* e, const VmArgs& a) {
     return cudaGetLastError();
 }
 
+
+// inside *_create, after the handle exists: a failing CUDA call frees it before returning
+#define CKD(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) { maro_vm_destroy(e); return fail(std::string(#call) + ": " + cudaGetErrorString(e__)); } \
+    } while (0)
+extern "C" int maro_vm_destroy(MaroVmEnv* e);
 extern "C" {
 
 int maro_vm_destroy(MaroVmEnv* e) {
@@ -157,7 +165,7 @@ int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmE
     static const char* gn[] = {"empty_machine_num", "id", "total_machine_num"};
     for (int a = 0; a < 3; a++) e->attrs[5].push_back({gn[a], s.o_region + a * s.RG, 1, 0, s.RG});
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, e->device));
+    CKD(cudaGetDeviceProperties(&prop, e->device));
     int w = 4;
     while (w > 1 && (e->B + w - 1) / w < prop.multiProcessorCount) w >>= 1;
     // per-warp scratch of 2 N doubles: fewer warps per CTA for big clusters, then the opt-in shared-memory carve-out
@@ -166,15 +174,15 @@ int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmE
     e->smem_bytes = (size_t)w * 2 * s.N * sizeof(double);
     if (e->smem_bytes > 48 * 1024) {
         if (e->smem_bytes > prop.sharedMemPerBlockOptin) { delete e; return fail("maro_vm_create: too many PMs for the per-warp scratch"); }
-        CK(cudaFuncSetAttribute(vm_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+        CKD(cudaFuncSetAttribute(vm_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     }
     e->grid = std::min((e->B + w - 1) / w, prop.multiProcessorCount * (48 / w));
     e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
     e->off_tick = s.FWp + VC_TICK; e->off_counters = s.FWp + VC_NSTEPS;
     e->dec_words = s.DW; e->max_actions = s.max_actions; e->met_words = MARO_VM_METRIC_WORDS;
     if (common_alloc(e)) { maro_vm_destroy(e); return 1; }
-    CK(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
-    CK(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
+    CKD(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
+    CKD(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
     *out = e;
     int rc = vm_reset_impl(e, nullptr, 1);
     if (rc) { maro_vm_destroy(e); *out = nullptr; return rc; }

@@ -16,8 +16,12 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    dis = ""  # one cubin per translation unit: take the one that holds the kernel
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+        if any(ln.startswith("//---") and ".text." in ln and kern in ln for ln in d.splitlines()):
+            dis = d
+            break
     # address -> (file, line) for the requested kernel
     amap, cur, infn = {}, None, False
     for ln in dis.splitlines():
