@@ -23,7 +23,8 @@ class CimDeviceRollout:
         self.shaper = shaper or CimShaper(batch)
         self.store_states = store_states
         B = batch.n_replicas
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device("cuda", batch.device)
+        batch.set_stream(torch.cuda.current_stream(dev).cuda_stream)  # step kernels and torch ops share one stream
         self._dec = torch.zeros((B, 8), dtype=torch.int32, device=dev)
         self._met = torch.zeros((B, 3), dtype=torch.int64, device=dev)
 

@@ -32,7 +32,10 @@ class CimShaper:
         self.state_dim = batch.rl_state_dim(self.look_back, len(self._pa), len(self._va))
         self.time_window = int(time_window)
         self.fulfillment_factor, self.shortage_factor = float(fulfillment_factor), float(shortage_factor)
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device("cuda", batch.device)
+        # the shaping kernels and the caller's torch ops touch the same tensors: run the library on torch's current stream
+        # of the batch's device (its own non-blocking stream would race with them)
+        batch.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         # decay_list = [time_decay ** i ...] evaluated on the host exactly like the example (env_sampler.py:75)
         self._decay = torch.tensor(np.asarray([time_decay ** i for i in range(self.time_window)], np.float64), device=dev)
         B = batch.n_replicas

@@ -35,6 +35,16 @@ def make_metrics(row) -> DocableDict:
                                      "operation_number": int(row[2])})
 
 
+def parse_query_key(key: slice):
+    """``[ticks : nodes : attrs]`` -> (ticks, nodes, attrs) lists; empty = "all", attrs None = no query (frame.pyx:754-801)"""
+    ticks = [] if key.start is None else (list(key.start) if isinstance(key.start, (tuple, list, np.ndarray)) else [key.start])
+    nodes = [] if key.stop is None else (list(key.stop) if isinstance(key.stop, (tuple, list, np.ndarray)) else [key.stop])
+    if key.step is None:
+        return ticks, nodes, None
+    attrs = list(key.step) if isinstance(key.step, (tuple, list)) else [key.step]
+    return ticks, nodes, attrs
+
+
 class SnapshotNode:
     """``env.snapshot_list["ports"][ticks:nodes:attrs]`` (frame.pyx:734-801) -> 1-D float64 (np_backend.pyx:520-549)."""
 
@@ -45,11 +55,9 @@ class SnapshotNode:
         return self._n
 
     def __getitem__(self, key: slice):
-        ticks = [] if key.start is None else (list(key.start) if isinstance(key.start, (tuple, list)) else [key.start])
-        nodes = [] if key.stop is None else (list(key.stop) if isinstance(key.stop, (tuple, list)) else [key.stop])
-        if key.step is None:
+        ticks, nodes, attrs = parse_query_key(key)
+        if attrs is None:
             return None
-        attrs = list(key.step) if isinstance(key.step, (tuple, list)) else [key.step]
         return self._owner._query(self._node, ticks, nodes, attrs)
 
 
@@ -244,7 +252,16 @@ class Env:
             seed = next_topology_seed(self._topo)
         if seed is not None:
             self._topo = build_topology(self._config, self._start_tick + self._durations, seed=seed)
-            self._batch.set_topology(0, self._topo)
+            try:
+                self._batch.set_topology(0, self._topo)
+            except RuntimeError:
+                # the new instance needs a longer event horizon / larger pool than the handle was sized for
+                # (maro_cim_set_topology refuses instead of aliasing buckets): a fresh handle, like the reference's
+                # reset rebuilds its data container (cim_data_container_helpers.py:56-70)
+                self._batch.close()
+                self._batch = CimBatch(self._topo, 1, self._start_tick, self._snapshot_resolution, self._max_snapshots,
+                                       device=self._device, max_actions=8)
+                self._snapshots = SnapshotList(self._batch, 0)
             self._pending_seed = None
         self._batch.reset()
         self._tick = self._start_tick

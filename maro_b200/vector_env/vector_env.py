@@ -13,8 +13,8 @@ import numpy as np
 from .. import _abi
 from ..batch import BikeBatch, CimBatch, VmBatch
 from ..scenarios.cim.common import ActionScope, DecisionEvent, encode_action
-from ..scenarios.cim.topology import build_topology, load_config
-from ..simulator.env import DecisionMode, SnapshotList, make_metrics
+from ..scenarios.cim.topology import build_topology, load_config, next_topology_seed
+from ..simulator.env import DecisionMode, SnapshotList, make_metrics, parse_query_key
 
 
 class VectorEnv:
@@ -66,6 +66,8 @@ class VectorEnv:
             uniq = sorted(set(seeds))
             topos = [build_topology(conf, start_tick + durations, seed=s) for s in uniq]
             rt = np.asarray([uniq.index(s) for s in seeds], np.int32)
+        self._conf, self._max_tick, self._rt = conf, start_tick + durations, rt
+        self._ctor = (batch_num, start_tick, snapshot_resolution, max_snapshots, device)
         self._batch = CimBatch(topos, batch_num, start_tick, snapshot_resolution, max_snapshots, device=device,
                                max_actions=4, replica_topology=rt)
         self._finish_init(batch_num, start_tick)
@@ -186,7 +188,21 @@ class VectorEnv:
         self._done |= (st == _abi.STATUS_DONE) | (st == _abi.STATUS_FINISHED)
         return dec, met, bool(self._done.all())
 
-    def reset(self):
+    def reset(self, keep_seed: bool = False):
+        """Every env process of the reference calls ``env.reset()`` (env_process.py:55-57), i.e. ``keep_seed=False``: each
+        environment draws a new topology seed from its own route_init stream (cim_data_container_helpers.py:56-66).  Here:
+        one re-seeded instance per distinct topology of the batch (envs that shared a seed keep sharing the new one, exactly
+        like identical processes do).  ``keep_seed=True`` replays the same instances."""
+        if self._scenario == "cim" and not keep_seed:
+            new = [build_topology(self._conf, self._max_tick, seed=next_topology_seed(t)) for t in self._batch.topologies]
+            try:
+                for k, t in enumerate(new):
+                    self._batch.set_topology(k, t)
+            except RuntimeError:  # a new instance does not fit the handle's event horizon / pool: fresh handle
+                B, start_tick, res, max_snaps, device = self._ctor
+                self._batch.close()
+                self._batch = CimBatch(new, B, start_tick, res, max_snaps, device=device, max_actions=4, replica_topology=self._rt)
+                self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(B)]
         self._batch.reset()
         self._done[:] = False
         self._ticks[:] = self._start_tick
@@ -207,7 +223,24 @@ class VectorEnv:
             pass
 
     def _query(self, node_name: str, args: slice):
-        return [sl[node_name][args] for sl in self._snapshot_lists]
+        """``env.snapshot_list[node][ticks:nodes:attrs]`` -> one array per env (vector_env.py:177-217 asks every process);
+        here ONE batched device gather + one copy for all envs when the ticks are given."""
+        ticks, nodes, attrs = parse_query_key(args)
+        if attrs is None:
+            return [None] * self._batch_num
+        if len(ticks) == 0:  # "all frames" differs per env (each has its own frame list)
+            return [sl[node_name][args] for sl in self._snapshot_lists]
+        node = self._snapshot_lists[0][node_name]
+        if node is None:
+            return [None] * self._batch_num
+        if len(nodes) == 0:
+            nodes = list(range(len(node)))
+        try:
+            ids = [self._batch.attr_id(node_name, a) for a in attrs]
+        except KeyError:
+            raise KeyError(f"invalid attribute for {node_name}: {attrs}")
+        out = self._batch.query(node_name, ticks, nodes, ids)
+        return [out[i] for i in range(self._batch_num)]
 
     @property
     def batch(self) -> CimBatch:

@@ -17,7 +17,43 @@ if [ ! -d "$REF/maro" ]; then
   echo "build_ref: $REF not present (GPU box) - keeping prebuilt $OUT" >&2
   exit 0
 fi
+# import-time stubs for the networking packages maro.rl's distributed workers import (absent from this image; the
+# single-process rollout / training path the tests drive never touches them)
+write_rl_stubs() {
+  mkdir -p "$OUT/_stubs/zmq/eventloop" "$OUT/_stubs/tornado"
+  cat > "$OUT/_stubs/zmq/__init__.py" <<'PY'
+class _Unavailable:
+    def __init__(self, *a, **k): raise RuntimeError("zmq is not installed in this image (import-time stub)")
+Context = Poller = _Unavailable
+DEALER = ROUTER = PUSH = PULL = POLLIN = IDENTITY = LINGER = 0
+PY
+  cat > "$OUT/_stubs/zmq/asyncio.py" <<'PY'
+from . import Context, Poller  # noqa: F401
+PY
+  : > "$OUT/_stubs/zmq/eventloop/__init__.py"
+  cat > "$OUT/_stubs/zmq/eventloop/zmqstream.py" <<'PY'
+from .. import _Unavailable as ZMQStream  # noqa: F401
+PY
+  : > "$OUT/_stubs/tornado/__init__.py"
+  cat > "$OUT/_stubs/tornado/ioloop.py" <<'PY'
+class IOLoop:
+    def __init__(self, *a, **k): raise RuntimeError("tornado is not installed in this image (import-time stub)")
+PY
+}
+# the reference's example scripts (unmodified; run by tests/test_gpu_shim.py on top of the maro_b200 import shim)
+copy_examples() {
+  mkdir -p "$OUT/examples"
+  for d in hello_world/cim hello_world/citi_bike vector_env cim/rl citi_bike/greedy vm_scheduling/rule_based_algorithm; do
+    [ -d "$REF/examples/$d" ] || continue
+    mkdir -p "$OUT/examples/$d"
+    cp -r "$REF/examples/$d/." "$OUT/examples/$d/"
+  done
+  [ -f "$REF/examples/__init__.py" ] && cp "$REF/examples/__init__.py" "$OUT/examples/" || true
+  [ -f "$REF/examples/cim/__init__.py" ] && cp "$REF/examples/cim/__init__.py" "$OUT/examples/cim/" || true
+}
 if [ -f "$OUT/maro/backends/frame.cpython-312-x86_64-linux-gnu.so" ] && [ -z "${FORCE:-}" ]; then
+  copy_examples
+  write_rl_stubs
   echo "build_ref: $OUT already built"; exit 0
 fi
 TMP="$(mktemp -d /tmp/maro_ref_build.XXXXXX)"
@@ -79,4 +115,6 @@ def distance(a, b):
     h = math.sin((p2 - p1) / 2) ** 2 + math.cos(p1) * math.cos(p2) * math.sin(math.radians(lo2 - lo1) / 2) ** 2
     return _D(2 * 6371.0088 * math.asin(math.sqrt(h)))
 PY
+copy_examples
+write_rl_stubs
 echo "build_ref: built into $OUT"

@@ -1,0 +1,111 @@
+"""TEST INFRASTRUCTURE — runs the reference's own example code, UNMODIFIED, either on the reference itself or on the
+CUDA core through the ``maro`` import shim (maro_b200/shim.py), and prints one JSON summary.  tests/test_gpu_shim.py
+runs it twice (``--mode reference`` / ``--mode shim``) in fresh processes and compares the summaries.
+
+    python tests/run_reference_script.py --mode reference|shim [--emulate] --what hello_cim|hello_vector|rl_cim [--seed K]
+
+The scripts come from oracle/_ref/examples (copied there, unmodified, by oracle/build_ref.sh; git-ignored):
+  hello_cim     examples/hello_world/cim/hello.py          (Env, random agent from the `random` module, two episodes)
+  hello_vector  examples/vector_env/hello.py               (VectorEnv: dict / list stepping, snapshot_list, reset)
+  rl_cim        examples/cim/rl (rl_component_bundle + CIMEnvSampler on maro.rl's AbsEnvSampler): one sample() episode
+                with the bundle's DQN policies, then TrainingManager.record_experiences + train_step
+``--emulate`` (CPU suite) swaps the CUDA batch for the host emulation of the device code (tests/emul_batch.py).
+"""
+import argparse
+import contextlib
+import hashlib
+import io
+import json
+import os
+import random
+import re
+import runpy
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def digest(arrs) -> str:
+    import numpy as np
+
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", required=True, choices=["reference", "shim"])
+    ap.add_argument("--what", required=True, choices=["hello_cim", "hello_vector", "rl_cim"])
+    ap.add_argument("--emulate", action="store_true")
+    ap.add_argument("--seed", type=int, default=20240923)
+    args = ap.parse_args()
+    os.environ["SKIP_DEPLOYMENT"] = "TRUE"
+    sys.path[:0] = [REF, os.path.join(REF, "_stubs")]   # maro.rl / maro.utils / examples.* always come from the reference
+    if args.mode == "shim":
+        sys.path.insert(0, ROOT)
+        if args.emulate:
+            sys.path.insert(0, HERE)
+            import emul_batch
+            import maro_b200.simulator.env as env_mod
+            import maro_b200.vector_env.vector_env as venv_mod
+
+            for mod in (env_mod, venv_mod):
+                mod.CimBatch, mod.BikeBatch, mod.VmBatch = emul_batch.EmulCimBatch, emul_batch.EmulBikeBatch, emul_batch.EmulVmBatch
+        import maro_b200.shim
+
+        maro_b200.shim.install()
+    random.seed(args.seed)
+    out = {"mode": args.mode, "what": args.what}
+    buf = io.StringIO()
+    if args.what in ("hello_cim", "hello_vector"):
+        rel = "hello_world/cim/hello.py" if args.what == "hello_cim" else "vector_env/hello.py"
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(os.path.join(REF, "examples", rel), run_name="__main__")
+        text = buf.getvalue()
+        if args.what == "hello_cim":
+            out["lines"] = [ln for ln in text.splitlines() if ln.startswith("ep:")]
+            m = re.search(r"'node_mapping': (\{.*?\}\})", text)
+            out["summary_has_node_mapping"] = bool(m)
+        else:
+            out["lines"] = [ln for ln in text.splitlines() if ln.startswith(("When env 0", "Final"))]
+    else:
+        import numpy as np
+        import torch
+
+        np.random.seed(args.seed)
+        torch.manual_seed(args.seed)
+        torch.set_num_threads(1)
+        with contextlib.redirect_stdout(buf):
+            from examples.cim.rl.rl_component_bundle import rl_component_bundle as bundle
+            from maro.rl.training import TrainingManager
+
+            sampler = bundle.env_sampler
+            result = sampler.sample()
+            exps = result["experiences"][0]
+            sampler.post_collect(result["info"], 1)
+            tm = TrainingManager(rl_component_bundle=bundle, explicit_assign_device=True)
+            tm.record_experiences(result["experiences"])
+            tm.train_step()
+            state = tm.get_policy_state()
+        rewards = [float(sum(e.reward_dict.values())) for e in exps]
+        out.update({
+            "env_class": type(sampler.env).__module__,
+            "n_experiences": len(exps),
+            "ticks": [int(e.tick) for e in exps],
+            "states": digest([e.state for e in exps]),
+            "actions": digest([np.asarray([np.asarray(v).ravel() for v in e.action_dict.values()]) for e in exps]),
+            "reward_sum": float(np.sum(rewards)),
+            "rewards": [round(r, 3) for r in rewards[:50]],
+            "env_metric": {k: int(v) for k, v in result["info"][0]["env_metric"].items()},
+            "policy_state": digest([t.detach().cpu().numpy() for name in sorted(state) for ps in [state[name]]
+                                    for t in (ps.values() if isinstance(ps, dict) else []) if hasattr(t, "detach")]),
+        })
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

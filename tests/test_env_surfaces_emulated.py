@@ -75,3 +75,18 @@ def test_vm_float_queries_are_lifted_to_the_reference_float64_values():
             assert q[f, p, 2] == ((idle + (busy - idle) * (2 * x - pow(x, calib))) / topo.ticks_per_hour) / 1000
     only_e = b.query("pms", frames, np.arange(n), ["energy_consumption"])[0].reshape(3, n)
     assert np.array_equal(only_e, q[:3, :, 2])                 # energy alone: utilisation fetched behind the scenes
+
+
+def test_reference_examples_run_unchanged_on_the_shim_emulated():
+    """maro import shim: hello_world/cim/hello.py, vector_env/hello.py and the maro.rl CIM sampler + DQN train step, unmodified"""
+    import test_gpu_shim as shim_cases
+
+    if not shim_cases.HAVE_REF:
+        pytest.skip("oracle/_ref/examples not built")
+    shim_cases.test_hello_world_cim_unchanged(emulate=True)
+    shim_cases.test_vector_env_hello_unchanged(emulate=True)
+    shim_cases.test_rl_toolkit_sampler_and_train_step_unchanged(emulate=True)
+
+
+def test_vector_env_reset_reseeds_like_the_reference_processes_emulated():
+    surfaces.test_vector_env_reset_reseeds_like_the_reference_processes()

@@ -150,3 +150,44 @@ def test_env_reset_new_seed_matches_reference():
         step += 1
     assert np.array_equal(np.asarray(rows), gold)
     env.close()
+
+
+def test_vector_env_reset_reseeds_like_the_reference_processes():
+    """VectorEnv.reset(): every env process of the reference calls env.reset() -> keep_seed=False -> a new topology seed from
+    the route_init stream (env_process.py:55-57, cim_data_container_helpers.py:56-66).  The second episode of every env must
+    be the reference's second-episode trace; snapshot_list queries go out as one batched call."""
+    from helpers import policy_random_py
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.vector_env import VectorEnv
+
+    spec = CASES["toy4p_l08_120_reset_newseed"]
+    gold = load_golden("toy4p_l08_120_reset_newseed")["steps"]
+    B = 3
+    with VectorEnv(batch_num=B, scenario="cim", topology=spec["topology"], durations=spec["durations"]) as env:
+        m, ev, done = env.step(None)
+        while not done:
+            m, ev, done = env.step(None)
+        env.reset()
+        rows, step = [[] for _ in range(B)], 0
+        m, ev, done = env.step(None)
+        while not done:
+            acts = []
+            for i in range(B):
+                e = ev[i]
+                d = [e.tick, e.port_idx, e.vessel_idx, e.action_scope.load, e.action_scope.discharge, e.early_discharge]
+                rows[i].append(d + [m[i]["order_requirements"], m[i]["container_shortage"], m[i]["operation_number"]])
+                v, p, q, t = policy_random_py(d, spec["pseed"], spec["replica"], step)  # the same tape for every env
+                acts.append(Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD))
+            if step == 5:  # batched query == per-env queries
+                tick = ev[0].tick
+                got = env.snapshot_list["ports"][[tick - 1, tick]::["empty", "full"]]
+                for i in range(B):
+                    one = env._snapshot_lists[i]["ports"][[tick - 1, tick]::["empty", "full"]]
+                    assert np.array_equal(got[i], one) and got[i].shape == one.shape
+            m, ev, done = env.step(acts)
+            step += 1
+        for i in range(B):
+            assert np.array_equal(np.asarray(rows[i]), gold)
+        env.reset(keep_seed=True)  # same instances again: the first decisions repeat
+        m, ev, done = env.step(None)
+        assert [ev[0].tick, ev[0].port_idx, ev[0].vessel_idx, ev[0].action_scope.load] == gold[0][:4].tolist()
