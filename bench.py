@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--seeds", type=int, default=1, help="cim: distinct topology seeds in the batch (replica r runs seed 4096 + r %% seeds; "
                     "only noisy topologies differ by seed)")
     ap.add_argument("--launch-per-step", action="store_true", help="cim: time the one-launch-per-Env.step path as `value` instead of fused rollouts")
+    ap.add_argument("--matrix", action="store_true", help="north-star measurement matrix: CIM toy.4p_ssdd_l0.0 and citi_bike toy.3s_4t at "
+                    "1 k / 8 k / 64 k envs per GPU, short runs; the line's top-level keys are the first (headline) entry's")
+    ap.add_argument("--matrix-sizes", default="1024,8192,65536")
     ap.add_argument("--skip-extras", action="store_true", help="cim: only the contract keys (value, e2e, roofline, cpu_baseline, clocks)")
     return ap.parse_args()
 
@@ -338,34 +341,84 @@ def run_reference_vm(args, line, ref_root, cores):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def _all_cores(make_oracle, run_one, seconds):
+    """`cores` host threads, each with its own oracle replica, run whole episodes for `seconds` (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    cores = os.cpu_count() or 1
+    oracles = [make_oracle() for _ in range(cores)]
+
+    def work(k):
+        o, steps, eps, t0 = oracles[k], 0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            o.reset()
+            steps += run_one(o, k * 100003 + eps)
+            eps += 1
+        return steps, eps
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        res = list(ex.map(work, range(cores)))
+    dt = time.perf_counter() - t0
+    return sum(r[0] for r in res) / dt, cores, sum(r[1] for r in res)
+
+
+def _one_thread(make_oracle, run_one, seconds):
+    o, steps, eps, t0 = make_oracle(), 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        o.reset()
+        steps += run_one(o, eps)
+        eps += 1
+    return steps / (time.perf_counter() - t0), eps, steps
+
+
+def reference_inprocess(scenario, topology, ticks, seconds):
+    """the unmodified reference's single in-process Env loop (no VectorEnv pipes), static and dynamic
+    backends, one host core each; tools/ref_inprocess.py in a fresh process per backend (the backend is an import-time choice)."""
+    import subprocess
+
+    out = {}
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "maro")):
+        return out
+    for backend in ("static", "dynamic"):
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_inprocess.py"), scenario, topology, str(ticks),
+                                str(seconds), backend], capture_output=True, text=True, timeout=120 + 4 * seconds)
+            out[backend] = json.loads(p.stdout.strip().splitlines()[-1])
+        except Exception as ex:  # pragma: no cover
+            out[backend] = {"error": repr(ex)[:200]}
+    return out
+
+
+def _baseline(args, make_oracle, run_one, what, scenario, topology, ticks):
+    """cpu_baseline object: `value` = the C port of the reference on ALL host cores (one replica per thread), next to the
+    same port on one thread and the unmodified reference's in-process Env loop (static / dynamic backend, one core)."""
+    if args.cpu_seconds <= 0:
+        return None
+    sec = max(0.2, args.cpu_seconds)
+    v1, ep1, st1 = _one_thread(make_oracle, run_one, sec / 2)
+    vall, cores, eps = _all_cores(make_oracle, run_one, sec)
+    out = {"value": vall, "unit": "env-steps/s", "cores": cores, "kind": "port",
+           "sample": f"{eps} full episodes of {what} in {sec:.1f} s, one replica per host thread ({cores} threads), same workload / policy",
+           "one_thread": {"value": v1, "cores": 1, "sample": f"{ep1} full episodes ({st1} env-steps)"}}
+    if args.cpu_seconds >= 2 and not args.matrix:
+        out["reference_inprocess"] = reference_inprocess(scenario, topology, ticks, min(6.0, args.cpu_seconds))
+    return out
+
+
 def cpu_baseline_port(args, topo):
     from oracle.cim_oracle import CimOracle
 
-    o = CimOracle(topo)
-    env_steps, ep, t0 = 0, 0, time.perf_counter()
-    while time.perf_counter() - t0 < args.cpu_seconds:
-        o.reset()
-        n, _ = o.run_episode(1, 0, ep)
-        env_steps += n
-        ep += 1
-    dt = time.perf_counter() - t0
-    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/cim_oracle.c, same topology/ticks/policy, 1 thread"}
+    return _baseline(args, lambda: CimOracle(topo), lambda o, ep: o.run_episode(1, 0, ep)[0], "oracle/cim_oracle.c",
+                     "cim", args.topology, args.ticks)
 
 
 def cpu_baseline_bike(args, topo):
     from oracle.bike_oracle import BikeOracle
+    from tools.workloads import bike_toy_config_dir
 
-    o = BikeOracle(topo, 10)
-    env_steps, ep, t0 = 0, 0, time.perf_counter()
-    while time.perf_counter() - t0 < args.cpu_seconds:
-        o.reset()
-        n, _ = o.run_episode(1)
-        env_steps += n
-        ep += 1
-    dt = time.perf_counter() - t0
-    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/bike_oracle.c, same trace/policy, 1 thread"}
+    return _baseline(args, lambda: BikeOracle(topo, 10), lambda o, ep: o.run_episode(1)[0], "oracle/bike_oracle.c",
+                     "citi_bike", bike_toy_config_dir(), topo.max_tick)
 
 
 def load_host_agent():
@@ -403,16 +456,12 @@ def vm_workload(args):
 def cpu_baseline_vm(args, topo, max_snapshots):
     from oracle.vm_oracle import VmOracle
 
-    o = VmOracle(topo, 1, max_snapshots)
-    env_steps, ep, t0 = 0, 0, time.perf_counter()
-    while time.perf_counter() - t0 < args.cpu_seconds:
-        o.reset()
-        n, _ = o.run_episode(1)
-        env_steps += n
-        ep += 1
-    dt = time.perf_counter() - t0
-    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"{ep} full episodes ({env_steps} env-steps) of oracle/vm_oracle.c, same trace / best-fit policy, 1 thread"}
+    saved, args.matrix = args.matrix, True  # (no in-process reference leg: the reference needs ~5 min per episode here)
+    try:
+        return _baseline(args, lambda: VmOracle(topo, 1, max_snapshots), lambda o, ep: o.run_episode(1)[0],
+                         "oracle/vm_oracle.c", "vm_scheduling", "", 0)
+    finally:
+        args.matrix = saved
 
 
 def host_policy_numpy(dec, seed, base, np):
@@ -485,6 +534,46 @@ def _rl_extras(torch, env, dec, topo, B, stream):
     return shaping
 
 
+def _facade_e2e(args, device, B, base):
+    """The literal drop-in surface, measured: maro_b200.vector_env.VectorEnv.step with a Python list of `Action` objects (one
+    per env, built by a Python agent from the `DecisionEvent`s) + one `snapshot_list` query per step — what a caller of the
+    reference's VectorEnv (maro/vector_env/vector_env.py:131-217) does.  Python object construction per env dominates."""
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.vector_env import VectorEnv
+    from tools.workloads import cim_policy_random
+
+    n_steps = 60 if B <= 2048 else 12
+    with VectorEnv(batch_num=B, scenario="cim", topology=args.topology, durations=args.ticks, device=device,
+                   max_snapshots=args.max_snapshots or None) as env:
+        metrics, decisions, done = env.step(None)
+        t_agent = t_query = 0.0
+        t0 = time.perf_counter()
+        for k in range(n_steps):
+            ta = time.perf_counter()
+            acts = []
+            for i, d in enumerate(decisions):
+                if d is None:
+                    acts.append(None)
+                    continue
+                v, p, q, t = cim_policy_random((d.tick, d.port_idx, d.vessel_idx, d.action_scope.load, d.action_scope.discharge), 0, base + i, k)
+                acts.append(Action(v, p, q, ActionType.DISCHARGE if t else ActionType.LOAD))
+            t_agent += time.perf_counter() - ta
+            tq = time.perf_counter()
+            tick = next(d.tick for d in decisions if d is not None)
+            states = env.snapshot_list["ports"][tick::["empty", "full", "shortage"]]
+            t_query += time.perf_counter() - tq
+            metrics, decisions, done = env.step(acts)
+            if done:
+                break
+        dt = time.perf_counter() - t0
+        n = k + 1
+    return {"value": n * B / dt, "unit": "env-steps/s", "steps": n, "us_per_step": 1e6 * dt / n,
+            "python_agent_us_per_step": 1e6 * t_agent / n, "query_us_per_step": 1e6 * t_query / n,
+            "query_floats_per_step": int(sum(len(x) for x in states)),
+            "api": "maro_b200.vector_env.VectorEnv.step(list of Action) + snapshot_list['ports'][tick::attrs] (one batched query) per step; "
+                   "Python agent building one Action per env"}
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
@@ -519,7 +608,7 @@ def run_cim(args, rank, local_rank, world):
     from maro_b200.scenarios.cim.topology import build_topology, load_config
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.replicas
     conf = load_config(args.topology)
@@ -624,6 +713,12 @@ def run_cim(args, rank, local_rank, world):
         except Exception as ex:  # pragma: no cover
             extras["rl_shaping"] = {"error": repr(ex)}
 
+    if not args.skip_extras:
+        try:
+            extras["facade_e2e"] = _facade_e2e(args, local_rank, B, base)
+        except Exception as ex:  # pragma: no cover
+            extras["facade_e2e"] = {"error": repr(ex)[:300]}
+
     # ------------------------------------------------------------------ e2e: host buffers, agent on the host
     # The loop is user code in C on top of the C ABI (tools/host_agent.c:e2e_loop_cim): per sub-batch wait for the decision
     # rows, run the agent, submit the actions.  n_sub = 1 is the lock-step loop (one maro_cim_step_pinned per step); with more
@@ -697,6 +792,7 @@ def run_cim(args, rank, local_rank, world):
     total_ms, kernel_ms, wall_ms, e2e_ms = (float(x) for x in t.cpu())
     g_steps, g_ticks, g_events, g_snaps, g_e2e_steps = (int(x) for x in cnt.cpu())
 
+    line = None
     if rank == 0:
         peaks = _peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -739,10 +835,8 @@ def run_cim(args, rank, local_rank, world):
                            "by_sub_batches": {str(k): v for k, v in e2e_variants.items()}}
         line.update(extras)
         line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
-        emit(line)
     env.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def run_ours(args, rank, local_rank, world):
@@ -755,7 +849,7 @@ def run_ours(args, rank, local_rank, world):
     from oracle.cim_oracle import CimOracle  # checker / cpu_baseline leg only
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.replicas
     bike = args.scenario == "citi_bike"
@@ -970,6 +1064,7 @@ def run_ours(args, rank, local_rank, world):
     total_ms, kernel_ms, wall_ms, e2e_ms, graph_ms = (float(x) for x in t.cpu())
     g_steps, g_ticks, g_events, g_snaps, g_e2e_steps, g_graph_steps = (int(x) for x in cnt.cpu())
 
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -1038,10 +1133,8 @@ def run_ours(args, rank, local_rank, world):
                                   "l2": "flushed between graph chunks"}
         line["cpu_baseline"] = (cpu_baseline_vm(args, topo, vm_snaps) if vm else
                                 (cpu_baseline_bike(args, topo) if bike else cpu_baseline_port(args, topo))) if world == 1 else None
-        emit(line)
     env.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def main():
@@ -1057,10 +1150,44 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.scenario == "cim":
-        run_cim(args, rank, local_rank, world)
+        return
+    run = lambda a: run_cim(a, rank, local_rank, world) if a.scenario == "cim" else run_ours(a, rank, local_rank, world)
+    if not args.matrix:
+        line = run(args)
     else:
-        run_ours(args, rank, local_rank, world)
+        # north-star matrix: {CIM toy.4p_ssdd_l0.0, citi_bike toy.3s_4t} x {1 k, 8 k, 64 k} envs per GPU; short runs of the same
+        # legs as the default line (value / e2e / roofline / cpu_baseline); the first entry is the headline configuration
+        import copy
+
+        entries = []
+        sizes = [int(x) for x in args.matrix_sizes.split(",") if x]
+        for scenario in ("cim", "citi_bike"):
+            for B in sizes:
+                a = copy.copy(args)
+                a.scenario, a.replicas, a.skip_extras, a.graph_chunk = scenario, B, True, 0
+                a.topology, a.ticks = "toy.4p_ssdd_l0.0", 1000
+                a.steps = args.steps if B <= 8192 else max(64, args.steps // 4)
+                a.cpu_seconds = min(args.cpu_seconds, 3.0) if B == sizes[0] else 0.0
+                try:
+                    ln = run(a)
+                except Exception as ex:  # one configuration failing (e.g. out of memory) must not lose the others
+                    ln = {"error": repr(ex)[:300], "config": {"workload": f"{scenario} {B} envs"}}
+                if ln is not None:
+                    ln["scenario"], ln["replicas_per_gpu"] = scenario, B
+                    entries.append(ln)
+        line = None
+        if rank == 0:
+            line = dict(entries[0])
+            line["matrix"] = [{k: e.get(k) for k in ("scenario", "replicas_per_gpu", "value", "unit", "n_gpus", "ms_per_step", "e2e",
+                                                     "roofline", "cpu_baseline", "config", "steps", "error") if k in e}
+                              for e in entries]
+    if line is not None:
+        emit(line)
+    if world > 1:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -304,6 +304,11 @@ int maro_bike_step_pinned(MaroBikeEnv* env, int32_t use_actions, int32_t use_n_a
 int maro_bike_step_device(MaroBikeEnv* env, const uint8_t* d_active, const int32_t* d_actions,
                           const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
 int maro_bike_reset(MaroBikeEnv* env, const uint8_t* mask);
+/* Per-replica seeds of the transfer_time stream: the reference draws `round(np.random.normal(mean, std))` per action
+ * (citi_bike/decision_strategy.py:213-216) from the process-global numpy RandomState, and every env of a VectorEnv is its
+ * own process (maro/vector_env/env_process.py:26-67) — `seeds[k]` is the `np.random.seed` of env k.  uint32 [n_replicas];
+ * takes effect at each replica's next reset; NULL = every replica uses the topology's transfer_seed. */
+int maro_bike_set_transfer_seeds(MaroBikeEnv* env, const uint32_t* seeds);
 int maro_bike_query(MaroBikeEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
                     const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
                     const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);

@@ -288,6 +288,17 @@ class BikeBatch:
     def node_counts(self) -> dict:
         return {"stations": self.topology.n_stations, "matrices": 1}
 
+    def set_transfer_seeds(self, seeds):
+        """Per-replica ``np.random.seed`` of the transfer_time stream (every env of the reference's VectorEnv is its own
+        process with its own numpy RandomState); uint32 [n_replicas] or None (= the topology's transfer_seed for all).
+        Takes effect at each replica's next ``reset``."""
+        if seeds is None:
+            _native.check(self._f("set_transfer_seeds")(self._h, None))
+            return
+        sd = np.ascontiguousarray(seeds, np.uint32)
+        assert sd.shape == (self.n_replicas,)
+        _native.check(self._f("set_transfer_seeds")(self._h, sd.ctypes.data))
+
     def __init__(self, topology, n_replicas: int, snapshot_resolution: int = 1, max_snapshots: Optional[int] = None,
                  device: int = 0, max_actions: int = 1, queue_capacity: int = 0):
         self.topology = topology

@@ -48,6 +48,7 @@ struct BikeReplica {
     uint32_t* rng;
     int32_t* snap;
     int32_t* snap_frame;
+    int64_t seed;  // >= 0: this replica's own np.random seed for transfer_time (set at reset); < 0: the topology's transfer_seed
 };
 
 MARO_DEV int32_t& BA(const BikeShape& s, const BikeReplica& r, int attr, int i) { return r.f[attr * s.S + i]; }
@@ -384,7 +385,15 @@ MARO_DEV void bike_replica_reset(const BikeShape& s, const Grp<G>& g, const Bike
     LANE_LOOP(i, s.QN) { r.q[2 * i] = 0; r.q[2 * i + 1] = 0; nx[i] = Q_NIL; fs[i] = (uint16_t)(s.QN - 1 - i); }
     LANE_LOOP(i, s.QH) bq_bucket(s, r)[i] = Q_NIL | (Q_NIL << 16);
     LANE_LOOP(i, s.ring_rows) r.snap_frame[i] = -1;
-    LANE_LOOP(i, 624) r.rng[i] = (uint32_t)r.t[s.t_mt + i];
+    if (r.seed < 0) {
+        LANE_LOOP(i, 624) r.rng[i] = (uint32_t)r.t[s.t_mt + i];
+    } else if (g.lane == 0) {  // numpy legacy seeding (mt19937_seed): a serial recurrence, once per reset
+        uint32_t x = (uint32_t)r.seed;
+        for (int i = 0; i < 624; i++) {
+            r.rng[i] = x;
+            x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i + 1u;
+        }
+    }
     g.sync();
     if (g.lane == 0) {
         r.rng[624] = 624; r.rng[625] = 0; r.rng[626] = 0; r.rng[627] = 0;

@@ -10,6 +10,7 @@ struct BikeArgs {
     int32_t* snap;
     int32_t* snap_frame;
     uint32_t* rng;
+    const uint32_t* replica_seed;  // [B] per-replica np.random seeds of the transfer_time stream, or nullptr (all replicas share the topology's)
     const int32_t* tables;
     const uint8_t* active;
     const int32_t* actions;
@@ -25,6 +26,7 @@ __device__ __forceinline__ BikeReplica make_bike_replica(const BikeShape& s, con
     r.q = st + s.FWp + s.CWp;
     r.t = a.tables;
     r.rng = a.rng + (int64_t)rep * s.rng_words;
+    r.seed = a.replica_seed ? (int64_t)a.replica_seed[rep] : -1;
     r.snap = a.snap + (int64_t)rep * s.ring_rows * s.FWp;
     r.snap_frame = a.snap_frame + (int64_t)rep * s.ring_rows;
     return r;
@@ -109,6 +111,7 @@ struct MaroBikeEnv : EnvCommon {
     size_t smem_bytes = 0;
     int32_t* d_tables = nullptr;
     uint32_t* d_rng = nullptr;
+    uint32_t* d_replica_seed = nullptr;
     std::vector<int32_t> h_tables;
 };
 
@@ -116,6 +119,7 @@ static BikeArgs bike_base_args(MaroBikeEnv* e) {
     BikeArgs a;
     memset(&a, 0, sizeof(a));
     a.state = e->d_state; a.snap = e->d_snap; a.snap_frame = e->d_snap_frame; a.rng = e->d_rng; a.tables = e->d_tables;
+    a.replica_seed = e->d_replica_seed;
     return a;
 }
 
@@ -162,7 +166,7 @@ extern "C" {
 int maro_bike_destroy(MaroBikeEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaFree(e->d_tables); cudaFree(e->d_rng);
+    cudaFree(e->d_tables); cudaFree(e->d_rng); cudaFree(e->d_replica_seed);
     common_free(e);
     delete e;
     return 0;
@@ -248,6 +252,22 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
 int maro_bike_set_stream(MaroBikeEnv* e, void* cuda_stream, int32_t external) {
     if (!e) return fail("null handle");
     e->stream = external ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+/* Per-replica seeds of the transfer_time stream (np.random.seed(k) in the process of env k); they take effect at the next
+   reset of each replica.  NULL returns to the topology's single transfer_seed. */
+int maro_bike_set_transfer_seeds(MaroBikeEnv* e, const uint32_t* seeds) {
+    if (!e) return fail("null handle");
+    CK(cudaSetDevice(e->device));
+    if (!seeds) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_replica_seed);
+        e->d_replica_seed = nullptr;
+        return 0;
+    }
+    if (!e->d_replica_seed) CK(cudaMalloc(&e->d_replica_seed, (size_t)e->B * 4));
+    CK(cudaMemcpyAsync(e->d_replica_seed, seeds, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 int32_t maro_bike_decision_words(MaroBikeEnv* e) { return e ? e->s.DW : -1; }

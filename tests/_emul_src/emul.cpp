@@ -97,6 +97,7 @@ struct BikeEmul {
     BikeShape s;
     std::vector<int32_t> tables, state, snap, snap_frame;
     std::vector<uint32_t> rng;
+    std::vector<int64_t> seeds;  // per-replica transfer seeds (-1: the topology's)
     int B = 0, lanes = 8;
 };
 static BikeReplica bike_rep_of(BikeEmul* e, int i) {
@@ -105,6 +106,7 @@ static BikeReplica bike_rep_of(BikeEmul* e, int i) {
     r.f = st; r.c = st + e->s.FWp; r.q = st + e->s.FWp + e->s.CWp;
     r.t = e->tables.data();
     r.rng = e->rng.data() + (size_t)i * e->s.rng_words;
+    r.seed = e->seeds.empty() ? -1 : e->seeds[i];
     r.snap = e->snap.data() + (size_t)i * e->s.ring_rows * e->s.FWp;
     r.snap_frame = e->snap_frame.data() + (size_t)i * e->s.ring_rows;
     return r;
@@ -138,6 +140,12 @@ BikeEmul* bike_emul_create(const MaroBikeTopology* topo, const MaroCimConfig* cf
     return e;
 }
 void bike_emul_destroy(BikeEmul* e) { delete e; }
+// maro_bike_set_transfer_seeds + reset of replica `rep`
+void bike_emul_reseed(BikeEmul* e, int rep, int64_t seed) {
+    if (e->seeds.empty()) e->seeds.assign(e->B, -1);
+    e->seeds[rep] = seed;
+    if (e->lanes == 1) bike_reset_g<1>(e, rep); else if (e->lanes == 8) bike_reset_g<8>(e, rep); else bike_reset_g<32>(e, rep);
+}
 int bike_emul_dec_words(BikeEmul* e) { return e->s.DW; }
 int bike_emul_frame_words(BikeEmul* e) { return e->s.FW; }
 void bike_emul_step(BikeEmul* e, const int32_t* actions, const int32_t* n_actions, int32_t* decisions, int64_t* metrics) {

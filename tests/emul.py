@@ -43,6 +43,7 @@ def lib():
         _lib.bike_emul_create.restype = C.c_void_p
         _lib.bike_emul_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib.bike_emul_destroy.argtypes = [C.c_void_p]
+        _lib.bike_emul_reseed.argtypes = [C.c_void_p, C.c_int, C.c_int64]
         _lib.bike_emul_dec_words.argtypes = [C.c_void_p]
         _lib.bike_emul_frame_words.argtypes = [C.c_void_p]
         _lib.bike_emul_step.argtypes = [C.c_void_p] * 5

@@ -40,6 +40,10 @@ CASES = {
                                         reset_new_seed=True),
     "toy4p_l03_start7_90": dict(topology="toy.4p_ssdd_l0.3", durations=90, policy=1, pseed=6, replica=1, start_tick=7,
                                 snapshot_resolution=2),
+    # BASELINE config #4 at full length: global_trade.22p_l0.8, 500 ticks, topology seed 4096 + 3 (replica 3 of a batch whose
+    # replica r runs seed 4096 + r % 8), hashed random agent; every 20th snapshot + the last one are kept
+    "gt22p_l08_500_rand_seed4099": dict(topology="global_trade.22p_l0.8", durations=500, policy=1, pseed=0, replica=3,
+                                        topo_seed=4099, keep_frames=20),
     "toy4p_l00_start5": dict(topology="toy.4p_ssdd_l0.0", durations=60, policy=1, pseed=2, replica=0, start_tick=0,
                              snapshot_resolution=3),
 }
@@ -141,6 +145,8 @@ def run_case(name, spec, out_dir=None):
     if spec.get("snapshots", True):
         sl = env.snapshot_list
         frames = sorted(sl.get_frame_index_list())
+        if spec.get("keep_frames"):
+            frames = [f for f in frames if f % spec["keep_frames"] == 0 or f == frames[-1]]
         out["frames"] = np.asarray(frames, np.int32)
         nf = len(frames)
         P, V = len(sl["ports"]), len(sl["vessels"])

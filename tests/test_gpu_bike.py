@@ -129,3 +129,60 @@ def test_bike_env_surface_like_reference_tests(tmp_path):
     assert [st.capacity for st in fr.stations] == env.snapshot_list["stations"][0::"capacity"].astype(int).tolist()
     assert fr.matrices[0].trips_adj.shape == (len(fr.stations) ** 2,) and env.summary["node_detail"]["stations"]["number"] == len(fr.stations)
     env.close()
+
+
+def test_bike_per_replica_transfer_seeds():
+    """a per-replica transfer_time stream (every env of the reference's VectorEnv is its own process with
+    its own numpy RandomState).  One handle, every replica its own np.random seed: the replica holding the golden case's
+    seed reproduces the reference trace; the others follow oracles built with their seeds; the replicas really differ."""
+    from maro_b200.batch import BikeBatch
+    from maro_b200.scenarios.citi_bike.data import build_bike_topology
+    from bike_helpers import bike_config
+    from oracle.bike_oracle import BikeOracle
+
+    name = "toy_1440_greedy_res10"
+    spec, gold = BIKE_CASES[name], load_bike_golden(name)
+    conf = bike_config(spec["data"])
+    B, gold_rep = 16, 5
+    seeds = np.arange(1000, 1000 + B, dtype=np.uint32)
+    seeds[gold_rep] = spec["np_seed"]
+    topo = build_bike_topology(conf, 0, spec["durations"], transfer_seed=77)  # the handle's own seed is none of them
+    env = BikeBatch(topo, B, spec["snapshot_resolution"], spec.get("max_snapshots"))
+    env.set_transfer_seeds(seeds)
+    env.reset()
+    oracles = [BikeOracle(build_bike_topology(conf, 0, spec["durations"], transfer_seed=int(s)), spec["snapshot_resolution"],
+                          spec.get("max_snapshots")) for s in seeds]
+    o_out = [o.step(None) for o in oracles]
+    d0, m0 = env.step(None)
+    dec, met = d0.copy(), m0.copy()  # last rows of every replica (inactive replicas keep theirs)
+    rows = []
+    while (dec[:, 6] == 0).any():
+        live = dec[:, 6] == 0
+        acts = np.zeros((B, 1, 4), np.int32)
+        for i in range(B):
+            st, od, om = o_out[i]
+            assert od.tolist() == dec[i].tolist() and om.tolist() == met[i].tolist(), (i, od, dec[i])
+            if live[i]:
+                acts[i, 0] = greedy_py(dec[i])
+        if live[gold_rep]:
+            rows.append([dec[gold_rep, k] for k in range(5)] + met[gold_rep].tolist())
+        o_out = [o.step(acts[i]) if live[i] else o_out[i] for i, o in enumerate(oracles)]
+        d1, m1 = env.step(acts, active=live.astype(np.uint8))
+        dec[live], met[live] = d1[live], m1[live]
+    for i in range(B):
+        assert o_out[i][0] == 1 and o_out[i][2].tolist() == met[i].tolist()
+    assert np.array_equal(np.asarray(rows, np.int64), gold["steps"])
+    assert met[gold_rep].tolist() == gold["final_metrics"].tolist()
+    assert_bike_snapshots_equal(lambda f: env.snapshot_row(f, gold_rep), gold, topo.n_stations)
+    for i in range(B):
+        assert np.array_equal(env.read_frame(i), oracles[i].frame())
+    assert len({env.read_frame(i).tobytes() for i in range(B)}) > B // 2  # distinct streams -> distinct episodes
+    env.set_transfer_seeds(None)  # back to the topology's seed: clones again
+    env.reset()
+    d, m = env.step(None)
+    for _ in range(30):
+        a = np.zeros((B, 1, 4), np.int32)
+        a[:, 0] = greedy_py(d[0])
+        d, m = env.step(a)
+    assert (d == d[0]).all()
+    env.close()

@@ -253,3 +253,89 @@ def test_cuda_pinned_step_matches_copying_step():
     assert np.array_equal(dec, p_dec) and np.array_equal(met, p_met)
     a_env.close()
     b_env.close()
+
+
+def test_cuda_config4_full_size_distinct_seeds():
+    """BASELINE config #4 at full size on one GPU's share: global_trade.22p_l0.8, 500 ticks, 1 024 replicas, 8 distinct
+    topology seeds in ONE handle (replica r runs seed 4096 + r % 8: its own stop tables and MT19937 order / buffer streams),
+    hashed random agent per replica.  (a) replica 3 must reproduce the 500-tick trace of the unmodified reference run with
+    set_seed(4099) — decisions, metrics and the kept snapshots; (b) 12 sampled replicas across all seeds are replayed on the
+    oracle step by step; (c) the fused resident rollout of the same batch ends in the same metrics / frames; (d) container
+    conservation and booking = fulfillment + shortage for every replica."""
+    import torch
+
+    from maro_b200.scenarios.cim.topology import build_topology, load_config
+    from oracle.cim_oracle import CimOracle, policy_random
+
+    spec = CASES["gt22p_l08_500_rand_seed4099"]
+    gold = load_golden("gt22p_l08_500_rand_seed4099")
+    conf = load_config("global_trade.22p_l0.8")
+    K, B, T = 8, 1024, 500
+    topos = [build_topology(conf, T, seed=4096 + k) for k in range(K)]
+    rt = (np.arange(B) % K).astype(np.int32)
+    env = _batch(topos, B, replica_topology=rt)
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    act = torch.zeros((B, 1, 4), dtype=torch.int32, device="cuda")
+    sample = sorted({3, 0, 1, 2, 4, 5, 6, 7, 515, 777, 1022, 1023})
+    sidx = torch.tensor(sample, device="cuda")
+    tapes = {i: [] for i in sample}
+    mets = {i: [] for i in sample}
+    env.step_device(dec.data_ptr(), met.data_ptr())
+    for step in range(4000):
+        d = dec[sidx].cpu().numpy()
+        if step % 16 == 0 and bool((dec[:, 6] != 0).all().item()):
+            break
+        env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0)
+        a = act[sidx].cpu().numpy()
+        m = met[sidx].cpu().numpy()
+        for k, i in enumerate(sample):
+            if d[k, 6] == 0:
+                tapes[i].append((d[k].copy(), a[k, 0].copy()))
+                mets[i].append(m[k].copy())
+        env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
+    torch.cuda.synchronize()
+    dn, mn = dec.cpu().numpy(), met.cpu().numpy()
+    assert (dn[:, 6] != 0).all() and (env.ticks() == T - 1).all()
+    # (a) the reference trace (seed 4099 = replica 3, policy tape (pseed 0, replica 3))
+    rows = np.asarray([list(d[:6]) + list(m) for (d, _), m in zip(tapes[3], mets[3])], np.int64)
+    assert rows.shape == gold["steps"].shape and np.array_equal(rows, gold["steps"])
+    assert mn[3].tolist() == gold["final_metrics"].tolist()
+    assert_snapshots_equal(lambda f: env.snapshot_row(f, 3), gold, topos[3])
+    assert len({tuple(mn[k]) for k in range(K)}) == K  # the seeds really differ
+    # (b) oracle replay
+    for i in sample:
+        o = CimOracle(topos[rt[i]])
+        st, od, om = o.step(None)
+        for k, (gd, ga) in enumerate(tapes[i]):
+            assert od[:7].tolist() == gd[:7].tolist(), (i, k, od, gd)
+            assert om.tolist() == mets[i][k].tolist()
+            assert policy_random(od, 0, i, k).tolist() == ga.tolist()
+            st, od, om = o.step(ga.reshape(1, 4))
+        assert st == 1 and om.tolist() == mn[i].tolist()
+        assert np.array_equal(env.read_frame(i), o.frame())
+        assert env.counters()[i].tolist() == o.counters().tolist()
+        for f in (T - 1, T - 37, 123):
+            assert np.array_equal(env.snapshot_row(f, i), o.snapshot(f))
+    # (d) invariants over every replica
+    frames = np.stack([env.read_frame(i) for i in range(0, B, 9)])
+    fr = named_frames(frames, topos[0])
+    total = (fr["ports/empty"] + fr["ports/full"] + fr["ports/on_shipper"] + fr["ports/on_consignee"]).sum(1) + \
+        (fr["vessels/empty"][:, :, 0] + fr["vessels/full"][:, :, 0]).sum(1)
+    assert (total == topos[0].total_containers).all()
+    assert ((fr["ports/acc_booking"] - fr["ports/acc_shortage"]) == fr["ports/acc_fulfillment"]).all()
+    final_frames = {i: env.read_frame(i) for i in sample}
+    # (c) the same episode as fused resident rollouts (agent as a device callback)
+    env.reset()
+    dec.zero_()
+    for _ in range(64):
+        env.rollout_device(dec.data_ptr(), met.data_ptr(), 64, 1, 0, 0)
+        if bool((dec[:, 6] != 0).all().item()):
+            break
+    torch.cuda.synchronize()
+    assert np.array_equal(met.cpu().numpy(), mn)
+    for i in sample:
+        assert np.array_equal(env.read_frame(i), final_frames[i])
+    assert_snapshots_equal(lambda f: env.snapshot_row(f, 3), gold, topos[3])
+    env.close()

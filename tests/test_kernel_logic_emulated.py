@@ -76,3 +76,20 @@ def test_emulated_bike_kernel_matches_reference_trace(name, lanes):
     o = BikeOracle(topo, spec["snapshot_resolution"], spec.get("max_snapshots"))
     drive_bike(lambda a: o.step(a), spec, topo.n_stations)
     assert e.counters().tolist() == o.counters().tolist()
+
+
+def test_emulated_bike_per_replica_transfer_seed():
+    """maro_bike_set_transfer_seeds: a replica re-seeded on the device (numpy legacy seeding recurrence in bike_replica_reset)
+    follows the reference trace recorded with that np.random seed, whatever the topology's own transfer_seed is."""
+    from bike_helpers import bike_config
+    from emul import lib as emul_lib
+    from maro_b200.scenarios.citi_bike.data import build_bike_topology
+
+    name = "toy_600_greedy_res1"
+    spec, gold = BIKE_CASES[name], load_bike_golden(name)
+    topo = build_bike_topology(bike_config(spec["data"]), 0, spec["durations"], transfer_seed=spec["np_seed"] + 12345)
+    e = BikeEmulEnv(topo, spec["snapshot_resolution"], spec.get("max_snapshots"))
+    emul_lib().bike_emul_reseed(e._h, 0, spec["np_seed"])
+    rows, scopes, final, st, dec = drive_bike(lambda a: e.step1(a), spec, topo.n_stations)
+    assert np.array_equal(rows, gold["steps"]) and final.tolist() == gold["final_metrics"].tolist()
+    assert_bike_snapshots_equal(e.snapshot, gold, topo.n_stations)
