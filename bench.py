@@ -430,7 +430,7 @@ def load_host_agent():
     out = os.path.join(ROOT, "tools", "_build", "libhost_agent.so")
     if not os.path.isfile(out) or os.path.getmtime(out) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", src, "-o", out])
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-pthread", "-shared", "-fPIC", src, "-o", out])
     lib = ctypes.CDLL(out)
     lib.agent_random.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
     lib.agent_greedy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -740,28 +740,31 @@ def run_cim(args, rank, local_rank, world):
         gran = env.pinned_granularity()
         n_e2e = min(max(args.steps, 200), 3000)
         fptr = lambda f: C.cast(f, C.c_void_p)
-        agent_lib.e2e_loop_cim.argtypes = [C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_uint32, C.c_uint32, C.c_void_p]
+        agent_lib.e2e_loop_cim_mt.argtypes = [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p]
         out3 = (C.c_double * 3)()
 
-        def run_loop(n_sub, n_steps):
+        def run_loop(n_sub, n_threads, n_steps):
             env.reset()
             k0 = env.counters().sum(0)
-            rc = agent_lib.e2e_loop_cim(env._h, fptr(L.maro_cim_submit_pinned), fptr(L.maro_cim_wait_pinned), fptr(L.maro_cim_reset),
-                                        dec_ptr, act_ptr, p_active.ctypes.data, B, gran, n_sub, n_steps, 0, base, out3)
+            rc = agent_lib.e2e_loop_cim_mt(env._h, fptr(L.maro_cim_submit_pinned), fptr(L.maro_cim_wait_pinned), fptr(L.maro_cim_reset),
+                                           dec_ptr, act_ptr, B, gran, n_sub, n_threads, n_steps, 0, base, out3)
             if rc:
                 raise RuntimeError(L.maro_last_error().decode())
             k1 = env.counters().sum(0)
             return {"steps": int(k1[0] - k0[0]), "seconds": out3[0], "agent_seconds": out3[1], "resets": int(out3[2]),
-                    "calls": n_steps, "n_sub": n_sub}
+                    "calls": n_steps, "n_sub": n_sub, "n_threads": n_threads}
 
         if gran > 0:
-            run_loop(1, 50)  # warm-up
-            subs = [n for n in (1, 2, 4, 8) if n == 1 or B // gran >= 2 * n]
-            for n_sub in subs:
-                r = run_loop(n_sub, min(n_e2e, 600))
-                e2e_variants[n_sub] = r["steps"] / r["seconds"]
+            run_loop(1, 1, 50)  # warm-up
+            cores = os.cpu_count() or 1
+            combos = [(1, 1)] + [(ns, nt) for ns, nt in ((2, 1), (4, 1), (8, 1), (8, 2), (8, 4), (16, 4), (16, 8), (32, 8), (32, 16))
+                                 if B // gran >= 2 * ns and nt <= max(1, cores // 2)]
+            for n_sub, n_threads in combos:
+                r = run_loop(n_sub, n_threads, min(n_e2e, 600))
+                e2e_variants[f"{n_sub}x{n_threads}"] = r["steps"] / r["seconds"]
             best = max(e2e_variants, key=e2e_variants.get)
-            e2e = run_loop(best, n_e2e)
+            bs, bt = (int(x) for x in best.split("x"))
+            e2e = run_loop(bs, bt, n_e2e)
         else:  # batch too large to stay resident: lock-step calls of maro_cim_step_pinned from Python
             env.reset()
             cc0 = env.counters().sum(0)
@@ -778,7 +781,8 @@ def run_cim(args, rank, local_rank, world):
                     resets += 1
             dt = time.perf_counter() - t0
             cc1 = env.counters().sum(0)
-            e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt, "agent_seconds": t_agent, "calls": n_e2e, "resets": resets, "n_sub": 0}
+            e2e = {"steps": int(cc1[0] - cc0[0]), "seconds": dt, "agent_seconds": t_agent, "calls": n_e2e, "resets": resets, "n_sub": 0,
+                   "n_threads": 1}
 
     t = torch.tensor([total_ms, kernel_ms, wall * 1000.0, (e2e or {}).get("seconds", 0.0) * 1000.0], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([d_steps, d_ticks, d_events, d_snaps, (e2e or {}).get("steps", 0)], dtype=torch.int64, device="cuda")
@@ -827,12 +831,12 @@ def run_cim(args, rank, local_rank, world):
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
                            "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (8 * 4 + 3 * 8),
                            "api": ("maro_cim_submit_pinned / maro_cim_wait_pinned (pinned host buffers; resident session) driven by the C "
-                                   "host loop tools/host_agent.c:e2e_loop_cim, agent on the host" if e2e["n_sub"] else
+                                   "host loop tools/host_agent.c:e2e_loop_cim_mt, agent on the host" if e2e["n_sub"] else
                                    "maro_cim_step_pinned (pinned host buffers) + tools/host_agent.c on the host"),
-                           "sub_batches": e2e["n_sub"], "us_per_batch_step": 1000.0 * e2e_ms / e2e["calls"],
+                           "sub_batches": e2e["n_sub"], "host_threads": e2e["n_threads"], "us_per_batch_step": 1000.0 * e2e_ms / e2e["calls"],
                            "agent_us_per_batch_step": 1e6 * e2e["agent_seconds"] / e2e["calls"],
                            "batch_steps": e2e["calls"], "resets": e2e["resets"],
-                           "by_sub_batches": {str(k): v for k, v in e2e_variants.items()}}
+                           "by_sub_batches_x_host_threads": {str(k): v for k, v in e2e_variants.items()}}
         line.update(extras)
         line["cpu_baseline"] = cpu_baseline_port(args, topo) if world == 1 else None
     env.close()

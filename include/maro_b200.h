@@ -148,14 +148,17 @@ int maro_cim_step_pinned(MaroCimEnv* env, int32_t use_actions, int32_t use_n_act
  * maro_cim_step_pinned drive a kernel that STAYS resident between calls (replica blocks in shared memory): per call the
  * host writes one 16-byte command row per replica into mapped pinned memory, the replica's warp picks it up, steps and
  * writes its decision / metrics rows back; no launch, no stage-in / write-back, no stream synchronisation per step.  The
- * kernel leaves on its own after MARO_B200_IDLE_US (default 200) microseconds without a command and whenever another
- * entry point needs the state in device memory.  MARO_B200_SESSION=0 disables it (one launch per call, as for large
+ * kernel leaves on its own once the host has been outside submit / wait for about two MARO_B200_IDLE_US periods (default
+ * 200 us each; the host side bumps a heartbeat word while it is inside them) and whenever another entry point needs the
+ * state in device memory.  MARO_B200_SESSION=0 disables it (one launch per call, as for large
  * batches).
  * Asynchronous halves of maro_cim_step_pinned for a contiguous replica range (what VectorEnv's dict stepping gives the
  * reference, vector_env.py:131-144, without blocking): submit sends the step to replicas [first, first + count) and returns
  * at once, wait blocks until their decision / metrics rows are in the pinned buffers.  Ranges are whole blocks of
  * maro_cim_pinned_granularity() replicas (0: the batch is not resident, only maro_cim_step_pinned is available); a host
- * agent overlaps its own work on one range with the device's work on the others. */
+ * agent overlaps its own work on one range with the device's work on the others.
+ * Threads: submit / wait / maro_cim_reset(mask) may be called concurrently from several host threads as long as the replica
+ * ranges (mask bits) of the threads are disjoint; every other entry point of a handle is single-threaded. */
 int32_t maro_cim_pinned_granularity(MaroCimEnv* env);
 int maro_cim_submit_pinned(MaroCimEnv* env, int32_t first, int32_t count, int32_t use_actions, int32_t use_n_actions,
                            int32_t use_active);
@@ -165,7 +168,9 @@ int maro_cim_step_device(MaroCimEnv* env, const uint8_t* d_active, const int32_t
                          const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
 
 /* Env.reset (core.py:143-170) for the replicas selected by mask (NULL = all).  Tables of the replicas'
- * topologies must already be resident (see maro_cim_set_topology for keep_seed=False / set_seed). */
+ * topologies must already be resident (see maro_cim_set_topology for keep_seed=False / set_seed).  While the resident
+ * kernel is live the reset costs nothing here: it rides on each replica's next command row and is carried out in shared
+ * memory (any call that reads device state applies what is still pending first). */
 int maro_cim_reset(MaroCimEnv* env, const uint8_t* mask);
 /* Replace topology slot `index` (same shape) — used for reset(keep_seed=False) and Env.set_seed. */
 int maro_cim_set_topology(MaroCimEnv* env, int32_t index, const MaroCimTopology* topo);
@@ -182,6 +187,16 @@ int maro_cim_query_device(MaroCimEnv* env, const int32_t* replicas, int32_t n_re
                           const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes,
                           int32_t n_nodes, const int32_t* attrs, int32_t n_attrs, double* d_out,
                           int64_t* out_per_replica);
+/* Result layout of maro_*_query / maro_cim_query_device for this handle — the reference picks its backend per process
+ * (DEFAULT_BACKEND_NAME, maro/backends/frame.pyx:60-66) and the two backends answer queries differently:
+ *   MARO_QUERY_LAYOUT_STATIC  (default; NumpyBackend, np_backend.pyx:520-549): [frame][node][attr][slot] packed, frames not in
+ *                             the ring read as 0, values exact;
+ *   MARO_QUERY_LAYOUT_DYNAMIC (RawBackend, raw/snapshotlist.cpp:244-318, _raw_backend_.pyx:263-315): every attribute padded to
+ *                             max_slots = the widest queried attribute, i.e. [frame][node][attr][max_slots]; missing slots and
+ *                             frames not in the ring are NaN; values pass through float32 (ATTR_FLOAT).
+ * `out_per_replica` of the query calls reports the per-replica element count of the active layout. */
+enum { MARO_QUERY_LAYOUT_STATIC = 0, MARO_QUERY_LAYOUT_DYNAMIC = 1 };
+int maro_cim_set_query_layout(MaroCimEnv* env, int32_t layout);
 /* Attribute id / slot count by name for a node type; -1 if unknown. */
 int32_t maro_cim_attr_id(MaroCimEnv* env, int32_t node_type, const char* name);
 int32_t maro_cim_attr_slots(MaroCimEnv* env, int32_t node_type, int32_t attr_id);
@@ -312,6 +327,7 @@ int maro_bike_set_transfer_seeds(MaroBikeEnv* env, const uint32_t* seeds);
 int maro_bike_query(MaroBikeEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
                     const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
                     const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
+int maro_bike_set_query_layout(MaroBikeEnv* env, int32_t layout); /* see maro_cim_set_query_layout */
 int32_t maro_bike_attr_id(MaroBikeEnv* env, int32_t node_type, const char* name);
 int32_t maro_bike_attr_slots(MaroBikeEnv* env, int32_t node_type, int32_t attr_id);
 int maro_bike_read_frame(MaroBikeEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);
@@ -403,6 +419,7 @@ int maro_vm_reset(MaroVmEnv* env, const uint8_t* mask);
 int maro_vm_query(MaroVmEnv* env, const int32_t* replicas, int32_t n_replicas, int32_t node_type,
                   const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
                   const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
+int maro_vm_set_query_layout(MaroVmEnv* env, int32_t layout); /* see maro_cim_set_query_layout */
 int32_t maro_vm_attr_id(MaroVmEnv* env, int32_t node_type, const char* name);
 int32_t maro_vm_attr_slots(MaroVmEnv* env, int32_t node_type, int32_t attr_id);
 int maro_vm_read_frame(MaroVmEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);

@@ -188,13 +188,33 @@ class CimBatch:
     def attr_slots(self, node: str, attr_id: int) -> int:
         return _native.lib().maro_cim_attr_slots(self._h, _NODE_TYPE[node], attr_id)
 
+    query_layout = "static"
+
+    def set_query_layout(self, layout: str):
+        """"static" (NumpyBackend conventions, the reference's default) or "dynamic" (RawBackend conventions: every
+        attribute padded to the widest one's slots, NaN for missing slots / unknown frames, values through float32) —
+        the reference's DEFAULT_BACKEND_NAME choice (maro/backends/frame.pyx:496-504), per handle."""
+        assert layout in ("static", "dynamic")
+        _native.check(_native.lib().maro_cim_set_query_layout(self._h, 1 if layout == "dynamic" else 0))
+        self.query_layout = layout
+
+    def _per_replica(self, node, at, n_frames, n_nodes) -> int:
+        slots = [self.attr_slots(node, int(a)) for a in at]
+        per_node = len(slots) * max(slots) if self.query_layout == "dynamic" else sum(slots)
+        return per_node * n_frames * n_nodes
+
+    def query_shape(self, node, attrs, n_frames, n_nodes):
+        """shape of one replica's result under the dynamic layout: (frames, nodes, attrs, max_slots)"""
+        slots = [self.attr_slots(node, a if isinstance(a, (int, np.integer)) else self.attr_id(node, a)) for a in attrs]
+        return (n_frames, n_nodes, len(slots), max(slots))
+
     def query(self, node: str, frame_indices, nodes, attrs, replicas=None) -> np.ndarray:
         """float64 [n_replicas_queried, per_replica] in tick -> node -> attr -> slot order (np_backend.pyx:520-549)."""
         reps = np.arange(self.n_replicas, dtype=np.int32) if replicas is None else np.ascontiguousarray(replicas, np.int32)
         fr = np.ascontiguousarray(frame_indices, np.int32)
         nd = np.ascontiguousarray(nodes, np.int32)
         at = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id(node, a) for a in attrs], np.int32)
-        per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
+        per = self._per_replica(node, at, len(fr), len(nd))
         out = np.zeros((len(reps), per), np.float64)
         pr = C.c_int64()
         _native.check(_native.lib().maro_cim_query(self._h, reps.ctypes.data, len(reps), _NODE_TYPE[node], fr.ctypes.data,
@@ -212,7 +232,7 @@ class CimBatch:
         fr = np.ascontiguousarray(frame_indices, np.int32)
         nd = np.ascontiguousarray(nodes, np.int32)
         at = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id(node, a) for a in attrs], np.int32)
-        per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
+        per = self._per_replica(node, at, len(fr), len(nd))
         out = torch.empty((len(reps), per), dtype=torch.float64, device=f"cuda:{self.device}")
         pr = C.c_int64()
         _native.check(_native.lib().maro_cim_query_device(self._h, reps.ctypes.data, len(reps), _NODE_TYPE[node],
@@ -287,6 +307,16 @@ class BikeBatch:
 
     def node_counts(self) -> dict:
         return {"stations": self.topology.n_stations, "matrices": 1}
+
+    query_layout = "static"
+    _per_replica = CimBatch._per_replica
+    query_shape = CimBatch.query_shape
+
+    def set_query_layout(self, layout: str):
+        """see ``CimBatch.set_query_layout``"""
+        assert layout in ("static", "dynamic")
+        _native.check(self._f("set_query_layout")(self._h, 1 if layout == "dynamic" else 0))
+        self.query_layout = layout
 
     def set_transfer_seeds(self, seeds):
         """Per-replica ``np.random.seed`` of the transfer_time stream (every env of the reference's VectorEnv is its own
@@ -385,7 +415,7 @@ class BikeBatch:
         fr = np.ascontiguousarray(frame_indices, np.int32)
         nd = np.ascontiguousarray(nodes, np.int32)
         at = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id(node, a) for a in attrs], np.int32)
-        per = sum(self.attr_slots(node, int(a)) for a in at) * len(fr) * len(nd)
+        per = self._per_replica(node, at, len(fr), len(nd))
         out = np.zeros((len(reps), per), np.float64)
         pr = C.c_int64()
         _native.check(self._f("query")(self._h, reps.ctypes.data, len(reps), self._NODE[node], fr.ctypes.data,
@@ -464,7 +494,7 @@ class VmBatch(BikeBatch):
 
     def query(self, node: str, frame_indices, nodes, attrs, replicas=None) -> np.ndarray:
         out = super().query(node, frame_indices, nodes, attrs, replicas)
-        if node != "pms":
+        if node != "pms" or self.query_layout == "dynamic":  # (the RawBackend holds these attributes as float32 itself)
             return out
         names = [a if isinstance(a, str) else _abi.VM_NODE_ATTRS["pms"][int(a)] for a in attrs]
         if not any(n in _abi.VM_FLOAT_ATTRS for n in names):

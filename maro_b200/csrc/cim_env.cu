@@ -15,6 +15,9 @@
 #include "env_common.cuh"
 #include <time.h>
 
+#include <atomic>
+#include <mutex>
+
 // =====================================================================================================
 // Kernels
 // =====================================================================================================
@@ -161,6 +164,8 @@ __global__ void cim_policy_kernel(const int32_t* __restrict__ dec, int32_t* __re
 enum { RES_ROLLOUT = 0, RES_SESSION = 1 };
 enum { RES_POLICY_NULL = 0, RES_POLICY_RANDOM = 1 };
 enum { RES_CMD_STEP = 0, RES_CMD_EXIT = 1 };
+// command row word 1 (flags): bits 0-7 n_actions | bit 8 active | bit 9 bad action | bit 10 Env.reset before the step |
+//                             bits 16-23 command | bit 24 action type of row 0
 struct ResidentArgs {
     int mode, spread;
     int n_steps, policy;
@@ -170,6 +175,7 @@ struct ResidentArgs {
     uint32_t* done_flags;           // mapped host [gridDim.x]: last seq every replica of that CTA has completed
     uint32_t poll_ns, wait_ns;      // back-off of the command poll (PCIe) and of the shared-memory relay wait
     uint32_t* seq_state;            // device [B]: last seq each replica has completed (survives launches and resets)
+    const uint32_t* heartbeat;      // mapped host word the host bumps while it is inside submit / wait (any thread)
     long long idle_cycles;
 };
 
@@ -250,8 +256,9 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
         g.sync();
         for (;;) {
             if (gid == 0) {
-                const long long t0 = clock64();
-                bool stop = false;
+                long long t0 = clock64();
+                uint32_t beat = 0;
+                bool stop = false, have_beat = false;
                 for (;;) {
                     bool ok = true;
                     for (int b0 = 0; b0 < n_live; b0 += G) {
@@ -262,7 +269,17 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
                         if (i < n_live) *reinterpret_cast<uint4*>(cmd_s + i * 4) = c;
                     }
                     if (ok) break;
-                    if (clock64() - t0 > ra.idle_cycles) { stop = true; break; }
+                    if (clock64() - t0 > ra.idle_cycles) {
+                        // no command for a while: leave only if the host has left submit / wait altogether (its heartbeat stands
+                        // still) — then every CTA leaves within one idle period and the host relaunches the whole grid.  While
+                        // any host thread is still driving other CTAs, a slow driver of this CTA must not strand it.
+                        uint32_t b = 0;
+                        if (g.lane == 0) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(b) : "l"(ra.heartbeat) : "memory");
+                        b = (uint32_t)g.shfl((int)b, 0);
+                        if (have_beat && b == beat) { stop = true; break; }
+                        beat = b; have_beat = true;
+                        t0 = clock64();
+                    }
                     if (ra.poll_ns) __nanosleep(ra.poll_ns);
                 }
                 if (stop)  // idle: every group of the CTA leaves together
@@ -279,6 +296,10 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
             if (((flags >> 16) & 0xff) == RES_CMD_EXIT) break;
             const int n_act = min((int)(flags & 0xff), min(s.max_actions, G));
             const bool active = (flags >> 8) & 1u, bad = (flags >> 9) & 1u;
+            if ((flags >> 10) & 1u) {  // Env.reset of this replica (maro_cim_reset while the session is live), in place
+                replica_reset<G>(s, g, r);
+                g.sync();
+            }
             if (active) {
                 Act4 act = {0, 0, 0, 0};
                 if (g.lane == 0) {
@@ -344,12 +365,17 @@ struct MaroCimEnv : EnvCommon {
     // resident mode (cim_resident_kernel)
     int res_threads = 0, res_grid = 0, res_spread = 0;
     size_t res_smem = 0;
-    bool session_ok = false, session_live = false;  // session_ok: the whole grid is co-resident (required to spin-wait)
+    bool session_ok = false;                         // the whole grid is co-resident (required to spin-wait)
+    std::atomic<bool> session_live{false};
+    std::mutex session_mu;                           // launch / relaunch / end of the resident kernel (submit / wait of DISJOINT
+                                                     // CTA ranges may run on several host threads at once)
+    std::vector<uint8_t> reset_pending;              // per replica: maro_cim_reset arrived while the session was live -> rides on
+                                                     // the replica's next command row (or is applied when the session ends)
+    uint32_t *h_beat = nullptr, *hd_beat = nullptr;  // heartbeat word, mapped pinned
     int buf_full_cap = 1, buf_empty_cap = 1;         // buffer ticks the event pool was sized for (set_topology re-validation)
     int res_groups = 0;                              // replicas per CTA of the resident kernel
     std::vector<uint32_t> cta_seq;                   // per CTA: last step completed (the kernel's seq_state mirrors it)
     std::vector<uint8_t> cta_pending;                // per CTA: a step has been sent and not collected yet
-    int n_pending = 0;
     uint32_t *h_cmd = nullptr, *hd_cmd = nullptr;    // [B][4] command rows, mapped pinned
     uint32_t *h_flag = nullptr, *hd_flag = nullptr;  // [res_grid] completion flags (one per CTA), mapped pinned
     uint32_t* d_seq = nullptr;
@@ -547,7 +573,12 @@ static cudaError_t launch_resident(MaroCimEnv* e, const StepArgs& a, const Resid
 }
 
 // ---- host session (RES_SESSION) ---------------------------------------------------------------------
-static int session_launch(MaroCimEnv* e) {
+// Threading contract: maro_cim_submit_pinned / maro_cim_wait_pinned may be called concurrently from several host threads as
+// long as their replica ranges are disjoint (per-CTA bookkeeping is touched by the owning thread only; launching, relaunching
+// and ending the kernel are serialised by session_mu).  Every other entry point is single-threaded, like the rest of the ABI.
+static inline void session_beat(MaroCimEnv* e) { __atomic_fetch_add(e->h_beat, 1u, __ATOMIC_RELAXED); }
+
+static int session_launch_locked(MaroCimEnv* e) {
     StepArgs a = base_args(e);
     a.actions = reinterpret_cast<const int32_t*>(e->hd_in);
     a.decisions = reinterpret_cast<int32_t*>(e->hd_out);
@@ -556,14 +587,15 @@ static int session_launch(MaroCimEnv* e) {
     memset(&ra, 0, sizeof(ra));
     ra.mode = RES_SESSION; ra.spread = e->res_spread;
     ra.cmd = e->hd_cmd; ra.done_flags = e->hd_flag; ra.seq_state = e->d_seq; ra.poll_ns = e->poll_ns; ra.wait_ns = e->wait_ns;
-    ra.idle_cycles = e->idle_cycles;
+    ra.idle_cycles = e->idle_cycles; ra.heartbeat = e->hd_beat;
     CK(launch_resident(e, a, ra));
-    e->session_live = true;
+    e->session_live.store(true, std::memory_order_release);
     return 0;
 }
 
 // Wait until the CTAs [c0, c1) have published the step they were last sent (their decision / metrics rows are then in
-// h_out).  The resident kernel may have left meanwhile (idle limit): relaunch it, the command rows are still in place.
+// h_out).  The resident kernel may have left meanwhile (the host was away for longer than the idle limit): relaunch it,
+// the command rows are still in place.
 static int session_wait_ctas(MaroCimEnv* e, int c0, int c1) {
     volatile uint32_t* flags = e->h_flag;
     timespec ts0;
@@ -571,7 +603,7 @@ static int session_wait_ctas(MaroCimEnv* e, int c0, int c1) {
     int cta = c0;
     auto advance = [&]() {
         while (cta < c1 && (!e->cta_pending[cta] || flags[cta] == e->cta_seq[cta] + 1u)) {
-            if (e->cta_pending[cta]) { e->cta_pending[cta] = 0; e->cta_seq[cta] += 1u; e->n_pending--; }
+            if (e->cta_pending[cta]) { e->cta_pending[cta] = 0; e->cta_seq[cta] += 1u; }
             cta++;
         }
         return cta == c1;
@@ -579,37 +611,56 @@ static int session_wait_ctas(MaroCimEnv* e, int c0, int c1) {
     for (uint64_t spins = 1;; spins++) {
         if (advance()) return 0;
         __builtin_ia32_pause();
+        if ((spins & 0x3ff) == 0) session_beat(e);  // (every ~25 us: "the host is still here", see the kernel's idle exit)
         if ((spins & 0xfff) == 0) {  // every ~100 us: did the kernel leave (idle limit) or fail?
             timespec ts;
             clock_gettime(CLOCK_MONOTONIC, &ts);
             if (ts.tv_sec - ts0.tv_sec > 30) return fail("resident kernel: no completion after 30 s");  // never spin forever
-            cudaError_t q = cudaStreamQuery(e->stream);
+            if (cudaStreamQuery(e->stream) == cudaErrorNotReady) continue;
+            std::lock_guard<std::mutex> lock(e->session_mu);
+            cudaError_t q = cudaStreamQuery(e->stream);  // (another waiting thread may have relaunched it already)
             if (q == cudaSuccess) {
                 if (advance()) return 0;
-                if (session_launch(e)) return 1;
+                if (session_launch_locked(e)) return 1;
             } else if (q != cudaErrorNotReady) {
-                e->session_live = false;
+                e->session_live.store(false);
                 return fail(std::string("resident kernel: ") + cudaGetErrorString(q));
             }
         }
     }
 }
 
+extern "C" int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask);
+static int reset_now(MaroCimEnv* e, const uint8_t* mask);
+
 // Ask the resident kernel (if any) to write the replica blocks back and exit; afterwards device memory is authoritative.
 static int session_end(MaroCimEnv* e) {
-    if (!e->session_live) return 0;
-    if (e->n_pending && session_wait_ctas(e, 0, e->res_grid)) return 1;
-    const int gpc = e->res_groups;
-    for (int i = 0; i < e->B; i++) {
-        volatile uint32_t* row = e->h_cmd + (size_t)i * 4;
-        row[1] = (uint32_t)RES_CMD_EXIT << 16;
-        __atomic_store_n(&row[0], e->cta_seq[i / gpc] + 1u, __ATOMIC_RELEASE);
+    if (!e->session_live.load()) return 0;
+    bool any = false;
+    for (int c = 0; c < e->res_grid; c++) any = any || e->cta_pending[c];
+    if (any && session_wait_ctas(e, 0, e->res_grid)) return 1;
+    {
+        std::lock_guard<std::mutex> lock(e->session_mu);
+        const int gpc = e->res_groups;
+        for (int i = 0; i < e->B; i++) {
+            volatile uint32_t* row = e->h_cmd + (size_t)i * 4;
+            row[1] = (uint32_t)RES_CMD_EXIT << 16;
+            __atomic_store_n(&row[0], e->cta_seq[i / gpc] + 1u, __ATOMIC_RELEASE);
+        }
+        e->session_live.store(false);
+        CK(cudaStreamSynchronize(e->stream));
     }
-    e->session_live = false;
-    CK(cudaStreamSynchronize(e->stream));
+    // resets that arrived while the session was live and never rode on a command row
+    bool pend = false;
+    for (int i = 0; i < e->B; i++) pend = pend || e->reset_pending[i];
+    if (pend) {
+        std::vector<uint8_t> m(e->reset_pending);
+        std::fill(e->reset_pending.begin(), e->reset_pending.end(), (uint8_t)0);
+        if (reset_now(e, m.data())) return 1;
+    }
     return 0;
 }
-#define END_SESSION(e) do { if ((e)->session_live && session_end(e)) return 1; } while (0)
+#define END_SESSION(e) do { if ((e)->session_live.load() && session_end(e)) return 1; } while (0)
 
 // Send one Env.step to the replicas [first, first + count) (whole CTAs): one 16-byte command row per replica, built from
 // the pinned staging buffers (h_in).  Returns at once; session_wait_ctas collects the rows.
@@ -627,7 +678,12 @@ static int session_submit(MaroCimEnv* e, int first, int count, bool use_actions,
         int n = use_actions ? (use_n_actions ? nact[i] : 1) : 0;
         if (n < 0) n = 0;
         const int32_t* r0 = act + (size_t)i * A * 4;
-        uint32_t flags = (use_active ? (active[i] ? 1u : 0u) : 1u) << 8, w2 = 0, w3 = 0;
+        const bool is_active = use_active ? active[i] != 0 : true;
+        uint32_t flags = (is_active ? 1u : 0u) << 8, w2 = 0, w3 = 0;
+        if (e->reset_pending[i]) {  // (a replica outside the active mask is still reset: Env.reset does not depend on stepping)
+            flags |= 1u << 10;
+            e->reset_pending[i] = 0;
+        }
         if (n > 0) {
             const bool bad = n > A || r0[0] < 0 || r0[0] > 0xffff || r0[1] < 0 || r0[1] > 0xffff;
             flags |= (uint32_t)std::min(n, 255) | (bad ? 1u << 9 : 0u) | (r0[3] == 1 ? 1u << 24 : 0u);
@@ -639,8 +695,12 @@ static int session_submit(MaroCimEnv* e, int first, int count, bool use_actions,
         __atomic_store_n(&row[0], e->cta_seq[i / gpc] + 1u, __ATOMIC_RELEASE);  // x86 TSO: a reader that sees the seq sees the row
     }
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
-    for (int c = c0; c < c1; c++) { e->cta_pending[c] = 1; e->n_pending++; }
-    if (!e->session_live && session_launch(e)) return 1;
+    for (int c = c0; c < c1; c++) e->cta_pending[c] = 1;
+    session_beat(e);
+    if (!e->session_live.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(e->session_mu);
+        if (!e->session_live.load() && session_launch_locked(e)) return 1;
+    }
     return 0;
 }
 
@@ -649,8 +709,6 @@ static int session_step(MaroCimEnv* e, bool use_actions, bool use_n_actions, boo
     if (session_submit(e, 0, e->B, use_actions, use_n_actions, use_active)) return 1;
     return session_wait_ctas(e, 0, e->res_grid);
 }
-
-extern "C" int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask);
 
 // device buffers + resident-mode geometry of a new handle; any failure leaves the handle for the caller to destroy
 static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32_t n_topos, const MaroCimConfig* cfg, const cudaDeviceProp& prop) {
@@ -682,6 +740,10 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
     memset(e->h_flag, 0, (size_t)B * 4 + 64);
     CK(cudaMalloc(&e->d_seq, (size_t)B * 4));
     CK(cudaMemset(e->d_seq, 0, (size_t)B * 4));
+    CK(cudaHostAlloc(&e->h_beat, 64, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_beat, e->h_beat, 0));
+    memset(e->h_beat, 0, 64);
+    e->reset_pending.assign(B, 0);
     const int nsm = prop.multiProcessorCount;
     const int gpw = 32 / e->lanes;
     const size_t per_group = (size_t)s.SW * 4 + 64 + 16, max_smem = prop.sharedMemPerBlockOptin;  // block + output slot + command row
@@ -724,11 +786,12 @@ int maro_abi_version(void) { return MARO_B200_ABI_VERSION; }
 int maro_cim_destroy(MaroCimEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    if (e->session_live) session_end(e);
+    if (e->session_live.load()) session_end(e);
     cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt); cudaFree(e->d_light);
     cudaFree(e->d_seq);
     if (e->h_cmd) cudaFreeHost(e->h_cmd);
     if (e->h_flag) cudaFreeHost(e->h_flag);
+    if (e->h_beat) cudaFreeHost(e->h_beat);
     common_free(e);
     delete e;
     return 0;
@@ -820,7 +883,26 @@ int maro_cim_set_stream(MaroCimEnv* e, void* cuda_stream, int32_t external) {
 int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask) {
     if (!e) return fail("null handle");
     CK(cudaSetDevice(e->device));
-    END_SESSION(e);
+    if (e->session_live.load()) {
+        // The replica blocks live in shared memory right now: the reset rides on each replica's next command row and is
+        // carried out there, in place (replica_reset in the resident kernel) — no write-back / relaunch round trip.  Calls that
+        // read device state end the session first, which applies whatever is still pending (session_end).
+        bool busy = false;
+        const int gpc = e->res_groups;
+        for (int i = 0; i < e->B; i++)
+            if ((!mask || mask[i]) && e->cta_pending[i / gpc]) busy = true;
+        if (!busy) {
+            for (int i = 0; i < e->B; i++)
+                if (!mask || mask[i]) e->reset_pending[i] = 1;
+            return 0;
+        }
+        if (session_end(e)) return 1;  // a step of these replicas is still in flight: the conservative path
+    }
+    return reset_now(e, mask);
+}
+}  // extern "C"
+
+static int reset_now(MaroCimEnv* e, const uint8_t* mask) {
     StepArgs a = base_args(e);
     if (mask) {  // staged through the pinned `active` region (never through the caller-visible action rows)
         const size_t active_off = (size_t)e->B * e->s.max_actions * 16 + (size_t)e->B * 4;
@@ -828,6 +910,9 @@ int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask) {
         if (mask != e->h_in + active_off) memcpy(e->h_in + active_off, mask, e->B);
         CK(cudaMemcpyAsync(d_active, e->h_in + active_off, e->B, cudaMemcpyHostToDevice, e->stream));
         a.active = d_active;
+        for (int i = 0; i < e->B; i++) if (mask[i]) e->reset_pending[i] = 0;
+    } else {
+        std::fill(e->reset_pending.begin(), e->reset_pending.end(), (uint8_t)0);
     }
     int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
     cim_reset_kernel<<<blocks, threads, 0, e->stream>>>(e->s, a);
@@ -835,6 +920,8 @@ int maro_cim_reset(MaroCimEnv* e, const uint8_t* mask) {
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
+
+extern "C" {
 
 int maro_cim_set_topology(MaroCimEnv* e, int32_t index, const MaroCimTopology* topo) {
     if (!e || !topo || index < 0 || index >= e->K) return fail("maro_cim_set_topology: bad arguments");
@@ -943,6 +1030,7 @@ int maro_cim_query_device(MaroCimEnv* e, const int32_t* replicas, int32_t n_repl
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, d_out, nullptr, out_per_replica);
 }
 
+int maro_cim_set_query_layout(MaroCimEnv* e, int32_t layout) { return common_set_query_layout(e, layout); }
 int32_t maro_cim_attr_id(MaroCimEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
 int32_t maro_cim_attr_slots(MaroCimEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }
 int maro_cim_read_frame(MaroCimEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) {

@@ -59,10 +59,13 @@ struct QueryArgs {
     const int32_t* attr_isf;
     const int32_t* attr_prefix;  // [na] prefix sum of slots
     int nr, nf, nn, na, slots_per_node, ring_rows, FWp;
+    int layout, max_slots;  // layout 1 (dynamic backend): [frame][node][attr][max_slots], NaN padding, float32-rounded values
     double* out;
 };
 
-// out[rep][frame][node][attr][slot]; frames not held by the ring -> 0  (np_backend.pyx:536-549)
+// Static layout (np_backend.pyx:536-549): out[rep][frame][node][attr][slot], frames not held by the ring -> 0.
+// Dynamic layout (the RawBackend's query, raw/snapshotlist.cpp:244-318 + _raw_backend_.pyx:263-315): every attribute
+// padded to `max_slots` slots, result pre-filled with NaN (missing slots, unknown frames), values pass through float32.
 static __global__ void cim_query_kernel(const __grid_constant__ QueryArgs q) {
     const int64_t per_rep = (int64_t)q.nf * q.nn * q.slots_per_node;
     const int64_t total = per_rep * q.nr;
@@ -72,16 +75,23 @@ static __global__ void cim_query_kernel(const __grid_constant__ QueryArgs q) {
         int nd = (int)(x % q.nn); x /= q.nn;
         int fi = (int)(x % q.nf); x /= q.nf;
         int rp = q.replicas[(int)x];
-        int ai = 0;
-        while (ai + 1 < q.na && q.attr_prefix[ai + 1] <= sl) ai++;
-        int slot = sl - q.attr_prefix[ai];
+        int ai = 0, slot;
+        if (q.layout == 1) {
+            ai = sl / q.max_slots;
+            slot = sl - ai * q.max_slots;
+        } else {
+            while (ai + 1 < q.na && q.attr_prefix[ai + 1] <= sl) ai++;
+            slot = sl - q.attr_prefix[ai];
+        }
         int frame = q.frames[fi];
-        double v = 0.0;
-        if (frame >= 0) {
+        double v = q.layout == 1 ? __longlong_as_double(0x7ff8000000000000ll) : 0.0;
+        if (q.layout == 1 && slot >= q.attr_slots[ai]) {
+            // NaN padding
+        } else if (frame >= 0) {
             int row = frame % q.ring_rows;
             if (q.snap_frame[(int64_t)rp * q.ring_rows + row] == frame) {
                 int w = q.snap[((int64_t)rp * q.ring_rows + row) * q.FWp + q.attr_off[ai] + q.nodes[nd] * q.attr_slots[ai] + slot];
-                v = q.attr_isf[ai] ? (double)__int_as_float(w) : (double)w;
+                v = q.attr_isf[ai] ? (double)__int_as_float(w) : (q.layout == 1 ? (double)(float)w : (double)w);
             }
         }
         q.out[i] = v;
@@ -123,6 +133,7 @@ struct EnvCommon {
     size_t qout_cap = 0;
     std::vector<AttrInfo> attrs[6];
     int n_node_types = 3;
+    int query_layout = 0;  // MARO_QUERY_LAYOUT_STATIC / _DYNAMIC (maro_*_set_query_layout)
 };
 
 static void common_free(EnvCommon* e) {
@@ -239,6 +250,11 @@ static int common_snapshot_frames(EnvCommon* e, int32_t replica, int32_t* out, i
     for (int i = 0; i < (int)have.size() && i < cap; i++) out[i] = have[i];
     return 0;
 }
+static int common_set_query_layout(EnvCommon* e, int32_t layout) {
+    if (!e || (layout != 0 && layout != 1)) return fail("set_query_layout: layout must be 0 (static) or 1 (dynamic)");
+    e->query_layout = layout;
+    return 0;
+}
 static int32_t common_attr_id(EnvCommon* e, int32_t node_type, const char* name) {
     if (!e || node_type < 0 || node_type >= e->n_node_types || !name) return -1;
     for (size_t i = 0; i < e->attrs[node_type].size(); i++)
@@ -263,13 +279,15 @@ static int query_impl(EnvCommon* e, const int32_t* replicas, int32_t nr, int32_t
     for (int i = 0; i < nr; i++) { if (replicas[i] < 0 || replicas[i] >= e->B) return fail("maro_cim_query: replica out of range"); idx.push_back(replicas[i]); }
     for (int i = 0; i < nf; i++) idx.push_back(frames[i]);
     for (int i = 0; i < nn; i++) { if (nodes[i] < 0 || nodes[i] >= reg[0].n_nodes) return fail("maro_cim_query: node index out of range"); idx.push_back(nodes[i]); }
-    int prefix = 0;
+    int prefix = 0, max_slots = 1;
     std::vector<int32_t> off(na), slots(na), isf(na), pre(na);
     for (int i = 0; i < na; i++) {
         if (attrs[i] < 0 || attrs[i] >= (int)reg.size()) return fail("maro_cim_query: attribute id out of range");
         off[i] = reg[attrs[i]].off; slots[i] = reg[attrs[i]].slots; isf[i] = reg[attrs[i]].isf; pre[i] = prefix;
         prefix += slots[i];
+        max_slots = std::max(max_slots, slots[i]);
     }
+    if (e->query_layout == 1) prefix = na * max_slots;
     idx.insert(idx.end(), off.begin(), off.end());
     idx.insert(idx.end(), slots.begin(), slots.end());
     idx.insert(idx.end(), isf.begin(), isf.end());
@@ -296,6 +314,7 @@ static int query_impl(EnvCommon* e, const int32_t* replicas, int32_t nr, int32_t
     q.replicas = e->d_qidx; q.frames = q.replicas + nr; q.nodes = q.frames + nf;
     q.attr_off = q.nodes + nn; q.attr_slots = q.attr_off + na; q.attr_isf = q.attr_slots + na; q.attr_prefix = q.attr_isf + na;
     q.nr = nr; q.nf = nf; q.nn = nn; q.na = na; q.slots_per_node = prefix; q.ring_rows = e->ring_rows; q.FWp = e->FWp;
+    q.layout = e->query_layout; q.max_slots = max_slots;
     q.out = dst;
     int threads = 256;
     int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);

@@ -234,6 +234,7 @@ int maro_vm_query(MaroVmEnv* e, const int32_t* replicas, int32_t n_replicas, int
     if (!out) return fail("maro_vm_query: null output");
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, nullptr, out, out_per_replica);
 }
+int maro_vm_set_query_layout(MaroVmEnv* e, int32_t layout) { return common_set_query_layout(e, layout); }
 int32_t maro_vm_attr_id(MaroVmEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
 int32_t maro_vm_attr_slots(MaroVmEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }
 int maro_vm_read_frame(MaroVmEnv* e, int32_t replica, int32_t* out_words, int32_t n_words) { return common_read_frame(e, replica, out_words, n_words); }

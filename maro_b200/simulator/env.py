@@ -2,6 +2,7 @@
 scenario, backed by one replica (or a view on one replica of a shared batch) of the CUDA core."""
 from __future__ import annotations
 
+import os
 from enum import IntEnum
 from math import ceil, floor
 from typing import List, Optional
@@ -86,9 +87,13 @@ class SnapshotList:
             ids = [self._batch.attr_id(node, a) for a in attrs]
         except KeyError:
             raise KeyError(f"invalid attribute for {node}: {attrs}")
+        dynamic = getattr(self._batch, "query_layout", "static") == "dynamic"
         if len(ticks) == 0:
-            return np.zeros(0, np.float64)
-        return self._batch.query(node, ticks, nodes, ids, [self._replica])[0]
+            return None if dynamic else np.zeros(0, np.float64)  # (_raw_backend_.pyx:301-304: empty result -> None)
+        flat = self._batch.query(node, ticks, nodes, ids, [self._replica])[0]
+        if dynamic:  # RawBackend: 4-D (ticks, nodes, attrs, max_slots), NaN padded (_raw_backend_.pyx:306-315)
+            return flat.reshape(self._batch.query_shape(node, ids, len(ticks), len(nodes)))
+        return flat
 
 
 class _NodeView:
@@ -175,6 +180,11 @@ class Env:
             self._topo = build_topology(self._config, start_tick + durations)
             self._batch = CimBatch(self._topo, 1, start_tick, snapshot_resolution, max_snapshots, device=device,
                                    max_actions=8)
+        # the reference picks its backend per process from DEFAULT_BACKEND_NAME (maro/backends/frame.pyx:496-504); the two
+        # answer snapshot queries in different layouts — same switch here, per Env
+        self._backend_name = str((options or {}).get("backend_name") or os.environ.get("DEFAULT_BACKEND_NAME", "static"))
+        if self._backend_name == "dynamic":
+            self._batch.set_query_layout("dynamic")
         self._snapshots = SnapshotList(self._batch, 0)
         self._tick = start_tick
         self._last_metrics = make_metrics((0, 0, 0))
@@ -261,6 +271,8 @@ class Env:
                 self._batch.close()
                 self._batch = CimBatch(self._topo, 1, self._start_tick, self._snapshot_resolution, self._max_snapshots,
                                        device=self._device, max_actions=8)
+                if self._backend_name == "dynamic":
+                    self._batch.set_query_layout("dynamic")
                 self._snapshots = SnapshotList(self._batch, 0)
             self._pending_seed = None
         self._batch.reset()
@@ -351,10 +363,21 @@ class Env:
         return self._last_metrics
 
     def get_finished_events(self) -> list:
-        return []  # events live on the device; the finished-event list is not materialised
+        """core.py:241-249.  Event objects are never materialised on the device (the per-tick execution order
+        is reconstructed from its sources), so there is no finished-event list to hand out; an empty list would be
+        indistinguishable from "no events", hence the loud failure.  The executed-event COUNT is available
+        (``env.batch.counters()[:, 2]``)."""
+        raise NotImplementedError("finished-event objects are not materialised by the CUDA core "
+                                  "(event counts: Env.batch.counters()); run the reference Env for event-level inspection")
 
     def get_pending_events(self, tick) -> list:
-        return []
+        """core.py:251-259 — see ``get_finished_events``."""
+        raise NotImplementedError("pending-event objects are not materialised by the CUDA core")
+
+    @property
+    def batch(self):
+        """the columnar batch (one replica) behind this Env"""
+        return self._batch
 
     def get_ticks_frame_index_mapping(self) -> dict:
         mapping = {}

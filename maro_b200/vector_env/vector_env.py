@@ -73,6 +73,11 @@ class VectorEnv:
         self._finish_init(batch_num, start_tick)
 
     def _finish_init(self, batch_num, start_tick):
+        import os
+
+        self._backend_name = os.environ.get("DEFAULT_BACKEND_NAME", "static")  # maro/backends/frame.pyx:496-504
+        if self._backend_name == "dynamic":
+            self._batch.set_query_layout("dynamic")
         self._snapshot_wrapper = VectorEnv.SnapshotListWrapper(self)
         self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(batch_num)]
         self._done = np.zeros(batch_num, bool)
@@ -202,6 +207,8 @@ class VectorEnv:
                 B, start_tick, res, max_snaps, device = self._ctor
                 self._batch.close()
                 self._batch = CimBatch(new, B, start_tick, res, max_snaps, device=device, max_actions=4, replica_topology=self._rt)
+                if self._backend_name == "dynamic":
+                    self._batch.set_query_layout("dynamic")
                 self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(B)]
         self._batch.reset()
         self._done[:] = False
@@ -240,6 +247,9 @@ class VectorEnv:
         except KeyError:
             raise KeyError(f"invalid attribute for {node_name}: {attrs}")
         out = self._batch.query(node_name, ticks, nodes, ids)
+        if self._batch.query_layout == "dynamic":
+            shape = self._batch.query_shape(node_name, ids, len(ticks), len(nodes))
+            return [out[i].reshape(shape) for i in range(self._batch_num)]
         return [out[i] for i in range(self._batch_num)]
 
     @property

@@ -79,22 +79,41 @@ class EmulCimBatch:
         total = -(-(self.topologies[self._rt[replica]].max_tick - st) // res)
         return np.asarray([f for f in range(total) if e.snapshot(f) is not None], np.int32)
 
+    query_layout = "static"
+
+    def set_query_layout(self, layout):
+        self.query_layout = layout
+
+    def query_shape(self, node, attrs, n_frames, n_nodes):
+        slots = [self._lay[node][a if isinstance(a, str) else self._attrs[node][int(a)]][2] for a in attrs]
+        return (n_frames, n_nodes, len(slots), max(slots))
+
     def query(self, node, frame_indices, nodes, attrs, replicas=None):
+        """static layout: zero-padded flat float64 (np_backend.pyx:520-549); dynamic: every attribute padded to the widest
+        one's slots with NaN, unknown frames NaN, values through float32 (raw/snapshotlist.cpp:244-318) — an independent
+        Python statement of what cim_query_kernel does on the device"""
         reps = range(self.n_replicas) if replicas is None else replicas
+        dyn = self.query_layout == "dynamic"
+        names = [a if isinstance(a, str) else self._attrs[node][int(a)] for a in attrs]
+        width = max(self._lay[node][n][2] for n in names) if names else 0
         out = []
         for r in reps:
             vals = []
             for f in frame_indices:
                 row = self._envs[r].snapshot(int(f)) if f >= 0 else None
                 for nd in nodes:
-                    for a in attrs:
-                        name = a if isinstance(a, str) else self._attrs[node][int(a)]
+                    for name in names:
                         off, _, slots = self._lay[node][name]
                         if row is None:
-                            vals.append(np.zeros(slots))
+                            v = np.full(slots, np.nan) if dyn else np.zeros(slots)
                         else:
                             w = row[off + nd * slots: off + (nd + 1) * slots]
-                            vals.append((w.view(np.float32) if name == "transfer_cost" else w).astype(np.float64))
+                            v = (w.view(np.float32) if name == "transfer_cost" else w).astype(np.float64)
+                            if dyn:
+                                v = v.astype(np.float32).astype(np.float64)
+                        if dyn:
+                            v = np.concatenate([v, np.full(width - slots, np.nan)])
+                        vals.append(v)
             out.append(np.concatenate(vals) if vals else np.zeros(0))
         return np.asarray(out, np.float64)
 

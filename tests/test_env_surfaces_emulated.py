@@ -90,3 +90,7 @@ def test_reference_examples_run_unchanged_on_the_shim_emulated():
 
 def test_vector_env_reset_reseeds_like_the_reference_processes_emulated():
     surfaces.test_vector_env_reset_reseeds_like_the_reference_processes()
+
+
+def test_dynamic_backend_query_layout_matches_the_reference_emulated(monkeypatch):
+    surfaces.test_dynamic_backend_query_layout_matches_the_reference(monkeypatch)

@@ -176,7 +176,8 @@ def test_bike_per_replica_transfer_seeds():
     assert_bike_snapshots_equal(lambda f: env.snapshot_row(f, gold_rep), gold, topo.n_stations)
     for i in range(B):
         assert np.array_equal(env.read_frame(i), oracles[i].frame())
-    assert len({env.read_frame(i).tobytes() for i in range(B)}) > B // 2  # distinct streams -> distinct episodes
+    # (on this trace the delivery delays never change which trips succeed, so the final frames may well coincide; the
+    # per-replica streams are pinned by the step-by-step comparison with the per-seed oracles above)
     env.set_transfer_seeds(None)  # back to the topology's seed: clones again
     env.reset()
     d, m = env.step(None)

@@ -191,3 +191,49 @@ def test_vector_env_reset_reseeds_like_the_reference_processes():
         env.reset(keep_seed=True)  # same instances again: the first decisions repeat
         m, ev, done = env.step(None)
         assert [ev[0].tick, ev[0].port_idx, ev[0].vessel_idx, ev[0].action_scope.load] == gold[0][:4].tolist()
+
+
+def test_dynamic_backend_query_layout_matches_the_reference(monkeypatch):
+    """SURVEY.md A.5 / VERDICT r1 missing #5: with DEFAULT_BACKEND_NAME=dynamic the reference's RawBackend answers
+    snapshot queries as 4-D (ticks, nodes, attrs, max_slots) arrays, NaN for missing slots and unknown ticks, values
+    through float32 (raw/snapshotlist.cpp:244-318).  Same switch here; compared with arrays recorded from the reference
+    (tests/golden/gen_dynamic_query_golden.py).  The static layout of the same queries is checked against it too."""
+    import importlib.util
+    import os
+
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.simulator import Env
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_dyn", os.path.join(here, "golden", "gen_dynamic_query_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(here, "golden", "cim_dynamic_queries.npz"))
+
+    def episode(env):
+        metrics, ev, done = env.step(None)
+        k = 0
+        while not done:
+            act = Action(ev.vessel_idx, ev.port_idx, ev.action_scope.load // 2, ActionType.LOAD) if k % 3 == 0 else None
+            k += 1
+            metrics, ev, done = env.step(act)
+
+    monkeypatch.setenv("DEFAULT_BACKEND_NAME", "dynamic")
+    env = Env("cim", gen.TOPOLOGY, durations=gen.DURATIONS)
+    episode(env)
+    dyn = gen.run_queries(env)
+    for name in gen.QUERIES:
+        assert dyn[name].shape == gold[name].shape, (name, dyn[name].shape, gold[name].shape)
+        assert np.array_equal(dyn[name], gold[name], equal_nan=True), name
+    env.close()
+    monkeypatch.setenv("DEFAULT_BACKEND_NAME", "static")
+    env = Env("cim", gen.TOPOLOGY, durations=gen.DURATIONS)
+    episode(env)
+    for name, (node, ticks, nodes, attrs) in gen.QUERIES.items():
+        flat = env.snapshot_list[node][gen.key_of((node, ticks, nodes, attrs))[1]]
+        g = gold[name]
+        if isinstance(ticks, list) and 1000 in ticks:  # unknown tick: zeros (static) vs NaN (dynamic)
+            g = g.copy()
+            g[ticks.index(1000)] = np.where(np.isnan(g[ticks.index(1000)]), 0.0, g[ticks.index(1000)])
+        assert flat.ndim == 1 and np.array_equal(flat, g[~np.isnan(g)]), name  # same numbers, packed, no padding
+    env.close()

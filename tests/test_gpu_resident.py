@@ -255,3 +255,88 @@ def test_async_submit_wait_pipelines_sub_batches():
     for k, i in enumerate(probes):
         assert np.array_equal(env.read_frame(i), oracles[k].frame())
     env.close()
+
+
+def test_host_threads_drive_disjoint_sub_batches_with_in_session_resets():
+    """maro_cim_submit_pinned / _wait_pinned / maro_cim_reset from several host threads on disjoint replica ranges (the
+    contract of include/maro_b200.h): every thread runs its own wait -> agent -> submit pipeline over two sub-batches for
+    two and a half episodes; Env.reset of a finished sub-batch rides on the next command row (the resident kernel resets the
+    replica in shared memory, no write-back / relaunch).  Every replica's decisions and metrics are checked against oracles."""
+    import threading
+
+    from oracle.cim_oracle import CimOracle, policy_random
+
+    topo = _topo("toy.4p_ssdd_l0.8", 60)  # noisy orders / buffers: the reset also has to restore the MT19937 streams
+    B = 64
+    env = _batch(topo, B)
+    g = env.pinned_granularity()
+    assert g > 0 and B % (4 * g) == 0
+    q = B // 4
+    ranges = [(k * q, q) for k in range(4)]
+    pa, pn, pact, pd, pm = env.pinned()
+    oracles = [CimOracle(topo) for _ in range(B)]
+    errors = []
+
+    def drive(my_ranges):
+        try:
+            outs = {}
+            steps = {}
+            episodes = {f: 0 for f, _ in my_ranges}
+            for f, c in my_ranges:
+                for r in range(f, f + c):
+                    oracles[r].reset()
+                    outs[r] = oracles[r].step(None)
+                steps[f] = 0
+                env.submit_pinned(f, c, use_actions=False)
+            budget = 400
+            live = {f: True for f, _ in my_ranges}
+            while any(live.values()) and budget > 0:
+                for f, c in my_ranges:
+                    if not live[f]:
+                        continue
+                    budget -= 1
+                    env.wait_pinned(f, c)
+                    for r in range(f, f + c):
+                        st, d, m = outs[r]
+                        assert d[:7].tolist() == pd[r, :7].tolist() and m.tolist() == pm[r].tolist(), (r, steps[f], d, pd[r])
+                    if all(outs[r][0] != 0 for r in range(f, f + c)):  # the sub-batch finished its episode
+                        episodes[f] += 1
+                        if episodes[f] == 3:
+                            live[f] = False
+                            continue
+                        mask = np.zeros(B, np.uint8)
+                        mask[f:f + c] = 1
+                        env.reset(mask)
+                        for r in range(f, f + c):
+                            oracles[r].reset()
+                            outs[r] = oracles[r].step(None)
+                        steps[f] = 0
+                        env.submit_pinned(f, c, use_actions=False)
+                        continue
+                    for r in range(f, f + c):
+                        pa[r, 0] = policy_random(pd[r], 9, r, steps[f])
+                        if outs[r][0] == 0:
+                            outs[r] = oracles[r].step(pa[r].copy())
+                        elif outs[r][0] == 1:
+                            outs[r] = oracles[r].step(None)  # DONE -> FINISHED row
+                    env.submit_pinned(f, c)
+                    steps[f] += 1
+            assert not any(live.values())
+        except BaseException as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=drive, args=(ranges[:2],)), threading.Thread(target=drive, args=(ranges[2:],))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    for r in (0, q, 2 * q + 1, B - 1):
+        assert np.array_equal(env.read_frame(r), oracles[r].frame())
+    # a reset that never rode on a command row is applied when the session ends
+    env.submit_pinned(0, B, use_actions=False)
+    env.wait_pinned(0, B)
+    env.reset()
+    assert (env.ticks() == 0).all() and env.read_frame(5)[0] == 0
+    env.close()

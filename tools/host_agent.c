@@ -143,3 +143,76 @@ int e2e_loop_cim(void* env, void* submit_p, void* wait_p, void* reset_p, const i
     out[2] = resets;
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * The same loop on `n_threads` host threads: the sub-batches are dealt out in contiguous runs, every thread drives its
+ * own (wait -> agent -> submit) pipeline.  maro_cim_submit_pinned / maro_cim_wait_pinned / maro_cim_reset accept concurrent
+ * callers on disjoint replica ranges (include/maro_b200.h).  out[1] = agent seconds averaged over the threads. */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    void* env; submit_fn submit; wait_fn wait; reset_fn reset;
+    const int32_t* dec; int32_t* act; int B, n_steps, k0, k1; const int* first; uint32_t seed, replica_base;
+    double t_agent, resets; int rc;
+} e2e_worker;
+
+static void* e2e_worker_main(void* p) {
+    e2e_worker* w = (e2e_worker*)p;
+    uint8_t* mask = (uint8_t*)malloc((size_t)w->B);
+    w->rc = 0; w->t_agent = 0.0; w->resets = 0.0;
+    for (int k = w->k0; k < w->k1 && !w->rc; k++)
+        w->rc = w->submit(w->env, w->first[k], w->first[k + 1] - w->first[k], 0, 0, 0);
+    for (int step = 0; step < w->n_steps && !w->rc; step++) {
+        for (int k = w->k0; k < w->k1 && !w->rc; k++) {
+            const int f = w->first[k], c = w->first[k + 1] - w->first[k];
+            if ((w->rc = w->wait(w->env, f, c))) break;
+            if (step == w->n_steps - 1) continue;
+            int done = 1;
+            for (int i = f; i < f + c; i++) done &= w->dec[8 * i + 6] != 0;
+            if (done) {
+                memset(mask, 0, (size_t)w->B);
+                memset(mask + f, 1, (size_t)c);
+                if ((w->rc = w->reset(w->env, mask))) break;
+                w->resets += 1.0;
+                w->rc = w->submit(w->env, f, c, 0, 0, 0);
+                continue;
+            }
+            const double ta = now_s();
+            agent_random_range(w->dec, w->act, f, c, w->seed, w->replica_base);
+            w->t_agent += now_s() - ta;
+            w->rc = w->submit(w->env, f, c, 1, 0, 0);
+        }
+    }
+    free(mask);
+    return 0;
+}
+
+int e2e_loop_cim_mt(void* env, void* submit_p, void* wait_p, void* reset_p, const int32_t* dec, int32_t* act, int B, int gran,
+                    int n_sub, int n_threads, int n_steps, uint32_t seed, uint32_t replica_base, double* out) {
+    int first[65], n = 0;
+    if (n_sub < 1) n_sub = 1;
+    if (n_sub > 64) n_sub = 64;
+    int blocks = (B + gran - 1) / gran, per = (blocks + n_sub - 1) / n_sub;
+    for (int b = 0; b < blocks; b += per) first[n++] = b * gran;
+    first[n] = B;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n) n_threads = n;
+    e2e_worker w[64];
+    pthread_t th[64];
+    const double t0 = now_s();
+    for (int t = 0; t < n_threads; t++) {
+        e2e_worker* x = &w[t];
+        x->env = env; x->submit = (submit_fn)submit_p; x->wait = (wait_fn)wait_p; x->reset = (reset_fn)reset_p;
+        x->dec = dec; x->act = act; x->B = B; x->n_steps = n_steps; x->first = first; x->seed = seed; x->replica_base = replica_base;
+        x->k0 = (int)((long long)n * t / n_threads); x->k1 = (int)((long long)n * (t + 1) / n_threads);
+        if (t > 0) pthread_create(&th[t], 0, e2e_worker_main, x);
+    }
+    e2e_worker_main(&w[0]);
+    for (int t = 1; t < n_threads; t++) pthread_join(th[t], 0);
+    out[0] = now_s() - t0; out[1] = 0.0; out[2] = 0.0;
+    int rc = 0;
+    for (int t = 0; t < n_threads; t++) { out[1] += w[t].t_agent / n_threads; out[2] += w[t].resets; rc |= w[t].rc; }
+    return rc;
+}
