@@ -196,6 +196,13 @@ int maro_cim_query_device(MaroCimEnv* env, const int32_t* replicas, int32_t n_re
  *                             frames not in the ring are NaN; values pass through float32 (ATTR_FLOAT).
  * `out_per_replica` of the query calls reports the per-replica element count of the active layout. */
 enum { MARO_QUERY_LAYOUT_STATIC = 0, MARO_QUERY_LAYOUT_DYNAMIC = 1 };
+/* Device-state checkpoint — what the reference leaves unimplemented in Env.dump ("Dump environment for restore",
+ * maro/simulator/core.py:135-141): the complete simulation state of the handle (replica blocks incl. event queues, snapshot
+ * ring, RNG streams, topology tables) goes to one file; `load` restores it into a handle created with the same topologies /
+ * configuration (checked) and the episode continues bit for bit.  with_snapshots = 0 leaves the ring rows out (the ring then
+ * restarts empty after a load). */
+int maro_cim_save(MaroCimEnv* env, const char* path, int32_t with_snapshots);
+int maro_cim_load(MaroCimEnv* env, const char* path);
 int maro_cim_set_query_layout(MaroCimEnv* env, int32_t layout);
 /* Attribute id / slot count by name for a node type; -1 if unknown. */
 int32_t maro_cim_attr_id(MaroCimEnv* env, int32_t node_type, const char* name);
@@ -328,6 +335,8 @@ int maro_bike_query(MaroBikeEnv* env, const int32_t* replicas, int32_t n_replica
                     const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
                     const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
 int maro_bike_set_query_layout(MaroBikeEnv* env, int32_t layout); /* see maro_cim_set_query_layout */
+int maro_bike_save(MaroBikeEnv* env, const char* path, int32_t with_snapshots); /* see maro_cim_save */
+int maro_bike_load(MaroBikeEnv* env, const char* path);
 int32_t maro_bike_attr_id(MaroBikeEnv* env, int32_t node_type, const char* name);
 int32_t maro_bike_attr_slots(MaroBikeEnv* env, int32_t node_type, int32_t attr_id);
 int maro_bike_read_frame(MaroBikeEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);
@@ -420,6 +429,8 @@ int maro_vm_query(MaroVmEnv* env, const int32_t* replicas, int32_t n_replicas, i
                   const int32_t* frame_indices, int32_t n_frames, const int32_t* nodes, int32_t n_nodes,
                   const int32_t* attrs, int32_t n_attrs, double* out, int64_t* out_per_replica);
 int maro_vm_set_query_layout(MaroVmEnv* env, int32_t layout); /* see maro_cim_set_query_layout */
+int maro_vm_save(MaroVmEnv* env, const char* path, int32_t with_snapshots); /* see maro_cim_save */
+int maro_vm_load(MaroVmEnv* env, const char* path);
 int32_t maro_vm_attr_id(MaroVmEnv* env, int32_t node_type, const char* name);
 int32_t maro_vm_attr_slots(MaroVmEnv* env, int32_t node_type, int32_t attr_id);
 int maro_vm_read_frame(MaroVmEnv* env, int32_t replica, int32_t* out_words, int32_t n_words);

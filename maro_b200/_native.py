@@ -27,6 +27,7 @@ EXPORTS = (
     "maro_bike_read_frame", "maro_bike_frame_words", "maro_bike_ticks", "maro_bike_counters", "maro_bike_snapshot_frames",
     "maro_bike_greedy_policy_device", "maro_bike_set_transfer_seeds",
     "maro_cim_set_query_layout", "maro_bike_set_query_layout", "maro_vm_set_query_layout",
+    "maro_cim_save", "maro_cim_load", "maro_bike_save", "maro_bike_load", "maro_vm_save", "maro_vm_load",
     "maro_vm_create", "maro_vm_destroy", "maro_vm_set_stream", "maro_vm_decision_words", "maro_vm_step",
     "maro_vm_step_device", "maro_vm_pinned_buffers", "maro_vm_step_pinned", "maro_vm_reset", "maro_vm_query",
     "maro_vm_attr_id", "maro_vm_attr_slots", "maro_vm_read_frame", "maro_vm_frame_words", "maro_vm_ticks",
@@ -109,6 +110,9 @@ def lib():
     L.maro_bike_set_transfer_seeds.argtypes = [vp, vp]
     for name in ("maro_cim_set_query_layout", "maro_bike_set_query_layout", "maro_vm_set_query_layout"):
         getattr(L, name).argtypes = [vp, i32]
+    for pre in ("maro_cim", "maro_bike", "maro_vm"):
+        getattr(L, pre + "_save").argtypes = [vp, C.c_char_p, i32]
+        getattr(L, pre + "_load").argtypes = [vp, C.c_char_p]
     for pre in ("maro_vm",):  # same shapes as the citi_bike entry points
         getattr(L, pre + "_create").argtypes = [vp, vp, C.POINTER(vp)]
         getattr(L, pre + "_destroy").argtypes = [vp]

@@ -6,6 +6,7 @@ sit on.  All arrays are numpy (host) unless a method says ``_device``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -54,6 +55,7 @@ class CimBatch:
         cfg.start_tick = self.start_tick
         cfg.snapshot_resolution = self.snapshot_resolution
         cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
+        self._max_snapshots = cfg.max_snapshots
         cfg.device = self.device
         cfg.queue_capacity = int(queue_capacity)
         cfg.max_actions = self.max_actions
@@ -188,6 +190,20 @@ class CimBatch:
     def attr_slots(self, node: str, attr_id: int) -> int:
         return _native.lib().maro_cim_attr_slots(self._h, _NODE_TYPE[node], attr_id)
 
+    def ring_rows(self) -> int:
+        """rows of the snapshot ring: ``max_snapshots`` or the number of frames of the episode (np_backend.pyx:481-518)"""
+        total = -(-(self.topologies[0].max_tick - self.start_tick) // self.snapshot_resolution)
+        return min(self._max_snapshots, total) if self._max_snapshots else total
+
+    def save(self, path: str, with_snapshots: bool = True):
+        """Device-state checkpoint of the whole batch (replica blocks, event queues, snapshot ring, RNG streams, topology
+        tables) into one file — what ``Env.dump`` promises and the reference leaves unimplemented (core.py:135-141)."""
+        _native.check(_native.lib().maro_cim_save(self._h, os.fsencode(path), int(with_snapshots)))
+
+    def load(self, path: str):
+        """Restore a checkpoint written by ``save`` on a batch of the same topologies / configuration."""
+        _native.check(_native.lib().maro_cim_load(self._h, os.fsencode(path)))
+
     query_layout = "static"
 
     def set_query_layout(self, layout: str):
@@ -308,6 +324,17 @@ class BikeBatch:
     def node_counts(self) -> dict:
         return {"stations": self.topology.n_stations, "matrices": 1}
 
+    def ring_rows(self) -> int:
+        total = -(-(int(self.topology.max_tick) - int(self.topology.start_tick)) // self.snapshot_resolution)
+        return min(self._max_snapshots, total) if self._max_snapshots else total
+
+    def save(self, path: str, with_snapshots: bool = True):
+        """see ``CimBatch.save``"""
+        _native.check(self._f("save")(self._h, os.fsencode(path), int(with_snapshots)))
+
+    def load(self, path: str):
+        _native.check(self._f("load")(self._h, os.fsencode(path)))
+
     query_layout = "static"
     _per_replica = CimBatch._per_replica
     query_shape = CimBatch.query_shape
@@ -339,6 +366,7 @@ class BikeBatch:
         cfg.start_tick = int(topology.start_tick)
         cfg.snapshot_resolution = int(snapshot_resolution)
         cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
+        self.snapshot_resolution, self._max_snapshots = cfg.snapshot_resolution, cfg.max_snapshots
         cfg.device = int(device)
         cfg.queue_capacity = int(queue_capacity)
         cfg.max_actions = self.max_actions

@@ -243,6 +243,8 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
     CKD(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
     CKD(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
     CKD(cudaMalloc(&e->d_rng, (size_t)e->B * s.rng_words * 4));
+    e->scenario_id = 2;
+    e->ckpt_extra = {{"rng", (void**)&e->d_rng, (size_t)e->B * s.rng_words * 4}};
     *out = e;
     int rc = maro_bike_reset(e, nullptr);
     if (rc) { maro_bike_destroy(e); *out = nullptr; return rc; }
@@ -310,6 +312,8 @@ int maro_bike_query(MaroBikeEnv* e, const int32_t* replicas, int32_t n_replicas,
     if (!out) return fail("maro_bike_query: null output");
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, nullptr, out, out_per_replica);
 }
+int maro_bike_save(MaroBikeEnv* e, const char* path, int32_t with_snapshots) { return common_save(e, path, with_snapshots); }
+int maro_bike_load(MaroBikeEnv* e, const char* path) { return common_load(e, path); }
 int maro_bike_set_query_layout(MaroBikeEnv* e, int32_t layout) { return common_set_query_layout(e, layout); }
 int32_t maro_bike_attr_id(MaroBikeEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
 int32_t maro_bike_attr_slots(MaroBikeEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }

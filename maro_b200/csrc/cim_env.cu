@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
                         if (i < n_live) *reinterpret_cast<uint4*>(cmd_s + i * 4) = c;
                     }
                     if (ok) break;
-                    if (clock64() - t0 > ra.idle_cycles) {
+                    if (g.shfl((int)(clock64() - t0 > ra.idle_cycles), 0)) {  // (the leader's clock decides for the group)
                         // no command for a while: leave only if the host has left submit / wait altogether (its heartbeat stands
                         // still) — then every CTA leaves within one idle period and the host relaunches the whole grid.  While
                         // any host thread is still driving other CTAs, a slow driver of this CTA must not strand it.
@@ -649,6 +649,9 @@ static int session_end(MaroCimEnv* e) {
         }
         e->session_live.store(false);
         CK(cudaStreamSynchronize(e->stream));
+        // the EXIT rows must not be taken for commands by the next launch (a CTA whose first command row has not been written
+        // yet when the kernel comes up would leave at once): park every row on a sequence number nobody waits for
+        for (int i = 0; i < e->B; i++) __atomic_store_n(e->h_cmd + (size_t)i * 4, e->cta_seq[i / gpc], __ATOMIC_RELEASE);
     }
     // resets that arrived while the session was live and never rode on a command row
     bool pend = false;
@@ -772,6 +775,9 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
         const char* se = getenv("MARO_B200_SESSION");
         e->session_ok = (se ? atoi(se) != 0 : true) && (int64_t)per_sm * nsm >= e->res_grid;
     }
+    e->scenario_id = 1;
+    e->ckpt_extra = {{"tables", (void**)&e->d_tables, e->h_tables.size() * 4}, {"replica_topology", (void**)&e->d_topo, (size_t)B * 4},
+                     {"mt19937", (void**)&e->d_mt, (size_t)B * e->mt_words * 4}, {"light", (void**)&e->d_light, (size_t)B}};
     if (const char* v = getenv("MARO_B200_POLL_NS")) e->poll_ns = (uint32_t)atoi(v);
     if (const char* v = getenv("MARO_B200_WAIT_NS")) e->wait_ns = (uint32_t)atoi(v);
     if (const char* iu = getenv("MARO_B200_IDLE_US")) e->idle_cycles = (long long)(atof(iu) * 1e-6 * prop.clockRate * 1e3);
@@ -780,7 +786,13 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
 
 extern "C" {
 
-const char* maro_last_error(void) { return g_err.c_str(); }
+const char* maro_last_error(void) {
+    if (g_err.empty()) {  // nothing failed on this thread: the latest failure of any thread (worker threads of a host loop)
+        std::lock_guard<std::mutex> lock(g_err_mu);
+        g_err = g_err_any;
+    }
+    return g_err.c_str();
+}
 int maro_abi_version(void) { return MARO_B200_ABI_VERSION; }
 
 int maro_cim_destroy(MaroCimEnv* e) {
@@ -1030,6 +1042,20 @@ int maro_cim_query_device(MaroCimEnv* e, const int32_t* replicas, int32_t n_repl
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, d_out, nullptr, out_per_replica);
 }
 
+/* Env.dump / restore: the whole simulation state of the handle (replica blocks, snapshot ring, RNG streams, topology tables) */
+int maro_cim_save(MaroCimEnv* e, const char* path, int32_t with_snapshots) {
+    if (e) END_SESSION(e);
+    return common_save(e, path, with_snapshots);
+}
+int maro_cim_load(MaroCimEnv* e, const char* path) {
+    if (e) END_SESSION(e);
+    int rc = common_load(e, path);
+    if (!rc) {  // host mirror of the topology tables (set_topology edits it in place)
+        CK(cudaMemcpy(e->h_tables.data(), e->d_tables, e->h_tables.size() * 4, cudaMemcpyDeviceToHost));
+        std::fill(e->reset_pending.begin(), e->reset_pending.end(), (uint8_t)0);
+    }
+    return rc;
+}
 int maro_cim_set_query_layout(MaroCimEnv* e, int32_t layout) { return common_set_query_layout(e, layout); }
 int32_t maro_cim_attr_id(MaroCimEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
 int32_t maro_cim_attr_slots(MaroCimEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -102,7 +103,14 @@ static __global__ void cim_query_kernel(const __grid_constant__ QueryArgs q) {
 // Host side
 // =====================================================================================================
 inline thread_local std::string g_err;  // one instance for the library: maro_last_error() lives in cim_env.cu
-static int fail(const std::string& m) { g_err = m; return 1; }
+inline std::mutex g_err_mu;             // + the most recent error of ANY thread (host loops that drive a handle from worker
+inline std::string g_err_any;           //   threads report through the thread that joins them)
+static int fail(const std::string& m) {
+    g_err = m;
+    std::lock_guard<std::mutex> lock(g_err_mu);
+    g_err_any = m;
+    return 1;
+}
 #define CK(call)                                                                                      \
     do {                                                                                              \
         cudaError_t e__ = (call);                                                                     \
@@ -134,6 +142,11 @@ struct EnvCommon {
     std::vector<AttrInfo> attrs[6];
     int n_node_types = 3;
     int query_layout = 0;  // MARO_QUERY_LAYOUT_STATIC / _DYNAMIC (maro_*_set_query_layout)
+    // device buffers beyond [state | ring] that belong to the simulation state (RNG streams, topology tables ...): the
+    // scenario registers them at create time so that a checkpoint carries them (common_save / common_load)
+    struct ExtraBuffer { const char* name; void** d_ptr; size_t bytes; };
+    std::vector<ExtraBuffer> ckpt_extra;
+    int scenario_id = 0;
 };
 
 static void common_free(EnvCommon* e) {
@@ -250,6 +263,87 @@ static int common_snapshot_frames(EnvCommon* e, int32_t replica, int32_t* out, i
     for (int i = 0; i < (int)have.size() && i < cap; i++) out[i] = have[i];
     return 0;
 }
+// ---- device-state checkpoint ("enables env.dump / checkpoint of device state") -------------------
+// File: CkptHeader | state [B][SW] i32 | snap_frame [B][ring] i32 | (snap [B][ring][FWp] i32 when with_snapshots) | extras.
+// A checkpoint restores into a handle created with the same topology / configuration (the header's shape must match).
+struct CkptHeader {
+    char magic[8];
+    int32_t version, scenario, B, SW, FWp, ring_rows, with_snapshots, n_extra;
+    int64_t extra_bytes[8];
+};
+
+static int ckpt_copy(FILE* fp, void* d_ptr, size_t bytes, bool save, cudaStream_t stream) {
+    const size_t chunk = 32u << 20;
+    std::vector<uint8_t> host(std::min(bytes, chunk));
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t n = std::min(chunk, bytes - off);
+        if (save) {
+            CK(cudaMemcpyAsync(host.data(), (uint8_t*)d_ptr + off, n, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (fwrite(host.data(), 1, n, fp) != n) return fail("checkpoint: short write");
+        } else {
+            if (fread(host.data(), 1, n, fp) != n) return fail("checkpoint: short read (truncated file)");
+            CK(cudaMemcpyAsync((uint8_t*)d_ptr + off, host.data(), n, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+    }
+    return 0;
+}
+
+static int common_save(EnvCommon* e, const char* path, int32_t with_snapshots) {
+    if (!e || !path) return fail("save: bad arguments");
+    if (e->ckpt_extra.size() > 8) return fail("save: too many extra buffers");
+    CK(cudaSetDevice(e->device));
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(std::string("save: cannot open ") + path);
+    CkptHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "MAROB2CK", 8);
+    h.version = 1; h.scenario = e->scenario_id; h.B = e->B; h.SW = e->SW; h.FWp = e->FWp; h.ring_rows = e->ring_rows;
+    h.with_snapshots = with_snapshots ? 1 : 0; h.n_extra = (int32_t)e->ckpt_extra.size();
+    for (size_t i = 0; i < e->ckpt_extra.size(); i++) h.extra_bytes[i] = *e->ckpt_extra[i].d_ptr ? (int64_t)e->ckpt_extra[i].bytes : 0;
+    int rc = fwrite(&h, sizeof(h), 1, fp) == 1 ? 0 : fail("save: short write");
+    const size_t B = (size_t)e->B;
+    if (!rc) rc = ckpt_copy(fp, e->d_state, B * e->SW * 4, true, e->stream);
+    if (!rc) rc = ckpt_copy(fp, e->d_snap_frame, B * e->ring_rows * 4, true, e->stream);
+    if (!rc && with_snapshots) rc = ckpt_copy(fp, e->d_snap, B * e->ring_rows * e->FWp * 4, true, e->stream);
+    for (size_t i = 0; !rc && i < e->ckpt_extra.size(); i++)
+        if (h.extra_bytes[i]) rc = ckpt_copy(fp, *e->ckpt_extra[i].d_ptr, (size_t)h.extra_bytes[i], true, e->stream);
+    if (fclose(fp) != 0 && !rc) rc = fail("save: close failed");
+    return rc;
+}
+
+static int common_load(EnvCommon* e, const char* path) {
+    if (!e || !path) return fail("load: bad arguments");
+    CK(cudaSetDevice(e->device));
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(std::string("load: cannot open ") + path);
+    CkptHeader h;
+    int rc = 0;
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "MAROB2CK", 8) != 0 || h.version != 1) rc = fail("load: not a maro_b200 checkpoint");
+    if (!rc && (h.scenario != e->scenario_id || h.B != e->B || h.SW != e->SW || h.FWp != e->FWp || h.ring_rows != e->ring_rows ||
+                h.n_extra != (int32_t)e->ckpt_extra.size()))
+        rc = fail("load: the checkpoint was written by a handle of a different shape (scenario / replicas / topology / snapshot ring)");
+    for (size_t i = 0; !rc && i < e->ckpt_extra.size(); i++) {
+        const int64_t have = *e->ckpt_extra[i].d_ptr ? (int64_t)e->ckpt_extra[i].bytes : 0;
+        if (h.extra_bytes[i] != have) rc = fail(std::string("load: buffer '") + e->ckpt_extra[i].name + "' differs in size");
+    }
+    const size_t B = (size_t)e->B;
+    if (!rc) rc = ckpt_copy(fp, e->d_state, B * e->SW * 4, false, e->stream);
+    if (!rc) rc = ckpt_copy(fp, e->d_snap_frame, B * e->ring_rows * 4, false, e->stream);
+    if (!rc) {
+        if (h.with_snapshots) rc = ckpt_copy(fp, e->d_snap, B * e->ring_rows * e->FWp * 4, false, e->stream);
+        else {  // rows were not saved: the ring restarts empty (queries of earlier frames read as "not held")
+            CK(cudaMemsetAsync(e->d_snap_frame, 0xff, B * e->ring_rows * 4, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+        }
+    }
+    for (size_t i = 0; !rc && i < e->ckpt_extra.size(); i++)
+        if (h.extra_bytes[i]) rc = ckpt_copy(fp, *e->ckpt_extra[i].d_ptr, (size_t)h.extra_bytes[i], false, e->stream);
+    fclose(fp);
+    return rc;
+}
+
 static int common_set_query_layout(EnvCommon* e, int32_t layout) {
     if (!e || (layout != 0 && layout != 1)) return fail("set_query_layout: layout must be 0 (static) or 1 (dynamic)");
     e->query_layout = layout;

@@ -183,6 +183,7 @@ int maro_vm_create(const MaroVmTopology* topo, const MaroCimConfig* cfg, MaroVmE
     if (common_alloc(e)) { maro_vm_destroy(e); return 1; }
     CKD(cudaMalloc(&e->d_tables, e->h_tables.size() * 4));
     CKD(cudaMemcpy(e->d_tables, e->h_tables.data(), e->h_tables.size() * 4, cudaMemcpyHostToDevice));
+    e->scenario_id = 3;
     *out = e;
     int rc = vm_reset_impl(e, nullptr, 1);
     if (rc) { maro_vm_destroy(e); *out = nullptr; return rc; }
@@ -234,6 +235,8 @@ int maro_vm_query(MaroVmEnv* e, const int32_t* replicas, int32_t n_replicas, int
     if (!out) return fail("maro_vm_query: null output");
     return query_impl(e, replicas, n_replicas, node_type, frame_indices, n_frames, nodes, n_nodes, attrs, n_attrs, nullptr, out, out_per_replica);
 }
+int maro_vm_save(MaroVmEnv* e, const char* path, int32_t with_snapshots) { return common_save(e, path, with_snapshots); }
+int maro_vm_load(MaroVmEnv* e, const char* path) { return common_load(e, path); }
 int maro_vm_set_query_layout(MaroVmEnv* e, int32_t layout) { return common_set_query_layout(e, layout); }
 int32_t maro_vm_attr_id(MaroVmEnv* e, int32_t node_type, const char* name) { return common_attr_id(e, node_type, name); }
 int32_t maro_vm_attr_slots(MaroVmEnv* e, int32_t node_type, int32_t attr_id) { return common_attr_slots(e, node_type, attr_id); }

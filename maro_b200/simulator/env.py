@@ -78,6 +78,17 @@ class SnapshotList:
     def get_frame_index_list(self) -> List[int]:
         return self._batch.snapshot_frames(self._replica).tolist()
 
+    def dump(self, folder: str):
+        """``SnapshotList.dump`` (frame.pyx:839-846).  Static layout: what NumpyBackend.dump writes per node type
+        (np_backend.pyx:391-401) — ``<node>.npy``, one structured array ``[1 + snapshots][nodes]`` whose row 0 is the live frame
+        and rows 1.. the snapshots in ring order, in the node's declared dtypes, and ``<node>.meta`` (attribute names / slot
+        counts).  Dynamic layout: ``snapshots_<node>.csv`` like the RawBackend (raw/snapshotlist.cpp:420-487)."""
+        if not os.path.exists(folder):
+            return
+        from .dump import dump_snapshots
+
+        dump_snapshots(self._batch, self._replica, folder)
+
     def _query(self, node, ticks, nodes, attrs):
         if len(ticks) == 0:
             ticks = self.get_frame_index_list()
@@ -247,8 +258,19 @@ class Env:
         event = DecisionEvent(int(d[0]), int(d[1]), int(d[2]), self._snapshots, ActionScope(int(d[3]), int(d[4])), int(d[5]))
         return self._last_metrics, event, False
 
-    def dump(self) -> None:
-        return
+    def dump(self, path: Optional[str] = None, with_snapshots: bool = True) -> None:
+        """``Env.dump`` — "Dump environment for restore", a no-op in the reference (core.py:135-141).  With a ``path`` the
+        complete device state of the environment (frame, event queue, snapshot ring, RNG streams, topology tables) is written
+        to that file; ``restore(path)`` on an Env built with the same arguments continues the episode bit for bit.  Without
+        a path it stays the reference's no-op."""
+        if path is not None:
+            self._batch.save(path, with_snapshots)
+
+    def restore(self, path: str) -> None:
+        """Load a checkpoint written by ``dump(path)``; the next ``step`` continues from where the dump was taken (it expects
+        the action for the decision that was pending then, exactly like the ``step`` that would have followed)."""
+        self._batch.load(path)
+        self._tick = int(self._batch.ticks()[0])
 
     def reset(self, keep_seed: bool = False) -> None:
         """core.py:143-170 + cim_data_container_helpers.py:56-66: ``keep_seed=False`` draws a new topology seed from

@@ -35,6 +35,14 @@ class EmulCimBatch:
         t = self.topologies[0]
         return {"ports": t.n_ports, "vessels": t.n_vessels, "matrices": 1}
 
+    def ring_rows(self):
+        st, res, ms = self._cfg
+        total = -(-(self.topologies[0].max_tick - st) // res)
+        return min(int(ms), total) if ms else total
+
+    def snapshot_row(self, frame_index, replica=0):
+        return self._envs[replica].snapshot(int(frame_index))
+
     def close(self):
         self._envs = []
 

@@ -94,3 +94,7 @@ def test_vector_env_reset_reseeds_like_the_reference_processes_emulated():
 
 def test_dynamic_backend_query_layout_matches_the_reference_emulated(monkeypatch):
     surfaces.test_dynamic_backend_query_layout_matches_the_reference(monkeypatch)
+
+
+def test_frame_dump_is_byte_identical_to_the_reference_emulated(tmp_path):
+    surfaces.test_frame_dump_is_byte_identical_to_the_reference(tmp_path)

@@ -42,7 +42,11 @@ def test_cuda_matches_reference_trace(name):
     assert st == 1
     assert step_fn(None)[0] == 2  # finished env -> (None, None, True)
     if "frames" in gold:
-        assert env.snapshot_frames(B - 1).tolist() == gold["frames"].tolist()
+        held = env.snapshot_frames(B - 1).tolist()
+        if spec.get("keep_frames"):  # the trace keeps every n-th frame only
+            assert set(gold["frames"].tolist()) <= set(held)
+        else:
+            assert held == gold["frames"].tolist()
         assert_snapshots_equal(lambda f: env.snapshot_row(f, B - 1), gold, topo)
     env.close()
 

@@ -237,3 +237,28 @@ def test_dynamic_backend_query_layout_matches_the_reference(monkeypatch):
             g[ticks.index(1000)] = np.where(np.isnan(g[ticks.index(1000)]), 0.0, g[ticks.index(1000)])
         assert flat.ndim == 1 and np.array_equal(flat, g[~np.isnan(g)]), name  # same numbers, packed, no padding
     env.close()
+
+
+def test_frame_dump_is_byte_identical_to_the_reference(tmp_path):
+    """``snapshot_list.dump(folder)`` writes the static backend's on-disk format — one structured
+    ``<node>.npy`` ([1 + snapshots][nodes], row 0 the live frame, rows 1.. the ring) + ``<node>.meta`` per node type
+    (np_backend.pyx:391-401) — compared byte for byte with the files the reference wrote for the same episode
+    (tests/golden/gen_dump_golden.py)."""
+    import importlib.util
+    import os
+
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.simulator import Env
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_dump", os.path.join(here, "golden", "gen_dump_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    env = Env("cim", gen.TOPOLOGY, durations=gen.DURATIONS, max_snapshots=gen.MAX_SNAPSHOTS)
+    gen.drive(env, Action, ActionType)
+    env.snapshot_list.dump(str(tmp_path))
+    gold = os.path.join(here, "golden", "dump_toy4p_20")
+    for name in sorted(os.listdir(gold)):
+        with open(os.path.join(gold, name), "rb") as a, open(tmp_path / name, "rb") as b:
+            assert a.read() == b.read(), name
+    env.close()
