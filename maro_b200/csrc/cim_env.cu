@@ -176,6 +176,8 @@ struct ResidentArgs {
     uint32_t poll_ns, wait_ns;      // back-off of the command poll (PCIe) and of the shared-memory relay wait
     uint32_t* seq_state;            // device [B]: last seq each replica has completed (survives launches and resets)
     const uint32_t* heartbeat;      // mapped host word the host bumps while it is inside submit / wait (any thread)
+    uint32_t* exit_flag;            // device word: set (to `epoch`) by the first CTA that gives up waiting; every CTA of the launch
+    uint32_t epoch;                 //   leaves at its next poll once it is set, so a launch never ends for only SOME of its CTAs
     long long idle_cycles;
 };
 
@@ -261,6 +263,9 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
                 bool stop = false, have_beat = false;
                 for (;;) {
                     bool ok = true;
+                    // (issued ahead of the PCIe reads so that both are in flight together: has another CTA given up on this launch?)
+                    uint32_t f = 0;
+                    if (g.lane == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(ra.exit_flag) : "memory");
                     for (int b0 = 0; b0 < n_live; b0 += G) {
                         const int i = b0 + g.lane;
                         uint4 c = make_uint4(expect, 0, 0, 0);
@@ -269,6 +274,9 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
                         if (i < n_live) *reinterpret_cast<uint4*>(cmd_s + i * 4) = c;
                     }
                     if (ok) break;
+                    // another CTA has given up: leave with it (the host relaunches the whole grid; a command that arrives
+                    // meanwhile stays in its row and is picked up by the next launch) — a launch never ends for only SOME CTAs
+                    if ((uint32_t)g.shfl((int)f, 0) == ra.epoch) { stop = true; break; }
                     if (g.shfl((int)(clock64() - t0 > ra.idle_cycles), 0)) {  // (the leader's clock decides for the group)
                         // no command for a while: leave only if the host has left submit / wait altogether (its heartbeat stands
                         // still) — then every CTA leaves within one idle period and the host relaunches the whole grid.  While
@@ -276,7 +284,11 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
                         uint32_t b = 0;
                         if (g.lane == 0) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(b) : "l"(ra.heartbeat) : "memory");
                         b = (uint32_t)g.shfl((int)b, 0);
-                        if (have_beat && b == beat) { stop = true; break; }
+                        if (have_beat && b == beat) {
+                            if (g.lane == 0) atomicExch(ra.exit_flag, ra.epoch);
+                            stop = true;
+                            break;
+                        }
                         beat = b; have_beat = true;
                         t0 = clock64();
                     }
@@ -372,6 +384,8 @@ struct MaroCimEnv : EnvCommon {
     std::vector<uint8_t> reset_pending;              // per replica: maro_cim_reset arrived while the session was live -> rides on
                                                      // the replica's next command row (or is applied when the session ends)
     uint32_t *h_beat = nullptr, *hd_beat = nullptr;  // heartbeat word, mapped pinned
+    uint32_t* d_exit = nullptr;                      // exit flag of the resident kernel (device), compared with launch_epoch
+    uint32_t launch_epoch = 0;
     int buf_full_cap = 1, buf_empty_cap = 1;         // buffer ticks the event pool was sized for (set_topology re-validation)
     int res_groups = 0;                              // replicas per CTA of the resident kernel
     std::vector<uint32_t> cta_seq;                   // per CTA: last step completed (the kernel's seq_state mirrors it)
@@ -588,6 +602,7 @@ static int session_launch_locked(MaroCimEnv* e) {
     ra.mode = RES_SESSION; ra.spread = e->res_spread;
     ra.cmd = e->hd_cmd; ra.done_flags = e->hd_flag; ra.seq_state = e->d_seq; ra.poll_ns = e->poll_ns; ra.wait_ns = e->wait_ns;
     ra.idle_cycles = e->idle_cycles; ra.heartbeat = e->hd_beat;
+    ra.exit_flag = e->d_exit; ra.epoch = ++e->launch_epoch;  // (epochs start at 1; the flag holds 0 or an older epoch)
     CK(launch_resident(e, a, ra));
     e->session_live.store(true, std::memory_order_release);
     return 0;
@@ -743,6 +758,8 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
     memset(e->h_flag, 0, (size_t)B * 4 + 64);
     CK(cudaMalloc(&e->d_seq, (size_t)B * 4));
     CK(cudaMemset(e->d_seq, 0, (size_t)B * 4));
+    CK(cudaMalloc(&e->d_exit, 64));
+    CK(cudaMemset(e->d_exit, 0, 64));
     CK(cudaHostAlloc(&e->h_beat, 64, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&e->hd_beat, e->h_beat, 0));
     memset(e->h_beat, 0, 64);
@@ -800,7 +817,7 @@ int maro_cim_destroy(MaroCimEnv* e) {
     cudaSetDevice(e->device);
     if (e->session_live.load()) session_end(e);
     cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt); cudaFree(e->d_light);
-    cudaFree(e->d_seq);
+    cudaFree(e->d_seq); cudaFree(e->d_exit);
     if (e->h_cmd) cudaFreeHost(e->h_cmd);
     if (e->h_flag) cudaFreeHost(e->h_flag);
     if (e->h_beat) cudaFreeHost(e->h_beat);

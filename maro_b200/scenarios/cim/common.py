@@ -19,8 +19,7 @@ class _Record:
     _shown: tuple = ()
 
     def _assign(self, values):
-        for name, value in zip(self._fields, values):
-            setattr(self, name, value)
+        self.__dict__.update(zip(self._fields, values))  # (one dict update: VectorEnv builds these per env per step)
 
     def __repr__(self):
         body = ", ".join(f"{k}: {self._show(k)!r}" for k in (self._shown or self._fields))
@@ -48,7 +47,8 @@ class ActionScope(_Record):
     _fields = ("load", "discharge")
 
     def __init__(self, load: int, discharge: int):
-        self._assign((load, discharge))
+        self.load = load
+        self.discharge = discharge
 
 
 class DecisionEvent(_Record):
@@ -61,7 +61,12 @@ class DecisionEvent(_Record):
     _shown = ("port_idx", "vessel_idx", "action_scope", "early_discharge")
 
     def __init__(self, tick, port_idx, vessel_idx, snapshot_list, action_scope, early_discharge):
-        self._assign((tick, port_idx, vessel_idx, snapshot_list, action_scope, early_discharge))
+        self.tick = tick
+        self.port_idx = port_idx
+        self.vessel_idx = vessel_idx
+        self.snapshot_list = snapshot_list
+        self.action_scope = action_scope
+        self.early_discharge = early_discharge
 
     def __getstate__(self):
         return {k: getattr(self, k) for k in self._fields if k != "snapshot_list"}
@@ -70,6 +75,17 @@ class DecisionEvent(_Record):
         self.snapshot_list = None
         for k, v in state.items():
             setattr(self, k, v)
+
+
+def action_row(action) -> tuple:
+    """(vessel, port, quantity, type) of one Action (ours or the reference's — duck-typed) as plain ints"""
+    t = action.action_type
+    if t is ActionType.LOAD:
+        return (action.vessel_idx, action.port_idx, action.quantity, 0)
+    if t is ActionType.DISCHARGE:
+        return (action.vessel_idx, action.port_idx, action.quantity, 1)
+    kind = getattr(t, "name", None) or str(t)  # the reference's own ActionType enum (duck typing)
+    return (action.vessel_idx, action.port_idx, action.quantity, 1 if kind.upper().endswith("DISCHARGE") else 0)
 
 
 def encode_action(action, out_row) -> None:

@@ -31,9 +31,15 @@ class DocableDict(dict):
 _METRICS_DOC = """CIM metrics: order_requirements (int), container_shortage (int), operation_number (int)."""
 
 
+class _CimMetrics(DocableDict):
+    __doc__ = _METRICS_DOC
+
+    def __init__(self, a, b, c):  # (built per env per step by VectorEnv: no intermediate dict, no per-instance __doc__)
+        dict.__init__(self, order_requirements=a, container_shortage=b, operation_number=c)
+
+
 def make_metrics(row) -> DocableDict:
-    return DocableDict(_METRICS_DOC, {"order_requirements": int(row[0]), "container_shortage": int(row[1]),
-                                     "operation_number": int(row[2])})
+    return _CimMetrics(int(row[0]), int(row[1]), int(row[2]))
 
 
 def parse_query_key(key: slice):

@@ -12,7 +12,7 @@ import numpy as np
 
 from .. import _abi
 from ..batch import BikeBatch, CimBatch, VmBatch
-from ..scenarios.cim.common import ActionScope, DecisionEvent, encode_action
+from ..scenarios.cim.common import ActionScope, DecisionEvent, action_row, encode_action
 from ..scenarios.cim.topology import build_topology, load_config, next_topology_seed
 from ..simulator.env import DecisionMode, SnapshotList, make_metrics, parse_query_key
 
@@ -121,13 +121,38 @@ class VectorEnv:
                 encode_action(a, self._act[i, k])
         self._nact[i] = len(acts)
 
+    def _encode_all_cim(self, actions):
+        """one action (or None / list) per env -> the int32 action rows, filled with ONE array assignment per column block
+        instead of four element writes per env (the per-env Python objects are the caller's, the loop stays)"""
+        A = self._act.shape[1]
+        rows = [[(0, 0, 0, 0)] * A for _ in range(self._batch_num)]
+        counts = [0] * self._batch_num
+        for i, a in enumerate(actions):
+            if a is None:
+                continue
+            if isinstance(a, list):
+                if len(a) > A:
+                    raise ValueError("too many actions for one decision event")
+                for k, x in enumerate(a):
+                    rows[i][k] = action_row(x)
+                counts[i] = len(a)
+            else:
+                rows[i][0] = action_row(a)
+                counts[i] = 1
+        self._act[:] = rows
+        self._nact[:] = counts
+
     def step(self, action):
         """list -> one action per env; dict -> only those envs advance; anything else -> broadcast."""
         B = self._batch_num
+        cim = self._scenario == "cim"
         if type(action) is list:
             assert len(action) == B
-            for i in range(B):
-                self._encode(i, action[i])
+            if cim:
+                self._encode_all_cim(action)
+            else:
+                for i in range(B):
+                    self._encode(i, action[i])
             self._active[:] = 1
         elif type(action) is dict:
             self._active[:] = 0
@@ -135,10 +160,15 @@ class VectorEnv:
                 self._encode(i, a)
                 self._active[i] = 1
         else:
-            for i in range(B):
-                self._encode(i, action)
+            if cim:
+                self._encode_all_cim([action] * B)
+            else:
+                for i in range(B):
+                    self._encode(i, action)
             self._active[:] = 1
         dec, met = self._batch.step(self._act, self._nact, self._active)
+        if cim:
+            return self._decode_cim(dec, met)
         metrics, events = [], []
         for i in range(B):
             if not self._active[i]:
@@ -164,24 +194,45 @@ class VectorEnv:
                 else:
                     events.append(decode_bike_decision(dec[i], self._snapshot_lists[i]))
                 continue
-            if self._scenario == "vm_scheduling":
-                from ..scenarios.vm_scheduling.common import decode_vm_decision, decode_vm_metrics
+            from ..scenarios.vm_scheduling.common import decode_vm_decision, decode_vm_metrics
 
-                metrics.append(decode_vm_metrics(met[i]))
-                if st == _abi.STATUS_DONE:
-                    self._done[i] = True
-                    events.append(None)
-                else:
-                    events.append(decode_vm_decision(dec[i]))
-                continue
-            metrics.append(make_metrics(met[i]))
+            metrics.append(decode_vm_metrics(met[i]))
             if st == _abi.STATUS_DONE:
                 self._done[i] = True
                 events.append(None)
             else:
-                d = dec[i]
-                events.append(DecisionEvent(int(d[0]), int(d[1]), int(d[2]), self._snapshot_lists[i],
-                                            ActionScope(int(d[3]), int(d[4])), int(d[5])))
+                events.append(decode_vm_decision(dec[i]))
+        return metrics, events, bool(self._done.all())
+
+    def _decode_cim(self, dec, met):
+        """decision / metrics rows -> the reference's per-env Python objects; the arrays are converted to Python ints in
+        one ``tolist()`` each (per-element numpy indexing costs more than building the objects)"""
+        st_col = dec[:, _abi.DEC_STATUS]
+        active = self._active.astype(bool)
+        bad = active & (st_col < 0)
+        if bad.any():
+            i = int(np.argmax(bad))
+            if st_col[i] == _abi.STATUS_BAD_ACTION:
+                raise AssertionError(f"env {i}: invalid action (outside the action scope / unknown VM or PM id)")
+            raise RuntimeError(f"env {i}: event queue overflow")
+        live = active & ((st_col == _abi.STATUS_DECISION) | (st_col == _abi.STATUS_DONE))
+        self._ticks[live] = dec[live, 0]
+        self._done |= active & (st_col == _abi.STATUS_DONE)
+        rows, mets, snaps = dec.tolist(), met.tolist(), self._snapshot_lists
+        metrics, events = [], []
+        ST_DEC, ST_DONE = _abi.STATUS_DECISION, _abi.STATUS_DONE
+        for i in (range(self._batch_num) if active.all() else np.flatnonzero(active).tolist()):
+            d = rows[i]
+            st = d[6]
+            if st == ST_DEC:
+                metrics.append(make_metrics(mets[i]))
+                events.append(DecisionEvent(d[0], d[1], d[2], snaps[i], ActionScope(d[3], d[4]), d[5]))
+            elif st == ST_DONE:
+                metrics.append(make_metrics(mets[i]))
+                events.append(None)
+            else:  # STATUS_FINISHED: (None, None, True) from that env (env_process.py:37-40)
+                metrics.append(None)
+                events.append(None)
         return metrics, events, bool(self._done.all())
 
     def step_columnar(self, actions: Optional[np.ndarray] = None, n_actions=None, active=None):

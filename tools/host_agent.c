@@ -1,7 +1,9 @@
+#define _GNU_SOURCE
 /* Bench infrastructure: the hello-world random agent (examples/hello_world/cim/hello.py:24-32) on the host, as the
  * same counter hash of (replica, decision ordinal) that cim_policy_kernel evaluates on the device.  This is the
  * *agent* of the end-to-end measurement (user code outside the library), compiled by bench.py with gcc. */
 #include <stdint.h>
+#include <unistd.h>
 
 static inline uint32_t hash_u32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -149,17 +151,24 @@ int e2e_loop_cim(void* env, void* submit_p, void* wait_p, void* reset_p, const i
  * own (wait -> agent -> submit) pipeline.  maro_cim_submit_pinned / maro_cim_wait_pinned / maro_cim_reset accept concurrent
  * callers on disjoint replica ranges (include/maro_b200.h).  out[1] = agent seconds averaged over the threads. */
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
 typedef struct {
     void* env; submit_fn submit; wait_fn wait; reset_fn reset;
     const int32_t* dec; int32_t* act; int B, n_steps, k0, k1; const int* first; uint32_t seed, replica_base;
-    double t_agent, resets; int rc;
+    double t_agent, resets; int rc, cpu;
 } e2e_worker;
 
 static void* e2e_worker_main(void* p) {
     e2e_worker* w = (e2e_worker*)p;
+    if (w->cpu >= 0) {  /* next to the thread that created the handle (same socket as its pinned buffers) */
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(w->cpu, &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
     uint8_t* mask = (uint8_t*)malloc((size_t)w->B);
     w->rc = 0; w->t_agent = 0.0; w->resets = 0.0;
     for (int k = w->k0; k < w->k1 && !w->rc; k++)
@@ -207,7 +216,12 @@ int e2e_loop_cim_mt(void* env, void* submit_p, void* wait_p, void* reset_p, cons
         x->env = env; x->submit = (submit_fn)submit_p; x->wait = (wait_fn)wait_p; x->reset = (reset_fn)reset_p;
         x->dec = dec; x->act = act; x->B = B; x->n_steps = n_steps; x->first = first; x->seed = seed; x->replica_base = replica_base;
         x->k0 = (int)((long long)n * t / n_threads); x->k1 = (int)((long long)n * (t + 1) / n_threads);
-        if (t > 0) pthread_create(&th[t], 0, e2e_worker_main, x);
+        x->cpu = -1;
+        if (t > 0) {
+            const int cpu0 = sched_getcpu(), ncpu = (int)sysconf(_SC_NPROCESSORS_ONLN);
+            if (cpu0 >= 0 && ncpu > 0) x->cpu = (cpu0 + t) % ncpu;
+            pthread_create(&th[t], 0, e2e_worker_main, x);
+        }
     }
     e2e_worker_main(&w[0]);
     for (int t = 1; t < n_threads; t++) pthread_join(th[t], 0);
