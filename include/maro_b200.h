@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MARO_B200_ABI_VERSION 1
+#define MARO_B200_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------------------
  * Static tables of one CIM topology instance (config + max_tick + seed).
@@ -274,6 +274,8 @@ int maro_cim_rl_reward_device(MaroCimEnv* env, const int32_t* d_ticks, const int
  * maro/data_lib/binary_reader.py (trace format + ItemTickPicker), citi_bike/business_engine.py:218-396 and
  * decision_strategy.py:385-397.
  * ============================================================================================== */
+#define MARO_BIKE_MAX_FILTERS 4
+enum { MARO_BIKE_FILTER_DISTANCE = 0, MARO_BIKE_FILTER_REQUIREMENTS = 1, MARO_BIKE_FILTER_TRIP_WINDOW = 2 };
 typedef struct MaroBikeTopology {
     int32_t n_stations, n_days;
     int32_t max_tick;            /* start_tick + durations                                            */
@@ -293,6 +295,11 @@ typedef struct MaroBikeTopology {
     const int32_t* trip_dur;         /* ticks until the bike is returned                              */
     const int32_t* day_of_tick;      /* [max_tick] row of day_feat                                    */
     const int32_t* day_feat;         /* [n_days][4] weekday, holiday, weather, temperature            */
+    /* decision.action_scope.filters, applied in order to the neighbour scope (decision_strategy.py:15-163, 282-283):
+     * type 0 "distance" (the `num` nearest neighbours), 1 "requirements" (the `num` largest scope values), 2 "trip_window"
+     * (the `num` neighbours with the fewest / most trips over the latest `windows` snapshot frames, per-frame cache incl.) */
+    int32_t n_filters;
+    int32_t filter_type[MARO_BIKE_MAX_FILTERS], filter_num[MARO_BIKE_MAX_FILTERS], filter_windows[MARO_BIKE_MAX_FILTERS];
 } MaroBikeTopology;
 
 /* Decision row: MARO_BIKE_DEC_HEAD int32 header + 2 * n_stations words of (station, scope) pairs in ascending

@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DEC_TICK, DEC_PORT, DEC_VESSEL, DEC_SCOPE_LOAD, DEC_SCOPE_DISCHARGE, DEC_EARLY_DISCHARGE, DEC_STATUS, DEC_STEP = range(8)
 DECISION_WORDS = 8
@@ -118,6 +118,7 @@ class MaroBikeTopology(C.Structure):
         ("station_bikes", _i32p), ("station_capacity", _i32p), ("station_id", _i32p), ("nbr_offset", _i32p),
         ("nbr_idx", _i32p), ("trip_offset", _i32p), ("trip_src", _i32p), ("trip_dst", _i32p), ("trip_dur", _i32p),
         ("day_of_tick", _i32p), ("day_feat", _i32p),
+        ("n_filters", C.c_int32), ("filter_type", C.c_int32 * 4), ("filter_num", C.c_int32 * 4), ("filter_windows", C.c_int32 * 4),
     ]
 
 
@@ -137,6 +138,12 @@ def bike_topology_struct(topo):
     s.transfer_seed = topo.transfer_seed
     for name in ("time_mean", "time_std", "supply_ratio", "demand_ratio", "scope_low", "scope_high"):
         setattr(s, name, float(getattr(topo, name)))
+    filters = list(getattr(topo, "filters", ()) or ())
+    if len(filters) > 4:
+        raise ValueError("at most 4 action-scope filters")
+    s.n_filters = len(filters)
+    for k, (ftype, num, windows) in enumerate(filters):
+        s.filter_type[k], s.filter_num[k], s.filter_windows[k] = int(ftype), int(num), int(windows)
     for field, attr in (("station_bikes", "station_bikes"), ("station_capacity", "station_capacity"),
                         ("station_id", "station_id"), ("nbr_offset", "nbr_offset"), ("nbr_idx", "nbr_idx"),
                         ("trip_offset", "trip_offset"), ("trip_src", "trip_src"), ("trip_dst", "trip_dst"),

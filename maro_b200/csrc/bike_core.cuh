@@ -37,7 +37,12 @@ struct BikeShape {
     // table blob offsets
     int t_bikes, t_capacity, t_id, t_nbr_offset, t_nbr_idx, t_trip_offset, t_trip_src, t_trip_dst, t_trip_dur;
     int t_day_of_tick, t_day_feat, t_mt;
-    int rng_words;  // per-replica RNG block: 624 state + idx + has_gauss + gauss (2 words)
+    int rng_words;  // per-replica RNG block: 624 state + idx + has_gauss + gauss (2 words), then the scope-filter area
+    // decision.action_scope.filters (decision_strategy.py:15-163); scope-filter area inside the per-replica global block:
+    // [tw_frame W][tw_cache W*S][scratch 4*S] at word offset `scope_off` (W = tw_windows = the widest trip-window filter)
+    int n_filters, filter_type[4], filter_num[4], filter_windows[4];
+    int drops;  // some filter can drop a neighbour (num < S - 1): the chain has to be run (otherwise it only permutes a dict)
+    int scope_off, tw_windows;
 };
 
 struct BikeReplica {
@@ -203,25 +208,96 @@ MARO_DEV void bike_on_actions(const BikeShape& s, const Grp<G>& g, const BikeRep
     }
 }
 
-// BikeDecisionStrategy.action_scope (decision_strategy.py:253-293) with identity filters; pairs in station order
-MARO_DEV int bike_action_scope(const BikeShape& s, const BikeReplica& r, int station, int type, int32_t* pairs) {
-    int lo = r.t[s.t_nbr_offset + station], hi = r.t[s.t_nbr_offset + station + 1];
-    int n = 0;
-    for (int i = 0; i < s.S; i++) {
-        bool is_nb = false;
-        for (int k = lo; k < hi; k++) is_nb |= r.t[s.t_nbr_idx + k] == i;
-        int bikes = BA(s, r, BA_BIKES, i), cap = BA(s, r, BA_CAPACITY, i);
-        if (i == station) {
-            pairs[2 * n] = i;
-            pairs[2 * n + 1] = type == 0 ? (int)maro_floor((double)bikes * (1.0 - s.scope_low)) : cap - bikes;
-            n++;
-        } else if (is_nb) {
-            pairs[2 * n] = i;
-            pairs[2 * n + 1] = type == 0 ? cap - bikes : (int)maro_floor((double)bikes * s.scope_high);
-            n++;
+// sorted(items, key=(value, index), reverse)[:out] by selection: position j takes the best remaining entry (keys are unique)
+MARO_DEV void bike_select_top(int n, int out, int32_t* idx, int32_t* val, int32_t* key, bool reverse) {
+    for (int j = 0; j < out; j++) {
+        int best = j;
+        for (int k = j + 1; k < n; k++) {
+            bool less = key[k] < key[best] || (key[k] == key[best] && idx[k] < idx[best]);
+            if (reverse ? !less : less) best = k;
+        }
+        if (best != j) {
+            int t = idx[j]; idx[j] = idx[best]; idx[best] = t;
+            t = val[j]; val[j] = val[best]; val[best] = t;
+            t = key[j]; key[j] = key[best]; key[best] = t;
         }
     }
-    return n;
+}
+
+// BikeDecisionStrategy.action_scope (decision_strategy.py:253-293): neighbour scope -> filter chain (DistanceFilter :15-52,
+// RequirementsFilter :55-88, TripsWindowFilter :91-166 incl. its per-frame cache) -> the station itself; pairs in station
+// order (the reference's dict carries no order).  Leader lane only; the pre-decision snapshot of this tick has been taken.
+MARO_DEV int bike_action_scope(const BikeShape& s, const BikeReplica& r, int station, int type, int frame_now, int32_t* pairs) {
+    const int lo = r.t[s.t_nbr_offset + station], hi = r.t[s.t_nbr_offset + station + 1];
+    const int S = s.S;
+    int32_t* area = reinterpret_cast<int32_t*>(r.rng) + s.scope_off;
+    int32_t* tw_frame = area;
+    int32_t* tw_cache = area + s.tw_windows;
+    int32_t* idx = tw_cache + s.tw_windows * S;
+    int32_t* val = idx + S;
+    int32_t* key = val + S;
+    int32_t* res = key + S;  // value per station, -1 = not in the scope
+    for (int i = 0; i < S; i++) res[i] = -1;
+    int n = 0;
+    for (int k = lo; k < hi; k++) {
+        const int nb = r.t[s.t_nbr_idx + k];
+        const int bikes = BA(s, r, BA_BIKES, nb), cap = BA(s, r, BA_CAPACITY, nb);
+        idx[n] = nb;
+        val[n] = type == 0 ? cap - bikes : (int)maro_floor((double)bikes * s.scope_high);
+        n++;
+    }
+    if (s.drops) {
+        for (int f = 0; f < s.n_filters; f++) {
+            const int out = s.filter_num[f] < n ? s.filter_num[f] : n;
+            if (s.filter_type[f] == 0) {
+                // the `out` nearest of the station's FULL neighbour list, with their values from the current scope
+                for (int k = 0; k < out; k++) {
+                    const int nb = r.t[s.t_nbr_idx + lo + k];
+                    int at = -1;
+                    for (int j = k; j < n; j++) if (idx[j] == nb) { at = j; break; }
+                    if (at < 0) { r.c[BC_ERR] = -3; break; }  // KeyError in the reference (a filter before it dropped `nb`)
+                    int t = idx[k]; idx[k] = idx[at]; idx[at] = t;
+                    t = val[k]; val[k] = val[at]; val[at] = t;
+                }
+            } else if (s.filter_type[f] == 1) {
+                for (int j = 0; j < n; j++) key[j] = val[j];
+                bike_select_top(n, out, idx, val, key, true);
+            } else {
+                // the latest `windows` frames the ring holds; frames are consecutive, the newest is the pre-decision snapshot
+                const int W = s.filter_windows[f];
+                int first = frame_now - (s.ring_rows - 1);
+                if (first < 0) first = 0;
+                int held = 0;
+                for (int fr = first; fr <= frame_now; fr++) held += r.snap_frame[fr < s.ring_rows ? fr : fr % s.ring_rows] == fr;
+                const int avail = W < held ? W : held;
+                for (int j = 0; j < n; j++) key[j] = 0;
+                int taken = 0;
+                for (int fr = frame_now; fr >= first && taken < avail; fr--) {
+                    const int row = fr < s.ring_rows ? fr : fr % s.ring_rows;
+                    if (r.snap_frame[row] != fr) continue;
+                    taken++;
+                    int32_t* c = tw_cache + (fr % s.tw_windows) * S;
+                    if (fr == frame_now || tw_frame[fr % s.tw_windows] != fr) {  // latest: always re-read; others: once
+                        const int32_t* src = r.snap + (int64_t)row * s.FWp + BA_TRIP_REQUIREMENT * S;
+                        for (int i = 0; i < S; i++) c[i] = src[i];
+                        tw_frame[fr % s.tw_windows] = fr;
+                    }
+                    for (int j = 0; j < n; j++) key[j] += c[idx[j]];
+                }
+                bike_select_top(n, out, idx, val, key, type == 1);
+            }
+            n = out;
+        }
+    }
+    for (int j = 0; j < n; j++) res[idx[j]] = val[j];
+    {
+        const int bikes = BA(s, r, BA_BIKES, station), cap = BA(s, r, BA_CAPACITY, station);
+        res[station] = type == 0 ? (int)maro_floor((double)bikes * (1.0 - s.scope_low)) : cap - bikes;
+    }
+    int m = 0;
+    for (int i = 0; i < S; i++)
+        if (res[i] >= 0 || i == station) { pairs[2 * m] = i; pairs[2 * m + 1] = res[i]; m++; }
+    return m;
 }
 
 template <int G>
@@ -352,7 +428,7 @@ MARO_DEV void bike_replica_step(const BikeShape& s, const Grp<G>& g, const BikeR
         if (decided) {
             int st_i = r.c[BC_PEND_STATION], ty = r.c[BC_PEND_TYPE];
             dec[1] = st_i; dec[2] = bike_frame_index(s, tick); dec[3] = ty;
-            dec[4] = bike_action_scope(s, r, st_i, ty, dec + 8);
+            dec[4] = bike_action_scope(s, r, st_i, ty, bike_frame_index(s, tick), dec + 8);
         }
         if (r.c[BC_ERR] == -2) { state = ST_ERROR; status = -2; }
         dec[6] = status;
@@ -395,6 +471,7 @@ MARO_DEV void bike_replica_reset(const BikeShape& s, const Grp<G>& g, const Bike
         }
     }
     g.sync();
+    LANE_LOOP(i, s.tw_windows) (reinterpret_cast<int32_t*>(r.rng) + s.scope_off)[i] = -1;  // TripsWindowFilter.reset (:165-166)
     if (g.lane == 0) {
         r.rng[624] = 624; r.rng[625] = 0; r.rng[626] = 0; r.rng[627] = 0;
         r.c[BC_STATE] = ST_START;

@@ -200,7 +200,12 @@ int maro_bike_create(const MaroBikeTopology* topo, const MaroCimConfig* cfg, Mar
     e->device = cfg->device;
     e->B = cfg->n_replicas;
     BikeShape& s = e->s;
-    if (bike_compute_shape_and_tables(*topo, cfg, s, e->h_tables)) { delete e; return fail("maro_bike_create: bad topology (1..255 stations, durations > 0)"); }
+    if (int rc = bike_compute_shape_and_tables(*topo, cfg, s, e->h_tables)) {
+        delete e;
+        return fail(rc == 2 ? "maro_bike_create: a 'distance' action-scope filter behind a filter that drops neighbours raises KeyError in the "
+                              "reference (decision_strategy.py:45-48); put it first"
+                            : "maro_bike_create: bad topology (1..255 stations, durations > 0, at most 4 action-scope filters)");
+    }
     e->n_node_types = 2;
     static const char* an[] = {"bikes", "capacity", "extra_cost", "failed_return", "fulfillment", "holiday", "id", "min_bikes",
                                "shortage", "temperature", "transfer_cost", "trip_requirement", "weather", "weekday"};

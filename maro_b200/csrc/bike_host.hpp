@@ -48,7 +48,25 @@ inline int bike_compute_shape_and_tables(const MaroBikeTopology& t, const MaroCi
     s.QN = round_up(qn, 4);
     s.SW = round_up(s.FWp + s.CWp + s.QN * 2 + s.QH + s.QN, 4);
     s.DW = MARO_BIKE_DEC_HEAD + 2 * S;
-    s.rng_words = 632;
+    // action-scope filter chain
+    if (t.n_filters < 0 || t.n_filters > MARO_BIKE_MAX_FILTERS) return 1;
+    s.n_filters = t.n_filters;
+    s.tw_windows = 1;
+    bool dropped = false;  // has an earlier filter been able to drop a neighbour?
+    for (int f = 0; f < t.n_filters; f++) {
+        s.filter_type[f] = t.filter_type[f]; s.filter_num[f] = t.filter_num[f]; s.filter_windows[f] = t.filter_windows[f];
+        if (t.filter_type[f] < 0 || t.filter_type[f] > 2 || t.filter_num[f] < 0) return 1;
+        if (t.filter_type[f] == MARO_BIKE_FILTER_TRIP_WINDOW) {
+            if (t.filter_windows[f] < 1) return 1;
+            s.tw_windows = std::max(s.tw_windows, t.filter_windows[f]);
+        }
+        // a distance filter behind a dropping filter indexes the dropped neighbour: KeyError in the reference
+        // (decision_strategy.py:45-48) — such a configuration cannot run there either
+        if (t.filter_type[f] == MARO_BIKE_FILTER_DISTANCE && dropped) return 2;
+        if (t.filter_num[f] < S - 1) { dropped = true; s.drops = 1; }
+    }
+    s.scope_off = 632;
+    s.rng_words = round_up(632 + s.tw_windows + s.tw_windows * S + 4 * S, 4);
     tables.clear();
     BlobBuilder b(tables);
     s.t_bikes = b.put_i(t.station_bikes, S, S);

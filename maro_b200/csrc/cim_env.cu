@@ -172,7 +172,7 @@ struct ResidentArgs {
     uint32_t seed, replica_base;
     int32_t* trace;                 // [n_steps][B][8] decision rows of every fused step, or nullptr
     const uint32_t* cmd;            // [B][4] command rows (mapped host memory)
-    uint32_t* done_flags;           // mapped host [gridDim.x]: last seq every replica of that CTA has completed
+    uint32_t* results;              // mapped host [B][16]: tagged result lines (see "publish" in the session loop)
     uint32_t poll_ns, wait_ns;      // back-off of the command poll (PCIe) and of the shared-memory relay wait
     uint32_t* seq_state;            // device [B]: last seq each replica has completed (survives launches and resets)
     const uint32_t* heartbeat;      // mapped host word the host bumps while it is inside submit / wait (any thread)
@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
             if (ra.trace && g.lane < 2)
                 reinterpret_cast<int4*>(ra.trace + ((int64_t)k * s.n_replicas + rep) * 8)[g.lane] = reinterpret_cast<const int4*>(dslot)[g.lane];
             const int status = dslot[MARO_DEC_STATUS];
-            if (status == MARO_STATUS_FINISHED) { k++; break; }  // every further step would return the same row
+            // the episode is over: stop here and keep the DONE row with the final metrics (a further step — in this launch
+            // or the next — returns the all-zero FINISHED row, core.py:128-131)
+            if (status == MARO_STATUS_FINISHED || status == MARO_STATUS_DONE) { k++; break; }
         }
         if (ra.trace)
             for (; k < ra.n_steps; k++)
@@ -247,11 +249,10 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
         // last copies all slots to the mapped host rows (coalesced), fences once and bumps the completion counter.
         uint32_t* cmd_s = reinterpret_cast<uint32_t*>(smem_raw + 256 + (size_t)n_groups * 64 + (size_t)n_groups * s.SW * 4);  // [n_groups][4]
         volatile uint32_t* seq_s = cmd_s + n_groups * 4;
-        uint32_t* done_s = cmd_s + n_groups * 4 + 1;
         const int rep0 = blockIdx.x * n_groups;
         const int n_live = min(n_groups, s.n_replicas - rep0);
         uint32_t expect = ra.seq_state[rep0] + 1u;
-        if (threadIdx.x == 0) { *seq_s = expect - 1u; *done_s = 0; }
+        if (threadIdx.x == 0) *seq_s = expect - 1u;
         __syncthreads();  // (threads that left above do not take part in CTA barriers)
         if (g.lane < 8) dslot[g.lane] = gdec[g.lane];  // rows of inactive replicas keep their previous contents
         if (g.lane < 3) mslot[g.lane] = gmet[g.lane];
@@ -326,26 +327,26 @@ __global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_const
                 dslot[MARO_DEC_STATUS] = MARO_STATUS_INACTIVE;
             }
             g.sync();
-            int last = 0;
-            if (g.lane == 0) {
-                __threadfence_block();
-                last = atomicAdd_block(done_s, 1u) + 1u == (uint32_t)n_live;
-            }
-            last = g.shfl(last, 0);
-            if (last) {
-                __threadfence_block();
-                const int4* slots4 = reinterpret_cast<const int4*>(smem_raw + 256);  // 4 int4 per group: 2 decision, 1.5 metrics
-                const int64_t* slots8 = reinterpret_cast<const int64_t*>(smem_raw + 256);
-                int4* od = reinterpret_cast<int4*>(a.decisions + (int64_t)rep0 * 8);
-                int64_t* om = a.metrics + (int64_t)rep0 * 3;
-                for (int j = g.lane; j < n_live * 2; j += G) od[j] = slots4[(j >> 1) * 4 + (j & 1)];
-                for (int j = g.lane; j < n_live * 3; j += G) om[j] = slots8[(j / 3) * 8 + 4 + j % 3];
-                __threadfence_system();  // the rows are visible to the host before the CTA's flag is
-                g.sync();
+            // ---- publish: one 64-byte result line per replica in mapped host memory, two 32-byte sectors, each written by ONE
+            // 256-bit store that carries the sequence number in its last word:
+            //     sector 0 = decision words 0..6 | seq        sector 1 = metrics (3 x int64) | decision word 7 | seq
+            // The host takes a line once both tags show the step it is waiting for — no system fence, no separate flag
+            // (a 32-byte aligned store reaches host memory as one write: tag and payload become visible together).
+            if (g.lane < 2) {
+                uint32_t w[8];
                 if (g.lane == 0) {
-                    *done_s = 0;
-                    *reinterpret_cast<volatile uint32_t*>(ra.done_flags + blockIdx.x) = expect;
+#pragma unroll
+                    for (int i = 0; i < 7; i++) w[i] = (uint32_t)dslot[i];
+                } else {
+                    const uint32_t* m32 = reinterpret_cast<const uint32_t*>(mslot);
+#pragma unroll
+                    for (int i = 0; i < 6; i++) w[i] = m32[i];
+                    w[6] = (uint32_t)dslot[7];
                 }
+                w[7] = expect;
+                asm volatile("st.relaxed.sys.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ra.results + (int64_t)rep * 16 + g.lane * 8),
+                             "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                             : "memory");
             }
             expect++;
         }
@@ -391,7 +392,7 @@ struct MaroCimEnv : EnvCommon {
     std::vector<uint32_t> cta_seq;                   // per CTA: last step completed (the kernel's seq_state mirrors it)
     std::vector<uint8_t> cta_pending;                // per CTA: a step has been sent and not collected yet
     uint32_t *h_cmd = nullptr, *hd_cmd = nullptr;    // [B][4] command rows, mapped pinned
-    uint32_t *h_flag = nullptr, *hd_flag = nullptr;  // [res_grid] completion flags (one per CTA), mapped pinned
+    uint32_t *h_res = nullptr, *hd_res = nullptr;    // [B][16] tagged result lines, mapped pinned (64-byte aligned)
     uint32_t* d_seq = nullptr;
     long long idle_cycles = 400000;
     uint32_t poll_ns = 0, wait_ns = 20;
@@ -600,7 +601,7 @@ static int session_launch_locked(MaroCimEnv* e) {
     ResidentArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.mode = RES_SESSION; ra.spread = e->res_spread;
-    ra.cmd = e->hd_cmd; ra.done_flags = e->hd_flag; ra.seq_state = e->d_seq; ra.poll_ns = e->poll_ns; ra.wait_ns = e->wait_ns;
+    ra.cmd = e->hd_cmd; ra.results = e->hd_res; ra.seq_state = e->d_seq; ra.poll_ns = e->poll_ns; ra.wait_ns = e->wait_ns;
     ra.idle_cycles = e->idle_cycles; ra.heartbeat = e->hd_beat;
     ra.exit_flag = e->d_exit; ra.epoch = ++e->launch_epoch;  // (epochs start at 1; the flag holds 0 or an older epoch)
     CK(launch_resident(e, a, ra));
@@ -612,16 +613,34 @@ static int session_launch_locked(MaroCimEnv* e) {
 // h_out).  The resident kernel may have left meanwhile (the host was away for longer than the idle limit): relaunch it,
 // the command rows are still in place.
 static int session_wait_ctas(MaroCimEnv* e, int c0, int c1) {
-    volatile uint32_t* flags = e->h_flag;
+    const int gpc = e->res_groups, B = e->B;
+    int32_t* dec = reinterpret_cast<int32_t*>(e->h_out);
+    int64_t* met = reinterpret_cast<int64_t*>(e->h_out + (size_t)B * e->dec_words * 4);
     timespec ts0;
     clock_gettime(CLOCK_MONOTONIC, &ts0);
-    int cta = c0;
+    int cta = c0, rep = c0 * gpc;
+    // take the result lines in order; a line is complete when both sector tags carry the awaited sequence number
     auto advance = [&]() {
-        while (cta < c1 && (!e->cta_pending[cta] || flags[cta] == e->cta_seq[cta] + 1u)) {
-            if (e->cta_pending[cta]) { e->cta_pending[cta] = 0; e->cta_seq[cta] += 1u; }
+        while (cta < c1) {
+            if (!e->cta_pending[cta]) { cta++; rep = cta * gpc; continue; }
+            const uint32_t want = e->cta_seq[cta] + 1u;
+            const int end = std::min(B, (cta + 1) * gpc);
+            while (rep < end) {
+                const volatile uint32_t* line = e->h_res + (size_t)rep * 16;
+                if (line[7] != want || line[15] != want) return false;
+                __atomic_thread_fence(__ATOMIC_ACQUIRE);  // (x86: loads are not reordered; this stops the compiler)
+                const uint32_t* l = const_cast<const uint32_t*>(line);
+                int32_t* d = dec + (size_t)rep * 8;
+                memcpy(d, l, 28);
+                d[7] = (int32_t)l[14];
+                memcpy(met + (size_t)rep * 3, l + 8, 24);
+                rep++;
+            }
+            e->cta_pending[cta] = 0;
+            e->cta_seq[cta] += 1u;
             cta++;
         }
-        return cta == c1;
+        return true;
     };
     for (uint64_t spins = 1;; spins++) {
         if (advance()) return 0;
@@ -751,11 +770,11 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
     }
     // ---- resident mode: one replica per warp while the batch is small (spread), packed lane groups otherwise
     CK(cudaHostAlloc(&e->h_cmd, (size_t)B * 16, cudaHostAllocMapped));
-    CK(cudaHostAlloc(&e->h_flag, (size_t)B * 4 + 64, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&e->h_res, (size_t)B * 64, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&e->hd_cmd, e->h_cmd, 0));
-    CK(cudaHostGetDevicePointer((void**)&e->hd_flag, e->h_flag, 0));
+    CK(cudaHostGetDevicePointer((void**)&e->hd_res, e->h_res, 0));
     memset(e->h_cmd, 0, (size_t)B * 16);
-    memset(e->h_flag, 0, (size_t)B * 4 + 64);
+    memset(e->h_res, 0, (size_t)B * 64);
     CK(cudaMalloc(&e->d_seq, (size_t)B * 4));
     CK(cudaMemset(e->d_seq, 0, (size_t)B * 4));
     CK(cudaMalloc(&e->d_exit, 64));
@@ -819,7 +838,7 @@ int maro_cim_destroy(MaroCimEnv* e) {
     cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt); cudaFree(e->d_light);
     cudaFree(e->d_seq); cudaFree(e->d_exit);
     if (e->h_cmd) cudaFreeHost(e->h_cmd);
-    if (e->h_flag) cudaFreeHost(e->h_flag);
+    if (e->h_res) cudaFreeHost(e->h_res);
     if (e->h_beat) cudaFreeHost(e->h_beat);
     common_free(e);
     delete e;

@@ -93,6 +93,9 @@ class BikeTopology:
     scope_high: float
     extra_cost_mode: int  # 0 source, 1 target, 2 target_neighbors
     transfer_seed: int
+    #: decision.action_scope.filters as (type, num, windows): 0 distance / 1 requirements / 2 trip_window
+    #: (decision_strategy.py:15-163, 345-362)
+    filters: tuple = ()
 
     @property
     def max_delay(self) -> int:
@@ -124,10 +127,13 @@ def build_bike_topology(config: dict, start_tick: int, max_tick: int, transfer_s
         nb = sorted([(i, d) for i, d in enumerate(adj[s]) if d != 0.0], key=lambda kv: kv[1])
         nbr_idx += [i for i, _ in nb]
         nbr_offset.append(len(nbr_idx))
-    # every scope filter must be the identity on the neighbour *set* (it is for topologies with few stations)
-    for f in dec["action_scope"]["filters"]:
-        if int(f["num"]) < S - 1:
-            raise NotImplementedError("action-scope filters that drop neighbours are not implemented on the CUDA core")
+    # the action-scope filter chain, in configuration order (decision_strategy.py:345-362)
+    kinds = {"distance": 0, "requirements": 1, "trip_window": 2}
+    filters = []
+    for f in dec["action_scope"].get("filters", []) or []:
+        if f["type"] not in kinds:
+            raise KeyError(f"unknown action-scope filter type {f['type']!r}")
+        filters.append((kinds[f["type"]], int(f["num"]), int(f.get("windows", 0) or 0)))
     # ---- trips -> per-tick lists (ItemTickPicker.items, binary_reader.py:80-113)
     items, st, et = read_bin(config["trip_data"])
     ts = items["timestamp"].astype(np.int64)
@@ -169,7 +175,7 @@ def build_bike_topology(config: dict, start_tick: int, max_tick: int, transfer_s
         time_mean=float(dec["effective_time_mean"]), time_std=float(dec["effective_time_std"]),
         supply_ratio=float(dec["supply_water_mark_ratio"]), demand_ratio=float(dec["demand_water_mark_ratio"]),
         scope_low=float(dec["action_scope"]["low"]), scope_high=float(dec["action_scope"]["high"]),
-        extra_cost_mode=mode, transfer_seed=int(transfer_seed) & 0xFFFFFFFF)
+        extra_cost_mode=mode, transfer_seed=int(transfer_seed) & 0xFFFFFFFF, filters=tuple(filters))
 
 
 def load_bike_config(topology: str) -> dict:

@@ -106,6 +106,12 @@ typedef struct BikeOracle {
     int frame_words;
     int32_t* ring;
     int32_t* ring_frame;
+    /* TripsWindowFilter._window_states_cache (decision_strategy.py:106, 136-142): frame index -> trip_requirement of every
+     * station as it stood when the frame was last queried as the LATEST one (or first queried at all) */
+    int total_frames;
+    int32_t* tw_cache;   /* [total_frames][S] */
+    char* tw_has;        /* [total_frames] */
+    int scope_error;     /* a filter asked for a neighbour an earlier filter had dropped: KeyError in the reference */
 } BikeOracle;
 
 static void* dup_arr(const void* p, size_t bytes) { void* q = malloc(bytes ? bytes : 1); if (bytes) memcpy(q, p, bytes); return q; }
@@ -332,6 +338,8 @@ void bike_oracle_reset(BikeOracle* o) { /* core.py:143-170, business_engine.py:1
     }
     memset(o->trips_adj, 0, sizeof(int32_t) * o->S * o->S);
     for (int i = 0; i < o->ring_rows; i++) o->ring_frame[i] = -1;
+    memset(o->tw_has, 0, (size_t)o->total_frames); /* BikeDecisionStrategy.reset -> TripsWindowFilter.reset (:165-166) */
+    o->scope_error = 0;
     np_seed(&o->rng, o->t.transfer_seed);
     o->total_trips = o->total_shortages = o->total_operate = 0;
     o->last_day = -1;
@@ -360,36 +368,101 @@ BikeOracle* bike_oracle_create(const MaroBikeTopology* t, int start_tick, int sn
     o->frame_words = 14 * S + S * S;
     o->ring = (int32_t*)calloc((size_t)o->ring_rows * o->frame_words, 4);
     o->ring_frame = (int32_t*)calloc(o->ring_rows, 4);
+    o->total_frames = total_frames > 0 ? total_frames : 1;
+    o->tw_cache = (int32_t*)calloc((size_t)o->total_frames * S, 4);
+    o->tw_has = (char*)calloc((size_t)o->total_frames, 1);
     bike_oracle_reset(o);
     return o;
 }
 void bike_oracle_destroy(BikeOracle* o) {
     if (!o) return;
     free_events(o);
-    free(o->pending); free(o->ring); free(o->ring_frame); free(o->st); free(o->trips_adj);
+    free(o->pending); free(o->ring); free(o->ring_frame); free(o->st); free(o->trips_adj); free(o->tw_cache); free(o->tw_has);
     free((void*)o->t.station_bikes); free((void*)o->t.station_capacity); free((void*)o->t.station_id);
     free((void*)o->t.nbr_offset); free((void*)o->t.nbr_idx); free((void*)o->t.trip_offset); free((void*)o->t.trip_src);
     free((void*)o->t.trip_dst); free((void*)o->t.trip_dur); free((void*)o->t.day_of_tick); free((void*)o->t.day_feat);
     free(o);
 }
 
-/* BikeDecisionStrategy.action_scope (decision_strategy.py:253-293) with identity filters: value per station */
-static int action_scope(const BikeOracle* o, int station, int type, int32_t* pairs) {
+/* sorted(items, key=lambda kv: (kv[1], kv[0]), reverse=rev)[:out]  on parallel arrays (idx, val, key); keys are unique pairs */
+static void sort_by_key(int n, int32_t* idx, int32_t* val, int64_t* key, int reverse) {
+    for (int i = 1; i < n; i++) { /* insertion sort: n <= stations */
+        int32_t ii = idx[i], vv = val[i];
+        int64_t kk = key[i];
+        int j = i - 1;
+        while (j >= 0) {
+            /* order of (key[j], idx[j]) vs (kk, ii) */
+            int less = key[j] < kk || (key[j] == kk && idx[j] < ii);
+            int wrong = reverse ? less : !less;
+            if (!wrong) break;
+            idx[j + 1] = idx[j]; val[j + 1] = val[j]; key[j + 1] = key[j];
+            j--;
+        }
+        idx[j + 1] = ii; val[j + 1] = vv; key[j + 1] = kk;
+    }
+}
+
+/* BikeDecisionStrategy.action_scope (decision_strategy.py:253-293): neighbour scope, the filter chain
+ * (DistanceFilter :15-52, RequirementsFilter :55-88, TripsWindowFilter :91-166), then the station itself.
+ * `pairs` = (station, value) in ascending station order (the reference returns a dict: order carries no meaning). */
+static int action_scope(BikeOracle* o, int station, int type, int32_t* pairs) {
+    const int S = o->S;
+    int32_t idx[4096], val[4096];
+    int64_t key[4096];
     int n = 0;
-    int32_t val[4096];
-    char has[4096];
-    memset(has, 0, (size_t)o->S);
     for (int k = o->t.nbr_offset[station]; k < o->t.nbr_offset[station + 1]; k++) {
         int nb = o->t.nbr_idx[k];
         const Station* s = &o->st[nb];
-        val[nb] = type == 0 ? s->capacity - s->bikes : (int)floor(s->bikes * o->t.scope_high);
-        has[nb] = 1;
+        idx[n] = nb;
+        val[n] = type == 0 ? s->capacity - s->bikes : (int)floor(s->bikes * o->t.scope_high);
+        n++;
     }
+    for (int f = 0; f < o->t.n_filters; f++) {
+        int out = o->t.filter_num[f] < n ? o->t.filter_num[f] : n; /* output_num = min(num, len(source)) */
+        if (o->t.filter_type[f] == MARO_BIKE_FILTER_DISTANCE) {
+            /* result[n] = source[n] for the first `out` entries of the station's FULL neighbour list */
+            int32_t nidx[4096], nval[4096];
+            for (int k = 0; k < out; k++) {
+                int nb = o->t.nbr_idx[o->t.nbr_offset[station] + k], at = -1;
+                for (int j = 0; j < n; j++) if (idx[j] == nb) at = j;
+                if (at < 0) { o->scope_error = 1; nval[k] = 0; } else nval[k] = val[at];
+                nidx[k] = nb;
+            }
+            memcpy(idx, nidx, sizeof(int32_t) * (size_t)out); memcpy(val, nval, sizeof(int32_t) * (size_t)out);
+        } else if (o->t.filter_type[f] == MARO_BIKE_FILTER_REQUIREMENTS) {
+            for (int j = 0; j < n; j++) key[j] = val[j];
+            sort_by_key(n, idx, val, key, 1);
+        } else {
+            /* frames held by the snapshot list in insertion (= ascending) order; the latest `available_windows` of them */
+            int frames[4096], nf = 0;
+            int first = o->total_frames, last = -1;
+            for (int r = 0; r < o->ring_rows; r++) if (o->ring_frame[r] >= 0) { if (o->ring_frame[r] < first) first = o->ring_frame[r]; if (o->ring_frame[r] > last) last = o->ring_frame[r]; }
+            for (int fr = first; fr <= last && nf < 4096; fr++) if (o->ring_frame[fr % o->ring_rows] == fr) frames[nf++] = fr;
+            int avail = o->t.filter_windows[f] < nf ? o->t.filter_windows[f] : nf;
+            for (int j = 0; j < n; j++) key[j] = 0;
+            for (int i = 0; i < avail; i++) {
+                int fr = frames[nf - avail + i];
+                if (i == avail - 1 || !o->tw_has[fr]) { /* the latest frame may still change: always re-read; others once */
+                    const int32_t* row = o->ring + (size_t)(fr % o->ring_rows) * o->frame_words;
+                    memcpy(o->tw_cache + (size_t)fr * S, row + 11 * S, sizeof(int32_t) * (size_t)S); /* trip_requirement */
+                    o->tw_has[fr] = 1;
+                }
+                for (int j = 0; j < n; j++) key[j] += o->tw_cache[(size_t)fr * S + idx[j]];
+            }
+            sort_by_key(n, idx, val, key, type == 1); /* Demand: most trips first; Supply: fewest first */
+        }
+        n = out;
+    }
+    int32_t res[4096];
+    char has[4096];
+    memset(has, 0, (size_t)S);
+    for (int j = 0; j < n; j++) { res[idx[j]] = val[j]; has[idx[j]] = 1; }
     const Station* s = &o->st[station];
-    val[station] = type == 0 ? (int)floor(s->bikes * (1 - o->t.scope_low)) : s->capacity - s->bikes;
+    res[station] = type == 0 ? (int)floor(s->bikes * (1 - o->t.scope_low)) : s->capacity - s->bikes;
     has[station] = 1;
-    for (int i = 0; i < o->S; i++) if (has[i]) { pairs[2 * n] = i; pairs[2 * n + 1] = val[i]; n++; }
-    return n;
+    int m = 0;
+    for (int i = 0; i < S; i++) if (has[i]) { pairs[2 * m] = i; pairs[2 * m + 1] = res[i]; m++; }
+    return m;
 }
 
 static void fill_metrics(const BikeOracle* o, int64_t* m) { m[0] = o->total_trips; m[1] = o->total_shortages; m[2] = o->total_operate; }

@@ -54,6 +54,14 @@ CASES = {
     # tick that has already run and never executes (3 bikes vanish), event_buffer.py:166-175
     "toy_start300_773_negative_transfer": dict(data="bike_toy", start_tick=300, durations=773, policy=1, snapshot_resolution=20,
                                                np_seed=41130),
+    # 26 synthetic stations (tests/golden/bike_synth_gen.py): every action-scope filter DROPS neighbours (distance 14 ->
+    # requirements 9 -> trip_window 5 x 4; decision_strategy.py:15-163).  Snapshot resolution 7 does not divide the decision
+    # resolution 20, so the trip-window filter's per-frame cache holds mid-frame values (its staleness is part of the trace)
+    "synth26_1440_greedy_res7": dict(data="bike_synth26", durations=1440, policy=1, snapshot_resolution=7, np_seed=3),
+    "synth26_900_null_res10_ring3": dict(data="bike_synth26", durations=900, policy=0, snapshot_resolution=10, max_snapshots=3,
+                                         np_seed=8),
+    "synth26_start400_600_greedy_res1": dict(data="bike_synth26", start_tick=400, durations=600, policy=1, snapshot_resolution=1,
+                                             np_seed=21),
     "case1_30_null": dict(data="bike_case_1", durations=30, policy=0, snapshot_resolution=1, np_seed=1),
     "case2_30_greedy": dict(data="bike_case_2", durations=30, policy=1, snapshot_resolution=1, np_seed=2),
 }

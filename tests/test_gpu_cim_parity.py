@@ -286,9 +286,11 @@ def test_cuda_config4_full_size_distinct_seeds():
     sidx = torch.tensor(sample, device="cuda")
     tapes = {i: [] for i in sample}
     mets = {i: [] for i in sample}
+    final = torch.zeros_like(met)  # metrics returned with each replica's DONE row (a later step returns the zero FINISHED row)
     env.step_device(dec.data_ptr(), met.data_ptr())
     for step in range(4000):
         d = dec[sidx].cpu().numpy()
+        final = torch.where((dec[:, 6] == 1).unsqueeze(1), met, final)
         if step % 16 == 0 and bool((dec[:, 6] != 0).all().item()):
             break
         env.random_policy_device(dec.data_ptr(), act.data_ptr(), 0)
@@ -300,7 +302,7 @@ def test_cuda_config4_full_size_distinct_seeds():
                 mets[i].append(m[k].copy())
         env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
     torch.cuda.synchronize()
-    dn, mn = dec.cpu().numpy(), met.cpu().numpy()
+    dn, mn = dec.cpu().numpy(), final.cpu().numpy()
     assert (dn[:, 6] != 0).all() and (env.ticks() == T - 1).all()
     # (a) the reference trace (seed 4099 = replica 3, policy tape (pseed 0, replica 3))
     rows = np.asarray([list(d[:6]) + list(m) for (d, _), m in zip(tapes[3], mets[3])], np.int64)
@@ -333,12 +335,14 @@ def test_cuda_config4_full_size_distinct_seeds():
     # (c) the same episode as fused resident rollouts (agent as a device callback)
     env.reset()
     dec.zero_()
+    final2 = torch.zeros_like(met)
     for _ in range(64):
         env.rollout_device(dec.data_ptr(), met.data_ptr(), 64, 1, 0, 0)
+        final2 = torch.where((dec[:, 6] == 1).unsqueeze(1), met, final2)  # a fused rollout stops at its replica's DONE row
         if bool((dec[:, 6] != 0).all().item()):
             break
     torch.cuda.synchronize()
-    assert np.array_equal(met.cpu().numpy(), mn)
+    assert np.array_equal(final2.cpu().numpy(), mn)
     for i in sample:
         assert np.array_equal(env.read_frame(i), final_frames[i])
     assert_snapshots_equal(lambda f: env.snapshot_row(f, 3), gold, topos[3])
