@@ -266,6 +266,12 @@ int maro_cim_rl_action_device(MaroCimEnv* env, const int32_t* d_decisions, const
  * d_decay = [time_decay ** k] (time_window doubles on the device).  out: [n_replicas] float32. */
 int maro_cim_rl_reward_device(MaroCimEnv* env, const int32_t* d_ticks, const int32_t* d_ports, const double* d_decay,
                               int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out);
+/* The same for a whole trajectory in one launch: d_ticks / d_ports / d_out are [n_rows][n_replicas] (row = rollout step;
+ * a negative tick yields reward 0) — the reference computes them one Python call per cached transition
+ * (maro/rl/rollout/env_sampler.py:396-402, 500-506). */
+int maro_cim_rl_reward_batch_device(MaroCimEnv* env, const int32_t* d_ticks, const int32_t* d_ports, int32_t n_rows,
+                                    const double* d_decay, int32_t time_window, double fulfillment_factor,
+                                    double shortage_factor, float* d_out);
 
 
 /* ================================================================================================

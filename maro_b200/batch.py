@@ -175,6 +175,12 @@ class CimBatch:
         _native.check(_native.lib().maro_cim_rl_reward_device(self._h, d_ticks, d_ports, d_decay, time_window,
                                                               float(fulfillment_factor), float(shortage_factor), d_out))
 
+    def rl_reward_batch_device(self, d_ticks: int, d_ports: int, n_rows: int, d_decay: int, time_window: int,
+                               fulfillment_factor: float, shortage_factor: float, d_out: int):
+        """rewards of [n_rows][B] (tick, port) pairs in one launch"""
+        _native.check(_native.lib().maro_cim_rl_reward_batch_device(self._h, d_ticks, d_ports, n_rows, d_decay, time_window,
+                                                                    float(fulfillment_factor), float(shortage_factor), d_out))
+
     # -- inspection --------------------------------------------------------------------------------
     def node_counts(self) -> dict:
         """node type name -> number of nodes (what ``len(env.snapshot_list[name])`` reports)"""

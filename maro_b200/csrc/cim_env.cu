@@ -419,6 +419,7 @@ struct ShapeArgs {
     const int32_t* ports;      // [B] port that acted
     const double* decay;       // [time_window] time_decay ** i
     int time_window, off_fulfillment, off_shortage;
+    int n_rows;                // rewards for [n_rows][B] (tick, port) pairs in one launch (row-major; replica = item % B)
     double fulfillment_factor, shortage_factor;
     float* reward_out;         // [B]
     // action translation
@@ -476,10 +477,12 @@ __global__ void cim_rl_state_kernel(const __grid_constant__ ShapeArgs q) {
 __global__ void cim_rl_reward_kernel(const __grid_constant__ ShapeArgs q) {
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int rep = warp_global; rep < q.B; rep += n_warps) {
-        const int tick = q.ticks[rep], port = q.ports[rep];
+    const int64_t n_items = (int64_t)q.n_rows * q.B;
+    for (int64_t item = warp_global; item < n_items; item += n_warps) {
+        const int rep = (int)(item % q.B);
+        const int tick = q.ticks[item], port = q.ports[item];
         double f = 0.0, sh = 0.0;
-        if (port >= 0 && port < q.P) {
+        if (port >= 0 && port < q.P && tick >= 0) {
             for (int k = lane; k < q.time_window; k += 32) {
                 const int32_t* row = nullptr;
                 if (snap_row(q, rep, tick + 1 + k, row)) {
@@ -492,7 +495,7 @@ __global__ void cim_rl_reward_kernel(const __grid_constant__ ShapeArgs q) {
             f += __shfl_xor_sync(0xffffffffu, f, o);
             sh += __shfl_xor_sync(0xffffffffu, sh, o);
         }
-        if (lane == 0) q.reward_out[rep] = (float)(q.fulfillment_factor * f - q.shortage_factor * sh);
+        if (lane == 0) q.reward_out[item] = (float)(q.fulfillment_factor * f - q.shortage_factor * sh);
     }
 }
 
@@ -1238,21 +1241,35 @@ int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const i
     return 0;
 }
 
-int maro_cim_rl_reward_device(MaroCimEnv* e, const int32_t* d_ticks, const int32_t* d_ports, const double* d_decay,
-                              int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out) {
-    if (!e || !d_ticks || !d_ports || !d_decay || !d_out || time_window < 1) return fail("maro_cim_rl_reward_device: bad arguments");
+static int rl_reward_launch(MaroCimEnv* e, const int32_t* d_ticks, const int32_t* d_ports, int32_t n_rows, const double* d_decay,
+                            int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out) {
     CK(cudaSetDevice(e->device));
     END_SESSION(e);
     ShapeArgs q;
     shape_common(e, q);
-    q.ticks = d_ticks; q.ports = d_ports; q.decay = d_decay; q.time_window = time_window;
+    q.ticks = d_ticks; q.ports = d_ports; q.decay = d_decay; q.time_window = time_window; q.n_rows = n_rows;
     q.off_fulfillment = e->attrs[0][common_attr_id(e, 0, "fulfillment")].off;
     q.off_shortage = e->attrs[0][common_attr_id(e, 0, "shortage")].off;
     q.fulfillment_factor = fulfillment_factor; q.shortage_factor = shortage_factor; q.reward_out = d_out;
-    int threads = 128, blocks = std::min((e->B * 32 + threads - 1) / threads, 148 * 16);
+    const int64_t items = (int64_t)n_rows * e->B;
+    int threads = 128, blocks = (int)std::min<int64_t>((items * 32 + threads - 1) / threads, 148 * 16);
     cim_rl_reward_kernel<<<blocks, threads, 0, e->stream>>>(q);
     CK(cudaGetLastError());
     return 0;
+}
+
+int maro_cim_rl_reward_device(MaroCimEnv* e, const int32_t* d_ticks, const int32_t* d_ports, const double* d_decay,
+                              int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out) {
+    if (!e || !d_ticks || !d_ports || !d_decay || !d_out || time_window < 1) return fail("maro_cim_rl_reward_device: bad arguments");
+    return rl_reward_launch(e, d_ticks, d_ports, 1, d_decay, time_window, fulfillment_factor, shortage_factor, d_out);
+}
+
+/* the rewards of a whole trajectory in ONE launch: ticks / ports / out are [n_rows][n_replicas] (row = rollout step) */
+int maro_cim_rl_reward_batch_device(MaroCimEnv* e, const int32_t* d_ticks, const int32_t* d_ports, int32_t n_rows, const double* d_decay,
+                                    int32_t time_window, double fulfillment_factor, double shortage_factor, float* d_out) {
+    if (!e || !d_ticks || !d_ports || !d_decay || !d_out || time_window < 1 || n_rows < 1)
+        return fail("maro_cim_rl_reward_batch_device: bad arguments");
+    return rl_reward_launch(e, d_ticks, d_ports, n_rows, d_decay, time_window, fulfillment_factor, shortage_factor, d_out);
 }
 
 }  // extern "C"

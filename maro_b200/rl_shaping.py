@@ -59,6 +59,16 @@ class CimShaper:
                                     self.fulfillment_factor, self.shortage_factor, self._reward.data_ptr())
         return self._reward
 
+    def rewards_batch(self, ticks, ports):
+        """ticks, ports: int32 CUDA tensors [T][B] (a negative tick = no decision there -> reward 0) -> float32 [T][B], one launch"""
+        torch = self._torch
+        for t in (ticks, ports):
+            assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and t.dim() == 2
+        out = torch.empty(ticks.shape, dtype=torch.float32, device=ticks.device)
+        self.batch.rl_reward_batch_device(ticks.data_ptr(), ports.data_ptr(), ticks.shape[0], self._decay.data_ptr(), self.time_window,
+                                          self.fulfillment_factor, self.shortage_factor, out.data_ptr())
+        return out
+
     def env_actions(self, decisions, model_actions):
         """decisions int32 [B][8], model_actions int32 [B] (indices into the action space) -> int32 CUDA tensor
         [B][max_actions][4], the `actions` argument of ``CimBatch.step_device`` (env_sampler.py:38-64)."""

@@ -39,7 +39,7 @@ def digest(arrs) -> str:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", required=True, choices=["reference", "shim"])
-    ap.add_argument("--what", required=True, choices=["hello_cim", "hello_vector", "rl_cim"])
+    ap.add_argument("--what", required=True, choices=["hello_cim", "hello_vector", "rl_cim", "rl_cim_greedy", "rl_cim_batched"])
     ap.add_argument("--emulate", action="store_true")
     ap.add_argument("--seed", type=int, default=20240923)
     args = ap.parse_args()
@@ -72,6 +72,74 @@ def main():
             out["summary_has_node_mapping"] = bool(m)
         else:
             out["lines"] = [ln for ln in text.splitlines() if ln.startswith(("When env 0", "Final"))]
+    elif args.what in ("rl_cim_greedy", "rl_cim_batched"):
+        # The reference sampler with exploration switched off (so that a batched run can be compared transition by transition)
+        # vs maro_b200.rl_rollout.BatchedCimEnvSampler driving 16 replicas with the SAME per-port DQN policies.
+        import numpy as np
+        import torch
+
+        np.random.seed(args.seed)
+        torch.manual_seed(args.seed)
+        torch.set_num_threads(1)
+        with contextlib.redirect_stdout(buf):
+            from examples.cim.rl.rl_component_bundle import rl_component_bundle as bundle
+            from maro.rl.training import TrainingManager
+
+            sampler = bundle.env_sampler
+            policies = {p.name: p for p in bundle.policies}
+            for p in policies.values():
+                p.explore = p.exploit  # test driver only: greedy actions in sample()
+            if args.what == "rl_cim_greedy":
+                result = sampler.sample()
+            else:
+                from examples.cim.rl.config import env_conf
+                from maro_b200.batch import CimBatch
+                from maro_b200.rl_rollout import BatchedCimEnvSampler
+                from maro_b200.scenarios.cim.topology import build_topology
+
+                batch = CimBatch(build_topology(env_conf["topology"], env_conf["durations"]), 16)
+                a2p = bundle.agent2policy
+
+                def policy(states, decisions):  # per-port policies of the bundle, evaluated for the rows of each port
+                    st = states.cpu().numpy().astype(np.float64)
+                    ports = decisions[:, 1].cpu().numpy()
+                    live = decisions[:, 6].cpu().numpy() == 0
+                    out = np.zeros(len(st), np.int64)
+                    for port in np.unique(ports[live]):
+                        rows = np.flatnonzero(live & (ports == port))
+                        pol = policies[a2p[int(port)]]
+                        pol.eval()
+                        with torch.no_grad():
+                            out[rows] = np.asarray(pol.get_actions(st[rows])).reshape(-1)
+                    return torch.as_tensor(out, device=states.device)
+
+                bs = BatchedCimEnvSampler(batch, policy, policy_takes_decisions=True, use_graph=False)
+                result = bs.sample()
+                assert len(result["experiences"]) == 16
+                first = result["experiences"][0]
+                for other in result["experiences"][1:]:  # identical replicas, greedy policies: identical experience lists
+                    assert len(other) == len(first) and all(a.tick == b.tick and np.array_equal(a.state, b.state) for a, b in zip(first, other))
+                result = {"experiences": result["experiences"][:2], "info": result["info"][:2]}
+            exps = result["experiences"][0]
+            tm = TrainingManager(rl_component_bundle=bundle, explicit_assign_device=True)
+            tm.record_experiences(result["experiences"])
+            tm.train_step()
+            state = tm.get_policy_state()
+        agent = lambda e: sorted(e.agent_state_dict)[0]
+        out.update({
+            "exp_class": type(exps[0]).__module__,
+            "n_experiences": len(exps),
+            "ticks": [int(e.tick) for e in exps],
+            "agents": [int(agent(e)) for e in exps],
+            "states": digest([np.asarray(e.state, np.float64) for e in exps]),
+            "agent_states": digest([np.asarray(e.agent_state_dict[agent(e)], np.float64) for e in exps]),
+            "next_agent_states": digest([np.asarray(e.next_agent_state_dict[agent(e)], np.float64) for e in exps]),
+            "actions": [int(np.asarray(e.action_dict[agent(e)]).reshape(-1)[0]) for e in exps],
+            "rewards": [float(e.reward_dict[agent(e)]) for e in exps],
+            "terminals": [bool(e.terminal_dict[agent(e)]) for e in exps],
+            "env_metric": {k: int(v) for k, v in result["info"][0]["env_metric"].items()},
+            "trained": sorted(state),
+        })
     else:
         import numpy as np
         import torch

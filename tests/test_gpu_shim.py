@@ -69,3 +69,20 @@ def test_rl_toolkit_sampler_and_train_step_unchanged(emulate=False):
         assert ours[k] == ref[k], k
     assert abs(ours["reward_sum"] - ref["reward_sum"]) <= 1e-6 * max(1.0, abs(ref["reward_sum"]))
     assert ours["n_experiences"] > 300
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (maro.rl + examples) not built (oracle/build_ref.sh)")
+def test_batched_sampler_equals_the_reference_sampler_and_feeds_its_trainers():
+    """SURVEY.md §8f rank 2 / VERDICT r1 next #8: ``BatchedCimEnvSampler.sample()`` (device-resident collection for all
+    replicas, ExpElements materialised from the columns) against ``AbsEnvSampler.sample()`` of the reference run on the
+    reference Env with the same per-port DQN policies (exploration off in both): the same transitions — ticks, agents,
+    states, per-agent next states, actions, rewards (1e-6), terminal flags, the reward_eval_delay cut-off — as the real
+    ``maro.rl.rollout.ExpElement`` objects; ``TrainingManager.record_experiences`` + ``train_step`` run on them."""
+    ours, ref = run("shim", "rl_cim_batched"), run("reference", "rl_cim_greedy")
+    assert ours["exp_class"] == ref["exp_class"] == "maro.rl.rollout.env_sampler"
+    for k in ("n_experiences", "ticks", "agents", "states", "agent_states", "next_agent_states", "actions", "terminals", "env_metric",
+              "trained"):
+        assert ours[k] == ref[k], k
+    assert len(ours["rewards"]) == len(ref["rewards"]) > 300
+    for a, b in zip(ours["rewards"], ref["rewards"]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (a, b)
