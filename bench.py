@@ -530,7 +530,9 @@ def _rl_extras(torch, env, dec, topo, B, stream):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     shaping["rollout"] = {"env_steps_per_s": float(traj["valid"].sum().item()) / dt, "steps": int(traj["valid"].shape[0]),
-                          "seconds": dt, "what": "CimDeviceRollout: one episode, MLP policy on the same GPU, rewards included (wall clock)"}
+                          "seconds": dt, "cuda_graph": ro._graph is not None, "graph_error": ro.graph_error,
+                          "what": "BatchedCimEnvSampler.collect: one episode, MLP policy on the same GPU, sync-free fixed-length loop "
+                                  "in CUDA-graph chunks, rewards in one launch (wall clock)"}
     return shaping
 
 

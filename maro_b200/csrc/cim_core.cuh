@@ -225,6 +225,11 @@ struct CimShape {
     int t_frb_i, t_erb_i;                   // ceil(buffer_ticks) per port, valid when buffer_noise == 0
     int table_words;                        // stride between topology blobs
     int mt_scratch;                         // word offset of the scratch area inside a replica's MT block
+    // Delay lines (noise-free topologies with few ports; 0 = off): RETURN_FULL / RETURN_EMPTY fire a fixed, small number
+    // of ticks after they are created and are pure adds, so they are ACCUMULATED per due tick instead of queued as events:
+    // slot (tick & (DL-1)) = { rf[P*P] (src*P+dst -> quantity), re[P] (port -> quantity), n_rf, n_re (event counts) } at word
+    // offset o_dl of the state block.  Same arithmetic, same event counts, no list walking / free list / push machinery.
+    int DL, o_dl, dl_stride;
 };
 
 struct Replica {
@@ -352,6 +357,43 @@ MARO_DEV MtView mt_reserve(const CimShape& s, const Grp<G>& g, const Replica& r,
 MARO_DEV int32_t* q_bucket(const CimShape& s, const Replica& r) { return r.q + s.QN * 2; }
 MARO_DEV uint16_t* q_next(const CimShape& s, const Replica& r) { return reinterpret_cast<uint16_t*>(r.q + s.QN * 2 + s.QH); }
 MARO_DEV uint16_t* q_free(const CimShape& s, const Replica& r) { return q_next(s, r) + s.QN; }
+
+MARO_DEV int32_t* dl_slot(const CimShape& s, const Replica& r, int tick) { return r.f + s.o_dl + (tick & (s.DL - 1)) * s.dl_stride; }
+
+// Drain the delay-line slot of `tick`: every accumulated RETURN_FULL (:499-522) and RETURN_EMPTY (:695-706) of this tick.
+template <int G>
+MARO_DEV int run_delay_line(const CimShape& s, const Grp<G>& g, const Replica& r, int tick) {
+    int32_t* sl = dl_slot(s, r, tick);
+    const int PP = s.P * s.P;
+    const int n = sl[PP + s.P] + sl[PP + s.P + 1];
+    if (n == 0) return 0;  // group-uniform
+    g.sync();
+    int src = g.lane / s.P, dst = g.lane - src * s.P;
+    for (int i = g.lane; i < PP; i += G) {
+        const int q = sl[i];
+        if (q) {
+            atomic_add(&PA(s, r, PA_ON_SHIPPER, src), -q);
+            atomic_add(&PA(s, r, PA_FULL, src), q);
+            r.f[s.o_fop + i] += q;
+            sl[i] = 0;
+        }
+        dst += G;
+        while (dst >= s.P) { dst -= s.P; src++; }
+    }
+    g.sync();  // (on_consignee / empty below are plain updates of the lane's own port)
+    LANE_DIM(p, s.P) {
+        const int q = sl[PP + p];
+        if (q) {
+            PA(s, r, PA_ON_CONSIGNEE, p) -= q;
+            PA(s, r, PA_EMPTY, p) += q;
+            sl[PP + p] = 0;
+        }
+    }
+    g.sync();
+    if (g.lane == 0) { sl[PP + s.P] = 0; sl[PP + s.P + 1] = 0; }
+    g.sync();
+    return n;
+}
 
 template <int G>
 MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, bool want, int now, int tick, int w0, int qty) {
@@ -522,7 +564,18 @@ MARO_DEV int run_bucket(const CimShape& s, const Grp<G>& g, const Replica& r, in
         g.sync();
         if (g.lane == 0) { r.c[C_FREE_TOP] = top + n; r.c[C_Q_COUNT] -= n; }
         g.sync();
-        if (db) group_push(s, g, r, is_dis && buf > 0, tick, tick + buf, DE_RETURN_EMPTY | (c << 8), qty);
+        if (db) {
+            if (!kGeneral && s.DL) {
+                if (is_dis && buf > 0 && tick + buf < s.max_tick) {
+                    int32_t* sl = dl_slot(s, r, tick + buf);
+                    atomic_add(&sl[s.P * s.P + c], qty);
+                    atomic_add(&sl[s.P * s.P + s.P + 1], 1);
+                }
+                g.sync();
+            } else {
+                group_push(s, g, r, is_dis && buf > 0, tick, tick + buf, DE_RETURN_EMPTY | (c << 8), qty);
+            }
+        }
         nev += n;
     }
     g.sync();
@@ -582,7 +635,16 @@ MARO_DEV int run_orders(const CimShape& s, const Grp<G>& g, const Replica& r, in
             atomic_add(&r.f[s.o_fop + src * s.P + dst], exec);
         }
         nev += nv + maro_popc(g.ballot(imm));
-        group_push(s, g, r, valid && buf > 0, tick, tick + buf, DE_RETURN_FULL | (src << 8) | (dst << 16), exec);
+        if (!kGeneral && s.DL) {
+            if (valid && buf > 0 && tick + buf < s.max_tick) {
+                int32_t* sl = dl_slot(s, r, tick + buf);
+                atomic_add(&sl[src * s.P + dst], exec);
+                atomic_add(&sl[s.P * s.P + s.P], 1);
+            }
+            g.sync();
+        } else {
+            group_push(s, g, r, valid && buf > 0, tick, tick + buf, DE_RETURN_FULL | (src << 8) | (dst << 16), exec);
+        }
     }
     return nev;
 }
@@ -1045,6 +1107,7 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
             g.sync();
             // ---- (b) events queued by earlier ticks
             nev += run_bucket<G, kGeneral>(s, g, r, tick);
+            if (!kGeneral && s.DL) nev += run_delay_line(s, g, r, tick);
             // ---- (c) this tick's orders
             if (!kGeneral || s.order_table) {
                 int slot = TBL_I(r, s.t_ord_slot, tick);
@@ -1183,6 +1246,7 @@ MARO_DEV void replica_reset(const CimShape& s, const Grp<G>& g, const Replica& r
         fs[i] = (uint16_t)(s.QN - 1 - i);
     }
     LANE_LOOP(i, s.QH) q_bucket(s, r)[i] = Q_NIL | (Q_NIL << 16);
+    LANE_LOOP(i, s.DL * s.dl_stride) r.f[s.o_dl + i] = 0;
     LANE_LOOP(i, s.ring_rows) r.snap_frame[i] = -1;
     if (r.mt) {
         LANE_LOOP(i, 624) {

@@ -273,6 +273,19 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
     if (qn > 65000) qn = 65000;
     s.QN = round_up(qn, 4);
     s.SW = round_up(s.FWp + s.CWp + s.QN * 2 + s.QH + s.QN, 4);  // frame | ctrl | ev | buckets | next+free (u16)
+    // delay lines for the pure-add events of noise-free, small topologies (cim_core.cuh: CimShape::DL): sized for the longest
+    // container buffer time; the calendar queue then only carries DISCHARGE_FULL.  MARO_B200_DELAY_LINE=0 turns them off (A/B).
+    {
+        const bool noise_free = !s.order_noise && s.order_mode == 0 && !s.buffer_noise;
+        int dl = 2;
+        while (dl < std::max(buf_full, buf_empty) + 1) dl <<= 1;
+        const int stride = round_up(P * P + P + 2, 4);
+        const char* off = getenv("MARO_B200_DELAY_LINE");
+        if (noise_free && dl * stride <= 512 && !(off && atoi(off) == 0)) {
+            s.DL = dl; s.dl_stride = stride; s.o_dl = s.SW;  // (word offset from the start of the block = from r.f)
+            s.SW = round_up(s.SW + dl * stride, 4);
+        }
+    }
     s.res_is_one = s.resolution == 1 ? 1 : 0;
     s.vol_is_one = s.vol == 1.0 ? 1 : 0;
     s.max_targets = max_targets;

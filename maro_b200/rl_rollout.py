@@ -98,6 +98,7 @@ class BatchedCimEnvSampler:
         self._c_act = torch.zeros((K, B), dtype=torch.int32, device=self.device)
         self._c_state = torch.zeros((K, B, D), dtype=torch.float32, device=self.device) if store_states else None
         self._graph = None
+        self.graph_error = None
         self.last = None
 
     # ------------------------------------------------------------------------------------------------ device loop
@@ -131,9 +132,10 @@ class BatchedCimEnvSampler:
                         for k in range(n):
                             self._body(k)
                 self._graph = g
-            except Exception:  # a policy that cannot be captured: fall back to eager launches for good
+            except Exception as ex:  # a policy that cannot be captured: fall back to eager launches for good
                 self.use_graph = False
                 self._graph = None
+                self.graph_error = repr(ex)[:300]
             finally:
                 self.batch.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
                 torch.cuda.current_stream(self.device).wait_stream(side)

@@ -117,8 +117,13 @@ def main():
                 result = bs.sample()
                 assert len(result["experiences"]) == 16
                 first = result["experiences"][0]
-                for other in result["experiences"][1:]:  # identical replicas, greedy policies: identical experience lists
-                    assert len(other) == len(first) and all(a.tick == b.tick and np.array_equal(a.state, b.state) for a, b in zip(first, other))
+                for r, other in enumerate(result["experiences"][1:], 1):  # identical replicas, greedy policies: identical lists
+                    if len(other) != len(first):
+                        raise AssertionError(f"replica {r}: {len(other)} experiences, replica 0 has {len(first)}")
+                    for k, (a, b) in enumerate(zip(first, other)):
+                        if a.tick != b.tick or not np.array_equal(a.state, b.state):
+                            raise AssertionError(f"replica {r} transition {k}: tick {b.tick} vs {a.tick}, "
+                                                 f"state diff at {np.flatnonzero(np.asarray(a.state) != np.asarray(b.state))[:8].tolist()}")
                 result = {"experiences": result["experiences"][:2], "info": result["info"][:2]}
             exps = result["experiences"][0]
             tm = TrainingManager(rl_component_bundle=bundle, explicit_assign_device=True)
