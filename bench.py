@@ -57,6 +57,8 @@ def parse():
                     help="citi_bike = BASELINE config #3 (frozen toy.3s_4t trace, greedy agent, snapshot_resolution 10); "
                          "vm_scheduling = config #5 (synthetic azure.2019.10k-scale trace, best-fit agent)")
     ap.add_argument("--vm-count", type=int, default=10000, help="vm_scheduling: VMs in the synthetic trace")
+    ap.add_argument("--vm-query-agent", action="store_true", help="vm_scheduling e2e: the host agent makes the reference agent's snapshot "
+                    "query every step (3.3 MB D2H) instead of reading the decision row's remaining-cores extension")
     ap.add_argument("--vm-trace-dir", default="", help="vm_scheduling: where the synthetic trace is written (default: a temp dir)")
     ap.add_argument("--max-snapshots", type=int, default=0, help="0 = keep every frame (reference default)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
@@ -436,6 +438,7 @@ def load_host_agent():
     lib.agent_greedy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.agent_best_fit.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.agent_best_fit_row.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
 
@@ -1017,7 +1020,9 @@ def run_ours(args, rank, local_rank, world):
             pm_nodes = np.arange(topo.n_pm)
 
         def host_agent():
-            if vm:  # the reference agent's snapshot query (best_fit.py:38-44), batched over the replicas, then the argmin
+            if vm and not args.vm_query_agent:  # best fit from the decision row's extension (remaining cores per valid PM)
+                agent_lib.agent_best_fit_row(dec_ptr, act_ptr, B, 1, dec_words)
+            elif vm:  # the reference agent's snapshot query (best_fit.py:38-44), batched over the replicas, then the argmin
                 live = p_dec[:, 6] == 0
                 frames = np.unique(p_dec[live, 2]).astype(np.int32) if live.any() else np.zeros(1, np.int32)
                 q = env.query("pms", frames, pm_nodes, ["cpu_cores_capacity", "cpu_cores_allocated"])
@@ -1133,8 +1138,10 @@ def run_ours(args, rank, local_rank, world):
         }
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
-                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + met_words * 8) + (B * topo.n_pm * 16 if vm else 0),
-                           "api": ("maro_vm_step_pinned + maro_vm_query (the agent's snapshot query) + tools/host_agent.c on the host" if vm else
+                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + met_words * 8) + (B * topo.n_pm * 16 if vm and args.vm_query_agent else 0),
+                           "api": (("maro_vm_step_pinned + maro_vm_query (the agent's snapshot query) + tools/host_agent.c on the host"
+                                    if args.vm_query_agent else
+                                    "maro_vm_step_pinned + tools/host_agent.c:agent_best_fit_row (decision-row extension) on the host") if vm else
                                    "maro_%s_step_pinned (pinned host buffers) + tools/host_agent.c on the host" % ("bike" if bike else "cim")),
                            "us_per_call": 1000.0 * e2e_ms / max(1, min(args.steps, 2000)),
                            "agent_us_per_call": 1e6 * e2e["agent_seconds"] / max(1, min(args.steps, 2000))}

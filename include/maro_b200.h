@@ -406,6 +406,9 @@ enum {
     MARO_VM_DEC_CATEGORY = 8,
     MARO_VM_DEC_BUFFER_TIME = 9,
     MARO_VM_DEC_N_VALID = 10,
+    MARO_VM_DEC_EXT_OFFSET = 11, /* word offset of the extension area: remaining CPU cores (capacity - allocated in the
+                                    decision's frame) of valid PM k at row[EXT_OFFSET + k] — what the reference's rule-based
+                                    agents fetch with a snapshot query per decision (rule_based_algorithm/best_fit.py:38-44) */
     MARO_VM_DEC_HEAD = 12
 };
 /* Action row: 4 int32 {vm_id, kind, pm_id | postpone_step, 0}; kind 0 = AllocateAction, 1 = PostponeAction

@@ -195,7 +195,13 @@ MARO_DEV int vm_valid_pms(const VmShape& s, const Grp<G>& g, const VmReplica& r,
             }
         }
         uint32_t m = g.ballot(ok);
-        if (out && ok) out[n + maro_popc(m & ((1u << g.lane) - 1u))] = p;
+        if (out && ok) {
+            const int at = n + maro_popc(m & ((1u << g.lane) - 1u));
+            out[at] = p;
+            // extension behind the id area: the PM's remaining CPU cores in the decision's (= the live) frame, what the
+            // rule-based agents of the reference query the snapshot list for (rule_based_algorithm/best_fit.py:38-44)
+            out[s.N + at] = VPM(s, r, VPA_CPU_CAP, p) - VPM(s, r, VPA_CPU_ALLOC, p);
+        }
         n += maro_popc(m);
     }
     return n;
@@ -492,7 +498,8 @@ MARO_DEV void vm_replica_step(const VmShape& s, const Grp<G>& g, const VmReplica
         vm_snapshot(s, g, r, vm_frame_index(s, tick));  // core.py:345
         nsnaps++;
         int n_valid = vm_valid_pms<G>(s, g, r, cur_vm, dec + MARO_VM_DEC_HEAD);
-        for (int i = n_valid + g.lane; i < s.DW - MARO_VM_DEC_HEAD; i += G) dec[MARO_VM_DEC_HEAD + i] = 0;
+        for (int i = n_valid + g.lane; i < s.DW - MARO_VM_DEC_HEAD; i += G)
+            if (i < s.N || i >= s.N + n_valid) dec[MARO_VM_DEC_HEAD + i] = 0;  // (ids [0, n) and their extension [N, N + n) stay)
         status = MARO_STATUS_DECISION;
         if (g.lane == 0) {
             I4 r0 = ld4_ro(r.t + s.t_rec0 + 4 * cur_vm), r1 = ld4_ro(r.t + s.t_rec1 + 4 * cur_vm);
@@ -507,6 +514,7 @@ MARO_DEV void vm_replica_step(const VmShape& s, const Grp<G>& g, const VmReplica
             dec[MARO_VM_DEC_CATEGORY] = r1.w;
             dec[MARO_VM_DEC_BUFFER_TIME] = cur_budget;
             dec[MARO_VM_DEC_N_VALID] = n_valid;
+            dec[MARO_VM_DEC_EXT_OFFSET] = MARO_VM_DEC_HEAD + s.N;
             dec[11] = 0;
             r.c[VC_CUR_VM] = cur_vm;
             r.c[VC_CUR_BUDGET] = cur_budget;

@@ -46,7 +46,7 @@ inline std::string vm_compute_shape_and_tables(const MaroVmTopology& t, const Ma
     s.FW = s.o_region + 3 * s.RG;
     s.FWp = round_up(s.FW, 4);
     s.CWp = round_up(VC_COUNT, 4);
-    s.DW = round_up(MARO_VM_DEC_HEAD + N, 4);  // rows stay 16-byte aligned; the metrics block behind them 8-byte aligned
+    s.DW = round_up(MARO_VM_DEC_HEAD + 2 * N, 4);  // header | valid PM ids (<= N) | their remaining CPU cores (<= N)  // rows stay 16-byte aligned; the metrics block behind them 8-byte aligned
 
     // PM list slots: the most VMs the valid-PM rules let one PM hold (cpu / memory over-subscription bounds with the
     // smallest request of the trace), plus slack for agents that allocate outside the valid list

@@ -97,7 +97,9 @@ class BatchedCimEnvSampler:
         self._c_dec = torch.zeros((K, B, 8), dtype=torch.int32, device=self.device)
         self._c_act = torch.zeros((K, B), dtype=torch.int32, device=self.device)
         self._c_state = torch.zeros((K, B, D), dtype=torch.float32, device=self.device) if store_states else None
+        self._final_met = torch.zeros((B, 3), dtype=torch.int64, device=self.device)
         self._graph = None
+        self._warmed_up = False
         self.graph_error = None
         self.last = None
 
@@ -113,13 +115,18 @@ class BatchedCimEnvSampler:
             self._c_state[k].copy_(s)
         actions = sh.env_actions(self._dec, m)
         env.step_device(self._dec.data_ptr(), self._met.data_ptr(), actions.data_ptr())
+        # the episode's metrics come with the DONE row; a replica stepped past it answers all-zero FINISHED rows
+        self._final_met.copy_(torch.where((self._dec[:, 6] == 1).unsqueeze(1), self._met, self._final_met))
 
     def _run_chunk(self, n: int):
         torch = self._torch
-        if not self.use_graph or n != self.graph_chunk:
+        # the first full chunk always runs eagerly: libraries the policy uses (cuBLAS handles, workspaces, lazily compiled
+        # kernels) must be initialised outside of a stream capture
+        if not self.use_graph or n != self.graph_chunk or not self._warmed_up:
             with torch.no_grad():
                 for k in range(n):
                     self._body(k)
+            self._warmed_up = self._warmed_up or n == self.graph_chunk
             return
         if self._graph is None:
             side = torch.cuda.Stream(self.device)  # capture on a side stream (torch's rule), the batch follows it there
@@ -159,7 +166,7 @@ class BatchedCimEnvSampler:
         decs = torch.empty((T, B, 8), dtype=torch.int32, device=self.device)
         acts = torch.empty((T, B), dtype=torch.int32, device=self.device)
         states = torch.empty((T, B, self.shaper.state_dim), dtype=torch.float32, device=self.device) if self.store_states else None
-        final_met = torch.zeros_like(self._met)
+        self._final_met.zero_()
         t = 0
         while t < T:
             n = min(K, T - t)
@@ -168,8 +175,6 @@ class BatchedCimEnvSampler:
             acts[t:t + n].copy_(self._c_act[:n])
             if states is not None:
                 states[t:t + n].copy_(self._c_state[:n])
-            # metrics come with the DONE row; a replica stepped past it answers all-zero FINISHED rows
-            final_met = torch.where((self._dec[:, 6] == 1).unsqueeze(1), self._met, final_met)
             t += n
         valid = decs[:, :, 6] == 0
         ticks = torch.where(valid, decs[:, :, 0], torch.full_like(decs[:, :, 0], -1)).contiguous()
@@ -177,7 +182,7 @@ class BatchedCimEnvSampler:
         rewards = self.shaper.rewards_batch(ticks, ports)  # one launch over [T, B]
         rewards = torch.where(valid, rewards, torch.zeros_like(rewards))
         out = {"valid": valid, "ticks": decs[:, :, 0].contiguous(), "ports": ports, "vessels": decs[:, :, 2].contiguous(),
-               "model_actions": acts, "rewards": rewards, "metrics": final_met, "decisions": decs,
+               "model_actions": acts, "rewards": rewards, "metrics": self._final_met.clone(), "decisions": decs,
                "last_tick": torch.as_tensor(env.ticks(), device=self.device)}
         if states is not None:
             out["states"] = states

@@ -83,10 +83,15 @@ def encode_vm_action(action, out_row) -> None:
 
 def decode_vm_decision(row) -> DecisionEvent:
     n = int(row[_abi.VM_DEC_N_VALID])
-    return DecisionEvent(int(row[_abi.VM_DEC_FRAME_INDEX]), [int(x) for x in row[_abi.VM_DEC_HEAD:_abi.VM_DEC_HEAD + n]],
-                         int(row[_abi.VM_DEC_VM_ID]), int(row[_abi.VM_DEC_CPU]), int(row[_abi.VM_DEC_MEMORY]),
-                         int(row[_abi.VM_DEC_SUB_ID]), VmCategory(int(row[_abi.VM_DEC_CATEGORY])),
-                         int(row[_abi.VM_DEC_BUFFER_TIME]))
+    ev = DecisionEvent(int(row[_abi.VM_DEC_FRAME_INDEX]), [int(x) for x in row[_abi.VM_DEC_HEAD:_abi.VM_DEC_HEAD + n]],
+                       int(row[_abi.VM_DEC_VM_ID]), int(row[_abi.VM_DEC_CPU]), int(row[_abi.VM_DEC_MEMORY]),
+                       int(row[_abi.VM_DEC_SUB_ID]), VmCategory(int(row[_abi.VM_DEC_CATEGORY])),
+                       int(row[_abi.VM_DEC_BUFFER_TIME]))
+    # extension (not part of the reference's DecisionEvent): remaining CPU cores of each valid PM in the decision's frame — what
+    # the reference's rule-based agents fetch with a snapshot query (rule_based_algorithm/best_fit.py:38-44)
+    ext = int(row[11]) if len(row) > 11 else 0
+    ev.valid_pms_remaining_cpu_cores = [int(x) for x in row[ext:ext + n]] if ext else None
+    return ev
 
 
 def decode_vm_metrics(row) -> dict:

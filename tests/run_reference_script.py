@@ -88,7 +88,8 @@ def main():
             sampler = bundle.env_sampler
             policies = {p.name: p for p in bundle.policies}
             for p in policies.values():
-                p.explore = p.exploit  # test driver only: greedy actions in sample()
+                p.explore = p.exploit  # test driver only: greedy actions in sample() ...
+                p._warmup = 0          # ... from the first call on (the bundle's DQN policies act uniformly at random for 100 calls)
             if args.what == "rl_cim_greedy":
                 result = sampler.sample()
             else:

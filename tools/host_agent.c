@@ -70,6 +70,24 @@ void agent_best_fit(const int32_t* dec, int32_t* act, int n, int max_actions, in
     }
 }
 
+/* the same agent reading the decision row's extension area (remaining CPU cores per valid PM, include/maro_b200.h
+ * MARO_VM_DEC_EXT_OFFSET) instead of a snapshot query: same choice, no 3 MB query per step */
+void agent_best_fit_row(const int32_t* dec, int32_t* act, int n, int max_actions, int dec_words) {
+#pragma omp parallel for schedule(static) num_threads(16) if (n >= 1024)
+    for (int i = 0; i < n; i++) {
+        const int32_t* d = dec + (int64_t)i * dec_words;
+        int32_t* a = act + (int64_t)i * max_actions * 4;
+        const int nv = d[6] == 0 ? d[10] : 0, ext = d[11];
+        int best = -1, best_rem = 0;
+        for (int k = 0; k < nv; k++) {
+            const int rem = d[ext + k];
+            if (best < 0 || rem < best_rem) { best = d[12 + k]; best_rem = rem; }
+        }
+        if (best < 0) { a[0] = a[1] = -1; a[2] = a[3] = 0; }
+        else { a[0] = d[1]; a[1] = 0; a[2] = best; a[3] = 0; }
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------------------------
  * End-to-end host loop of the CIM bench (user code on top of the C ABI, include/maro_b200.h): the batch is cut into
  * `n_sub` contiguous sub-batches; for each one the loop waits for its decision rows, runs the agent on them and submits
