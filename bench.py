@@ -935,28 +935,66 @@ def run_ours(args, rank, local_rank, world):
             ev[2].record(stream)
         pos["i"] += 1
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
+    fused = bike and not args.launch_per_step  # citi_bike: fused rollouts (maro_bike_rollout_device), like the CIM arm
+    launches = 2 * args.steps
+
+    def timed_rollouts(total_steps, chunk, timed):
+        """`total_steps` batched env-steps in launches of <= chunk (greedy agent as a device callback); Env.reset when every
+        replica reports DONE.  Returns (device ms incl. resets, kernel ms, launches)."""
+        evs, n_launch, left, done = [], 0, total_steps, False
+        while left > 0:
+            n = min(chunk, left)
+            if flush is not None and timed:
+                flush.fill_(1)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(stream)
+            if done:
+                env.reset()
+                n_launch += 1
+            e[1].record(stream)
+            env.rollout_device(dec.data_ptr(), met.data_ptr(), n)
+            e[2].record(stream)
+            n_launch += 1
+            evs.append(e)
+            left -= n
+            done = bool((dec[:, 6] != 0).all().item())
+        torch.cuda.synchronize()
+        return sum(e[0].elapsed_time(e[2]) for e in evs), sum(e[1].elapsed_time(e[2]) for e in evs), n_launch
+
+    if fused:
+        chunk = max(1, min(args.chunk, args.steps))
+        timed_rollouts(max(args.warmup, 3), chunk, False)
+    else:
+        for _ in range(max(args.warmup, 3)):
+            one_step()
     torch.cuda.synchronize()
     c0 = env.counters().sum(0)
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(0 if fused else args.steps)]
     sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
     wall0 = time.perf_counter()
-    for k in range(args.steps):
-        one_step(events[k])
+    if fused:
+        total_ms, kernel_ms, launches = timed_rollouts(args.steps, chunk, True)
+    else:
+        for k in range(args.steps):
+            one_step(events[k])
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     if world > 1:
         dist.barrier()
-    total_ms = sum(e[0].elapsed_time(e[2]) for e in events)
-    kernel_ms = sum(e[1].elapsed_time(e[2]) for e in events)
+    if not fused:
+        total_ms = sum(e[0].elapsed_time(e[2]) for e in events)
+        kernel_ms = sum(e[1].elapsed_time(e[2]) for e in events)
     c1 = env.counters().sum(0)
     d_steps, d_ticks, d_events, d_snaps = (int(x) for x in (c1 - c0))
+    if fused:  # the extra legs below drive the per-step path from a fresh episode
+        env.reset()
+        dec.zero_()
+        pos["i"] = 0
 
     # ---- CUDA-graph mode (extra): chunks of `graph_chunk` (agent + step) pairs replayed from one graph; L2 flushed
     # between chunks.  This is how a device-resident RL loop would drive the env (no per-step launch cost).
@@ -1134,8 +1172,10 @@ def run_ours(args, rank, local_rank, world):
                          "n_snap": n_snap, "n_ev": n_ev, "kernel_us": 1000.0 * kernel_ms / args.steps,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "clocks": clocks,
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": launches,
         }
+        if fused:
+            line["config"]["mode"] = f"fused rollouts, {chunk} env-steps per launch, greedy agent as a device callback"
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
                            "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + met_words * 8) + (B * topo.n_pm * 16 if vm and args.vm_query_agent else 0),

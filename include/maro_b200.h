@@ -338,6 +338,9 @@ int maro_bike_pinned_buffers(MaroBikeEnv* env, void** actions, void** n_actions,
 int maro_bike_step_pinned(MaroBikeEnv* env, int32_t use_actions, int32_t use_n_actions, int32_t use_active);
 int maro_bike_step_device(MaroBikeEnv* env, const uint8_t* d_active, const int32_t* d_actions,
                           const int32_t* d_n_actions, int32_t* d_decisions, int64_t* d_metrics);
+/* Fused rollout (like maro_cim_rollout_device): n_steps env-steps per replica in one launch with the greedy top-1 agent of
+ * examples/citi_bike/greedy/launcher.py:35-65 as a device callback; d_decisions is in/out; a replica stops at its DONE row. */
+int maro_bike_rollout_device(MaroBikeEnv* env, int32_t n_steps, int32_t* d_decisions, int64_t* d_metrics);
 int maro_bike_reset(MaroBikeEnv* env, const uint8_t* mask);
 /* Per-replica seeds of the transfer_time stream: the reference draws `round(np.random.normal(mean, std))` per action
  * (citi_bike/decision_strategy.py:213-216) from the process-global numpy RandomState, and every env of a VectorEnv is its

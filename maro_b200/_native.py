@@ -25,7 +25,7 @@ EXPORTS = (
     "maro_bike_create", "maro_bike_destroy", "maro_bike_set_stream", "maro_bike_decision_words", "maro_bike_step",
     "maro_bike_step_device", "maro_bike_reset", "maro_bike_query", "maro_bike_attr_id", "maro_bike_attr_slots",
     "maro_bike_read_frame", "maro_bike_frame_words", "maro_bike_ticks", "maro_bike_counters", "maro_bike_snapshot_frames",
-    "maro_bike_greedy_policy_device", "maro_bike_set_transfer_seeds",
+    "maro_bike_greedy_policy_device", "maro_bike_set_transfer_seeds", "maro_bike_rollout_device",
     "maro_cim_set_query_layout", "maro_bike_set_query_layout", "maro_vm_set_query_layout",
     "maro_cim_save", "maro_cim_load", "maro_bike_save", "maro_bike_load", "maro_vm_save", "maro_vm_load",
     "maro_vm_create", "maro_vm_destroy", "maro_vm_set_stream", "maro_vm_decision_words", "maro_vm_step",
@@ -109,6 +109,7 @@ def lib():
     L.maro_bike_snapshot_frames.argtypes = [vp, i32, vp, i32, vp]
     L.maro_bike_greedy_policy_device.argtypes = [vp, vp, vp]
     L.maro_bike_set_transfer_seeds.argtypes = [vp, vp]
+    L.maro_bike_rollout_device.argtypes = [vp, i32, vp, vp]
     for name in ("maro_cim_set_query_layout", "maro_bike_set_query_layout", "maro_vm_set_query_layout"):
         getattr(L, name).argtypes = [vp, i32]
     for pre in ("maro_cim", "maro_bike", "maro_vm"):

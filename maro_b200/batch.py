@@ -435,6 +435,10 @@ class BikeBatch:
     def greedy_policy_device(self, d_decisions: int, d_actions: int):
         _native.check(self._f("greedy_policy_device")(self._h, d_decisions, d_actions))
 
+    def rollout_device(self, d_decisions: int, d_metrics: int, n_steps: int):
+        """``n_steps`` fused env-steps per replica in one launch, greedy top-1 agent on the device; ``d_decisions`` in/out"""
+        _native.check(self._f("rollout_device")(self._h, n_steps, d_decisions, d_metrics))
+
     def attr_id(self, node: str, name: str) -> int:
         i = self._f("attr_id")(self._h, self._NODE[node], name.encode())
         if i < 0:

@@ -17,7 +17,19 @@ struct BikeArgs {
     const int32_t* n_actions;
     int32_t* decisions;
     int64_t* metrics;
+    int n_steps;  // > 0: fused rollout — that many env-steps per replica in this launch, greedy top-1 agent as a device callback
 };
+
+// greedy top-1 agent (examples/citi_bike/greedy/launcher.py:35-65 with supply_top_k = demand_top_k = 1) on one decision row
+__device__ __forceinline__ int4 bike_greedy_row(const int32_t* d) {
+    int station = d[1], ns = d[4], best = -1, best_v = 0;
+    for (int k = 0; k < ns; k++) {
+        int idx = d[8 + 2 * k], v = d[9 + 2 * k];
+        if (idx == station) continue;
+        if (best < 0 || v > best_v || (v == best_v && idx > best)) { best = idx; best_v = v; }
+    }
+    return best < 0 ? make_int4(-1, -1, 0, 0) : (d[3] == 0 ? make_int4(station, best, best_v, 0) : make_int4(best, station, best_v, 0));
+}
 
 __device__ __forceinline__ BikeReplica make_bike_replica(const BikeShape& s, const BikeArgs& a, int rep, int32_t* st) {
     BikeReplica r;
@@ -64,6 +76,28 @@ __global__ void __launch_bounds__(kWarps * 32) bike_step_kernel(const __grid_con
         while (!mbar_try_wait(bar, phase)) {}
         phase ^= 1u;
         BikeReplica r = make_bike_replica(s, a, rep, st);
+        if (a.n_steps > 0) {
+            // ---- fused rollout: the block stays in shared memory for n_steps env-steps; the decision row lives in a
+            // per-group shared-memory slot between the steps and feeds the agent; stops at the replica's DONE row
+            const int slot_bytes = (s.DW * 4 + 24 + 15) & ~15;
+            int32_t* dslot = reinterpret_cast<int32_t*>(smem_raw + 256 + (size_t)kGroups * s.SW * 4 + (size_t)gid * slot_bytes);
+            int64_t* mslot = reinterpret_cast<int64_t*>(dslot + ((s.DW + 1) & ~1));
+            int32_t* gdec = a.decisions + (int64_t)rep * s.DW;
+            for (int i = g.lane; i < s.DW; i += G) dslot[i] = gdec[i];
+            g.sync();
+            for (int k = 0; k < a.n_steps; k++) {
+                Act4 act = {0, 0, 0, 0};
+                if (g.lane == 0) {
+                    int4 o = bike_greedy_row(dslot);
+                    act.v = o.x; act.p = o.y; act.qty = o.z; act.type = o.w;
+                }
+                bike_replica_step<G>(s, g, r, act, 1, dslot, mslot);
+                g.sync();
+                if (dslot[6] != MARO_STATUS_DECISION) break;  // DONE (final metrics stay in the slot) / FINISHED / error
+            }
+            for (int i = g.lane; i < s.DW; i += G) gdec[i] = dslot[i];
+            if (g.lane < 3) a.metrics[(int64_t)rep * 3 + g.lane] = mslot[g.lane];
+        } else {
         const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), min(s.max_actions, G)) : 1) : 0;
         Act4 act = {0, 0, 0, 0};
         if (g.lane < n_act) {
@@ -71,6 +105,7 @@ __global__ void __launch_bounds__(kWarps * 32) bike_step_kernel(const __grid_con
             act.v = v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
         }
         bike_replica_step<G>(s, g, r, act, n_act, a.decisions + (int64_t)rep * s.DW, a.metrics + (int64_t)rep * 3);
+        }
         const int4* src4 = reinterpret_cast<const int4*>(st);
         int4* dst4 = reinterpret_cast<int4*>(gstate);
         for (int i = g.lane; i < s.SW / 4; i += G) dst4[i] = src4[i];
@@ -93,15 +128,7 @@ __global__ void bike_reset_kernel(const __grid_constant__ BikeShape s, const __g
 __global__ void bike_greedy_kernel(const int32_t* __restrict__ dec, int32_t* __restrict__ act, int n, int dw, int max_actions) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t* d = dec + (int64_t)i * dw;
-    int station = d[1], ns = d[4], best = -1, best_v = 0;
-    for (int k = 0; k < ns; k++) {
-        int idx = d[8 + 2 * k], v = d[9 + 2 * k];
-        if (idx == station) continue;
-        if (best < 0 || v > best_v || (v == best_v && idx > best)) { best = idx; best_v = v; }
-    }
-    int4 o = best < 0 ? make_int4(-1, -1, 0, 0) : (d[3] == 0 ? make_int4(station, best, best_v, 0) : make_int4(best, station, best_v, 0));
-    *reinterpret_cast<int4*>(act + (int64_t)i * max_actions * 4) = o;
+    *reinterpret_cast<int4*>(act + (int64_t)i * max_actions * 4) = bike_greedy_row(dec + (int64_t)i * dw);
 }
 
 struct MaroBikeEnv : EnvCommon {
@@ -125,15 +152,18 @@ static BikeArgs bike_base_args(MaroBikeEnv* e) {
 
 template <int W, int G>
 static cudaError_t bike_launch_wg(MaroBikeEnv* e, const BikeArgs& a) {
+    // fused rollouts keep one decision-row slot per lane group behind the state blocks
+    const int groups = (G < 32 && W == 4 && e->spread) ? W : W * 32 / G;
+    const size_t smem = e->smem_bytes + (a.n_steps > 0 ? (size_t)groups * ((e->s.DW * 4 + 24 + 15) & ~15) : 0);
     if (G < 32 && W == 4 && e->spread) {
-        cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G, (G < 32 && W == 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+        cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G, (G < 32 && W == 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        bike_step_kernel<W, G, (G < 32 && W == 4)><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+        bike_step_kernel<W, G, (G < 32 && W == 4)><<<e->grid, W * 32, smem, e->stream>>>(e->s, a);
         return cudaGetLastError();
     }
-    cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes);
+    cudaError_t err = cudaFuncSetAttribute(bike_step_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    bike_step_kernel<W, G><<<e->grid, W * 32, e->smem_bytes, e->stream>>>(e->s, a);
+    bike_step_kernel<W, G><<<e->grid, W * 32, smem, e->stream>>>(e->s, a);
     return cudaGetLastError();
 }
 template <int G>
@@ -328,6 +358,17 @@ int maro_bike_counters(MaroBikeEnv* e, int64_t* out) { return common_counters(e,
 int maro_bike_snapshot_frames(MaroBikeEnv* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
     return common_snapshot_frames(e, replica, out, cap, n_out);
 }
+/* n_steps fused env-steps per replica in ONE launch (the replica block stays in shared memory), greedy top-1 agent evaluated on
+   the device between the steps; d_decisions is in/out (the rows the previous call returned feed the first action). */
+int maro_bike_rollout_device(MaroBikeEnv* e, int32_t n_steps, int32_t* d_decisions, int64_t* d_metrics) {
+    if (!e || !d_decisions || !d_metrics || n_steps < 1) return fail("maro_bike_rollout_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    BikeArgs a = bike_base_args(e);
+    a.decisions = d_decisions; a.metrics = d_metrics; a.n_steps = n_steps;
+    CK(bike_launch(e, a));
+    return 0;
+}
+
 int maro_bike_greedy_policy_device(MaroBikeEnv* e, const int32_t* d_decisions, int32_t* d_actions) {
     if (!e || !d_decisions || !d_actions) return fail("maro_bike_greedy_policy_device: bad arguments");
     CK(cudaSetDevice(e->device));

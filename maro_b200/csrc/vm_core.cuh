@@ -515,7 +515,6 @@ MARO_DEV void vm_replica_step(const VmShape& s, const Grp<G>& g, const VmReplica
             dec[MARO_VM_DEC_BUFFER_TIME] = cur_budget;
             dec[MARO_VM_DEC_N_VALID] = n_valid;
             dec[MARO_VM_DEC_EXT_OFFSET] = MARO_VM_DEC_HEAD + s.N;
-            dec[11] = 0;
             r.c[VC_CUR_VM] = cur_vm;
             r.c[VC_CUR_BUDGET] = cur_budget;
         }

@@ -187,3 +187,37 @@ def test_bike_per_replica_transfer_seeds():
         d, m = env.step(a)
     assert (d == d[0]).all()
     env.close()
+
+
+@pytest.mark.parametrize("name,B,chunks", [("toy_1440_greedy_res10", 48, [1, 3, 50, 1000]), ("synth26_1440_greedy_res7", 20, [7, 64, 64, 2000])])
+def test_bike_fused_rollout_matches_reference_trace(name, B, chunks):
+    """maro_bike_rollout_device (the replica block stays in shared memory, greedy agent as a device callback) ends every
+    replica in the reference trace's final state: metrics, tick, every snapshot the trace holds; rollouts stop at DONE."""
+    import torch
+
+    from maro_b200.batch import BikeBatch
+
+    spec, gold = BIKE_CASES[name], load_bike_golden(name)
+    topo = bike_topology(spec)
+    env = BikeBatch(topo, B, spec["snapshot_resolution"], spec.get("max_snapshots"))
+    env.set_stream(torch.cuda.current_stream().cuda_stream)
+    dec = torch.zeros((B, env.dec_words), dtype=torch.int32, device="cuda")
+    met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    total = 0
+    for n in chunks:
+        env.rollout_device(dec.data_ptr(), met.data_ptr(), n)
+        total += n
+        if bool((dec[:, 6] != 0).all().item()):
+            break
+    torch.cuda.synchronize()
+    d, m = dec.cpu().numpy(), met.cpu().numpy()
+    assert (d[:, 6] == 1).all() and (d[:, 0] == int(gold["final_tick"])).all()
+    assert (m == gold["final_metrics"]).all()
+    assert env.counters()[:, 0].tolist() == [len(gold["steps"]) + 1] * B  # every decision + the final step, nothing more
+    for rep in (0, B - 1):
+        assert env.snapshot_frames(rep).tolist() == gold["frames"].tolist()
+        assert_bike_snapshots_equal(lambda f: env.snapshot_row(f, rep), gold, topo.n_stations)
+    env.rollout_device(dec.data_ptr(), met.data_ptr(), 3)  # past the end: the FINISHED row, no state change
+    torch.cuda.synchronize()
+    assert (dec.cpu().numpy()[:, 6] == 2).all()
+    env.close()
