@@ -11,6 +11,12 @@ from vm_helpers import VM_CASES, assert_metrics_close, assert_vm_snapshots_equal
 EXACT_COLS = [0, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]
 
 
+
+def _row(dec, n_valid):
+    """header + valid PM ids of a decision row; word 11 (offset of this build's remaining-cores extension) is not part of the
+    reference's DecisionEvent and absent from the oracle's rows"""
+    return list(dec[:11]) + list(dec[12:12 + n_valid])
+
 def _abi_metrics(row):
     from maro_b200 import _abi
 
@@ -89,7 +95,7 @@ def test_vm_device_logic_tiny_and_denormal_utilisations(lanes):
     (st, dec, met), (ost, odec, omet) = e.step(None), o.step(None)
     n = 0
     while ost == 0:
-        assert st == 0 and dec[:12 + odec[10]].tolist() == odec[:12 + odec[10]].tolist(), n
+        assert st == 0 and _row(dec, odec[10]) == _row(odec, odec[10]), n
         assert np.array_equal(met[EXACT_COLS], omet[EXACT_COLS]), n
         a = o.best_fit(odec)
         (st, dec, met), (ost, odec, omet) = e.step(a.reshape(1, 4)), o.step(a.reshape(1, 4))
@@ -117,7 +123,7 @@ def test_vm_trace_generator_loads_and_kernel_matches_oracle(tmp_path):
     (st, dec, met), (ost, odec, omet) = e.step(None), o.step(None)
     n = 0
     while ost == 0:
-        assert st == 0 and dec[:12 + odec[10]].tolist() == odec[:12 + odec[10]].tolist(), n
+        assert st == 0 and _row(dec, odec[10]) == _row(odec, odec[10]), n
         a = o.best_fit(odec)
         (st, dec, met), (ost, odec, omet) = e.step(a.reshape(1, 4)), o.step(a.reshape(1, 4))
         n += 1
@@ -126,3 +132,29 @@ def test_vm_trace_generator_loads_and_kernel_matches_oracle(tmp_path):
     assert np.array_equal(e.frame(), o.frame()) and np.array_equal(e.counters(), o.counters())
     m = _abi_metrics(met)
     assert m["total_vm_requests"] == 400 and m["successful_allocation"] + m["failed_allocation"] == 400
+
+
+def test_vm_decision_row_extension_holds_remaining_cores():
+    """MARO_VM_DEC_EXT_OFFSET: the decision row carries capacity - allocated (cores) of every valid PM in the decision's frame,
+    what the reference's rule-based agents fetch with a snapshot query per decision (rule_based_algorithm/best_fit.py:38-44)"""
+    from emul_batch import EmulVmBatch
+    from maro_b200 import _abi
+    from vm_helpers import VM_CASES, vm_topology
+
+    topo = vm_topology(VM_CASES["synth_160_bestfit"])
+    b = EmulVmBatch(topo, 1)
+    lay, _ = _abi.vm_frame_layout(topo)
+    dec, met = b.step(None)
+    for k in range(40):
+        d = dec[0]
+        if d[6] != 0:
+            break
+        n, ext = int(d[10]), int(d[11])
+        f = b.read_frame(0)
+        rem = f[lay["pms"]["cpu_cores_capacity"][0]:][:topo.n_pm] - f[lay["pms"]["cpu_cores_allocated"][0]:][:topo.n_pm]
+        ids = d[12:12 + n]
+        assert ext == 12 + topo.n_pm and d[ext:ext + n].tolist() == rem[ids].tolist(), k
+        a = np.zeros((1, 1, 4), np.int32)
+        a[0, 0] = [d[1], 0, ids[int(np.argmin(d[ext:ext + n]))], 0]
+        dec, met = b.step(a)
+    assert k > 20
