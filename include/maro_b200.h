@@ -83,7 +83,12 @@ typedef struct MaroCimConfig {
     int32_t queue_capacity;      /* per-replica dynamic-event slots; <=0: library default             */
     int32_t max_actions;         /* actions per replica per step (A_MAX); <=0: 1                      */
     const int32_t* replica_topology; /* [n_replicas] index into topos[], NULL: all 0                  */
+    int32_t decision_mode;       /* 0 Sequential, 1 Joint (Env(decision_mode=), core.py:354-366; CIM only): a step returns EVERY
+                                    decision event of the tick — n_vessels rows of MARO_CIM_DECISION_WORDS per replica, the list
+                                    ends before the first row whose status is not MARO_STATUS_DECISION — and takes one action row
+                                    per decision in the same order (type MARO_ACTION_NONE = None; fewer rows = the rest unanswered) */
 } MaroCimConfig;
+enum { MARO_ACTION_NONE = 2 }; /* third value of the action row's type word (MARO_ACTION_LOAD / _DISCHARGE below) */
 
 /* Row layout of the decision output, one row of MARO_CIM_DECISION_WORDS int32 per replica.
  * Mirrors DecisionEvent (maro/simulator/scenarios/cim/common.py:72-150) + step status. */

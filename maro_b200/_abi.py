@@ -43,7 +43,7 @@ class MaroCimConfig(C.Structure):
     _fields_ = [
         ("n_replicas", C.c_int32), ("start_tick", C.c_int32), ("snapshot_resolution", C.c_int32),
         ("max_snapshots", C.c_int32), ("device", C.c_int32), ("queue_capacity", C.c_int32),
-        ("max_actions", C.c_int32), ("replica_topology", _i32p),
+        ("max_actions", C.c_int32), ("replica_topology", _i32p), ("decision_mode", C.c_int32),
     ]
 
 

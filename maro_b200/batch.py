@@ -34,12 +34,15 @@ _NODE_TYPE = {"ports": _abi.NODE_PORTS, "vessels": _abi.NODE_VESSELS, "matrices"
 class CimBatch:
     def __init__(self, topologies, n_replicas: int, start_tick: int = 0, snapshot_resolution: int = 1,
                  max_snapshots: Optional[int] = None, device: int = 0, max_actions: int = 1,
-                 replica_topology: Optional[Sequence[int]] = None, queue_capacity: int = 0):
+                 replica_topology: Optional[Sequence[int]] = None, queue_capacity: int = 0, decision_mode: int = 0):
         if isinstance(topologies, CimTopology):
             topologies = [topologies]
         self.topologies = list(topologies)
         self.n_replicas = int(n_replicas)
-        self.max_actions = int(max_actions)
+        self.decision_mode = int(decision_mode)  # 0 Sequential, 1 Joint (core.py:354-366)
+        # Joint: one answer row per decision event of a tick (at most one per vessel), V decision rows per replica
+        self.max_actions = max(int(max_actions), self.topologies[0].n_vessels) if self.decision_mode == 1 else int(max_actions)
+        self.dec_words = _abi.DECISION_WORDS * (self.topologies[0].n_vessels if self.decision_mode == 1 else 1)
         self.start_tick = int(start_tick)
         self.snapshot_resolution = int(snapshot_resolution)
         self.device = int(device)
@@ -59,6 +62,7 @@ class CimBatch:
         cfg.device = self.device
         cfg.queue_capacity = int(queue_capacity)
         cfg.max_actions = self.max_actions
+        cfg.decision_mode = self.decision_mode
         if replica_topology is not None:
             rt = np.ascontiguousarray(replica_topology, np.int32)
             assert rt.shape == (self.n_replicas,)
@@ -69,7 +73,7 @@ class CimBatch:
         self._h = h
         self.frame_words = L.maro_cim_frame_words(self._h)
         # reusable host output buffers
-        self.decisions = np.zeros((self.n_replicas, _abi.DECISION_WORDS), np.int32)
+        self.decisions = np.zeros((self.n_replicas, self.dec_words), np.int32)
         self.metrics = np.zeros((self.n_replicas, _abi.METRIC_WORDS), np.int64)
 
     # -- lifecycle ---------------------------------------------------------------------------------
@@ -122,7 +126,7 @@ class CimBatch:
         the inputs in place, call ``step_pinned`` and read the outputs in place — no host-side copies at all."""
         if getattr(self, "_pinned", None) is None:
             self._pinned = _pinned_views(_native.lib().maro_cim_pinned_buffers, self._h, self.n_replicas,
-                                         self.max_actions, _abi.DECISION_WORDS)
+                                         self.max_actions, self.dec_words)
         return self._pinned
 
     def step_pinned(self, use_actions: bool = True, use_n_actions: bool = False, use_active: bool = False):

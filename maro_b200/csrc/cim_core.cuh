@@ -230,6 +230,9 @@ struct CimShape {
     // slot (tick & (DL-1)) = { rf[P*P] (src*P+dst -> quantity), re[P] (port -> quantity), n_rf, n_re (event counts) } at word
     // offset o_dl of the state block.  Same arithmetic, same event counts, no list walking / free list / push machinery.
     int DL, o_dl, dl_stride;
+    // DecisionMode.Joint (core.py:354-366): every decision event of a tick is returned at once (V rows of 8 words), the
+    // answers are applied in list order when the replica is stepped again.  DW = words of a replica's decision block.
+    int joint, DW;
 };
 
 struct Replica {
@@ -933,6 +936,7 @@ MARO_DEV bool on_actions(const CimShape& s, const Grp<G>& g, const Replica& r, c
     for (int i = 0; i < n; i++) {
         int v = g.shfl(mine.v, i), p = g.shfl(mine.p, i), move = g.shfl(mine.qty, i), type = g.shfl(mine.type, i);
         if (g.lane != 0 || !ok) continue;
+        if (type == 2) continue;  // Joint mode: `None` for this decision event (an empty action list, core.py:308-309)
         if (v < 0 || v >= s.V || p < 0 || p >= s.P || move < 0) { ok = false; continue; }
         int port_empty = PA(s, r, PA_EMPTY, p), vessel_empty = VA(s, r, VA_EMPTY, v);
         if (type == 1) {  // DISCHARGE
@@ -1042,13 +1046,20 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
     if (state == ST_AWAIT) {
         // _assign_action (core.py:301-315): the decision event finishes, TAKE_ACTION runs as its immediate event
         g.sync();
-        bool ok = on_actions(s, g, r, act, n_act);
+        int n_apply = n_act;
+        if (s.joint) {  // answer k belongs to the k-th decision of the tick; surplus answers are dropped (zip, core.py:362)
+            const uint64_t pend = ((uint64_t)(uint32_t)r.c[C_ARR_HI] << 32) | (uint32_t)r.c[C_ARR_LO];
+            int n_dec = 0;
+            for (uint64_t m = pend; m; m &= m - 1) n_dec++;
+            n_apply = n_act < n_dec ? n_act : n_dec;
+        }
+        bool ok = on_actions(s, g, r, act, n_apply);
         if (g.lane == 0) {
             ctrl_add64(r, C_NSTEPS_LO, 1);
             if (!ok) { r.c[C_STATE] = ST_ERROR; r.c[C_ERR] = -1; }
         }
         g.sync();
-        nev += 2;
+        nev += s.joint ? 2 * n_apply : 2;  // decision event + TAKE_ACTION per answered decision
         if (r.c[C_STATE] == ST_ERROR) {
             if (g.lane == 0) { int32_t od[8] = {0, 0, 0, 0, 0, 0, -1, 0}; store_out(dec, met, od, 0, 0, 0); }
             g.sync();
@@ -1146,8 +1157,19 @@ MARO_DEV void replica_step(const CimShape& s, const Grp<G>& g, const Replica& r,
                 od[3] = pe < sp ? pe : sp;
                 od[4] = VA(s, r, VA_EMPTY, v);
                 od[5] = VA(s, r, VA_EARLY_DISCHARGE, v);
+                if (s.joint) {  // rows 1.. : the tick's other decisions, scopes from the same (pre-action) state; then a terminator
+                    int k = 1;
+                    for (uint64_t rest = m & (m - 1); rest; rest &= rest - 1, k++) {
+                        const int v2 = maro_ffs64(rest) - 1, port2 = VA(s, r, VA_LOC_PORT_IDX, v2);
+                        const int pe2 = PA(s, r, PA_EMPTY, port2), sp2 = VA(s, r, VA_REMAINING_SPACE, v2);
+                        int32_t row[8] = {tick, port2, v2, pe2 < sp2 ? pe2 : sp2, VA(s, r, VA_EMPTY, v2), VA(s, r, VA_EARLY_DISCHARGE, v2),
+                                          0, r.c[C_EP_STEP]};
+                        for (int i = 0; i < 8; i++) dec[8 * k + i] = row[i];
+                    }
+                    if (k < s.V) dec[8 * k + 6] = 3;  // MARO_STATUS_INACTIVE: end of this step's decision list
+                }
             }
-            dec_pos = v + 1;
+            dec_pos = s.joint ? 64 : v + 1;
             state = ST_AWAIT;
             status = 0;
             break;

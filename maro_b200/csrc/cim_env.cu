@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
     uint32_t phase = 0;
     for (int rep = blockIdx.x * kGroups + gid; rep < s.n_replicas; rep += gridDim.x * kGroups) {
         if (a.active && !a.active[rep]) {
-            if (g.lane == 0) a.decisions[rep * 8 + 6] = MARO_STATUS_INACTIVE;
+            if (g.lane == 0) a.decisions[(int64_t)rep * s.DW + 6] = MARO_STATUS_INACTIVE;
             continue;
         }
         int32_t* gstate = a.state + (int64_t)rep * s.SW;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kWarps * 32, kGeneral ? 1 : 32 / kWarps) cim_s
             int4 v = reinterpret_cast<const int4*>(a.actions + (int64_t)rep * s.max_actions * 4)[g.lane];
             act.v = too_many ? -1 : v.x; act.p = v.y; act.qty = v.z; act.type = v.w;
         }
-        replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * 8, a.metrics + (int64_t)rep * 3);
+        replica_step<G, kGeneral>(s, g, r, act, n_act, a.decisions + (int64_t)rep * s.DW, a.metrics + (int64_t)rep * 3);
         // ---- write back (128-bit coalesced) what this step could have changed
         if (g.lane == 0) snapshot_drain_lane();
         const int4* src4 = reinterpret_cast<const int4*>(st);
@@ -812,7 +812,7 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
         memset(&ra, 0, sizeof(ra));
         CK(launch_resident(e, a, ra, true, &per_sm));
         const char* se = getenv("MARO_B200_SESSION");
-        e->session_ok = (se ? atoi(se) != 0 : true) && (int64_t)per_sm * nsm >= e->res_grid;
+        e->session_ok = (se ? atoi(se) != 0 : true) && (int64_t)per_sm * nsm >= e->res_grid && !s.joint;  // (64-byte result lines)
     }
     e->scenario_id = 1;
     e->ckpt_extra = {{"tables", (void**)&e->d_tables, e->h_tables.size() * 4}, {"replica_topology", (void**)&e->d_topo, (size_t)B * 4},
@@ -916,7 +916,7 @@ int maro_cim_create(const MaroCimTopology* topos, int32_t n_topos, const MaroCim
 
     e->ring_rows = s.ring_rows; e->FW = s.FW; e->FWp = s.FWp; e->SW = s.SW;
     e->off_tick = s.FWp + C_TICK; e->off_counters = s.FWp + C_NSTEPS_LO;
-    e->dec_words = MARO_CIM_DECISION_WORDS; e->max_actions = s.max_actions;
+    e->dec_words = s.DW; e->max_actions = s.max_actions;
     if (common_alloc(e)) { maro_cim_destroy(e); return 1; }
     int rc = create_device_side(e, topos, n_topos, cfg, prop);
     if (rc) { maro_cim_destroy(e); return rc; }
@@ -1121,6 +1121,7 @@ int maro_cim_rollout_device(MaroCimEnv* e, int32_t policy, uint32_t seed, uint32
     if (!e || !d_decisions || !d_metrics || n_steps < 1 || (policy != RES_POLICY_NULL && policy != RES_POLICY_RANDOM))
         return fail("maro_cim_rollout_device: bad arguments");
     if (!e->res_threads) return fail("maro_cim_rollout_device: replica state does not fit the resident kernel");
+    if (e->s.joint) return fail("maro_cim_rollout_device: the device agents answer one decision at a time (Sequential mode)");
     CK(cudaSetDevice(e->device));
     END_SESSION(e);
     StepArgs a = base_args(e);

@@ -237,6 +237,9 @@ inline int compute_shape_and_tables(const MaroCimTopology* topos, int n_topos, c
     s.order_mode = t0.order_mode; s.total_containers = t0.total_containers; s.vol = t0.container_volume;
     s.max_actions = cfg->max_actions > 0 ? cfg->max_actions : 1;
     s.n_replicas = cfg->n_replicas;
+    s.joint = cfg->decision_mode == 1 ? 1 : 0;
+    s.DW = s.joint ? MARO_CIM_DECISION_WORDS * V : MARO_CIM_DECISION_WORDS;
+    if (s.joint && s.max_actions < V) s.max_actions = V;  // one answer row per decision event of a tick
     int max_stops = 0, max_targets = t0.target_offset[P], max_delay = 2, max_rl = 1, buf_full = 1, buf_empty = 1;
     for (int r = 0; r < t0.n_routes; r++) max_rl = std::max(max_rl, t0.route_offset[r + 1] - t0.route_offset[r]);
     s.max_route_len = max_rl;

@@ -171,8 +171,9 @@ class Env:
             raise NotImplementedError(f"scenario {scenario!r}: 'cim', 'citi_bike' and 'vm_scheduling' run on the CUDA core")
         if business_engine_cls is not None:
             raise NotImplementedError("custom business engines run on the reference Env, not on the CUDA core")
-        if int(decision_mode) != int(DecisionMode.Sequential):
-            raise NotImplementedError("DecisionMode.Joint is not implemented on the CUDA core")
+        self._joint = int(decision_mode) == int(DecisionMode.Joint)
+        if self._joint and scenario != "cim":
+            raise NotImplementedError("DecisionMode.Joint runs on the CUDA core for the cim scenario")
         self._scenario, self._topology = scenario, topology
         self._start_tick, self._durations = start_tick, durations
         self._snapshot_resolution, self._max_snapshots = snapshot_resolution, max_snapshots
@@ -196,7 +197,7 @@ class Env:
             self._config = load_config(topology)
             self._topo = build_topology(self._config, start_tick + durations)
             self._batch = CimBatch(self._topo, 1, start_tick, snapshot_resolution, max_snapshots, device=device,
-                                   max_actions=8)
+                                   max_actions=8, decision_mode=int(self._joint))
         # the reference picks its backend per process from DEFAULT_BACKEND_NAME (maro/backends/frame.pyx:496-504); the two
         # answer snapshot queries in different layouts — same switch here, per Env
         self._backend_name = str((options or {}).get("backend_name") or os.environ.get("DEFAULT_BACKEND_NAME", "static"))
@@ -205,11 +206,48 @@ class Env:
         self._snapshots = SnapshotList(self._batch, 0)
         self._tick = start_tick
         self._last_metrics = make_metrics((0, 0, 0))
-        self._act = np.zeros((1, 8, 4), np.int32)
+        self._act = np.zeros((1, self._batch.max_actions, 4), np.int32)
         self._nact = np.zeros(1, np.int32)
+
+    def _step_joint(self, action):
+        """DecisionMode.Joint (core.py:354-366): ``action`` = None or a list with one entry (Action or None) per decision event
+        the previous step returned, in the same order (a shorter list leaves the rest unanswered); returns the LIST of this
+        tick's decision events."""
+        answers = [] if action is None else (action if isinstance(action, list) else [action])
+        if len(answers) > self._act.shape[1]:
+            raise ValueError("more answers than decision events")
+        for k, a in enumerate(answers):
+            if a is None:
+                self._act[0, k] = (0, 0, 0, 2)
+            elif isinstance(a, list):
+                raise NotImplementedError("Joint mode on the CUDA core takes one Action (or None) per decision event")
+            else:
+                encode_action(a, self._act[0, k])
+        self._nact[0] = len(answers)
+        dec, met = self._batch.step(self._act, self._nact)
+        rows = dec[0].reshape(-1, _abi.DECISION_WORDS)
+        status = int(rows[0, _abi.DEC_STATUS])
+        if status == _abi.STATUS_BAD_ACTION:
+            raise AssertionError("invalid action: quantity exceeds the action scope (business_engine.py:731,736)")
+        if status == _abi.STATUS_QUEUE_OVERFLOW:
+            raise RuntimeError("event queue overflow: recreate the Env with a larger queue_capacity")
+        if status == _abi.STATUS_FINISHED:
+            return None, None, True
+        self._tick = int(rows[0, _abi.DEC_TICK])
+        self._last_metrics = make_metrics(met[0])
+        if status == _abi.STATUS_DONE:
+            return self._last_metrics, None, True
+        events = []
+        for d in rows:
+            if int(d[_abi.DEC_STATUS]) != _abi.STATUS_DECISION:
+                break
+            events.append(DecisionEvent(int(d[0]), int(d[1]), int(d[2]), self._snapshots, ActionScope(int(d[3]), int(d[4])), int(d[5])))
+        return self._last_metrics, events, False
 
     # ---- stepping (core.py:92-133)
     def step(self, action=None):
+        if self._joint:
+            return self._step_joint(action)
         if action is None:
             actions = []
         elif not isinstance(action, list):
@@ -298,7 +336,7 @@ class Env:
                 # reset rebuilds its data container (cim_data_container_helpers.py:56-70)
                 self._batch.close()
                 self._batch = CimBatch(self._topo, 1, self._start_tick, self._snapshot_resolution, self._max_snapshots,
-                                       device=self._device, max_actions=8)
+                                       device=self._device, max_actions=8, decision_mode=int(self._joint))
                 if self._backend_name == "dynamic":
                     self._batch.set_query_layout("dynamic")
                 self._snapshots = SnapshotList(self._batch, 0)

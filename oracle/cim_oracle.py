@@ -41,6 +41,7 @@ def lib():
         _lib.cim_oracle_read_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.cim_oracle_run_episode.restype = C.c_int64
         _lib.cim_oracle_run_episode.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.cim_oracle_step_joint.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.cim_policy_random.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     return _lib
 
@@ -75,6 +76,19 @@ class CimOracle:
             a = np.ascontiguousarray(actions, np.int32).reshape(-1, 4)
             st = lib().cim_oracle_step(self._h, a.ctypes.data, a.shape[0], dec.ctypes.data, met.ctypes.data)
         return st, dec, met
+
+    def step_joint(self, answers=None):
+        """DecisionMode.Joint: answers = list of (vessel, port, qty, type) or None per pending decision (may be shorter).
+        Returns (status, decision rows [n][8], metrics[3])."""
+        V = self._topo.n_vessels
+        dec = np.zeros((V, 8), np.int32)
+        met = np.zeros(3, np.int64)
+        n = C.c_int32()
+        rows = np.zeros((max(1, len(answers or [])), 4), np.int32)
+        for k, a in enumerate(answers or []):
+            rows[k] = (0, 0, 0, 2) if a is None else a
+        st = lib().cim_oracle_step_joint(self._h, rows.ctypes.data, len(answers or []), dec.ctypes.data, C.byref(n), met.ctypes.data)
+        return st, dec[:n.value] if st == 0 else dec[:1], met
 
     @property
     def tick(self) -> int:

@@ -70,14 +70,16 @@ void emul_step(Emul* e, const int32_t* actions, const int32_t* n_actions, int32_
         int n = actions ? (n_actions ? n_actions[i] : 1) : 0;
         const int32_t* act = actions ? actions + (size_t)i * e->s.max_actions * 4 : nullptr;
         switch (e->lanes) {
-            case 1: step_g<1>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
-            case 8: step_g<8>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
-            case 16: step_g<16>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
-            default: step_g<32>(e, i, act, n, decisions + i * 8, metrics + i * 3); break;
+            case 1: step_g<1>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3); break;
+            case 8: step_g<8>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3); break;
+            case 16: step_g<16>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3); break;
+            default: step_g<32>(e, i, act, n, decisions + (size_t)i * e->s.DW, metrics + i * 3); break;
         }
     }
 }
 int emul_frame_words(Emul* e) { return e->s.FW; }
+int emul_dec_words(Emul* e) { return e->s.DW; }
+int emul_max_actions(Emul* e) { return e->s.max_actions; }
 int emul_lanes(Emul* e) { return e->lanes; }
 void emul_read_frame(Emul* e, int rep, int32_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW, 4 * e->s.FW); }
 int emul_read_snapshot(Emul* e, int rep, int frame, int32_t* out) {

@@ -67,7 +67,7 @@ def lib():
 
 class EmulEnv:
     def __init__(self, topos, n_replicas=1, start_tick=0, snapshot_resolution=1, max_snapshots=None, max_actions=2,
-                 replica_topology=None, lanes=0):
+                 replica_topology=None, lanes=0, decision_mode=0):
         if not isinstance(topos, (list, tuple)):
             topos = [topos]
         self._keep = []
@@ -82,22 +82,39 @@ class EmulEnv:
         cfg.snapshot_resolution = snapshot_resolution
         cfg.max_snapshots = int(max_snapshots) if max_snapshots else 0
         cfg.max_actions = max_actions
+        cfg.decision_mode = int(decision_mode)
         if replica_topology is not None:
             rt = np.ascontiguousarray(replica_topology, np.int32)
             self._keep.append(rt)
             cfg.replica_topology = rt.ctypes.data_as(C.POINTER(C.c_int32))
-        self.B, self.A = n_replicas, max_actions
+        self.B = n_replicas
         self._h = lib().emul_create(arr, len(topos), C.byref(cfg), lanes)
         assert self._h
         self.frame_words = lib().emul_frame_words(self._h)
+        self.A = lib().emul_max_actions(self._h)
+        self.DW = lib().emul_dec_words(self._h)
 
     def __del__(self):
         if getattr(self, "_h", None):
             lib().emul_destroy(self._h)
             self._h = None
 
+    def step_joint(self, answers=None):
+        """DecisionMode.Joint, one replica: answers = list of (vessel, port, qty, type) or None -> (status, rows [n][8], metrics)"""
+        if answers is None:
+            dec, met = self.step(None)
+        else:
+            rows = np.asarray([(0, 0, 0, 2) if a is None else a for a in answers], np.int32).reshape(1, -1, 4)
+            dec, met = self.step(rows if rows.shape[1] else np.zeros((1, 1, 4), np.int32), np.asarray([rows.shape[1]], np.int32))
+        d = dec[0].reshape(-1, 8)
+        st = int(d[0, 6])
+        n = 0
+        while st == 0 and n < len(d) and d[n, 6] == 0:
+            n += 1
+        return st, d[:n] if st == 0 else d[:1], met[0]
+
     def step(self, actions=None, n_actions=None):
-        dec = np.zeros((self.B, 8), np.int32)
+        dec = np.zeros((self.B, self.DW), np.int32)
         met = np.zeros((self.B, 3), np.int64)
         if actions is None:
             lib().emul_step(self._h, None, None, dec.ctypes.data, met.ctypes.data)

@@ -13,23 +13,28 @@ _NODES = ("ports", "vessels", "matrices")
 
 class EmulCimBatch:
     def __init__(self, topologies, n_replicas, start_tick=0, snapshot_resolution=1, max_snapshots=None, device=0, max_actions=1,
-                 replica_topology=None, queue_capacity=0):
+                 replica_topology=None, queue_capacity=0, decision_mode=0):
         if isinstance(topologies, CimTopology):
             topologies = [topologies]
         self.topologies = list(topologies)
-        self.n_replicas, self.max_actions = int(n_replicas), int(max_actions)
+        self.decision_mode = int(decision_mode)
+        V = self.topologies[0].n_vessels
+        self.n_replicas = int(n_replicas)
+        self.max_actions = max(int(max_actions), V) if self.decision_mode == 1 else int(max_actions)
+        self.dec_words = 8 * (V if self.decision_mode == 1 else 1)
+        self.start_tick, self.snapshot_resolution = int(start_tick), int(snapshot_resolution)
         self._cfg = (start_tick, snapshot_resolution, max_snapshots)
         self._rt = [0] * self.n_replicas if replica_topology is None else [int(x) for x in replica_topology]
         self._envs = [self._make(i) for i in range(self.n_replicas)]
         t = self.topologies[0]
         self._lay, self.frame_words = _abi.frame_layout(t.n_ports, t.n_vessels, t.past_stop_number, t.future_stop_number)
         self._attrs = {n: list(self._lay[n]) for n in _NODES}
-        self.decisions = np.zeros((self.n_replicas, 8), np.int32)
+        self.decisions = np.zeros((self.n_replicas, self.dec_words), np.int32)
         self.metrics = np.zeros((self.n_replicas, 3), np.int64)
 
     def _make(self, i):
         st, res, ms = self._cfg
-        return EmulEnv(self.topologies[self._rt[i]], 1, st, res, ms, max_actions=self.max_actions)
+        return EmulEnv(self.topologies[self._rt[i]], 1, st, res, ms, max_actions=self.max_actions, decision_mode=self.decision_mode)
 
     def node_counts(self):
         t = self.topologies[0]

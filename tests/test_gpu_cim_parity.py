@@ -347,3 +347,43 @@ def test_cuda_config4_full_size_distinct_seeds():
         assert np.array_equal(env.read_frame(i), final_frames[i])
     assert_snapshots_equal(lambda f: env.snapshot_row(f, 3), gold, topos[3])
     env.close()
+
+
+@pytest.mark.parametrize("name", ["toy4p_l00_160", "toy5p_l03_140_res4", "gt22p_l08_70"])
+def test_cuda_joint_mode_matches_reference_trace(name):
+    """DecisionMode.Joint (core.py:354-366) on the device: a step returns every decision event of the tick, the answers are
+    applied in list order; 3 replicas through the C ABI against traces of the reference run in Joint mode, then the Env façade."""
+    import test_cim_joint as tj
+    from maro_b200.scenarios.cim.topology import build_topology
+
+    spec = tj.gen.CASES[name]
+    topo = build_topology(spec["topology"], spec["durations"])
+    B = 3
+    env = _batch(topo, B, 0, spec.get("snapshot_resolution", 1), spec.get("max_snapshots"), decision_mode=1)
+    A = env.max_actions
+
+    def step_fn(answers):
+        if answers is None:
+            dec, met = env.step(None)
+        else:
+            a = np.zeros((B, A, 4), np.int32)
+            for k, x in enumerate(answers):
+                a[:, k] = (0, 0, 0, 2) if x is None else x
+            dec, met = env.step(a, np.full(B, len(answers), np.int32))
+        assert (dec == dec[0]).all() and (met == met[0]).all()
+        rows = dec[0].reshape(-1, 8)
+        st, n = int(rows[0, 6]), 0
+        while st == 0 and n < len(rows) and rows[n, 6] == 0:
+            n += 1
+        return st, rows[:n].copy() if st == 0 else rows[:1].copy(), met[0].copy()
+
+    rows, mets, final, st = tj.drive_joint(step_fn, spec)
+    assert st == 1
+    gold = tj.check_against_gold(name, rows, mets, final, None)
+    frames = gold["frames"].tolist()
+    got = env.query("ports", frames, list(range(topo.n_ports)), ["empty", "full", "shortage"], [B - 1])[0].reshape(len(frames), -1, 3)
+    assert np.array_equal(got[:, :, 0], gold["ports/empty"]) and np.array_equal(got[:, :, 1], gold["ports/full"])
+    assert np.array_equal(got[:, :, 2], gold["ports/shortage"])
+    env.close()
+    if name == "toy5p_l03_140_res4":
+        tj.env_joint_case(name)

@@ -13,13 +13,13 @@ pytestmark = pytest.mark.gpu
 EXACT_COLS = [0, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]  # every metric except total_incomes (1) and total_profit (3)
 
 
-@pytest.mark.parametrize("name", sorted(VM_CASES))
-
 def _row(dec, n_valid):
     """header + valid PM ids of a decision row; word 11 (offset of this build's remaining-cores extension) is not part of the
     reference's DecisionEvent and absent from the oracle's rows"""
     return list(dec[:11]) + list(dec[12:12 + n_valid])
 
+
+@pytest.mark.parametrize("name", sorted(VM_CASES))
 def test_vm_cuda_matches_reference_trace(name):
     from maro_b200.batch import VmBatch
     from oracle.vm_oracle import VmOracle

@@ -17,6 +17,7 @@ def _row(dec, n_valid):
     reference's DecisionEvent and absent from the oracle's rows"""
     return list(dec[:11]) + list(dec[12:12 + n_valid])
 
+
 def _abi_metrics(row):
     from maro_b200 import _abi
 
