@@ -115,7 +115,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def start(self):
         if self._nv:
@@ -839,7 +839,8 @@ def run_cim(args, rank, local_rank, world):
         }
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
-                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (8 * 4 + 3 * 8),
+                           # session: one 16-byte command row in, one 64-byte tagged result line out per replica and step
+                           "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (64 if e2e["n_sub"] else 8 * 4 + 3 * 8),
                            "api": ("maro_cim_submit_pinned / maro_cim_wait_pinned (pinned host buffers; resident session) driven by the C "
                                    "host loop tools/host_agent.c:e2e_loop_cim_mt, agent on the host" if e2e["n_sub"] else
                                    "maro_cim_step_pinned (pinned host buffers) + tools/host_agent.c on the host"),

@@ -37,8 +37,9 @@ class VectorEnv:
                  decision_mode=DecisionMode.Sequential, business_engine_cls: type = None,
                  disable_finished_events: bool = False, options: dict = {}, device: int = 0, seeds=None):
         assert batch_num > 0
-        if scenario not in ("cim", "citi_bike", "vm_scheduling") or business_engine_cls is not None or int(decision_mode) != 0:
-            raise NotImplementedError("the CUDA core implements scenario='cim' / 'citi_bike' / 'vm_scheduling', Sequential mode")
+        self._joint = int(decision_mode) == int(DecisionMode.Joint)
+        if scenario not in ("cim", "citi_bike", "vm_scheduling") or business_engine_cls is not None or (self._joint and scenario != "cim"):
+            raise NotImplementedError("the CUDA core implements scenario='cim' / 'citi_bike' / 'vm_scheduling' (Joint mode: cim)")
         self._batch_num = batch_num
         self._scenario = scenario
         self._start_tick, self._resolution = start_tick, snapshot_resolution
@@ -69,7 +70,7 @@ class VectorEnv:
         self._conf, self._max_tick, self._rt = conf, start_tick + durations, rt
         self._ctor = (batch_num, start_tick, snapshot_resolution, max_snapshots, device)
         self._batch = CimBatch(topos, batch_num, start_tick, snapshot_resolution, max_snapshots, device=device,
-                               max_actions=4, replica_topology=rt)
+                               max_actions=4, replica_topology=rt, decision_mode=int(self._joint))
         self._finish_init(batch_num, start_tick)
 
     def _finish_init(self, batch_num, start_tick):
@@ -82,7 +83,7 @@ class VectorEnv:
         self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(batch_num)]
         self._done = np.zeros(batch_num, bool)
         self._ticks = np.full(batch_num, start_tick, np.int64)
-        self._act = np.zeros((batch_num, 4, 4), np.int32)
+        self._act = np.zeros((batch_num, self._batch.max_actions, 4), np.int32)
         self._nact = np.zeros(batch_num, np.int32)
         self._active = np.ones(batch_num, np.uint8)
 
@@ -121,6 +122,15 @@ class VectorEnv:
                 encode_action(a, self._act[i, k])
         self._nact[i] = len(acts)
 
+    def _encode_joint(self, i, answers):
+        """Joint mode: env i's answers = None or a list with one entry (Action or None) per decision event of its last step"""
+        answers = [] if answers is None else (answers if isinstance(answers, list) else [answers])
+        if len(answers) > self._act.shape[1]:
+            raise ValueError("more answers than decision events")
+        for k, a in enumerate(answers):
+            self._act[i, k] = (0, 0, 0, 2) if a is None else action_row(a)
+        self._nact[i] = len(answers)
+
     def _encode_all_cim(self, actions):
         """one action (or None / list) per env -> the int32 action rows, filled with ONE array assignment per column block
         instead of four element writes per env (the per-env Python objects are the caller's, the loop stays)"""
@@ -145,7 +155,20 @@ class VectorEnv:
     def step(self, action):
         """list -> one action per env; dict -> only those envs advance; anything else -> broadcast."""
         B = self._batch_num
-        cim = self._scenario == "cim"
+        cim = self._scenario == "cim" and not self._joint
+        if self._joint:  # list: one answer list per env; dict: only those envs; None: broadcast "no answers"
+            if type(action) is dict:
+                self._active[:] = 0
+                for i, a in action.items():
+                    self._encode_joint(i, a)
+                    self._active[i] = 1
+            else:
+                per_env = action if (type(action) is list and len(action) == B and all(a is None or isinstance(a, list) for a in action)) else [action] * B
+                for i in range(B):
+                    self._encode_joint(i, per_env[i])
+                self._active[:] = 1
+            dec, met = self._batch.step(self._act, self._nact, self._active)
+            return self._decode_cim(dec, met)
         if type(action) is list:
             assert len(action) == B
             if cim:
@@ -224,7 +247,15 @@ class VectorEnv:
         for i in (range(self._batch_num) if active.all() else np.flatnonzero(active).tolist()):
             d = rows[i]
             st = d[6]
-            if st == ST_DEC:
+            if st == ST_DEC and self._joint:  # every decision event of the tick: rows of 8 words up to the first non-decision row
+                metrics.append(make_metrics(mets[i]))
+                evs = []
+                for k in range(0, len(d), 8):
+                    if d[k + 6] != ST_DEC:
+                        break
+                    evs.append(DecisionEvent(d[k], d[k + 1], d[k + 2], snaps[i], ActionScope(d[k + 3], d[k + 4]), d[k + 5]))
+                events.append(evs)
+            elif st == ST_DEC:
                 metrics.append(make_metrics(mets[i]))
                 events.append(DecisionEvent(d[0], d[1], d[2], snaps[i], ActionScope(d[3], d[4]), d[5]))
             elif st == ST_DONE:
@@ -257,7 +288,8 @@ class VectorEnv:
             except RuntimeError:  # a new instance does not fit the handle's event horizon / pool: fresh handle
                 B, start_tick, res, max_snaps, device = self._ctor
                 self._batch.close()
-                self._batch = CimBatch(new, B, start_tick, res, max_snaps, device=device, max_actions=4, replica_topology=self._rt)
+                self._batch = CimBatch(new, B, start_tick, res, max_snaps, device=device, max_actions=4, replica_topology=self._rt,
+                                       decision_mode=int(self._joint))
                 if self._backend_name == "dynamic":
                     self._batch.set_query_layout("dynamic")
                 self._snapshot_lists = [SnapshotList(self._batch, i) for i in range(B)]

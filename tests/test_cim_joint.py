@@ -116,3 +116,40 @@ def test_env_facade_joint_mode_emulated(monkeypatch):
 
     monkeypatch.setattr(env_mod, "CimBatch", EmulCimBatch)
     env_joint_case()
+
+
+def vector_env_joint_case(name="toy4p_l00_160"):
+    """VectorEnv(decision_mode=Joint): every env returns the list of its tick's decision events and takes a list of answers"""
+    from maro_b200.scenarios.cim.common import Action, ActionType
+    from maro_b200.simulator import DecisionMode
+    from maro_b200.vector_env import VectorEnv
+
+    spec = gen.CASES[name]
+    gold = np.load(os.path.join(HERE, "golden", f"cim_joint_{name}.npz"))
+    B = 3
+    with VectorEnv(batch_num=B, scenario="cim", topology=spec["topology"], durations=spec["durations"],
+                   snapshot_resolution=spec.get("snapshot_resolution", 1), max_snapshots=spec.get("max_snapshots"),
+                   decision_mode=DecisionMode.Joint) as env:
+        rows, step, ordinal = [[] for _ in range(B)], 0, 0
+        metrics, decs, done = env.step(None)
+        while not done:
+            acts = []
+            for i in range(B):
+                cur = [[d.tick, d.port_idx, d.vessel_idx, d.action_scope.load, d.action_scope.discharge, d.early_discharge] for d in decs[i]]
+                rows[i] += [[step] + r for r in cur]
+                acts.append([None if a is None else Action(a[0], a[1], a[2], ActionType.DISCHARGE if a[3] else ActionType.LOAD)
+                             for a in gen.answers(cur, spec["pseed"], ordinal)])
+            ordinal += len(decs[0])
+            step += 1
+            metrics, decs, done = env.step(acts)
+        for i in range(B):
+            assert np.array_equal(np.asarray(rows[i], np.int64), gold["rows"])
+            assert [metrics[i][k] for k in ("order_requirements", "container_shortage", "operation_number")] == gold["final_metrics"].tolist()
+
+
+def test_vector_env_joint_mode_emulated(monkeypatch):
+    import maro_b200.vector_env.vector_env as venv_mod
+    from emul_batch import EmulCimBatch
+
+    monkeypatch.setattr(venv_mod, "CimBatch", EmulCimBatch)
+    vector_env_joint_case()

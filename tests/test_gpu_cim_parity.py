@@ -387,3 +387,5 @@ def test_cuda_joint_mode_matches_reference_trace(name):
     env.close()
     if name == "toy5p_l03_140_res4":
         tj.env_joint_case(name)
+    if name == "toy4p_l00_160":
+        tj.vector_env_joint_case(name)
