@@ -190,6 +190,10 @@ MARO_DEV void on_rebalance(const BikeShape& s, const BikeReplica& r, int tick) {
 // _on_action_received (:521-559)
 template <int G>
 MARO_DEV void bike_on_actions(const BikeShape& s, const Grp<G>& g, const BikeReplica& r, int tick, const Act4& mine, int n) {
+    // The decision event being answered has left this tick's list already.  If it was the LAST element, the reference's list
+    // keeps its tail pointer on the removed event (EventLinkedList._extract_sub_events, event_linked_list.py:86-92, does not
+    // update `_tail`), so events appended to this tick's list from now on — deliveries with transfer time 0 — are lost.
+    const bool tail_lost = (*(bq_bucket(s, r) + (tick & (s.QH - 1))) & 0xffff) == Q_NIL;
     for (int i = 0; i < n; i++) {
         int from = g.shfl(mine.v, i), to = g.shfl(mine.p, i), number = g.shfl(mine.qty, i);
         if (g.lane != 0) continue;
@@ -203,7 +207,7 @@ MARO_DEV void bike_on_actions(const BikeShape& s, const Grp<G>& g, const BikeRep
             int tt = (int)rint(x);  // python round(): half to even
             // a negative transfer time (normal(20, 5) can produce one) files the event under a tick that has already
             // been executed: the reference never runs it and the bikes are lost (event_buffer.py:166-175)
-            if (tt >= 0) bike_push(s, r, tick + tt, BE_DELIVER, from, to, executed);
+            if (tt > 0 || (tt == 0 && !tail_lost)) bike_push(s, r, tick + tt, BE_DELIVER, from, to, executed);
         }
     }
 }

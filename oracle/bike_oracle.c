@@ -85,7 +85,7 @@ typedef struct Event {
     struct Event* imm_tail;
     int imm_count;
 } Event;
-typedef struct { Event* head; Event* tail; int count; } EvList;
+typedef struct { Event* head; Event* tail; int count; int tail_lost; } EvList;
 
 typedef struct { int32_t bikes, shortage, trip_requirement, fulfillment, capacity, id, weekday, temperature, weather,
                  holiday, extra_cost, transfer_cost, failed_return, min_bikes; } Station;
@@ -130,6 +130,13 @@ static void insert_event(BikeOracle* o, Event* e) {
     if (e->tick < 0 || e->tick >= o->n_lists) { free(e); return; }
     EvList* l = &o->pending[e->tick];
     e->next = NULL;
+    if (l->tail_lost) {
+        /* the reference's list keeps its `_tail` on a cascade event that has already been removed (see clear_finished):
+         * whatever is appended now hangs off that dead node, is counted, and is never reached from the head again */
+        l->count++;
+        free(e);
+        return;
+    }
     if (l->tail) l->tail->next = e; else l->head = e;
     l->tail = e; l->count++;
 }
@@ -146,6 +153,11 @@ static void clear_finished(EvList* l) {
         if (!l->head) l->tail = NULL;
         l->count--;
         if (e->cascade && e->imm_count) {
+            /* EventLinkedList._extract_sub_events (event_linked_list.py:86-92) splices the immediate events in front of the
+             * rest but does not touch `_tail`: when the cascade event was the LAST element of the list, `_tail` keeps pointing
+             * at it after its removal, and events appended to this tick's list from then on (a DeliverBike with transfer time
+             * 0 issued by the action of a tick's last decision event) are lost.  Found by tools/fuzz_cim_bike_parity.py. */
+            if (!l->head) l->tail_lost = 1;
             e->imm_tail->next = l->head;
             if (!l->head) l->tail = e->imm_tail;
             l->head = e->imm_head;
@@ -321,7 +333,7 @@ static void free_events(BikeOracle* o) {
             free(e);
             e = n;
         }
-        o->pending[i].head = o->pending[i].tail = NULL; o->pending[i].count = 0;
+        o->pending[i].head = o->pending[i].tail = NULL; o->pending[i].count = 0; o->pending[i].tail_lost = 0;
     }
 }
 

@@ -17,15 +17,18 @@ _spec.loader.exec_module(gen)
 BIKE_CASES = gen.CASES
 
 
-def bike_config(data_name):
+def bike_config(data_name, decision_text=None):
     src = os.path.join(GOLDEN, data_name)
     if data_name == "bike_toy":
         conf = yaml.safe_load(gen.TOY_DECISION)
         files = dict(trip_data="trips.bin", weather_data="KNYC_daily.bin", stations_init_data="station_meta.csv",
                      distance_adj_data="distance_adj.csv")
     else:
-        with open(os.path.join(src, "decision.yml")) as fp:
-            conf = yaml.safe_load(fp)
+        if decision_text:
+            conf = yaml.safe_load(decision_text)
+        else:
+            with open(os.path.join(src, "decision.yml")) as fp:
+                conf = yaml.safe_load(fp)
         files = dict(trip_data="trips.bin", weather_data="weathers.bin", stations_init_data="stations.csv",
                      distance_adj_data="distance_adj.csv")
     for k, v in files.items():
@@ -35,7 +38,7 @@ def bike_config(data_name):
 
 def bike_topology(spec):
     st = spec.get("start_tick", 0)
-    return build_bike_topology(bike_config(spec["data"]), st, st + spec["durations"], transfer_seed=spec["np_seed"])
+    return build_bike_topology(bike_config(spec["data"], spec.get("decision_text")), st, st + spec["durations"], transfer_seed=spec["np_seed"])
 
 
 def load_bike_golden(name):

@@ -62,6 +62,14 @@ CASES = {
                                          np_seed=8),
     "synth26_start400_600_greedy_res1": dict(data="bike_synth26", start_tick=400, durations=600, policy=1, snapshot_resolution=1,
                                              np_seed=21),
+    # found by tools/fuzz_cim_bike_parity.py (bike_filter_spec(15)): at tick 144 the action of the tick's LAST decision event draws a
+    # transfer time of 0; the reference's event list keeps its tail on the removed decision event (event_linked_list.py:86-92
+    # does not update `_tail`), the DeliverBike appended to the running tick is lost and two bikes vanish
+    "synth26_lost_same_tick_delivery": dict(
+        data="bike_synth26", durations=300, policy=1, snapshot_resolution=7, np_seed=95996,
+        decision_text=('decision:\n  extra_cost_mode: target\n  resolution: 5\n  effective_time_mean: 7\n  effective_time_std: 4\n'
+                       '  supply_water_mark_ratio: 0.73\n  demand_water_mark_ratio: 0.18\n  action_scope:\n    low: 0.27\n    high: 0.73\n'
+                       '    filters:\n      - type: "requirements"\n        num: 3\ntime_zone: "America/New_York"\n')),
     "case1_30_null": dict(data="bike_case_1", durations=30, policy=0, snapshot_resolution=1, np_seed=1),
     "case2_30_greedy": dict(data="bike_case_2", durations=30, policy=1, snapshot_resolution=1, np_seed=2),
 }
@@ -70,7 +78,7 @@ STATION_ATTRS = ("bikes", "capacity", "extra_cost", "failed_return", "fulfillmen
                  "shortage", "temperature", "transfer_cost", "trip_requirement", "weather", "weekday")
 
 
-def data_config_dir(name):
+def data_config_dir(name, decision_text=None):
     """tests/golden/<name>/ holds trips.bin, weather bin, station + distance csv and (for the reference's cases) the
     decision config; returns a temp folder with a config.yml of absolute paths."""
     src = os.path.join(HERE, name)
@@ -80,7 +88,7 @@ def data_config_dir(name):
         files = dict(trip_data="trips.bin", weather_data="KNYC_daily.bin", stations_init_data="station_meta.csv",
                      distance_adj_data="distance_adj.csv")
     else:
-        body = open(os.path.join(src, "decision.yml")).read()
+        body = decision_text or open(os.path.join(src, "decision.yml")).read()
         files = dict(trip_data="trips.bin", weather_data="weathers.bin", stations_init_data="stations.csv",
                      distance_adj_data="distance_adj.csv")
     with open(os.path.join(d, "config.yml"), "w") as fp:
@@ -141,7 +149,7 @@ def run_case(name, spec, out_dir=None):
     from maro.simulator.scenarios.citi_bike.common import Action, DecisionType
 
     np.random.seed(spec["np_seed"])
-    env = Env("citi_bike", data_config_dir(spec["data"]), start_tick=spec.get("start_tick", 0), durations=spec["durations"],
+    env = Env("citi_bike", data_config_dir(spec["data"], spec.get("decision_text")), start_tick=spec.get("start_tick", 0), durations=spec["durations"],
               snapshot_resolution=spec["snapshot_resolution"], max_snapshots=spec.get("max_snapshots"))
     S = len(env.snapshot_list["stations"])
     rows, scopes = [], []

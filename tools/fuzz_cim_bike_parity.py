@@ -45,6 +45,30 @@ def bike_spec(seed):
     return spec
 
 
+def bike_filter_spec(seed):
+    """the 26-station synthetic dataset with a random action-scope filter chain (filters that DROP neighbours), decision /
+    snapshot resolutions that do not divide each other (stale trip-window cache entries), short rings"""
+    rng = np.random.default_rng(seed + 77777)
+    filters = ['      - type: "distance"\n        num: %d' % int(rng.integers(5, 26))] if rng.random() < 0.7 else []
+    for _ in range(int(rng.integers(1, 3))):
+        if rng.random() < 0.5:
+            filters.append('      - type: "requirements"\n        num: %d' % int(rng.integers(2, 20)))
+        else:
+            filters.append('      - type: "trip_window"\n        windows: %d\n        num: %d' % (int(rng.integers(1, 9)), int(rng.integers(2, 20))))
+    text = ("decision:\n  extra_cost_mode: %s\n  resolution: %d\n  effective_time_mean: %d\n  effective_time_std: %d\n"
+            "  supply_water_mark_ratio: %.2f\n  demand_water_mark_ratio: %.2f\n  action_scope:\n    low: %.2f\n    high: %.2f\n    filters:\n%s\n"
+            'time_zone: "America/New_York"\n') % (str(rng.choice(["source", "target", "target_neighbors"])), int(rng.choice([5, 12, 20, 30])),
+                                                  int(rng.integers(3, 25)), int(rng.integers(1, 6)), float(rng.uniform(0.6, 0.9)),
+                                                  float(rng.uniform(0.1, 0.3)), float(rng.uniform(0, 0.3)), float(rng.uniform(0.6, 1.0)),
+                                                  "\n".join(filters))
+    start = int(rng.choice([0, 0, 200, 600]))
+    spec = dict(data="bike_synth26", start_tick=start, durations=int(rng.integers(150, 800)), policy=int(rng.integers(0, 2)),
+                snapshot_resolution=int(rng.choice([1, 3, 7, 10, 20])), np_seed=int(rng.integers(0, 100000)), decision_text=text)
+    if rng.random() < 0.5:
+        spec["max_snapshots"] = int(rng.integers(2, 30))
+    return spec
+
+
 def main():
     import gen_bike_golden as gb
     import gen_cim_golden as gc
@@ -61,15 +85,15 @@ def main():
     p0.start(); p0.join()
     bad = 0
     for seed in range(first, first + n):
-        for kind in ("cim", "bike"):
-            spec = cim_spec(seed) if kind == "cim" else bike_spec(seed)
-            name = f"fuzz{seed}"
+        for kind in (("bikef",) if os.environ.get("FUZZ_ONLY") == "bike_filters" else ("cim", "bike", "bikef")):
+            spec = cim_spec(seed) if kind == "cim" else (bike_spec(seed) if kind == "bike" else bike_filter_spec(seed))
+            name = f"fuzz{seed}{'f' if kind == 'bikef' else ''}"
             p = ctx.Process(target=(gc if kind == "cim" else gb).run_case, args=(name, spec, out))
             p.start(); p.join()
             if p.exitcode != 0:
                 print(seed, kind, "reference failed (skipped)", spec)
                 continue
-            gold = np.load(os.path.join(out, f"{kind}_{name}.npz"))
+            gold = np.load(os.path.join(out, f"{'cim' if kind == 'cim' else 'bike'}_{name}.npz"))
             res, ring = spec.get("snapshot_resolution", 1), spec.get("max_snapshots")
             try:
                 if kind == "cim":
@@ -91,7 +115,7 @@ def main():
                 bad += 1
                 print(seed, kind, "MISMATCH", str(ex)[:300], spec)
                 continue
-            print(seed, kind, "ok", len(gold["steps"]), "steps", spec, flush=True)
+            print(seed, kind, "ok", len(gold["steps"]), "steps", {k: v for k, v in spec.items() if k != "decision_text"}, flush=True)
     print("mismatches:", bad)
     return bad
 
