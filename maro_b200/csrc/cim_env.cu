@@ -187,8 +187,14 @@ __device__ __forceinline__ uint4 ld_sys_v4(const uint32_t* p) {
     return v;
 }
 
-template <int G, bool kGeneral>
-__global__ void __launch_bounds__(256, 1) cim_resident_kernel(const __grid_constant__ CimShape s, const __grid_constant__ StepArgs a,
+// kMinBlocks = 3 caps the kernel at 77 registers (108 uncapped, no spills either way).  Measured (toy.4p, fused rollouts):
+// +12.5 % at 65 536 replicas, +14 % at 32 768, -7 % at 16 384, -1..2 % at <= 8 192 -- so it is chosen per handle (res_dense)
+// once the grid is several waves deep.  Shared memory, not registers, bounds residency here (2 CTAs per SM in both builds).
+#ifndef MARO_RES_DENSE_BLOCKS
+#define MARO_RES_DENSE_BLOCKS 3
+#endif
+template <int G, bool kGeneral, int kMinBlocks = 1>
+__global__ void __launch_bounds__(256, kMinBlocks) cim_resident_kernel(const __grid_constant__ CimShape s, const __grid_constant__ StepArgs a,
                                                            const __grid_constant__ ResidentArgs ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int n_groups = ra.spread ? (int)(blockDim.x >> 5) : (int)(blockDim.x / G);
@@ -376,7 +382,7 @@ struct MaroCimEnv : EnvCommon {
     uint8_t* d_light = nullptr;
     std::vector<int32_t> h_tables;
     // resident mode (cim_resident_kernel)
-    int res_threads = 0, res_grid = 0, res_spread = 0;
+    int res_threads = 0, res_grid = 0, res_spread = 0, res_dense = 0;
     size_t res_smem = 0;
     bool session_ok = false;                         // the whole grid is co-resident (required to spin-wait)
     std::atomic<bool> session_live{false};
@@ -579,7 +585,8 @@ static cudaError_t launch_resident_g(MaroCimEnv* e, const StepArgs& a, const Res
         kernel<<<e->res_grid, e->res_threads, e->res_smem, e->stream>>>(e->s, a, ra);
         return cudaGetLastError();
     };
-    return general ? go(cim_resident_kernel<G, true>) : go(cim_resident_kernel<G, false>);
+    if (general) return go(cim_resident_kernel<G, true>);
+    return e->res_dense ? go(cim_resident_kernel<G, false, MARO_RES_DENSE_BLOCKS>) : go(cim_resident_kernel<G, false>);
 }
 
 static cudaError_t launch_resident(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, bool query_only = false, int* blocks_per_sm = nullptr) {
@@ -804,6 +811,8 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
         e->res_smem = 256 + 16 + per_group * w * groups_per_warp;
         e->res_grid = (B + w * groups_per_warp - 1) / (w * groups_per_warp);
         e->res_groups = w * groups_per_warp;
+        const char* rd = getenv("MARO_B200_RES_DENSE");  // register-capped instantiation for grids several waves deep
+        e->res_dense = rd ? atoi(rd) != 0 : (!e->res_spread && w == 8 && e->res_grid > 5 * nsm);
         e->cta_seq.assign(e->res_grid, 0);
         e->cta_pending.assign(e->res_grid, 0);
         int per_sm = 0;
