@@ -398,6 +398,9 @@ MARO_DEV int run_delay_line(const CimShape& s, const Grp<G>& g, const Replica& r
     return n;
 }
 
+#if defined(MARO_HOST_EMULATION) && defined(MARO_TRACK_QPEAK)
+extern "C" int maro_emul_qpeak;
+#endif
 template <int G>
 MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, bool want, int now, int tick, int w0, int qty) {
     want = want && tick < s.max_tick && tick >= 0;  // later ticks are never visited by the Env (event_buffer.py:190)
@@ -431,6 +434,9 @@ MARO_DEV void group_push(const CimShape& s, const Grp<G>& g, const Replica& r, b
     int last_slot = g.shfl(slot, want ? last_lane : g.lane);
     g.sync();
     if (g.lane == 0) { r.c[C_FREE_TOP] = top - n; r.c[C_Q_COUNT] += n; }
+#if defined(MARO_HOST_EMULATION) && defined(MARO_TRACK_QPEAK)  // tools/cim_queue_peak.py: high-water mark of the calendar queue
+    if (g.lane == 0 && r.c[C_Q_COUNT] > maro_emul_qpeak) maro_emul_qpeak = r.c[C_Q_COUNT];
+#endif
     if (want) {
         int32_t* e = r.q + slot * 2;
         e[0] = w0; e[1] = qty;

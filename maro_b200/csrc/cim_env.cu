@@ -171,6 +171,8 @@ struct ResidentArgs {
     int n_steps, policy;
     uint32_t seed, replica_base;
     int32_t* trace;                 // [n_steps][B][8] decision rows of every fused step, or nullptr
+    int slice_steps;                // RES_ROLLOUT, sliced: > 0 = lane groups pull (replica, slice of `slice_steps` env-steps) work items
+    uint32_t* slice_sync;           //   device: {tickets taken, entries appended, entries[B x (n_slices - 1)]}, zeroed before the launch
     const uint32_t* cmd;            // [B][4] command rows (mapped host memory)
     uint32_t* results;              // mapped host [B][16]: tagged result lines (see "publish" in the session loop)
     uint32_t poll_ns, wait_ns;      // back-off of the command poll (PCIe) and of the shared-memory relay wait
@@ -200,32 +202,72 @@ __global__ void __launch_bounds__(256, kMinBlocks) cim_resident_kernel(const __g
     const int n_groups = ra.spread ? (int)(blockDim.x >> 5) : (int)(blockDim.x / G);
     if (ra.spread && (threadIdx.x & 31) >= G) return;
     const int gid = ra.spread ? (int)(threadIdx.x >> 5) : (int)(threadIdx.x / G);
-    const int rep = blockIdx.x * n_groups + gid;
-    if (rep >= s.n_replicas) return;
+    int rep = blockIdx.x * n_groups + gid;
     const Grp<G> g(threadIdx.x & 31);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + gid;                  // [32] mbarriers
     int32_t* dslot = reinterpret_cast<int32_t*>(smem_raw + 256) + gid * 16;      // 8 decision words + 3 int64 metrics
     int64_t* mslot = reinterpret_cast<int64_t*>(dslot + 8);
     int32_t* st = reinterpret_cast<int32_t*>(smem_raw + 256 + (size_t)n_groups * 64) + (size_t)gid * s.SW;
-    int32_t* gstate = a.state + (int64_t)rep * s.SW;
+    // Sliced rollouts (grids that do not fit the GPU at once, e.g. 1.16 waves): instead of one replica per lane group for the whole
+    // launch, the resident lane groups serve a FIFO of ready replicas.  A work item is one slice = `slice_steps` env-steps of one
+    // replica between a stage-in and a write-back; the group that finishes a slice appends the replica (with its next slice number)
+    // to the queue — release / acquire on the queue entry hands the block over through global memory, possibly to another SM.
+    // Entries are written once (the queue has B x (n_slices - 1) of them, tickets < B are the replicas' first slices), a group only
+    // ever waits for an entry that a running slice will write: no deadlock, no wait while any replica is ready.  The makespan
+    // becomes work / resident groups instead of ceil(waves) x the rollout time.
+    const bool sliced = ra.mode == RES_ROLLOUT && ra.slice_steps > 0;
+    const int n_slices = sliced ? (ra.n_steps + ra.slice_steps - 1) / ra.slice_steps : 1;
+    int k_begin = 0, k_end = ra.n_steps, slice = 0;
+    uint32_t phase = 0;
     if (g.lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
+    }
+    if (!sliced && rep >= s.n_replicas) return;
+  for (;;) {
+    if (sliced) {
+        uint32_t v = 0;
+        if (g.lane == 0) {
+            const uint32_t B = (uint32_t)s.n_replicas;
+            const uint32_t t = atomicAdd(ra.slice_sync, 1u);
+            if (t >= B * (uint32_t)n_slices) v = 0xffffffffu;
+            else if (t < B) v = t + 1u;
+            else
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ra.slice_sync + 2 + (t - B)) : "memory");
+                    if (v) break;
+                    __nanosleep(100);
+                }
+        }
+        v = (uint32_t)g.shfl((int)v, 0);
+        if (v == 0xffffffffu) return;
+        slice = (int)(v >> 24);
+        rep = (int)(v & 0xffffffu) - 1;
+        k_begin = slice * ra.slice_steps;
+        k_end = min(ra.n_steps, k_begin + ra.slice_steps);
+    }
+    int32_t* gstate = a.state + (int64_t)rep * s.SW;
+    if (g.lane == 0) {
+        if (sliced) asm volatile("fence.proxy.async;" ::: "memory");  // (the block in global memory was written by generic stores of another group)
         fence_proxy_async();
         mbar_expect_tx(bar, (uint32_t)s.SW * 4u);
         bulk_g2s(st, gstate, (uint32_t)s.SW * 4u, bar);
     }
     g.sync();
-    while (!mbar_try_wait(bar, 0)) {}
+    while (!mbar_try_wait(bar, phase)) {}
+    phase ^= 1u;
     Replica r = make_replica(s, a, rep, st);
     int32_t* gdec = a.decisions + (int64_t)rep * 8;
     int64_t* gmet = a.metrics + (int64_t)rep * 3;
 
     if (ra.mode == RES_ROLLOUT) {
-        if (g.lane < 8) dslot[g.lane] = gdec[g.lane];  // the decision the previous launch returned (feeds the agent)
+        if (g.lane < 8) dslot[g.lane] = gdec[g.lane];  // the decision the previous launch / slice returned (feeds the agent)
+        if (slice > 0 && g.lane < 3) mslot[g.lane] = gmet[g.lane];
         g.sync();
-        int k = 0;
-        for (; k < ra.n_steps; k++) {
+        int k = k_begin;
+        // (a later slice of a replica whose episode ended in an earlier one: nothing left to do but the trace rows)
+        const bool over = slice > 0 && (dslot[MARO_DEC_STATUS] == MARO_STATUS_FINISHED || dslot[MARO_DEC_STATUS] == MARO_STATUS_DONE);
+        for (; k < k_end && !over; k++) {
             Act4 act = {0, 0, 0, 0};
             int n_act = 0;
             if (ra.policy == RES_POLICY_RANDOM) {
@@ -244,7 +286,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) cim_resident_kernel(const __g
             if (status == MARO_STATUS_FINISHED || status == MARO_STATUS_DONE) { k++; break; }
         }
         if (ra.trace)
-            for (; k < ra.n_steps; k++)
+            for (; k < k_end; k++)
                 if (g.lane < 2)
                     reinterpret_cast<int4*>(ra.trace + ((int64_t)k * s.n_replicas + rep) * 8)[g.lane] = reinterpret_cast<const int4*>(dslot)[g.lane];
         if (g.lane < 2) reinterpret_cast<int4*>(gdec)[g.lane] = reinterpret_cast<const int4*>(dslot)[g.lane];
@@ -370,7 +412,17 @@ __global__ void __launch_bounds__(256, kMinBlocks) cim_resident_kernel(const __g
         const int dp = c[C_DEC_POS];
         a.light[rep] = (c[C_STATE] == ST_AWAIT && dp < 64 && (arr >> dp) != 0) ? 1 : 0;
     }
+    if (!sliced) return;
+    __threadfence();  // (every lane: its part of the block, the decision / metrics rows and the snapshot rows it drained)
+    g.sync();
+    if (g.lane == 0 && slice + 1 < n_slices) {
+        const uint32_t at = atomicAdd(ra.slice_sync + 1, 1u);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ra.slice_sync + 2 + at), "r"(((uint32_t)(slice + 1) << 24) | (uint32_t)(rep + 1)) : "memory");
+    }
+  }
 }
+
+enum { kMaxSlices = 16 };
 
 struct MaroCimEnv : EnvCommon {
     CimShape s;
@@ -391,6 +443,8 @@ struct MaroCimEnv : EnvCommon {
     std::vector<uint8_t> reset_pending;              // per replica: maro_cim_reset arrived while the session was live -> rides on
                                                      // the replica's next command row (or is applied when the session ends)
     uint32_t *h_beat = nullptr, *hd_beat = nullptr;  // heartbeat word, mapped pinned
+    uint32_t* d_slice = nullptr;                     // sliced rollouts: ready queue, 2 + B x (kMaxSlices - 1) words
+    int res_per_sm = 0, n_sm = 0, res_slice_steps = -1;       // resident CTAs per SM; steps per slice (-1 = decide per launch, 0 = never)
     uint32_t* d_exit = nullptr;                      // exit flag of the resident kernel (device), compared with launch_epoch
     uint32_t launch_epoch = 0;
     int buf_full_cap = 1, buf_empty_cap = 1;         // buffer ticks the event pool was sized for (set_topology re-validation)
@@ -787,6 +841,7 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
     memset(e->h_res, 0, (size_t)B * 64);
     CK(cudaMalloc(&e->d_seq, (size_t)B * 4));
     CK(cudaMemset(e->d_seq, 0, (size_t)B * 4));
+    CK(cudaMalloc(&e->d_slice, (2 + (size_t)B * (kMaxSlices - 1)) * 4));
     CK(cudaMalloc(&e->d_exit, 64));
     CK(cudaMemset(e->d_exit, 0, 64));
     CK(cudaHostAlloc(&e->h_beat, 64, cudaHostAllocMapped));
@@ -820,6 +875,9 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
         ResidentArgs ra;
         memset(&ra, 0, sizeof(ra));
         CK(launch_resident(e, a, ra, true, &per_sm));
+        e->res_per_sm = per_sm;
+        e->n_sm = nsm;
+        if (const char* sl = getenv("MARO_B200_RES_SLICE_STEPS")) e->res_slice_steps = atoi(sl);
         const char* se = getenv("MARO_B200_SESSION");
         e->session_ok = (se ? atoi(se) != 0 : true) && (int64_t)per_sm * nsm >= e->res_grid && !s.joint;  // (64-byte result lines)
     }
@@ -848,7 +906,7 @@ int maro_cim_destroy(MaroCimEnv* e) {
     cudaSetDevice(e->device);
     if (e->session_live.load()) session_end(e);
     cudaFree(e->d_tables); cudaFree(e->d_topo); cudaFree(e->d_mt); cudaFree(e->d_light);
-    cudaFree(e->d_seq); cudaFree(e->d_exit);
+    cudaFree(e->d_seq); cudaFree(e->d_exit); cudaFree(e->d_slice);
     if (e->h_cmd) cudaFreeHost(e->h_cmd);
     if (e->h_res) cudaFreeHost(e->h_res);
     if (e->h_beat) cudaFreeHost(e->h_beat);
@@ -1139,7 +1197,32 @@ int maro_cim_rollout_device(MaroCimEnv* e, int32_t policy, uint32_t seed, uint32
     memset(&ra, 0, sizeof(ra));
     ra.mode = RES_ROLLOUT; ra.spread = e->res_spread; ra.n_steps = n_steps; ra.policy = policy; ra.seed = seed;
     ra.replica_base = replica_base; ra.trace = d_trace;
-    CK(launch_resident(e, a, ra));
+    // Sliced launch when the grid does not fit the GPU at once and the last wave would be mostly empty (>= 10 % of the launch
+    // lost to it): resident lane groups pull (slice, replica) tickets instead (cim_resident_kernel).
+    const int capacity = e->res_per_sm * e->n_sm;
+    int slice_steps = 0;
+    // (one replica per warp only: lane groups that share a warp would serialise once they run different slices.  Measured on
+    // BASELINE config #4, 1 024 replicas = 171 CTAs on 148 SMs: 46.0 -> 32.4 us per batched env-step; 4 / 8 / 16 steps per slice
+    // within 3 % of each other)
+    const bool warp_per_replica = e->res_spread || e->lanes == 32;
+    if (e->res_slice_steps > 0) slice_steps = e->res_slice_steps;  // (forced: tests, A/B)
+    else if (e->res_slice_steps < 0 && capacity > 0 && e->res_grid > capacity && n_steps >= 16) {
+        const int waves = (e->res_grid + capacity - 1) / capacity;
+        if ((int64_t)waves * capacity * 10 >= (int64_t)e->res_grid * 11) slice_steps = 8;
+    }
+    if (!warp_per_replica) slice_steps = 0;
+    if (slice_steps) slice_steps = std::max(slice_steps, (n_steps + kMaxSlices - 1) / kMaxSlices);
+    if (slice_steps >= n_steps || e->B >= (1 << 24) - 1) slice_steps = 0;
+    const int full_grid = e->res_grid;
+    if (slice_steps) {
+        const int n_slices = (n_steps + slice_steps - 1) / slice_steps;
+        CK(cudaMemsetAsync(e->d_slice, 0, (2 + (size_t)e->B * (n_slices - 1)) * 4, e->stream));
+        ra.slice_steps = slice_steps; ra.slice_sync = e->d_slice;
+        e->res_grid = std::min(full_grid, std::max(1, capacity));
+    }
+    cudaError_t err = launch_resident(e, a, ra);
+    e->res_grid = full_grid;
+    CK(err);
     return 0;
 }
 

@@ -89,6 +89,9 @@ int emul_read_snapshot(Emul* e, int rep, int frame, int32_t* out) {
     return 1;
 }
 int emul_tick(Emul* e, int rep) { return e->state[(size_t)rep * e->s.SW + e->s.FWp + C_TICK]; }
+#ifdef MARO_TRACK_QPEAK
+int maro_emul_qpeak = 0;
+#endif
 void emul_counters(Emul* e, int rep, int64_t* out) { memcpy(out, e->state.data() + (size_t)rep * e->s.SW + e->s.FWp + C_NSTEPS_LO, 32); }
 }
 

@@ -26,12 +26,13 @@ def _ring_rows(env, replica, topo):
     return {int(f): env.snapshot_row(int(f), replica) for f in env.snapshot_frames(replica)}
 
 
+@pytest.mark.parametrize("slice_steps", [None, 3])            # 3: sliced launches forced (lane groups pull (slice, replica) tickets)
 @pytest.mark.parametrize("topology,ticks,B,chunks", [
     ("toy.4p_ssdd_l0.0", 200, 256, [1, 1, 7, 50, 3, 1000]),
     ("toy.4p_ssdd_l0.8", 120, 96, [5, 40, 1000]),          # general kernel: MT19937 order / buffer noise
     ("global_trade.22p_l0.8", 40, 24, [3, 1000]),           # one warp = one replica, 30 KB blocks
 ])
-def test_rollout_matches_step_loop_and_oracle(topology, ticks, B, chunks):
+def test_rollout_matches_step_loop_and_oracle(topology, ticks, B, chunks, slice_steps, monkeypatch):
     import torch
 
     from oracle.cim_oracle import CimOracle, policy_random
@@ -57,6 +58,8 @@ def test_rollout_matches_step_loop_and_oracle(topology, ticks, B, chunks):
     done_at = np.argmax(want[:, :, 6] == 1, axis=0)  # per replica: the step that returned its DONE row
     want_met = np.stack([mets[done_at[i]][i] for i in range(B)])
     # ---- fused rollouts on a second handle, uneven chunk sizes
+    if slice_steps:
+        monkeypatch.setenv("MARO_B200_RES_SLICE_STEPS", str(slice_steps))
     b = _batch(topo, B)
     b.set_stream(s)
     dec2 = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
@@ -104,6 +107,44 @@ def test_rollout_matches_step_loop_and_oracle(topology, ticks, B, chunks):
         assert np.array_equal(b.read_frame(i), o.frame())
     a.close()
     b.close()
+
+
+def test_sliced_rollouts_of_a_grid_larger_than_the_gpu_equal_whole_rollouts(monkeypatch):
+    """BASELINE config #4 at 1 024 replicas: 171 CTAs of six 37 KB blocks on 148 SMs.  The launch slices itself (resident lane
+    groups pull (slice, replica) tickets, a replica's slices hand the block over through global memory, possibly across SMs);
+    results must equal the unsliced launch bit for bit — decisions, metrics, counters, frames, snapshot rings."""
+    import torch
+
+    topo, B, seed = _topo("global_trade.22p_l0.8", 60), 1024, 3
+    s = torch.cuda.current_stream().cuda_stream
+    out = []
+    for forced in ("0", None):
+        if forced is None:
+            monkeypatch.delenv("MARO_B200_RES_SLICE_STEPS", raising=False)
+        else:
+            monkeypatch.setenv("MARO_B200_RES_SLICE_STEPS", forced)
+        env = _batch(topo, B)
+        env.set_stream(s)
+        dec = torch.zeros((B, 8), dtype=torch.int32, device="cuda")
+        met = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+        traces = []
+        for _ in range(40):
+            trace = torch.full((32, B, 8), -7, dtype=torch.int32, device="cuda")
+            env.rollout_device(dec.data_ptr(), met.data_ptr(), 32, 1, seed, 0, trace.data_ptr())
+            traces.append(trace.cpu().numpy())
+            if (dec.cpu().numpy()[:, 6] != 0).all():
+                break
+        assert (dec.cpu().numpy()[:, 6] != 0).all()
+        out.append((np.concatenate(traces), dec.cpu().numpy(), met.cpu().numpy(), env.counters(), env.ticks(),
+                    [env.read_frame(i) for i in range(0, B, 37)], [_ring_rows(env, i, topo) for i in (0, 500, B - 1)]))
+        env.close()
+    whole, sliced = out
+    for k in range(5):
+        assert np.array_equal(whole[k], sliced[k]), k
+    for fa, fb in zip(whole[5], sliced[5]):
+        assert np.array_equal(fa, fb)
+    for ra, rb in zip(whole[6], sliced[6]):
+        assert ra.keys() == rb.keys() and all(np.array_equal(ra[f], rb[f]) for f in ra)
 
 
 def _host_policy(dec, seed, base, step):
