@@ -255,6 +255,10 @@ int maro_cim_rollout_device(MaroCimEnv* env, int32_t policy, uint32_t seed, uint
 int32_t maro_cim_rl_state_dim(MaroCimEnv* env, int32_t look_back, int32_t n_port_attrs, int32_t n_vessel_attrs);
 int maro_cim_rl_state_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
                              int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out);
+/* the same state rounded to float32 (what the example's networks take: torch.from_numpy(states).float()), written straight into
+ * the caller's [n_replicas][dim] float buffer — saves the conversion launch inside a collection loop */
+int maro_cim_rl_state_f32_device(MaroCimEnv* env, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
+                                 int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, float* d_out);
 /* Action translation (env_sampler.py:38-64) for every replica: model action index m (into d_action_space, n doubles; the
  * example uses [(i - 10) / 10 for i in range(21)]) and the decision row -> action row {vessel, port, quantity, type}:
  *   m < n / 2:  LOAD       min(round(|space[m]| * scope.load), vessel.remaining_space if finite_vessel_space)

@@ -162,11 +162,12 @@ class CimBatch:
     def rl_state_dim(self, look_back: int, n_port_attrs: int, n_vessel_attrs: int) -> int:
         return _native.lib().maro_cim_rl_state_dim(self._h, look_back, n_port_attrs, n_vessel_attrs)
 
-    def rl_state_device(self, d_decisions: int, look_back: int, port_attrs, vessel_attrs, d_out: int):
+    def rl_state_device(self, d_decisions: int, look_back: int, port_attrs, vessel_attrs, d_out: int, f32: bool = False):
+        """d_out: [n_replicas][rl_state_dim] float64 (or float32 with ``f32``) device buffer"""
         pa = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id("ports", a) for a in port_attrs], np.int32)
         va = np.ascontiguousarray([a if isinstance(a, (int, np.integer)) else self.attr_id("vessels", a) for a in vessel_attrs], np.int32)
-        _native.check(_native.lib().maro_cim_rl_state_device(self._h, d_decisions, look_back, pa.ctypes.data, len(pa),
-                                                             va.ctypes.data, len(va), d_out))
+        fn = _native.lib().maro_cim_rl_state_f32_device if f32 else _native.lib().maro_cim_rl_state_device
+        _native.check(fn(self._h, d_decisions, look_back, pa.ctypes.data, len(pa), va.ctypes.data, len(va), d_out))
 
     def rl_action_device(self, d_decisions: int, d_model_actions: int, d_action_space: int, n_action_space: int,
                          finite_vessel_space: bool, has_early_discharge: bool, d_actions: int):

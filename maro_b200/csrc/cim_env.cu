@@ -474,6 +474,7 @@ struct ShapeArgs {
     int o_fut, fut;            // future_stop_list: word offset, slots per vessel
     int P, V;
     double* state_out;         // [B][look_back_ticks * n_ports_per_state * npa + nva]
+    float* state_out_f32;      // the same rounded to float32 (what the example feeds its networks), when state_out is null
     // reward
     const int32_t* ticks;      // [B] tick of the action
     const int32_t* ports;      // [B] port that acted
@@ -529,7 +530,8 @@ __global__ void cim_rl_state_kernel(const __grid_constant__ ShapeArgs q) {
                 }
             }
         }
-        q.state_out[i] = v;
+        if (q.state_out) q.state_out[i] = v;
+        else q.state_out_f32[i] = (float)v;
     }
 }
 
@@ -1287,10 +1289,10 @@ int32_t maro_cim_rl_state_dim(MaroCimEnv* e, int32_t look_back, int32_t n_port_a
     return (look_back - 1) * (1 + e->s.fut) * n_port_attrs + n_vessel_attrs;
 }
 
-int maro_cim_rl_state_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
-                             int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out) {
-    if (!e || !d_decisions || !d_out || !port_attrs || !vessel_attrs || look_back < 2 || n_port_attrs < 1 || n_port_attrs > 16 ||
-        n_vessel_attrs < 0 || n_vessel_attrs > 16)
+static int rl_state_launch(MaroCimEnv* e, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs, int32_t n_port_attrs,
+                           const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out, float* d_out_f32) {
+    if (!e || !d_decisions || (!d_out && !d_out_f32) || !port_attrs || !vessel_attrs || look_back < 2 || n_port_attrs < 1 ||
+        n_port_attrs > 16 || n_vessel_attrs < 0 || n_vessel_attrs > 16)
         return fail("maro_cim_rl_state_device: bad arguments");
     CK(cudaSetDevice(e->device));
     END_SESSION(e);
@@ -1307,12 +1309,24 @@ int maro_cim_rl_state_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t 
         q.vessel_attr_off[i] = e->attrs[1][a].off; q.vessel_attr_isf[i] = e->attrs[1][a].isf;
     }
     q.decisions = d_decisions; q.look_back_ticks = look_back - 1; q.n_ports_per_state = 1 + e->s.fut;
-    q.npa = n_port_attrs; q.nva = n_vessel_attrs; q.state_out = d_out;
+    q.npa = n_port_attrs; q.nva = n_vessel_attrs; q.state_out = d_out; q.state_out_f32 = d_out_f32;
     const int64_t total = (int64_t)e->B * maro_cim_rl_state_dim(e, look_back, n_port_attrs, n_vessel_attrs);
     int threads = 256, blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
     cim_rl_state_kernel<<<blocks, threads, 0, e->stream>>>(q);
     CK(cudaGetLastError());
     return 0;
+}
+
+int maro_cim_rl_state_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
+                             int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, double* d_out) {
+    if (!d_out) return fail("maro_cim_rl_state_device: bad arguments");
+    return rl_state_launch(e, d_decisions, look_back, port_attrs, n_port_attrs, vessel_attrs, n_vessel_attrs, d_out, nullptr);
+}
+
+int maro_cim_rl_state_f32_device(MaroCimEnv* e, const int32_t* d_decisions, int32_t look_back, const int32_t* port_attrs,
+                                 int32_t n_port_attrs, const int32_t* vessel_attrs, int32_t n_vessel_attrs, float* d_out) {
+    if (!d_out) return fail("maro_cim_rl_state_f32_device: bad arguments");
+    return rl_state_launch(e, d_decisions, look_back, port_attrs, n_port_attrs, vessel_attrs, n_vessel_attrs, nullptr, d_out);
 }
 
 int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const int32_t* d_model_actions, const double* d_action_space,

@@ -89,14 +89,14 @@ class BatchedCimEnvSampler:
         self.device = torch.device("cuda", batch.device)
         batch.set_stream(torch.cuda.current_stream(self.device).cuda_stream)  # step kernels and torch ops share one stream
         B, D = batch.n_replicas, self.shaper.state_dim
-        self._dec = torch.zeros((B, 8), dtype=torch.int32, device=self.device)
         self._met = torch.zeros((B, 3), dtype=torch.int64, device=self.device)
         self.n_steps = episode_step_bound(batch.topologies, batch.start_tick)
         K = self.graph_chunk
-        # one chunk of recorded columns (static addresses: the loop body may live in a CUDA graph)
-        self._c_dec = torch.zeros((K, B, 8), dtype=torch.int32, device=self.device)
+        # one chunk of recorded columns (static addresses: the loop body may live in a CUDA graph).  Decision rows: step k reads row
+        # k and the step kernel writes row k + 1 directly, so recording them costs no launch; row 0 is the chunk's input.
+        self._c_dec = torch.zeros((K + 1, B, 8), dtype=torch.int32, device=self.device)
         self._c_act = torch.zeros((K, B), dtype=torch.int32, device=self.device)
-        self._c_state = torch.zeros((K, B, D), dtype=torch.float32, device=self.device) if store_states else None
+        self._c_state = torch.zeros((K if store_states else 1, B, D), dtype=torch.float32, device=self.device)
         self._final_met = torch.zeros((B, 3), dtype=torch.int64, device=self.device)
         self._graph = None
         self._warmed_up = False
@@ -105,18 +105,19 @@ class BatchedCimEnvSampler:
 
     # ------------------------------------------------------------------------------------------------ device loop
     def _body(self, k: int):
-        """one env-step of every replica: state -> policy -> action -> step; records the decision it answered in slot k"""
+        """one env-step of every replica: state -> policy -> action -> step; slot k records the decision it answered.
+        Launches per step besides the policy's own: state kernel (float32, straight into the record), one copy (policy output ->
+        int32 record), action kernel, step kernel, one elementwise max."""
         torch, sh, env = self._torch, self.shaper, self.batch
-        self._c_dec[k].copy_(self._dec)
-        s = sh.states(self._dec).to(torch.float32)
-        m = (self.policy(s, self._dec) if self.policy_takes_decisions else self.policy(s)).to(torch.int32).contiguous()
-        self._c_act[k].copy_(m)
-        if self._c_state is not None:
-            self._c_state[k].copy_(s)
-        actions = sh.env_actions(self._dec, m)
-        env.step_device(self._dec.data_ptr(), self._met.data_ptr(), actions.data_ptr())
-        # the episode's metrics come with the DONE row; a replica stepped past it answers all-zero FINISHED rows
-        self._final_met.copy_(torch.where((self._dec[:, 6] == 1).unsqueeze(1), self._met, self._final_met))
+        dec = self._c_dec[k]
+        s = sh.states(dec, out=self._c_state[k if self.store_states else 0])
+        m = self.policy(s, dec) if self.policy_takes_decisions else self.policy(s)
+        self._c_act[k].copy_(m)  # (converts to int32)
+        actions = sh.env_actions(dec, self._c_act[k])
+        env.step_device(self._c_dec[k + 1].data_ptr(), self._met.data_ptr(), actions.data_ptr())
+        # the episode's metrics come with the DONE row; a replica stepped past it answers all-zero FINISHED rows.  The three
+        # metrics are non-negative running totals, so the value at DONE is the maximum over the episode.
+        torch.maximum(self._final_met, self._met, out=self._final_met)
 
     def _run_chunk(self, n: int):
         torch = self._torch
@@ -161,12 +162,11 @@ class BatchedCimEnvSampler:
         T = self.n_steps if max_steps is None else min(int(max_steps), self.n_steps)
         K = self.graph_chunk
         env.reset()
-        self._dec.zero_()
-        env.step_device(self._dec.data_ptr(), self._met.data_ptr())  # generator start: first decisions
+        self._final_met.zero_()
+        env.step_device(self._c_dec[0].data_ptr(), self._met.data_ptr())  # generator start: first decisions
         decs = torch.empty((T, B, 8), dtype=torch.int32, device=self.device)
         acts = torch.empty((T, B), dtype=torch.int32, device=self.device)
         states = torch.empty((T, B, self.shaper.state_dim), dtype=torch.float32, device=self.device) if self.store_states else None
-        self._final_met.zero_()
         t = 0
         while t < T:
             n = min(K, T - t)
@@ -175,6 +175,7 @@ class BatchedCimEnvSampler:
             acts[t:t + n].copy_(self._c_act[:n])
             if states is not None:
                 states[t:t + n].copy_(self._c_state[:n])
+            self._c_dec[0].copy_(self._c_dec[n])  # the next chunk's input
             t += n
         valid = decs[:, :, 6] == 0
         ticks = torch.where(valid, decs[:, :, 0], torch.full_like(decs[:, :, 0], -1)).contiguous()

@@ -45,9 +45,15 @@ class CimShaper:
         self.finite_vessel_space, self.has_early_discharge = bool(finite_vessel_space), bool(has_early_discharge)
         self._actions = torch.zeros((B, batch.max_actions, 4), dtype=torch.int32, device=dev)
 
-    def states(self, decisions):
-        """decisions: int32 CUDA tensor [B][8] (MARO_DEC_* rows of the last step) -> float64 CUDA tensor [B][state_dim]."""
-        assert decisions.is_cuda and decisions.dtype == self._torch.int32 and decisions.is_contiguous()
+    def states(self, decisions, out=None):
+        """decisions: int32 CUDA tensor [B][8] (MARO_DEC_* rows of the last step) -> float64 CUDA tensor [B][state_dim]; with
+        ``out`` (contiguous float32 CUDA tensor [B][state_dim]) the float32-rounded state is written there instead."""
+        torch = self._torch
+        assert decisions.is_cuda and decisions.dtype == torch.int32 and decisions.is_contiguous()
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == tuple(self._state.shape)
+            self.batch.rl_state_device(decisions.data_ptr(), self.look_back, self._pa, self._va, out.data_ptr(), f32=True)
+            return out
         self.batch.rl_state_device(decisions.data_ptr(), self.look_back, self._pa, self._va, self._state.data_ptr())
         return self._state
 

@@ -73,6 +73,8 @@ def test_device_shaping_at_batch_size_matches_restatement():
         env.step_device(dec.data_ptr(), met.data_ptr(), act.data_ptr())
     d = dec.cpu().numpy()
     states = shaper.states(dec).cpu().numpy()
+    s32 = torch.full(states.shape, -1.0, dtype=torch.float32, device="cuda")
+    assert shaper.states(dec, out=s32) is s32 and np.array_equal(s32.cpu().numpy(), states.astype(np.float32))  # maro_cim_rl_state_f32_device
     ticks = torch.tensor(np.maximum(d[:, 0] - 120, 0), dtype=torch.int32, device="cuda")
     ports = torch.tensor(d[:, 1] % topo.n_ports, dtype=torch.int32, device="cuda")
     rewards = shaper.rewards(ticks, ports).cpu().numpy()
