@@ -43,6 +43,7 @@ struct BikeShape {
     int n_filters, filter_type[4], filter_num[4], filter_windows[4];
     int drops;  // some filter can drop a neighbour (num < S - 1): the chain has to be run (otherwise it only permutes a dict)
     int scope_off, tw_windows;
+    int o_scratch;  // 4 x S words of action-scope scratch inside the replica block (word offset from the frame)
 };
 
 struct BikeReplica {
@@ -106,23 +107,71 @@ MARO_DEV uint32_t bike_mt_next(const BikeReplica& r) {
     r.rng[624] = (uint32_t)idx;
     return mt_temper(y);
 }
-MARO_DEV double bike_rk_double(const BikeReplica& r) {
-    uint32_t a = bike_mt_next(r) >> 5, b = bike_mt_next(r) >> 6;
-    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
-}
+// One iteration of legacy_gauss's rejection loop takes four words.  The stream position stays a multiple of four (624 = 4 x 156;
+// seeding leaves it at 624), so an iteration never straddles a regeneration: either four loads that do not depend on each other
+// (one L2 round trip on the leader's chain instead of four position-load -> word-load pairs), or the regeneration first.
 MARO_DEV double bike_gauss(const BikeReplica& r) {
+    // header words 624..627 = position | has_gauss | cached gauss (double), one 128-bit load
+#ifdef MARO_HOST_EMULATION
+    const uint32_t h0 = r.rng[624], h1 = r.rng[625], h2 = r.rng[626], h3 = r.rng[627];
+#else
+    const uint4 hv = *reinterpret_cast<const uint4*>(r.rng + 624);
+    const uint32_t h0 = hv.x, h1 = hv.y, h2 = hv.z, h3 = hv.w;
+#endif
     double* cache = reinterpret_cast<double*>(r.rng + 626);
-    if (r.rng[625]) { r.rng[625] = 0; double t = *cache; *cache = 0.0; return t; }
+    if (h1) {
+        r.rng[625] = 0;
+        *cache = 0.0;
+        const uint64_t bits = ((uint64_t)h3 << 32) | h2;
+        double t;
+        memcpy(&t, &bits, 8);
+        return t;
+    }
+    int idx = (int)h0;
     double f, x1, x2, r2;
     do {
-        x1 = 2.0 * bike_rk_double(r) - 1.0;
-        x2 = 2.0 * bike_rk_double(r) - 1.0;
+        uint32_t y0, y1, y2, y3;
+        if ((idx & 3) == 0 && idx + 4 <= 624) {
+            const uint32_t* mt = r.rng + idx;
+            y0 = mt[0]; y1 = mt[1]; y2 = mt[2]; y3 = mt[3];
+            y0 = mt_temper(y0); y1 = mt_temper(y1); y2 = mt_temper(y2); y3 = mt_temper(y3);
+            idx += 4;
+        } else {  // regeneration due (or a foreign stream position): word by word through the generic path
+            r.rng[624] = (uint32_t)idx;
+            y0 = bike_mt_next(r); y1 = bike_mt_next(r); y2 = bike_mt_next(r); y3 = bike_mt_next(r);
+            idx = (int)r.rng[624];
+        }
+        x1 = 2.0 * (((double)(y0 >> 5) * 67108864.0 + (double)(y1 >> 6)) / 9007199254740992.0) - 1.0;
+        x2 = 2.0 * (((double)(y2 >> 5) * 67108864.0 + (double)(y3 >> 6)) / 9007199254740992.0) - 1.0;
         r2 = x1 * x1 + x2 * x2;
     } while (r2 >= 1.0 || r2 == 0.0);
     f = sqrt(-2.0 * log(r2) / r2);
     *cache = f * x1;
+    r.rng[624] = (uint32_t)idx;
     r.rng[625] = 1;
     return f * x2;
+}
+
+// the regeneration of the 624 state words by all lanes of the group (same recurrence, G words at a time: the first 227 words mix
+// old words only, later ones reach back 227 words to new ones — further than G), when the stream stands exactly at its end
+template <int G>
+MARO_DEV void bike_mt_regenerate(const Grp<G>& g, const BikeReplica& r) {
+    if (r.rng[624] != 624u) return;  // (group-uniform: every lane reads the same word)
+    uint32_t* mt = r.rng;
+    g.sync();
+    for (int base = 0; base < 623; base += G) {
+        const int kk = base + g.lane;
+        uint32_t nv = 0;
+        if (kk < 623) nv = mt_mix(mt[kk], mt[kk + 1], kk < 227 ? mt[kk + 397] : mt[kk - 227]);
+        g.sync();  // every lane has read its (old) right-hand neighbour before anyone stores
+        if (kk < 623) mt[kk] = nv;
+        g.sync();
+    }
+    if (g.lane == 0) {
+        mt[623] = mt_mix(mt[623], mt[0], mt[396]);
+        r.rng[624] = 0;
+    }
+    g.sync();
 }
 
 // BikeDecisionStrategy.move_to_neighbor (decision_strategy.py:295-343)
@@ -194,6 +243,7 @@ MARO_DEV void bike_on_actions(const BikeShape& s, const Grp<G>& g, const BikeRep
     // keeps its tail pointer on the removed event (EventLinkedList._extract_sub_events, event_linked_list.py:86-92, does not
     // update `_tail`), so events appended to this tick's list from now on — deliveries with transfer time 0 — are lost.
     const bool tail_lost = (*(bq_bucket(s, r) + (tick & (s.QH - 1))) & 0xffff) == Q_NIL;
+    if (n > 0) bike_mt_regenerate(g, r);  // (a stream that stands at its end: regenerate with all lanes before the leader draws)
     for (int i = 0; i < n; i++) {
         int from = g.shfl(mine.v, i), to = g.shfl(mine.p, i), number = g.shfl(mine.qty, i);
         if (g.lane != 0) continue;
@@ -237,7 +287,7 @@ MARO_DEV int bike_action_scope(const BikeShape& s, const BikeReplica& r, int sta
     int32_t* area = reinterpret_cast<int32_t*>(r.rng) + s.scope_off;
     int32_t* tw_frame = area;
     int32_t* tw_cache = area + s.tw_windows;
-    int32_t* idx = tw_cache + s.tw_windows * S;
+    int32_t* idx = r.f + s.o_scratch;  // (shared memory, behind the event queue)
     int32_t* val = idx + S;
     int32_t* key = val + S;
     int32_t* res = key + S;  // value per station, -1 = not in the scope

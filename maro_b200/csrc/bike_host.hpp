@@ -46,7 +46,8 @@ inline int bike_compute_shape_and_tables(const MaroBikeTopology& t, const MaroCi
     int qn = cfg->queue_capacity > 0 ? cfg->queue_capacity
                                      : std::min(4096, std::max(32, max_per_tick * std::min(max_dur + 1, 64) + 3 * S + 8));
     s.QN = round_up(qn, 4);
-    s.SW = round_up(s.FWp + s.CWp + s.QN * 2 + s.QH + s.QN, 4);
+    s.o_scratch = round_up(s.FWp + s.CWp + s.QN * 2 + s.QH + s.QN, 4);
+    s.SW = s.o_scratch + round_up(4 * S, 4);  // (+ the action-scope scratch: it used to sit in the per-replica global block)
     s.DW = MARO_BIKE_DEC_HEAD + 2 * S;
     // action-scope filter chain
     if (t.n_filters < 0 || t.n_filters > MARO_BIKE_MAX_FILTERS) return 1;
