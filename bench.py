@@ -936,7 +936,9 @@ def run_ours(args, rank, local_rank, world):
             ev[2].record(stream)
         pos["i"] += 1
 
-    fused = bike and not args.launch_per_step  # citi_bike: fused rollouts (maro_bike_rollout_device), like the CIM arm
+    # citi_bike / vm_scheduling: fused rollouts (maro_bike_rollout_device / maro_vm_rollout_device: the scenario's rule-based agent as
+    # a device callback), like the CIM arm
+    fused = (bike or vm) and not args.launch_per_step
     launches = 2 * args.steps
 
     def timed_rollouts(total_steps, chunk, timed):
@@ -1169,14 +1171,15 @@ def run_ours(args, rank, local_rank, world):
             "ticks_per_s": g_ticks / (total_ms / 1000.0), "events_per_s": g_events / (total_ms / 1000.0),
             "wall_ms": wall_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "vm_step_kernel" if vm else ("bike_step_kernel" if bike else "cim_step_kernel"), "bytes_per_env_step": bytes_per_step,
+                         "traffic": traffic, "kernel": ("vm_rollout_kernel" if fused else "vm_step_kernel") if vm else ("bike_step_kernel" if bike else "cim_step_kernel"), "bytes_per_env_step": bytes_per_step,
                          "n_snap": n_snap, "n_ev": n_ev, "kernel_us": 1000.0 * kernel_ms / args.steps,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "clocks": clocks,
             "gpu_launches": launches,
         }
         if fused:
-            line["config"]["mode"] = f"fused rollouts, {chunk} env-steps per launch, greedy agent as a device callback"
+            line["config"]["mode"] = (f"fused rollouts, {chunk} env-steps per launch, "
+                                      f"{'best-fit' if vm else 'greedy'} agent as a device callback")
         if e2e:
             line["e2e"] = {"value": g_e2e_steps / (e2e_ms / 1000.0), "unit": "env-steps/s",
                            "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": B * (dec_words * 4 + met_words * 8) + (B * topo.n_pm * 16 if vm and args.vm_query_agent else 0),

@@ -468,6 +468,10 @@ int maro_vm_counters(MaroVmEnv* env, int64_t* out);
 int maro_vm_snapshot_frames(MaroVmEnv* env, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out);
 /* Agent helper for bench.py: best fit (examples/vm_scheduling/rule_based_algorithm/best_fit.py:27-64). */
 int maro_vm_best_fit_policy_device(MaroVmEnv* env, const int32_t* d_decisions, int32_t* d_actions);
+/* Fused rollouts (device-resident use): n_steps env-steps per launch, the best-fit agent above evaluated between the steps as a
+ * device callback; d_decisions / d_metrics carry the last row across launches like maro_cim_rollout_device (a replica stops at
+ * its DONE row and keeps the final metrics; the first step after a reset ignores its action, core.py:128). */
+int maro_vm_rollout_device(MaroVmEnv* env, int32_t n_steps, int32_t* d_decisions, int64_t* d_metrics);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ EXPORTS = (
     "maro_vm_create", "maro_vm_destroy", "maro_vm_set_stream", "maro_vm_decision_words", "maro_vm_step",
     "maro_vm_step_device", "maro_vm_pinned_buffers", "maro_vm_step_pinned", "maro_vm_reset", "maro_vm_query",
     "maro_vm_attr_id", "maro_vm_attr_slots", "maro_vm_read_frame", "maro_vm_frame_words", "maro_vm_ticks",
-    "maro_vm_counters", "maro_vm_snapshot_frames", "maro_vm_best_fit_policy_device",
+    "maro_vm_counters", "maro_vm_snapshot_frames", "maro_vm_best_fit_policy_device", "maro_vm_rollout_device",
 )
 
 
@@ -137,6 +137,7 @@ def lib():
         getattr(L, pre + "_counters").argtypes = [vp, vp]
         getattr(L, pre + "_snapshot_frames").argtypes = [vp, i32, vp, i32, vp]
     L.maro_vm_best_fit_policy_device.argtypes = [vp, vp, vp]
+    L.maro_vm_rollout_device.argtypes = [vp, i32, vp, vp]
     if L.maro_abi_version() != _abi.ABI_VERSION:
         raise NativeLibraryError("libmaro_b200.so ABI version mismatch; rebuild")
     _lib = L

@@ -564,6 +564,11 @@ class VmBatch(BikeBatch):
     def best_fit_policy_device(self, d_decisions: int, d_actions: int):
         _native.check(self._f("best_fit_policy_device")(self._h, d_decisions, d_actions))
 
+    def rollout_device(self, d_decisions: int, d_metrics: int, n_steps: int):
+        """``n_steps`` env-steps fused into one launch with the best-fit agent as a device callback (maro_vm_rollout_device);
+        d_decisions [B][dec_words] int32 / d_metrics [B][16] int64 carry the last row across launches."""
+        _native.check(_native.lib().maro_vm_rollout_device(self._h, int(n_steps), d_decisions, d_metrics))
+
     def snapshot_row(self, frame_index: int, replica: int = 0):
         if frame_index not in set(self.snapshot_frames(replica).tolist()):
             return None

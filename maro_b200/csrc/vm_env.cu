@@ -15,6 +15,7 @@ struct VmArgs {
     const int32_t* n_actions;
     int32_t* decisions;
     int64_t* metrics;
+    int n_steps;  // vm_rollout_kernel: env-steps fused into the launch
 };
 
 // One warp = one replica; the replica block stays in global memory (L2), see vm_core.cuh.
@@ -33,6 +34,61 @@ __global__ void __launch_bounds__(kWarps * 32) vm_step_kernel(const __grid_const
         const int n_act = a.actions ? (a.n_actions ? min(max(a.n_actions[rep], 0), s.max_actions) : 1) : 0;
         vm_replica_step<32>(s, g, r, a.actions ? a.actions + (int64_t)rep * s.max_actions * 4 : nullptr, n_act,
                             a.decisions + (int64_t)rep * s.DW, a.metrics + (int64_t)rep * MARO_VM_METRIC_WORDS, scratch);
+    }
+}
+
+// Fused rollouts: `n_steps` env-steps per launch with the rule-based best-fit agent of the reference's example as a device callback
+// (examples/vm_scheduling/rule_based_algorithm/best_fit.py:27-64, metric "remaining_cpu_cores": among the valid PMs the one with
+// the fewest remaining cores, first minimum wins — read from the decision row's remaining-cores extension).  The decision row, the
+// metrics and the action stay in shared memory between the steps; the replica's lines of the state block stay in this SM's L1.
+// per warp: scratch (2 N doubles, padded to 16 B) | metrics slot | action row | decision row
+__host__ __device__ inline size_t vm_rollout_scratch_bytes(int n_pm) { return ((size_t)2 * n_pm * sizeof(double) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t vm_rollout_warp_bytes(int n_pm, int dec_words) {
+    return vm_rollout_scratch_bytes(n_pm) + MARO_VM_METRIC_WORDS * 8 + 16 + (((size_t)dec_words * 4 + 15) & ~(size_t)15);
+}
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) vm_rollout_kernel(const __grid_constant__ VmShape s, const __grid_constant__ VmArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5;
+    const Grp<32> g(threadIdx.x & 31);
+    const size_t scratch_bytes = vm_rollout_scratch_bytes(s.N), per_warp = vm_rollout_warp_bytes(s.N, s.DW);
+    unsigned char* mine = smem_raw + (size_t)wid * per_warp;
+    double* scratch = reinterpret_cast<double*>(mine);
+    int64_t* mslot = reinterpret_cast<int64_t*>(mine + scratch_bytes);
+    int32_t* aslot = reinterpret_cast<int32_t*>(mslot + MARO_VM_METRIC_WORDS);
+    int32_t* dslot = aslot + 4;
+    for (int rep = blockIdx.x * kWarps + wid; rep < s.n_replicas; rep += gridDim.x * kWarps) {
+        VmReplica r = vm_replica_at(s, a.state, a.tables, a.snap, a.snap_frame, (size_t)rep);
+        int32_t* gdec = a.decisions + (int64_t)rep * s.DW;
+        int64_t* gmet = a.metrics + (int64_t)rep * MARO_VM_METRIC_WORDS;
+        for (int i = g.lane; i < s.DW; i += 32) dslot[i] = gdec[i];  // the decision the previous launch returned (feeds the agent)
+        if (g.lane < MARO_VM_METRIC_WORDS) mslot[g.lane] = gmet[g.lane];
+        g.sync();
+        for (int k = 0; k < a.n_steps; k++) {
+            const int n = dslot[MARO_VM_DEC_STATUS] == MARO_STATUS_DECISION ? dslot[MARO_VM_DEC_N_VALID] : 0;
+            const int ext = dslot[MARO_VM_DEC_EXT_OFFSET];
+            long long best = 0x7fffffffffffffffLL;
+            for (int j = g.lane; j < n; j += 32) {
+                const long long key = (long long)dslot[ext + j] * 4294967296LL + j;
+                best = key < best ? key : best;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other < best ? other : best;
+            }
+            if (g.lane == 0) {
+                const int4 row = n > 0 ? make_int4(dslot[MARO_VM_DEC_VM_ID], MARO_VM_ACTION_ALLOCATE, dslot[MARO_VM_DEC_HEAD + (int)(best & 0xffffffffLL)], 0)
+                                       : make_int4(-1, -1, 0, 0);
+                *reinterpret_cast<int4*>(aslot) = row;
+            }
+            g.sync();
+            vm_replica_step<32>(s, g, r, aslot, 1, dslot, mslot, scratch);
+            g.sync();
+            if (dslot[MARO_VM_DEC_STATUS] != MARO_STATUS_DECISION) break;  // DONE (final metrics stay in the slot) / FINISHED / error
+        }
+        for (int i = g.lane; i < s.DW; i += 32) gdec[i] = dslot[i];
+        if (g.lane < MARO_VM_METRIC_WORDS) gmet[g.lane] = mslot[g.lane];
+        g.sync();
     }
 }
 
@@ -246,6 +302,25 @@ int maro_vm_counters(MaroVmEnv* e, int64_t* out) { return common_counters(e, out
 int maro_vm_snapshot_frames(MaroVmEnv* e, int32_t replica, int32_t* out, int32_t cap, int32_t* n_out) {
     return common_snapshot_frames(e, replica, out, cap, n_out);
 }
+int maro_vm_rollout_device(MaroVmEnv* e, int32_t n_steps, int32_t* d_decisions, int64_t* d_metrics) {
+    if (!e || !d_decisions || !d_metrics || n_steps < 1) return fail("maro_vm_rollout_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    VmArgs a = vm_base_args(e);
+    a.decisions = d_decisions; a.metrics = d_metrics; a.n_steps = n_steps;
+    const int w = e->warps_per_cta;
+    const size_t smem = (size_t)w * vm_rollout_warp_bytes(e->s.N, e->s.DW);
+    auto go = [&](auto kernel) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+        }
+        kernel<<<e->grid, w * 32, smem, e->stream>>>(e->s, a);
+        return cudaGetLastError();
+    };
+    CK(w == 1 ? go(vm_rollout_kernel<1>) : (w == 2 ? go(vm_rollout_kernel<2>) : go(vm_rollout_kernel<4>)));
+    return 0;
+}
+
 int maro_vm_best_fit_policy_device(MaroVmEnv* e, const int32_t* d_decisions, int32_t* d_actions) {
     if (!e || !d_decisions || !d_actions) return fail("maro_vm_best_fit_policy_device: bad arguments");
     CK(cudaSetDevice(e->device));

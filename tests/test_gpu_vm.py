@@ -247,6 +247,28 @@ def test_vm_cuda_full_size_episode_matches_oracle():
     assert (c == c[0]).all() and c[0].tolist() == o.counters().tolist() and c[0, 0] == n_steps
     assert np.array_equal(env.read_frame(B - 1), o.frame())
     env.close()
+    # ---- the same episode as fused rollouts (maro_vm_rollout_device: best-fit as a device callback), uneven launch lengths
+    B2 = 296
+    env2 = VmBatch(topo, B2, 1, 8)
+    env2.set_stream(torch.cuda.current_stream().cuda_stream)
+    dec2 = torch.zeros((B2, env2.dec_words), dtype=torch.int32, device="cuda")
+    met2 = torch.zeros((B2, 16), dtype=torch.int64, device="cuda")
+    done = 0
+    for n in [1, 2, 777] + [2000] * 8:
+        env2.rollout_device(dec2.data_ptr(), met2.data_ptr(), n)
+        done += n
+        if (dec2[:, 6] != 0).all().item():
+            break
+    assert done >= n_steps
+    d2, m2 = dec2.cpu().numpy(), met2.cpu().numpy()
+    assert d2[:, 6].tolist() == [1] * B2 and (m2 == m[0]).all()   # stopped at the DONE row, final metrics kept: bit-identical
+    c2 = env2.counters()
+    assert (c2 == c[0]).all()
+    assert np.array_equal(env2.read_frame(B2 - 1), o.frame())
+    assert env2.snapshot_frames(0).tolist() == env2.snapshot_frames(B2 - 1).tolist() and len(env2.snapshot_frames(0)) == 8
+    env2.rollout_device(dec2.data_ptr(), met2.data_ptr(), 3)      # a further launch answers the all-zero FINISHED row
+    assert (dec2.cpu().numpy()[:, 6] == 2).all() and (met2.cpu().numpy() == 0).all()
+    env2.close()
 
 
 def test_vm_cuda_large_hierarchy_of_the_reference_test_config():
