@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) cim_resident_kernel(const __g
 }
 
 enum { kMaxSlices = 16 };
+struct ResGeom { int threads = 0, grid = 0; size_t smem = 0; int per_sm = 0; };  // launch shape of cim_resident_kernel
 
 struct MaroCimEnv : EnvCommon {
     CimShape s;
@@ -449,6 +450,7 @@ struct MaroCimEnv : EnvCommon {
     uint32_t launch_epoch = 0;
     int buf_full_cap = 1, buf_empty_cap = 1;         // buffer ticks the event pool was sized for (set_topology re-validation)
     int res_groups = 0;                              // replicas per CTA of the resident kernel
+    ResGeom roll;                                    // launch shape of the fused rollouts
     std::vector<uint32_t> cta_seq;                   // per CTA: last step completed (the kernel's seq_state mirrors it)
     std::vector<uint8_t> cta_pending;                // per CTA: a step has been sent and not collected yet
     uint32_t *h_cmd = nullptr, *hd_cmd = nullptr;    // [B][4] command rows, mapped pinned
@@ -632,26 +634,29 @@ static cudaError_t launch_step(MaroCimEnv* e, const StepArgs& a) {
 }
 
 template <int G>
-static cudaError_t launch_resident_g(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, bool query_only, int* blocks_per_sm) {
+static cudaError_t launch_resident_g(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, const ResGeom& geo, bool query_only,
+                                     int* blocks_per_sm) {
     const bool general = !(e->s.order_table && !e->s.buffer_noise);
     auto go = [&](auto kernel) -> cudaError_t {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->res_smem);
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem);
         if (err != cudaSuccess) return err;
-        if (query_only) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, e->res_threads, e->res_smem);
-        kernel<<<e->res_grid, e->res_threads, e->res_smem, e->stream>>>(e->s, a, ra);
+        if (query_only) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, geo.threads, geo.smem);
+        kernel<<<geo.grid, geo.threads, geo.smem, e->stream>>>(e->s, a, ra);
         return cudaGetLastError();
     };
     if (general) return go(cim_resident_kernel<G, true>);
     return e->res_dense ? go(cim_resident_kernel<G, false, MARO_RES_DENSE_BLOCKS>) : go(cim_resident_kernel<G, false>);
 }
 
-static cudaError_t launch_resident(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, bool query_only = false, int* blocks_per_sm = nullptr) {
+static cudaError_t launch_resident(MaroCimEnv* e, const StepArgs& a, const ResidentArgs& ra, const ResGeom& geo, bool query_only = false,
+                                   int* blocks_per_sm = nullptr) {
     switch (e->lanes) {
-        case 8: return launch_resident_g<8>(e, a, ra, query_only, blocks_per_sm);
-        case 16: return launch_resident_g<16>(e, a, ra, query_only, blocks_per_sm);
-        default: return launch_resident_g<32>(e, a, ra, query_only, blocks_per_sm);
+        case 8: return launch_resident_g<8>(e, a, ra, geo, query_only, blocks_per_sm);
+        case 16: return launch_resident_g<16>(e, a, ra, geo, query_only, blocks_per_sm);
+        default: return launch_resident_g<32>(e, a, ra, geo, query_only, blocks_per_sm);
     }
 }
+static ResGeom session_geom(const MaroCimEnv* e) { return ResGeom{e->res_threads, e->res_grid, e->res_smem, e->res_per_sm}; }
 
 // ---- host session (RES_SESSION) ---------------------------------------------------------------------
 // Threading contract: maro_cim_submit_pinned / maro_cim_wait_pinned may be called concurrently from several host threads as
@@ -670,7 +675,7 @@ static int session_launch_locked(MaroCimEnv* e) {
     ra.cmd = e->hd_cmd; ra.results = e->hd_res; ra.seq_state = e->d_seq; ra.poll_ns = e->poll_ns; ra.wait_ns = e->wait_ns;
     ra.idle_cycles = e->idle_cycles; ra.heartbeat = e->hd_beat;
     ra.exit_flag = e->d_exit; ra.epoch = ++e->launch_epoch;  // (epochs start at 1; the flag holds 0 or an older epoch)
-    CK(launch_resident(e, a, ra));
+    CK(launch_resident(e, a, ra, session_geom(e)));
     e->session_live.store(true, std::memory_order_release);
     return 0;
 }
@@ -853,35 +858,58 @@ static int create_device_side(MaroCimEnv* e, const MaroCimTopology* topos, int32
     const int nsm = prop.multiProcessorCount;
     const int gpw = 32 / e->lanes;
     const size_t per_group = (size_t)s.SW * 4 + 64 + 16, max_smem = prop.sharedMemPerBlockOptin;  // block + output slot + command row
+    // One replica per warp (spread) while every replica can be resident at once, else 32 / lanes replicas per warp (packed).  The
+    // resident kernel holds 16 warps per SM at 108-128 registers: toy.4p rollouts at 3 072 replicas run 13.1 us per batched step
+    // spread (1.3 waves) against 8.8 us packed, at 2 048 (one wave) 7.5 against 8.5.  MARO_B200_RES_SPREAD=0/1 forces a mode.
     const char* rs = getenv("MARO_B200_RES_SPREAD");
     e->res_spread = rs ? atoi(rs) != 0 : (B <= nsm * 32);
-    const int groups_per_warp = e->res_spread ? 1 : gpw;
-    int w = 8;
-    if (e->res_spread) {  // smallest power of two >= replicas per SM (command blocks of a CTA stay 64 / 128-byte aligned)
-        w = 1;
-        while (w < 8 && w * nsm < B) w <<= 1;
-    }
-    if (const char* rw = getenv("MARO_B200_RES_WARPS")) w = std::min(8, std::max(1, atoi(rw)));
-    while (w > 1 && 256 + 16 + per_group * w * groups_per_warp > max_smem) w--;
-    if (256 + 16 + per_group * w * groups_per_warp <= max_smem) {
+    e->n_sm = nsm;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int groups_per_warp = e->res_spread ? 1 : gpw;
+        int w = 8;
+        if (e->res_spread) {  // smallest power of two >= replicas per SM (command blocks of a CTA stay 64 / 128-byte aligned)
+            w = 1;
+            while (w < 8 && w * nsm < B) w <<= 1;
+        }
+        if (const char* rw = getenv("MARO_B200_RES_WARPS")) w = std::min(8, std::max(1, atoi(rw)));
+        while (w > 1 && 256 + 16 + per_group * w * groups_per_warp > max_smem) w--;
+        e->res_threads = 0;
+        if (256 + 16 + per_group * w * groups_per_warp > max_smem) break;  // (the block does not fit: per-step kernel only)
         e->res_threads = w * 32;
         e->res_smem = 256 + 16 + per_group * w * groups_per_warp;
         e->res_grid = (B + w * groups_per_warp - 1) / (w * groups_per_warp);
         e->res_groups = w * groups_per_warp;
         const char* rd = getenv("MARO_B200_RES_DENSE");  // register-capped instantiation for grids several waves deep
         e->res_dense = rd ? atoi(rd) != 0 : (!e->res_spread && w == 8 && e->res_grid > 5 * nsm);
-        e->cta_seq.assign(e->res_grid, 0);
-        e->cta_pending.assign(e->res_grid, 0);
         int per_sm = 0;
         StepArgs a = base_args(e);
         ResidentArgs ra;
         memset(&ra, 0, sizeof(ra));
-        CK(launch_resident(e, a, ra, true, &per_sm));
+        CK(launch_resident(e, a, ra, session_geom(e), true, &per_sm));
         e->res_per_sm = per_sm;
-        e->n_sm = nsm;
+        if (attempt == 0 && e->res_spread && !rs && gpw > 1 && (int64_t)per_sm * nsm < e->res_grid) {
+            e->res_spread = 0;
+            continue;
+        }
+        // Rollouts use the session's launch shape.  (Measured: CTAs of 1 / 2 / 8 warps give the same rollout time from 1 024 to
+        // 16 384 replicas and 8 warps are 2-5 % ahead at 65 536 — the kernel is latency bound per warp, not balance bound per
+        // SM.  MARO_B200_ROLL_WARPS forces a CTA size for A/B runs.)
+        e->roll = session_geom(e);
+        if (const char* fw = getenv("MARO_B200_ROLL_WARPS")) {
+            const int cw = std::min(w, std::max(1, atoi(fw)));
+            ResGeom g;
+            g.threads = cw * 32;
+            g.smem = 256 + 16 + per_group * cw * groups_per_warp;
+            g.grid = (B + cw * groups_per_warp - 1) / (cw * groups_per_warp);
+            CK(launch_resident(e, a, ra, g, true, &g.per_sm));
+            e->roll = g;
+        }
+        e->cta_seq.assign(e->res_grid, 0);
+        e->cta_pending.assign(e->res_grid, 0);
         if (const char* sl = getenv("MARO_B200_RES_SLICE_STEPS")) e->res_slice_steps = atoi(sl);
         const char* se = getenv("MARO_B200_SESSION");
         e->session_ok = (se ? atoi(se) != 0 : true) && (int64_t)per_sm * nsm >= e->res_grid && !s.joint;  // (64-byte result lines)
+        break;
     }
     e->scenario_id = 1;
     e->ckpt_extra = {{"tables", (void**)&e->d_tables, e->h_tables.size() * 4}, {"replica_topology", (void**)&e->d_topo, (size_t)B * 4},
@@ -1201,30 +1229,28 @@ int maro_cim_rollout_device(MaroCimEnv* e, int32_t policy, uint32_t seed, uint32
     ra.replica_base = replica_base; ra.trace = d_trace;
     // Sliced launch when the grid does not fit the GPU at once and the last wave would be mostly empty (>= 10 % of the launch
     // lost to it): resident lane groups pull (slice, replica) tickets instead (cim_resident_kernel).
-    const int capacity = e->res_per_sm * e->n_sm;
+    ResGeom geo = e->roll;
+    const int capacity = geo.per_sm * e->n_sm;
     int slice_steps = 0;
     // (one replica per warp only: lane groups that share a warp would serialise once they run different slices.  Measured on
     // BASELINE config #4, 1 024 replicas = 171 CTAs on 148 SMs: 46.0 -> 32.4 us per batched env-step; 4 / 8 / 16 steps per slice
     // within 3 % of each other)
     const bool warp_per_replica = e->res_spread || e->lanes == 32;
     if (e->res_slice_steps > 0) slice_steps = e->res_slice_steps;  // (forced: tests, A/B)
-    else if (e->res_slice_steps < 0 && capacity > 0 && e->res_grid > capacity && n_steps >= 16) {
-        const int waves = (e->res_grid + capacity - 1) / capacity;
-        if ((int64_t)waves * capacity * 10 >= (int64_t)e->res_grid * 11) slice_steps = 8;
+    else if (e->res_slice_steps < 0 && capacity > 0 && geo.grid > capacity && n_steps >= 16) {
+        const int waves = (geo.grid + capacity - 1) / capacity;
+        if ((int64_t)waves * capacity * 10 >= (int64_t)geo.grid * 11) slice_steps = 8;
     }
     if (!warp_per_replica) slice_steps = 0;
     if (slice_steps) slice_steps = std::max(slice_steps, (n_steps + kMaxSlices - 1) / kMaxSlices);
     if (slice_steps >= n_steps || e->B >= (1 << 24) - 1) slice_steps = 0;
-    const int full_grid = e->res_grid;
     if (slice_steps) {
         const int n_slices = (n_steps + slice_steps - 1) / slice_steps;
         CK(cudaMemsetAsync(e->d_slice, 0, (2 + (size_t)e->B * (n_slices - 1)) * 4, e->stream));
         ra.slice_steps = slice_steps; ra.slice_sync = e->d_slice;
-        e->res_grid = std::min(full_grid, std::max(1, capacity));
+        geo.grid = std::min(geo.grid, std::max(1, capacity));
     }
-    cudaError_t err = launch_resident(e, a, ra);
-    e->res_grid = full_grid;
-    CK(err);
+    CK(launch_resident(e, a, ra, geo));
     return 0;
 }
 
