@@ -528,12 +528,15 @@ def _rl_extras(torch, env, dec, topo, B, stream):
     ro = CimDeviceRollout(env, lambda st: mlp(st * 1e-4).argmax(1), shaper, store_states=False)
     ro.run_episode(max_steps=50)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    traj = ro.run_episode()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    runs = []
+    for _ in range(3):  # one episode each, wall clock; the best of three (the loop is host-enqueued: a busy host core shows)
+        t0 = time.perf_counter()
+        traj = ro.run_episode()
+        torch.cuda.synchronize()
+        runs.append(time.perf_counter() - t0)
+    dt = min(runs)
     shaping["rollout"] = {"env_steps_per_s": float(traj["valid"].sum().item()) / dt, "steps": int(traj["valid"].shape[0]),
-                          "seconds": dt, "cuda_graph": ro._graph is not None, "graph_error": ro.graph_error,
+                          "seconds": dt, "seconds_all_runs": runs, "cuda_graph": ro._graph is not None, "graph_error": ro.graph_error,
                           "what": "BatchedCimEnvSampler.collect: one episode, MLP policy on the same GPU, sync-free fixed-length loop "
                                   "in CUDA-graph chunks, rewards in one launch (wall clock)"}
     return shaping
