@@ -269,6 +269,14 @@ int maro_cim_rl_state_f32_device(MaroCimEnv* env, const int32_t* d_decisions, in
 int maro_cim_rl_action_device(MaroCimEnv* env, const int32_t* d_decisions, const int32_t* d_model_actions,
                               const double* d_action_space, int32_t n_action_space, int32_t finite_vessel_space,
                               int32_t has_early_discharge, int32_t* d_actions);
+/* The same translation with the bookkeeping a collection loop otherwise spends launches on (each pointer optional): the policy's
+ * output taken as int64 (torch argmax) or int32, the index used recorded as int32 [n_replicas], and the previous step's metrics
+ * [n_replicas][3] folded into a running maximum — the three CIM metrics are non-negative running totals and a replica stepped past
+ * its DONE row reports zeros, so the maximum over an episode is the DONE row's value. */
+int maro_cim_rl_action_ex_device(MaroCimEnv* env, const int32_t* d_decisions, const void* d_model_actions, int32_t model_actions_are_i64,
+                                 int32_t* d_model_actions_record, const int64_t* d_metrics_in, int64_t* d_metrics_final,
+                                 const double* d_action_space, int32_t n_action_space, int32_t finite_vessel_space,
+                                 int32_t has_early_discharge, int32_t* d_actions);
 /* Reward of replica i for the action it took at tick d_ticks[i] on port d_ports[i] (env_sampler.py:66-80):
  *   float32(fulfillment_factor * sum_k decay[k] * fulfillment[tick+1+k, port]
  *           - shortage_factor * sum_k decay[k] * shortage[tick+1+k, port]),   k = 0 .. time_window-1,

@@ -20,7 +20,7 @@ EXPORTS = (
     "maro_cim_query_device", "maro_cim_attr_id", "maro_cim_attr_slots", "maro_cim_read_frame",
     "maro_cim_frame_words", "maro_cim_ticks", "maro_cim_counters", "maro_cim_snapshot_frames",
     "maro_cim_random_policy_device", "maro_cim_pinned_buffers", "maro_cim_step_pinned", "maro_cim_rollout_device", "maro_cim_pinned_granularity", "maro_cim_submit_pinned", "maro_cim_wait_pinned",
-    "maro_cim_rl_state_dim", "maro_cim_rl_state_device", "maro_cim_rl_state_f32_device", "maro_cim_rl_reward_device", "maro_cim_rl_reward_batch_device", "maro_cim_rl_action_device",
+    "maro_cim_rl_state_dim", "maro_cim_rl_state_device", "maro_cim_rl_state_f32_device", "maro_cim_rl_reward_device", "maro_cim_rl_reward_batch_device", "maro_cim_rl_action_device", "maro_cim_rl_action_ex_device",
     "maro_bike_pinned_buffers", "maro_bike_step_pinned",
     "maro_bike_create", "maro_bike_destroy", "maro_bike_set_stream", "maro_bike_decision_words", "maro_bike_step",
     "maro_bike_step_device", "maro_bike_reset", "maro_bike_query", "maro_bike_attr_id", "maro_bike_attr_slots",
@@ -84,6 +84,7 @@ def lib():
     L.maro_cim_rl_reward_device.argtypes = [vp, vp, vp, vp, i32, C.c_double, C.c_double, vp]
     L.maro_cim_rl_reward_batch_device.argtypes = [vp, vp, vp, i32, vp, i32, C.c_double, C.c_double, vp]
     L.maro_cim_rl_action_device.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    L.maro_cim_rl_action_ex_device.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]
     pvp = C.POINTER(vp)
     for name in ("maro_cim_pinned_buffers", "maro_bike_pinned_buffers", "maro_vm_pinned_buffers"):
         getattr(L, name).argtypes = [vp, pvp, pvp, pvp, pvp, pvp]

@@ -175,6 +175,16 @@ class CimBatch:
                                                               n_action_space, int(finite_vessel_space),
                                                               int(has_early_discharge), d_actions))
 
+    def rl_action_ex_device(self, d_decisions: int, d_model_actions: int, model_actions_are_i64: bool, d_record: int, d_metrics_in: int,
+                            d_metrics_final: int, d_action_space: int, n_action_space: int, finite_vessel_space: bool,
+                            has_early_discharge: bool, d_actions: int):
+        """maro_cim_rl_action_ex_device: the translation + the sampler's bookkeeping (int64 policy output, int32 record, running
+        maximum of the metrics) in one launch; 0 for a pointer that is not wanted"""
+        _native.check(_native.lib().maro_cim_rl_action_ex_device(self._h, d_decisions, d_model_actions, int(model_actions_are_i64),
+                                                                 d_record or None, d_metrics_in or None, d_metrics_final or None,
+                                                                 d_action_space, n_action_space, int(finite_vessel_space),
+                                                                 int(has_early_discharge), d_actions))
+
     def rl_reward_device(self, d_ticks: int, d_ports: int, d_decay: int, time_window: int, fulfillment_factor: float,
                          shortage_factor: float, d_out: int):
         _native.check(_native.lib().maro_cim_rl_reward_device(self._h, d_ticks, d_ports, d_decay, time_window,

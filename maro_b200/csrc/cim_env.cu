@@ -490,6 +490,11 @@ struct ShapeArgs {
     const double* action_space;    // [n_action_space]
     int n_action_space, finite_vessel_space, has_early_discharge, max_actions, off_remaining_space, off_early_discharge;
     int32_t* actions_out;          // [B][max_actions][4]
+    // sampler extras of the action kernel (maro_cim_rl_action_ex_device), each optional
+    const int64_t* model_actions_i64;  // [B] the policy's output as int64 (torch argmax) instead of model_actions
+    int32_t* model_actions_record;     // [B] the index that was used, as int32 (the sampler's record)
+    const int64_t* met_in;             // [B][3] metrics of the previous step ...
+    int64_t* met_final;                // [B][3] ... folded into a running maximum (= the metrics of the DONE row, see rl_rollout.py)
 };
 
 // word `w` of snapshot `frame` of replica `rep`; frames not in the ring read as 0 (np_backend.pyx:543-549)
@@ -1272,10 +1277,16 @@ __global__ void cim_rl_action_kernel(const __grid_constant__ ShapeArgs q) {
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;
     if (rep >= q.B) return;
     const int32_t* d = q.decisions + (int64_t)rep * 8;
+    if (q.model_actions_record) q.model_actions_record[rep] = q.model_actions_i64 ? (int)q.model_actions_i64[rep] : q.model_actions[rep];
+    if (q.met_final)
+        for (int j = 0; j < 3; j++) {
+            const int64_t a = q.met_in[(int64_t)rep * 3 + j], b = q.met_final[(int64_t)rep * 3 + j];
+            if (a > b) q.met_final[(int64_t)rep * 3 + j] = a;
+        }
     int4 out = make_int4(0, 0, 0, 0);
     if (d[MARO_DEC_STATUS] == MARO_STATUS_DECISION) {
         const int tick = d[MARO_DEC_TICK], vessel = d[MARO_DEC_VESSEL];
-        int m = q.model_actions[rep];
+        int m = q.model_actions_i64 ? (int)q.model_actions_i64[rep] : q.model_actions[rep];
         m = m < 0 ? 0 : (m >= q.n_action_space ? q.n_action_space - 1 : m);
         const int32_t* now = nullptr;
         const bool have_now = snap_row(q, rep, tick, now);
@@ -1355,15 +1366,11 @@ int maro_cim_rl_state_f32_device(MaroCimEnv* e, const int32_t* d_decisions, int3
     return rl_state_launch(e, d_decisions, look_back, port_attrs, n_port_attrs, vessel_attrs, n_vessel_attrs, nullptr, d_out);
 }
 
-int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const int32_t* d_model_actions, const double* d_action_space,
-                              int32_t n_action_space, int32_t finite_vessel_space, int32_t has_early_discharge, int32_t* d_actions) {
-    if (!e || !d_decisions || !d_model_actions || !d_action_space || !d_actions || n_action_space < 1)
-        return fail("maro_cim_rl_action_device: bad arguments");
+static int rl_action_launch(MaroCimEnv* e, ShapeArgs& q, const int32_t* d_decisions, const double* d_action_space, int32_t n_action_space,
+                            int32_t finite_vessel_space, int32_t has_early_discharge, int32_t* d_actions) {
     CK(cudaSetDevice(e->device));
     END_SESSION(e);
-    ShapeArgs q;
-    shape_common(e, q);
-    q.decisions = d_decisions; q.model_actions = d_model_actions; q.action_space = d_action_space; q.n_action_space = n_action_space;
+    q.decisions = d_decisions; q.action_space = d_action_space; q.n_action_space = n_action_space;
     q.finite_vessel_space = finite_vessel_space; q.has_early_discharge = has_early_discharge; q.max_actions = e->s.max_actions;
     q.off_remaining_space = e->attrs[1][common_attr_id(e, 1, "remaining_space")].off;
     q.off_early_discharge = e->attrs[1][common_attr_id(e, 1, "early_discharge")].off;
@@ -1372,6 +1379,30 @@ int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const i
     cim_rl_action_kernel<<<blocks, threads, 0, e->stream>>>(q);
     CK(cudaGetLastError());
     return 0;
+}
+
+int maro_cim_rl_action_device(MaroCimEnv* e, const int32_t* d_decisions, const int32_t* d_model_actions, const double* d_action_space,
+                              int32_t n_action_space, int32_t finite_vessel_space, int32_t has_early_discharge, int32_t* d_actions) {
+    if (!e || !d_decisions || !d_model_actions || !d_action_space || !d_actions || n_action_space < 1)
+        return fail("maro_cim_rl_action_device: bad arguments");
+    ShapeArgs q;
+    shape_common(e, q);
+    q.model_actions = d_model_actions;
+    return rl_action_launch(e, q, d_decisions, d_action_space, n_action_space, finite_vessel_space, has_early_discharge, d_actions);
+}
+
+int maro_cim_rl_action_ex_device(MaroCimEnv* e, const int32_t* d_decisions, const void* d_model_actions, int32_t model_actions_are_i64,
+                                 int32_t* d_model_actions_record, const int64_t* d_metrics_in, int64_t* d_metrics_final,
+                                 const double* d_action_space, int32_t n_action_space, int32_t finite_vessel_space,
+                                 int32_t has_early_discharge, int32_t* d_actions) {
+    if (!e || !d_decisions || !d_model_actions || !d_action_space || !d_actions || n_action_space < 1 || (!d_metrics_in) != (!d_metrics_final))
+        return fail("maro_cim_rl_action_ex_device: bad arguments");
+    ShapeArgs q;
+    shape_common(e, q);
+    if (model_actions_are_i64) q.model_actions_i64 = static_cast<const int64_t*>(d_model_actions);
+    else q.model_actions = static_cast<const int32_t*>(d_model_actions);
+    q.model_actions_record = d_model_actions_record; q.met_in = d_metrics_in; q.met_final = d_metrics_final;
+    return rl_action_launch(e, q, d_decisions, d_action_space, n_action_space, finite_vessel_space, has_early_discharge, d_actions);
 }
 
 static int rl_reward_launch(MaroCimEnv* e, const int32_t* d_ticks, const int32_t* d_ports, int32_t n_rows, const double* d_decay,

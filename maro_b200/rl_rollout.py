@@ -106,18 +106,20 @@ class BatchedCimEnvSampler:
     # ------------------------------------------------------------------------------------------------ device loop
     def _body(self, k: int):
         """one env-step of every replica: state -> policy -> action -> step; slot k records the decision it answered.
-        Launches per step besides the policy's own: state kernel (float32, straight into the record), one copy (policy output ->
-        int32 record), action kernel, step kernel, one elementwise max."""
+        Launches per step besides the policy's own: state kernel (float32, straight into the record), action kernel (takes the
+        policy's int64 / int32 output as it is, records it as int32 and folds the previous step's metrics into the running
+        maximum), step kernel (writes the next decision row of the record)."""
         torch, sh, env = self._torch, self.shaper, self.batch
         dec = self._c_dec[k]
         s = sh.states(dec, out=self._c_state[k if self.store_states else 0])
         m = self.policy(s, dec) if self.policy_takes_decisions else self.policy(s)
-        self._c_act[k].copy_(m)  # (converts to int32)
-        actions = sh.env_actions(dec, self._c_act[k])
-        env.step_device(self._c_dec[k + 1].data_ptr(), self._met.data_ptr(), actions.data_ptr())
+        if m.dtype not in (torch.int32, torch.int64) or not m.is_contiguous():
+            m = m.to(torch.int32).contiguous()
         # the episode's metrics come with the DONE row; a replica stepped past it answers all-zero FINISHED rows.  The three
-        # metrics are non-negative running totals, so the value at DONE is the maximum over the episode.
-        torch.maximum(self._final_met, self._met, out=self._final_met)
+        # metrics are non-negative running totals, so the value at DONE is the maximum over the episode (the last step's
+        # metrics are folded in by collect()).
+        actions = sh.env_actions(dec, m, record=self._c_act[k], metrics=self._met, final_metrics=self._final_met)
+        env.step_device(self._c_dec[k + 1].data_ptr(), self._met.data_ptr(), actions.data_ptr())
 
     def _run_chunk(self, n: int):
         torch = self._torch
@@ -177,6 +179,7 @@ class BatchedCimEnvSampler:
                 states[t:t + n].copy_(self._c_state[:n])
             self._c_dec[0].copy_(self._c_dec[n])  # the next chunk's input
             t += n
+        torch.maximum(self._final_met, self._met, out=self._final_met)  # (the last step's metrics)
         valid = decs[:, :, 6] == 0
         ticks = torch.where(valid, decs[:, :, 0], torch.full_like(decs[:, :, 0], -1)).contiguous()
         ports = decs[:, :, 1].contiguous()

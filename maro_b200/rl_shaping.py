@@ -75,10 +75,22 @@ class CimShaper:
                                           self.fulfillment_factor, self.shortage_factor, out.data_ptr())
         return out
 
-    def env_actions(self, decisions, model_actions):
-        """decisions int32 [B][8], model_actions int32 [B] (indices into the action space) -> int32 CUDA tensor
-        [B][max_actions][4], the `actions` argument of ``CimBatch.step_device`` (env_sampler.py:38-64)."""
-        assert model_actions.is_cuda and model_actions.dtype == self._torch.int32 and model_actions.is_contiguous()
-        self.batch.rl_action_device(decisions.data_ptr(), model_actions.data_ptr(), self._space.data_ptr(), self._space.numel(),
-                                    self.finite_vessel_space, self.has_early_discharge, self._actions.data_ptr())
+    def env_actions(self, decisions, model_actions, record=None, metrics=None, final_metrics=None):
+        """decisions int32 [B][8], model_actions int32 or int64 [B] (indices into the action space) -> int32 CUDA tensor
+        [B][max_actions][4], the `actions` argument of ``CimBatch.step_device`` (env_sampler.py:38-64).  Optional bookkeeping of a
+        collection loop, done by the same launch: ``record`` int32 [B] receives the indices; ``metrics`` int64 [B][3] (the
+        previous step's) are folded into the running maximum ``final_metrics`` int64 [B][3]."""
+        torch = self._torch
+        assert model_actions.is_cuda and model_actions.is_contiguous() and model_actions.dtype in (torch.int32, torch.int64)
+        if record is None and metrics is None and model_actions.dtype == torch.int32:
+            self.batch.rl_action_device(decisions.data_ptr(), model_actions.data_ptr(), self._space.data_ptr(), self._space.numel(),
+                                        self.finite_vessel_space, self.has_early_discharge, self._actions.data_ptr())
+            return self._actions
+        for t, dt in ((record, torch.int32), (metrics, torch.int64), (final_metrics, torch.int64)):
+            assert t is None or (t.is_cuda and t.is_contiguous() and t.dtype == dt)
+        assert (metrics is None) == (final_metrics is None)
+        self.batch.rl_action_ex_device(decisions.data_ptr(), model_actions.data_ptr(), model_actions.dtype == torch.int64,
+                                       0 if record is None else record.data_ptr(), 0 if metrics is None else metrics.data_ptr(),
+                                       0 if final_metrics is None else final_metrics.data_ptr(), self._space.data_ptr(),
+                                       self._space.numel(), self.finite_vessel_space, self.has_early_discharge, self._actions.data_ptr())
         return self._actions

@@ -75,6 +75,15 @@ def test_device_shaping_at_batch_size_matches_restatement():
     states = shaper.states(dec).cpu().numpy()
     s32 = torch.full(states.shape, -1.0, dtype=torch.float32, device="cuda")
     assert shaper.states(dec, out=s32) is s32 and np.array_equal(s32.cpu().numpy(), states.astype(np.float32))  # maro_cim_rl_state_f32_device
+    # maro_cim_rl_action_ex_device: int64 policy output, int32 record and the running maximum of the metrics in the same launch
+    m32 = torch.remainder(dec[:, 7] * 7 + torch.arange(B, device="cuda", dtype=torch.int32), 21).to(torch.int32).contiguous()
+    plain = shaper.env_actions(dec, m32).clone()
+    record = torch.full((B,), -5, dtype=torch.int32, device="cuda")
+    fin = torch.zeros((B, 3), dtype=torch.int64, device="cuda")
+    fin[::2] = 1 << 40
+    want_fin = torch.maximum(fin, met)
+    ex = shaper.env_actions(dec, m32.to(torch.int64), record=record, metrics=met, final_metrics=fin)
+    assert torch.equal(ex, plain) and torch.equal(record, m32) and torch.equal(fin, want_fin) and int(met.sum()) > 0
     ticks = torch.tensor(np.maximum(d[:, 0] - 120, 0), dtype=torch.int32, device="cuda")
     ports = torch.tensor(d[:, 1] % topo.n_ports, dtype=torch.int32, device="cuda")
     rewards = shaper.rewards(ticks, ports).cpu().numpy()
