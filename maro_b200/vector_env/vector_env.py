@@ -192,11 +192,18 @@ class VectorEnv:
         dec, met = self._batch.step(self._act, self._nact, self._active)
         if cim:
             return self._decode_cim(dec, met)
+        # citi_bike / vm_scheduling: the decision rows become Python ints in one ``tolist()`` (per-element numpy indexing costs more
+        # than building the objects); the metrics rows stay arrays (vm_scheduling keeps float64 bit patterns in them)
         metrics, events = [], []
-        for i in range(B):
-            if not self._active[i]:
-                continue
-            st = int(dec[i, _abi.DEC_STATUS])
+        bike = self._scenario == "citi_bike"
+        if bike:
+            from ..scenarios.citi_bike.common import decode_bike_decision
+        else:
+            from ..scenarios.vm_scheduling.common import decode_vm_decision, decode_vm_metrics
+        rows, mets = dec.tolist(), (met.tolist() if bike else None)
+        for i in (range(B) if self._active.all() else np.flatnonzero(self._active).tolist()):
+            d = rows[i]
+            st = d[_abi.DEC_STATUS]
             if st == _abi.STATUS_BAD_ACTION:
                 raise AssertionError(f"env {i}: invalid action (outside the action scope / unknown VM or PM id)")
             if st == _abi.STATUS_QUEUE_OVERFLOW:
@@ -205,26 +212,22 @@ class VectorEnv:
                 metrics.append(None)
                 events.append(None)
                 continue
-            self._ticks[i] = dec[i, 0]
-            if self._scenario == "citi_bike":
-                from ..scenarios.citi_bike.common import decode_bike_decision
-
-                metrics.append({"trip_requirements": int(met[i, 0]), "bike_shortage": int(met[i, 1]),
-                                "operation_number": int(met[i, 2])})
+            self._ticks[i] = d[0]
+            if bike:
+                m = mets[i]
+                metrics.append({"trip_requirements": m[0], "bike_shortage": m[1], "operation_number": m[2]})
                 if st == _abi.STATUS_DONE:
                     self._done[i] = True
                     events.append(None)
                 else:
-                    events.append(decode_bike_decision(dec[i], self._snapshot_lists[i]))
+                    events.append(decode_bike_decision(d, self._snapshot_lists[i]))
                 continue
-            from ..scenarios.vm_scheduling.common import decode_vm_decision, decode_vm_metrics
-
             metrics.append(decode_vm_metrics(met[i]))
             if st == _abi.STATUS_DONE:
                 self._done[i] = True
                 events.append(None)
             else:
-                events.append(decode_vm_decision(dec[i]))
+                events.append(decode_vm_decision(d))
         return metrics, events, bool(self._done.all())
 
     def _decode_cim(self, dec, met):

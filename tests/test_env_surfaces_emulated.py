@@ -47,6 +47,58 @@ def test_vm_env_surface_replays_reference_trace_emulated():
     vm_surfaces.test_vm_env_surface_replays_reference_trace()
 
 
+def test_vm_vector_env_list_and_dict_stepping_emulated():
+    vm_surfaces.test_vm_vector_env_two_envs_and_pinned_api(pinned=False)
+
+
+def test_bike_vector_env_matches_the_env_facade_emulated(tmp_path):
+    """VectorEnv("citi_bike") with two envs, list stepping with a greedy agent: every env's DecisionEvents / metrics equal the
+    single-env façade's (and through it the reference trace the Env test replays)."""
+    import os
+    import shutil
+
+    import yaml
+
+    from maro_b200.scenarios.citi_bike.common import Action, DecisionType
+    from maro_b200.simulator import Env
+    from maro_b200.vector_env import VectorEnv
+
+    src = os.path.join(bike_surfaces.GOLDEN, "bike_case_2")
+    with open(os.path.join(src, "decision.yml")) as fp:
+        conf = yaml.safe_load(fp)
+    conf.update(trip_data=os.path.join(src, "trips.bin"), weather_data=os.path.join(src, "weathers.bin"),
+                stations_init_data=os.path.join(src, "stations.csv"), distance_adj_data=os.path.join(src, "distance_adj.csv"))
+    with open(tmp_path / "config.yml", "w") as fp:
+        yaml.safe_dump(conf, fp)
+
+    def agent(ev):
+        best = max((kv for kv in ev.action_scope.items() if kv[0] != ev.station_idx), key=lambda kv: (kv[1], kv[0]), default=None)
+        if best is None:
+            return None
+        return Action(ev.station_idx, best[0], best[1]) if ev.type == DecisionType.Supply else Action(best[0], ev.station_idx, best[1])
+
+    env = Env("citi_bike", str(tmp_path), durations=30, options={"transfer_seed": 2})
+    trace = []
+    metrics, ev, done = env.step(None)
+    while not done:
+        trace.append((ev.tick, ev.station_idx, ev.frame_index, ev.type, dict(ev.action_scope), dict(metrics)))
+        metrics, ev, done = env.step(agent(ev))
+    final = dict(metrics)
+    env.close()
+    assert len(trace) > 5
+    with VectorEnv(2, "citi_bike", str(tmp_path), durations=30, options={"transfer_seed": 2}) as venv:
+        metrics, events, done = venv.step(None)
+        for want in trace:
+            assert not done
+            for i in range(2):
+                e = events[i]
+                assert (e.tick, e.station_idx, e.frame_index, e.type, dict(e.action_scope), dict(metrics[i])) == want
+                assert list(e.action_scope)[-1] == e.station_idx
+            metrics, events, done = venv.step([agent(e) for e in events])
+        assert done and events == [None, None] and [dict(m) for m in metrics] == [final, final]
+        assert venv.step(None) == ([None, None], [None, None], True)
+
+
 def test_vm_float_queries_are_lifted_to_the_reference_float64_values():
     """VmBatch.query: cpu_utilization / energy_consumption come back as the float64 values the reference's static backend
     holds (k / 100 and the energy model at k), not as the float32 words of the ring; unknown frames stay zero."""

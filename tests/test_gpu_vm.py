@@ -166,7 +166,7 @@ def test_vm_env_surface_replays_reference_trace():
     env.close()
 
 
-def test_vm_vector_env_two_envs_and_pinned_api():
+def test_vm_vector_env_two_envs_and_pinned_api(pinned=True):
     from maro_b200.scenarios.vm_scheduling import AllocateAction
     from maro_b200.vector_env import VectorEnv
 
@@ -190,6 +190,9 @@ def test_vm_vector_env_two_envs_and_pinned_api():
         assert len(events) == 1 and events[0].vm_id == int(gold["steps"][1][1])  # env 1 moved on, env 0 did not
         metrics, events, done = venv.step({0: AllocateAction(first[0], 0)})
         assert len(events) == 1 and events[0].vm_id == int(gold["steps"][1][1])
+        assert events[0].valid_pms_remaining_cpu_cores is not None and len(events[0].valid_pms_remaining_cpu_cores) == len(events[0].valid_pms)
+        if not pinned:  # (the CPU suite runs this test on the emulator-backed batch: no staging buffers there)
+            return
         # zero-copy pinned staging buffers
         venv.reset()
         b = venv.batch
